@@ -1,0 +1,257 @@
+#!/usr/bin/env python
+"""Benchmark of the implicit conduction solve (BASELINE.json metric: CG GDOF/s + implicit steps/s on
+Q2 hexes; % of HBM roofline).
+
+A "step" is one implicit (backward Euler) time step of the nonlinear unsteady conduction solve --
+Newton on R(k) with a preconditioned Krylov solve per Newton iteration -- on a synthetic refined
+brick (BASELINE.json configs[3]: Q2, N=128 -> 257^3 = 16 974 593 DOFs, k(T) = 0.09 T - 17,
+heat flux on x0, isothermal x1), exactly SURVEY.md section 8d "C4".
+
+value  = N_dof x Krylov iterations / time of the timed steps, vectors resident in HBM;
+e2e    = the same through the C-ABI driver with HOST buffers (u copied host->device before and
+         device->host after every step inside the timed region);
+roofline = the Jacobian-vector apply (the dominant kernel), algorithmic 24 B/DOF, timed with CUDA
+         events on the launching stream.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+PROPS = [("Density_rho", "Uniform, 8000"), ("Specific_Heat_C", "Uniform, 500"),
+         ("Thermal_Conductivity_k", "Polynomial, 0.09, -17")]
+BCS = ["HeatFlux, 7.5e5", "HeatFlux, 0", "HeatFlux, 0", "Isothermal, 300", "HeatFlux, 0", "HeatFlux, 0"]
+METRIC = "Krylov GDOF/s (N_dof x Krylov iterations / solve time), nonlinear unsteady implicit step, Q2 hex"
+
+
+def write_ini(path, order, solver, prec, steps):
+    from cases import ini_text
+    with open(path, "w") as f:
+        f.write(ini_text("Nonlinear_Unsteady", "synthetic-brick", 300, PROPS, BCS, newton=100, solver=solver, prec=prec,
+                         steps=steps, order=order))
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index=0):
+        self.rows, self.stop_flag, self.index = [], False, index
+        self.thread = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([t.strip() for t in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def __enter__(self):
+        self.thread.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop_flag = True
+        self.thread.join(timeout=6)
+
+    def summary(self):
+        sm = sorted(float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 3 + i and r[3 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(self.rows)}
+
+
+def cpu_oracle_run(order, solver, prec, n, steps):
+    """The CPU restatement (oracle port) on a bounded sample of the same workload."""
+    from oracle import jots as OJ, mesh as OM
+    with tempfile.TemporaryDirectory() as d:
+        ini = os.path.join(d, "c.ini")
+        write_ini(ini, order, solver, prec, steps)
+        drv = OJ.JOTSDriver(OJ.Config(ini), mesh=OM.make_brick(n, n, n, 0.01, 0.01, 0.01))
+        t0 = time.perf_counter()
+        drv.run()
+        dt = time.perf_counter() - t0
+    st = drv.it.stats
+    return dict(ndof=drv.space.ndof, time=dt, krylov_iters=st["krylov_iters"], steps=st["steps"],
+                gdofs=drv.space.ndof * st["krylov_iters"] / dt / 1e9, steps_per_s=st["steps"] / dt)
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU algorithm (oracle port: full sparse assembly per Newton
+    iteration + SpMV Krylov; the reference itself cannot be built here)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n = args.cpu_n
+    for _ in range(args.warmup and 1):
+        cpu_oracle_run(args.order, args.solver, args.prec, max(2, n // 2), 1)
+    r = cpu_oracle_run(args.order, args.solver, args.prec, n, args.steps)
+    line = {"impl": "reference", "metric": METRIC, "value": r["gdofs"], "unit": "GDOF/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * r["time"] / max(r["steps"], 1), "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args, 1),
+            "steps_per_s": r["steps_per_s"],
+            "cpu_baseline": {"value": r["gdofs"], "unit": "GDOF/s", "cores": 1, "kind": "port",
+                             "sample": "same physics on a %d^3-element Q%d brick (%d DOFs), %d steps; NumPy/SciPy restatement, "
+                                       "1 process (BLAS threads as available)" % (n, args.order, r["ndof"], args.steps)},
+            "e2e": {"value": r["gdofs"], "unit": "GDOF/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def workload_config(args, world):
+    nd = (args.n * args.order + 1) ** 3
+    return {"workload": "configs[3]: synthetic refined brick, %d^3 Q%d hexes, %d DOFs, nonlinear unsteady (backward Euler, "
+                        "dt=1e-2), k(T)=0.09T-17, Newton + %s/%s rel 1e-10" % (args.n, args.order, nd, args.solver, args.prec),
+            "n_elem_per_dir": args.n, "order": args.order, "n_dof": nd, "solver": args.solver, "preconditioner": args.prec,
+            "parallelism": "1 subdomain per GPU" if world > 1 else "single GPU",
+            "l2_policy": "vectors (136 MB each at N=128) exceed the 126 MB L2; no explicit flush"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--n", type=int, default=128, help="elements per direction of the synthetic brick")
+    ap.add_argument("--order", type=int, default=2)
+    ap.add_argument("--solver", default="CG")
+    ap.add_argument("--prec", default="Jacobi")
+    ap.add_argument("--cpu-n", type=int, default=12, help="elements per direction of the CPU-baseline sample")
+    ap.add_argument("--apply-reps", type=int, default=20)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import numpy as np
+    import torch
+    import jots_b200 as J
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if J.load_library().jots_device_count() < 1:
+        raise SystemExit("bench.py needs a CUDA device: jots_b200 has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    W, K = args.warmup, args.steps
+    tmp = tempfile.mkdtemp()
+    ini = os.path.join(tmp, "bench.ini")
+    write_ini(ini, args.order, args.solver, args.prec, 10 ** 9)
+    mesh = J.Mesh.brick(args.n, args.n, args.n, 0.01, 0.01, 0.01)
+    drv = J.Driver(ini, local, mesh=mesh)
+    stream = torch.cuda.current_stream()
+    drv.ctx.set_stream(stream.cuda_stream)
+    ndof = drv.n
+
+    # ---- device-resident timing ---------------------------------------------------------------
+    for _ in range(W):
+        drv.run(1)
+    barrier()
+    drv.ctx.reset_stats()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clk:
+        e0.record(stream)
+        for _ in range(K):
+            drv.run(1)
+        e1.record(stream)
+        barrier()
+    ms = e0.elapsed_time(e1)
+    st = drv.ctx.stats()
+    t = torch.tensor([ms, float(st["krylov_iters"])], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t[0])
+    iters = int(t[1])
+    total_dof = ndof * world   # replicas until the interface exchange lands
+    value = total_dof * iters / (ms * 1e-3) / 1e9
+
+    # ---- end to end through the C ABI with host buffers ---------------------------------------------
+    u_host = torch.empty(ndof, dtype=torch.float64).pin_memory().numpy()
+    drv.get_u(u_host)
+    drv.set_u(u_host); drv.run(1); drv.get_u(u_host)
+    barrier()
+    drv.ctx.reset_stats()
+    t0 = time.perf_counter()
+    for _ in range(K):
+        drv.set_u(u_host)
+        drv.run(1)
+        drv.get_u(u_host)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    st2 = drv.ctx.stats()
+    t = torch.tensor([e2e_s, float(st2["krylov_iters"])], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = total_dof * int(t[1]) / float(t[0]) / 1e9
+
+    # ---- dominant kernel: Jacobian-vector apply -------------------------------------------------------
+    x = torch.empty(ndof, dtype=torch.float64, device="cuda").uniform_(-1.0, 1.0)
+    y = torch.empty_like(x)
+    z = torch.empty_like(x)
+    drv.get_u(z)
+    torch.cuda.synchronize()
+    for _ in range(3):
+        drv.op.form_time(J.FORM_SYSTEM, x, y, state_dev=z, reps=2)
+    apply_ms = drv.op.form_time(J.FORM_SYSTEM, x, y, state_dev=z, reps=args.apply_reps)
+    res_ms = drv.op.form_time(J.FORM_RESIDUAL, x, y, state_dev=z, reps=max(2, args.apply_reps // 4))
+    peaks = {}
+    pk_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(pk_path):
+        peaks = json.load(open(pk_path))
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    alg_bytes = 24.0 * ndof
+    achieved = alg_bytes / (apply_ms * 1e-3) / 1e9
+
+    if rank != 0:
+        return
+    line = {"metric": METRIC, "value": value, "unit": "GDOF/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": workload_config(args, world),
+            "steps_per_s": K / (ms * 1e-3), "krylov_iters": iters, "newton_iters": st["newton_iters"],
+            "apply_gdofs": ndof / (apply_ms * 1e-3) / 1e9, "apply_ms": apply_ms, "residual_ms": res_ms,
+            "clocks": clk.summary(),
+            "e2e": {"value": e2e_value, "unit": "GDOF/s", "h2d_bytes_per_step": 8 * ndof, "d2h_bytes_per_step": 8 * ndof,
+                    "ms_per_step": 1e3 * e2e_s / K},
+            "gpu_launches": st["kernel_launches"],
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "kernel": "form_apply_kernel<OP_JAC,CF_K> (Jacobian-vector apply, 24 B/DOF algorithmic)",
+                         "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6.65 TB/s",
+                         "frac_of_8TBs_spec": achieved / 8000.0}}
+    if not args.no_cpu and world == 1:
+        r = cpu_oracle_run(args.order, args.solver, args.prec, args.cpu_n, 2)
+        line["cpu_baseline"] = {"value": r["gdofs"], "unit": "GDOF/s", "cores": 1, "kind": "port",
+                                "sample": "same physics on a %d^3-element Q%d brick (%d DOFs), 2 steps, %.1f s; NumPy/SciPy "
+                                          "restatement of the reference's assemble+SpMV algorithm" % (args.cpu_n, args.order, r["ndof"], r["time"]),
+                                "steps_per_s": r["steps_per_s"]}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

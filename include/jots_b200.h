@@ -1,0 +1,137 @@
+/*
+ * jots_b200 -- C ABI of the B200-native implicit conduction solve for JOTS.
+ *
+ * The reference (j-signorelli/jots) has no C ABI for this path: its conduction operators sit
+ * behind C++ virtuals supplied by MFEM.  Each entry point below names the reference interface
+ * it replaces (file:line under /root/reference).  INTEGRATION.md shows the binding a JOTS
+ * maintainer adds on the reference side.
+ *
+ * Conventions
+ *   - every function returns 0 on success and a non-zero status on failure, or a handle that is
+ *     NULL on failure; jots_last_error() returns the message (thread-local).  No exceptions
+ *     cross the boundary.  The reference aborts the process on these errors
+ *     (MFEM_ABORT / MFEM_VERIFY: src/nl_conduction_operator.cpp:312, src/jots_driver.cpp:741).
+ *   - vectors are plain FP64 arrays of jots_ctx_size() entries (true-DOF vectors, the layout of
+ *     mfem::Vector u in src/jots_driver.hpp:48).  `loc` says where a pointer lives:
+ *     JOTS_HOST (caller-owned host memory: copied to the device and back inside the call) or
+ *     JOTS_DEVICE (device pointer on the context's GPU: used in place on the context's stream).
+ *   - one context per GPU / rank; there is no CPU fallback: creating a context without a CUDA
+ *     device fails.
+ */
+#ifndef JOTS_B200_H
+#define JOTS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct jots_mesh_s* jots_mesh_t;     /* host mesh (mfem::Mesh role) */
+typedef struct jots_space_s* jots_space_t;   /* host H1 space tables (mfem::ParFiniteElementSpace role) */
+typedef struct jots_ctx_s* jots_ctx_t;       /* device context of one subdomain */
+typedef struct jots_op_s* jots_op_t;         /* one conduction operator (JOTSIterator) */
+typedef struct jots_driver_s* jots_driver_t; /* hot-path callers of JOTSDriver */
+
+enum { JOTS_HOST = 0, JOTS_DEVICE = 1 };
+enum { JOTS_UNIFORM = 0, JOTS_POLYNOMIAL = 1 };                      /* src/option_structure.hpp:25-37 */
+enum { JOTS_BC_ISOTHERMAL = 0, JOTS_BC_HEATFLUX = 1, JOTS_BC_SINUSOIDAL_ISOTHERMAL = 2,
+       JOTS_BC_SINUSOIDAL_HEATFLUX = 3 };                            /* src/option_structure.hpp:56-71 */
+enum { JOTS_CG = 0, JOTS_GMRES = 1, JOTS_FGMRES = 2 };               /* src/option_structure.hpp:91-100 */
+enum { JOTS_JACOBI = 0, JOTS_CHEBYSHEV = 1 };                        /* src/option_structure.hpp:102-109 */
+enum { JOTS_EULER_IMPLICIT = 0, JOTS_EULER_EXPLICIT = 1, JOTS_RK4 = 2 }; /* src/option_structure.hpp:73-82 */
+enum { JOTS_LINEARIZED_UNSTEADY = 0, JOTS_NONLINEAR_UNSTEADY = 1, JOTS_STEADY = 2 }; /* :8-16 */
+enum { JOTS_DENSITY = 0, JOTS_SPECIFIC_HEAT = 1, JOTS_THERMAL_CONDUCTIVITY = 2 };    /* :18-23 */
+/* building-block forms exposed for parity tests */
+enum { JOTS_FORM_MASS = 0,        /* M: linearized int rho C phi phi | nonlinear unit mass, eliminated */
+       JOTS_FORM_STIFFNESS = 1,   /* K: int k grad phi . grad phi, not eliminated
+                                     (src/linear_conduction_operator.cpp:63,94-107) */
+       JOTS_FORM_SYSTEM = 2,      /* A = M + dt K eliminated (:109-120) | Jacobian of R at the state
+                                     (src/nl_conduction_operator.cpp:81-90) | steady Jacobian */
+       JOTS_FORM_RESIDUAL = 3 };  /* R(k) (src/nl_conduction_operator.cpp:70-79) | steady k(u) */
+
+const char* jots_last_error(void);
+int jots_device_count(void);
+const char* jots_version(void);
+
+/* ---- mesh: what the driver gets from mfem::Mesh (src/jots_driver.cpp:156-185) ---------------- */
+jots_mesh_t jots_mesh_read(const char* path);                       /* Mesh(file, 1) */
+jots_mesh_t jots_mesh_brick(int64_t nx, int64_t ny, int64_t nz, double lx, double ly, double lz);
+jots_mesh_t jots_mesh_rect(int64_t nx, int64_t ny, double lx, double ly, double x0, double y0);
+jots_mesh_t jots_mesh_refine(jots_mesh_t m);                        /* UniformRefinement */
+void jots_mesh_destroy(jots_mesh_t m);
+int jots_mesh_info(jots_mesh_t m, int* dim, int64_t* n_elem, int64_t* n_bdr, int64_t* n_verts);
+int jots_mesh_copy(jots_mesh_t m, double* verts, int64_t* elems, int64_t* bdr, int32_t* bdr_attr);
+
+/* ---- space: H1_FECollection + ParFiniteElementSpace (src/jots_driver.cpp:194-196) ------------- */
+jots_space_t jots_space_create(jots_mesh_t m, int order);
+void jots_space_destroy(jots_space_t s);
+int jots_space_info(jots_space_t s, int* dim, int* order, int64_t* n_elem, int64_t* n_dof, int64_t* n_bdr,
+                    int* dofs_per_elem, int* dofs_per_face);
+int jots_space_copy_gather(jots_space_t s, int32_t* gather);        /* [n_elem*dofs_per_elem] */
+int jots_space_copy_bdr(jots_space_t s, int32_t* bdr_gather, int32_t* bdr_attr, int64_t* bdr_elem, int32_t* bdr_face);
+int jots_space_copy_nodes(jots_space_t s, double* xyz);             /* [n_dof*dim] */
+/* GetEssentialTrueDofs (src/jots_iterator.cpp:30): returns the count, fills out[] when non-NULL */
+int64_t jots_space_essential_dofs(jots_space_t s, const int32_t* attrs, int n_attrs, int32_t* out);
+
+/* ---- device context ----------------------------------------------------------------------------- */
+jots_ctx_t jots_ctx_create(jots_space_t s, int device);
+void jots_ctx_destroy(jots_ctx_t c);
+int64_t jots_ctx_size(jots_ctx_t c);
+int jots_ctx_set_stream(jots_ctx_t c, void* cuda_stream);           /* run on the caller's stream */
+int jots_ctx_sync(jots_ctx_t c);
+/* MaterialProperty objects (src/material_property.cpp:6-81): model + coefficients, highest power first */
+int jots_ctx_set_material(jots_ctx_t c, int which, int model, const double* coeffs, int n_coeffs);
+/* BoundaryCondition objects, entry i <-> boundary attribute i+1 (src/jots_iterator.cpp:12-25):
+   params[4*i..] = value | amplitude, angular frequency, phase, vertical shift */
+int jots_ctx_set_bcs(jots_ctx_t c, int n_bc, const int32_t* kinds, const double* params);
+int64_t jots_ctx_essential_dofs(jots_ctx_t c, int32_t* out);        /* ess_tdof_list */
+int jots_ctx_update_bcs(jots_ctx_t c, double time);                 /* BoundaryCondition::UpdateCoeff */
+int jots_ctx_apply_dirichlet(jots_ctx_t c, double* u, int loc, int only_time_dependent); /* ProjectBdrCoefficient, src/jots_driver.cpp:684-707 */
+int jots_ctx_set_material_state(jots_ctx_t c, const double* u, int loc); /* UpdateAllCoeffs(u), src/jots_driver.cpp:664 */
+/* counters: applies, diag assemblies, krylov iters, newton iters, residual evals, steps,
+   kernel launches, dots, last linear iters, last linear converged, last newton iters, last newton converged */
+int jots_ctx_stats(jots_ctx_t c, int64_t out[12], double norms[2]);
+int jots_ctx_reset_stats(jots_ctx_t c);
+
+/* ---- operators (JOTSIterator + TimeDependentOperator) ------------------------------------------- */
+/* LinearConductionOperator / NonlinearConductionOperator / SteadyConductionOperator constructors
+   (src/linear_conduction_operator.cpp:15-74, src/nl_conduction_operator.cpp:166-278,
+   src/steady_conduction_operator.cpp:3-32); solver settings as in Config
+   (src/config_file.cpp:131-165).  The material state must be set before for T-dependent properties. */
+jots_op_t jots_op_create(jots_ctx_t c, int sim_type, double dt, int time_scheme,
+                         int solver, int prec, double rel_tol, double abs_tol, int max_iter,
+                         double newton_rel_tol, double newton_abs_tol, int newton_max_iter);
+void jots_op_destroy(jots_op_t op);
+int jots_op_iterate(jots_op_t op, double* u, int loc, double* time_inout);     /* JOTSIterator::Iterate */
+int jots_op_implicit_solve(jots_op_t op, double dt, const double* u, double* k, int loc); /* ImplicitSolve */
+int jots_op_mult(jots_op_t op, const double* u, double* k, int loc);           /* explicit Mult */
+int jots_op_process_mat_prop_update(jots_op_t op, int which);                  /* ProcessMatPropUpdate */
+int jots_op_update_neumann(jots_op_t op);                                      /* UpdateNeumann */
+int jots_op_get_neumann(jots_op_t op, double* b, int loc);                     /* b_vec */
+/* building blocks: y = form(x) at frozen state (state may be NULL where the form has none) */
+int jots_op_form_apply(jots_op_t op, int form, const double* x, const double* state, double* y, int loc);
+int jots_op_form_diagonal(jots_op_t op, int form, const double* state, double* d, int loc);
+/* repeat y = form(x) `reps` times on device-resident vectors; returns the mean milliseconds per
+   apply measured with CUDA events on the context's stream (bench.py's roofline leg) */
+int jots_op_form_time(jots_op_t op, int form, const double* x_dev, const double* state_dev, double* y_dev,
+                      int reps, double* ms_per_apply);
+
+/* ---- driver shim: Config + the hot-path part of JOTSDriver::Run (src/jots_driver.cpp:568-725) --- */
+jots_driver_t jots_driver_create(const char* ini_path, int device);
+jots_driver_t jots_driver_create_on_mesh(const char* ini_path, jots_mesh_t mesh, int device);
+void jots_driver_destroy(jots_driver_t d);
+int jots_driver_run(jots_driver_t d, int max_steps, int* steps_done);  /* max_steps < 0: to Max_Timesteps */
+int64_t jots_driver_size(jots_driver_t d);
+int jots_driver_get_u(jots_driver_t d, double* u, int loc);
+int jots_driver_set_u(jots_driver_t d, const double* u, int loc);
+double jots_driver_time(jots_driver_t d);
+jots_ctx_t jots_driver_ctx(jots_driver_t d);      /* borrowed */
+jots_op_t jots_driver_op(jots_driver_t d);        /* borrowed: the driver's JOTSIterator */
+int jots_driver_step_count(jots_driver_t d);      /* it_num */
+jots_space_t jots_driver_space(jots_driver_t d);  /* new handle, caller destroys */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* JOTS_B200_H */

@@ -1,0 +1,437 @@
+// extern "C" boundary of libjots_b200.so (declarations and reference citations: include/jots_b200.h)
+#include "../../include/jots_b200.h"
+
+#include <cstring>
+#include <exception>
+#include <string>
+
+#include "driver.hpp"
+#include "halo.hpp"
+#include "launch.hpp"
+
+using namespace jots;
+
+struct jots_mesh_s { Mesh m; };
+struct jots_space_s { Space s; };
+struct jots_ctx_s { std::unique_ptr<Ctx> own; Ctx* c = nullptr; };
+struct jots_op_s {
+    Ctx* c = nullptr;
+    int sim_type = 0;
+    std::unique_ptr<JOTSIterator> own;
+    JOTSIterator* it = nullptr;
+    DArr<double> un;  // u_n copy for residual building blocks
+};
+struct jots_driver_s { std::unique_ptr<JOTSDriver> d; jots_ctx_s ctx_view; jots_op_s op_view; };
+
+static thread_local std::string g_err;
+static int fail(const std::exception& e) { g_err = e.what(); return 1; }
+#define JOTS_TRY try {
+#define JOTS_CATCH_INT } catch (const std::exception& e) { return fail(e); } catch (...) { g_err = "unknown error"; return 1; }
+#define JOTS_CATCH_PTR } catch (const std::exception& e) { fail(e); return nullptr; } catch (...) { g_err = "unknown error"; return nullptr; }
+
+namespace {
+// stage a vector argument on the device
+struct In {
+    const double* p = nullptr;
+    DArr<double> tmp;
+    In(Ctx* c, const double* v, int loc) {
+        if (!v) return;
+        if (loc == JOTS_DEVICE) { p = v; return; }
+        tmp.alloc(c->n);
+        JOTS_CUDA(cudaMemcpyAsync(tmp.p, v, c->n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        p = tmp.p;
+    }
+};
+struct Out {
+    double* p = nullptr;
+    double* host = nullptr;
+    Ctx* c;
+    DArr<double> tmp;
+    Out(Ctx* ctx, double* v, int loc, bool load = false) : c(ctx) {
+        if (loc == JOTS_DEVICE) { p = v; return; }
+        host = v;
+        tmp.alloc(c->n);
+        p = tmp.p;
+        if (load) JOTS_CUDA(cudaMemcpyAsync(p, v, c->n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    }
+    void finish() {
+        if (host) JOTS_CUDA(cudaMemcpyAsync(host, p, c->n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        JOTS_CUDA(cudaStreamSynchronize(c->stream));
+    }
+};
+}  // namespace
+
+extern "C" {
+
+const char* jots_last_error(void) { return g_err.c_str(); }
+const char* jots_version(void) { return "jots_b200 0.1 (sm_100a)"; }
+int jots_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+// ---- mesh -------------------------------------------------------------------------------------
+jots_mesh_t jots_mesh_read(const char* path) {
+    JOTS_TRY auto* h = new jots_mesh_s; h->m = read_mfem_mesh(path); return h; JOTS_CATCH_PTR
+}
+jots_mesh_t jots_mesh_brick(int64_t nx, int64_t ny, int64_t nz, double lx, double ly, double lz) {
+    JOTS_TRY
+    if (nx < 1 || ny < 1 || nz < 1) throw std::runtime_error("brick needs at least one element per direction");
+    auto* h = new jots_mesh_s; h->m = make_brick(nx, ny, nz, lx, ly, lz); return h;
+    JOTS_CATCH_PTR
+}
+jots_mesh_t jots_mesh_rect(int64_t nx, int64_t ny, double lx, double ly, double x0, double y0) {
+    JOTS_TRY auto* h = new jots_mesh_s; h->m = make_rect(nx, ny, lx, ly, x0, y0); return h; JOTS_CATCH_PTR
+}
+jots_mesh_t jots_mesh_refine(jots_mesh_t m) {
+    JOTS_TRY auto* h = new jots_mesh_s; h->m = uniform_refine(m->m); return h; JOTS_CATCH_PTR
+}
+void jots_mesh_destroy(jots_mesh_t m) { delete m; }
+int jots_mesh_info(jots_mesh_t m, int* dim, int64_t* ne, int64_t* nb, int64_t* nv) {
+    JOTS_TRY
+    if (dim) *dim = m->m.dim;
+    if (ne) *ne = m->m.n_elem();
+    if (nb) *nb = m->m.n_bdr();
+    if (nv) *nv = m->m.n_verts();
+    return 0;
+    JOTS_CATCH_INT
+}
+int jots_mesh_copy(jots_mesh_t m, double* verts, int64_t* elems, int64_t* bdr, int32_t* bdr_attr) {
+    JOTS_TRY
+    const Mesh& M = m->m;
+    if (verts) std::memcpy(verts, M.verts.data(), M.verts.size() * sizeof(double));
+    if (elems) std::memcpy(elems, M.elems.data(), M.elems.size() * sizeof(int64_t));
+    if (bdr) std::memcpy(bdr, M.bdr.data(), M.bdr.size() * sizeof(int64_t));
+    if (bdr_attr) for (size_t i = 0; i < M.bdr_attr.size(); ++i) bdr_attr[i] = M.bdr_attr[i];
+    return 0;
+    JOTS_CATCH_INT
+}
+
+// ---- space ------------------------------------------------------------------------------------
+jots_space_t jots_space_create(jots_mesh_t m, int order) {
+    JOTS_TRY auto* h = new jots_space_s; h->s = make_space(m->m, order); return h; JOTS_CATCH_PTR
+}
+void jots_space_destroy(jots_space_t s) { delete s; }
+int jots_space_info(jots_space_t s, int* dim, int* order, int64_t* ne, int64_t* nd, int64_t* nb, int* dpe, int* dpf) {
+    JOTS_TRY
+    const Space& S = s->s;
+    if (dim) *dim = S.dim;
+    if (order) *order = S.p;
+    if (ne) *ne = S.nelem;
+    if (nd) *nd = S.ndof;
+    if (nb) *nb = S.nbdr;
+    if (dpe) *dpe = S.nloc;
+    if (dpf) *dpf = S.nfl;
+    return 0;
+    JOTS_CATCH_INT
+}
+int jots_space_copy_gather(jots_space_t s, int32_t* gather) {
+    JOTS_TRY std::memcpy(gather, s->s.gather.data(), s->s.gather.size() * sizeof(int)); return 0; JOTS_CATCH_INT
+}
+int jots_space_copy_bdr(jots_space_t s, int32_t* bg, int32_t* ba, int64_t* be, int32_t* bf) {
+    JOTS_TRY
+    const Space& S = s->s;
+    if (bg) std::memcpy(bg, S.bdr_gather.data(), S.bdr_gather.size() * sizeof(int));
+    if (ba) std::memcpy(ba, S.bdr_attr.data(), S.bdr_attr.size() * sizeof(int));
+    if (be) std::memcpy(be, S.bdr_elem.data(), S.bdr_elem.size() * sizeof(int64_t));
+    if (bf) std::memcpy(bf, S.bdr_face.data(), S.bdr_face.size() * sizeof(int));
+    return 0;
+    JOTS_CATCH_INT
+}
+int jots_space_copy_nodes(jots_space_t s, double* xyz) {
+    JOTS_TRY
+    std::vector<double> out;
+    s->s.node_coordinates(out);
+    std::memcpy(xyz, out.data(), out.size() * sizeof(double));
+    return 0;
+    JOTS_CATCH_INT
+}
+int64_t jots_space_essential_dofs(jots_space_t s, const int32_t* attrs, int n_attrs, int32_t* out) {
+    try {
+        std::vector<int> a(attrs, attrs + n_attrs), e;
+        s->s.essential_dofs(a, e);
+        if (out) std::memcpy(out, e.data(), e.size() * sizeof(int));
+        return (int64_t)e.size();
+    } catch (const std::exception& ex) { fail(ex); return -1; }
+}
+
+// ---- context ----------------------------------------------------------------------------------
+jots_ctx_t jots_ctx_create(jots_space_t s, int device) {
+    JOTS_TRY
+    auto* h = new jots_ctx_s;
+    h->own.reset(new Ctx(s->s, device));
+    h->c = h->own.get();
+    return h;
+    JOTS_CATCH_PTR
+}
+void jots_ctx_destroy(jots_ctx_t c) { delete c; }
+int64_t jots_ctx_size(jots_ctx_t c) { return c->c->n; }
+int jots_ctx_set_stream(jots_ctx_t c, void* s) {
+    JOTS_TRY
+    c->c->sync();
+    c->c->stream = (cudaStream_t)s;
+    return 0;
+    JOTS_CATCH_INT
+}
+int jots_ctx_sync(jots_ctx_t c) { JOTS_TRY c->c->sync(); return 0; JOTS_CATCH_INT }
+int jots_ctx_set_material(jots_ctx_t c, int which, int model, const double* coeffs, int n) {
+    JOTS_TRY
+    Poly p; p.n = 0; for (double& v : p.c) v = 0.0;
+    if (model == JOTS_UNIFORM) { if (n < 1) throw std::runtime_error("Uniform property needs a value"); p.n = 1; p.c[0] = coeffs[0]; }
+    else if (model == JOTS_POLYNOMIAL) {
+        if (n < 2) throw std::runtime_error("Polynomial property needs >= 2 coefficients");
+        if (n > MAX_POLY) throw std::runtime_error("Polynomial property with more than 8 coefficients is not supported");
+        p.n = n; for (int i = 0; i < n; ++i) p.c[i] = coeffs[i];
+    } else throw std::runtime_error("Unknown/Invalid material model specified");
+    MatSet m = c->c->mat;
+    if (which == JOTS_DENSITY) m.rho = p; else if (which == JOTS_SPECIFIC_HEAT) m.C = p;
+    else if (which == JOTS_THERMAL_CONDUCTIVITY) m.k = p; else throw std::runtime_error("unknown material property id");
+    c->c->set_materials(m.rho, m.C, m.k);
+    return 0;
+    JOTS_CATCH_INT
+}
+int jots_ctx_set_bcs(jots_ctx_t c, int n_bc, const int32_t* kinds, const double* params) {
+    JOTS_TRY
+    if ((size_t)n_bc != c->c->space.attributes.size()) throw std::runtime_error("Input file BC count and mesh BC counts do not match.");
+    std::vector<BCSpec> b(n_bc);
+    for (int i = 0; i < n_bc; ++i) {
+        if (kinds[i] < 0 || kinds[i] > 3) throw std::runtime_error("Invalid/Unknown boundary condition specified");
+        b[i].kind = kinds[i];
+        for (int j = 0; j < 4; ++j) b[i].v[j] = params[4 * i + j];
+        b[i].update(0.0);
+    }
+    c->c->set_bcs(b);
+    return 0;
+    JOTS_CATCH_INT
+}
+int64_t jots_ctx_essential_dofs(jots_ctx_t c, int32_t* out) {
+    if (out) std::memcpy(out, c->c->ess.data(), c->c->ess.size() * sizeof(int));
+    return (int64_t)c->c->ess.size();
+}
+int jots_ctx_update_bcs(jots_ctx_t c, double time) {
+    JOTS_TRY for (auto& b : c->c->bcs) b.update(time); return 0; JOTS_CATCH_INT
+}
+int jots_ctx_apply_dirichlet(jots_ctx_t c, double* u, int loc, int only_td) {
+    JOTS_TRY
+    Ctx* x = c->c;
+    Out o(x, u, loc, true);
+    for (size_t i = 0; i < x->bcs.size(); ++i)
+        if (x->bcs[i].essential() && (!only_td || !x->bcs[i].constant()))
+            v_set_idx(x->stream, (int)x->bc_dofs[i].size(), x->d_bc_dofs[i].p, x->bcs[i].value, o.p);
+    o.finish();
+    return 0;
+    JOTS_CATCH_INT
+}
+int jots_ctx_set_material_state(jots_ctx_t c, const double* u, int loc) {
+    JOTS_TRY In i(c->c, u, loc); c->c->set_mat_state(i.p); c->c->sync(); return 0; JOTS_CATCH_INT
+}
+int jots_ctx_stats(jots_ctx_t c, int64_t out[12], double norms[2]) {
+    const Stats& s = c->c->stats;
+    out[0] = s.applies; out[1] = s.diag_assemblies; out[2] = s.krylov_iters; out[3] = s.newton_iters;
+    out[4] = s.residual_evals; out[5] = s.steps; out[6] = s.kernel_launches; out[7] = s.dots;
+    out[8] = s.last_linear_iters; out[9] = s.last_linear_converged; out[10] = s.last_newton_iters; out[11] = s.last_newton_converged;
+    if (norms) { norms[0] = s.last_linear_norm; norms[1] = s.last_newton_norm; }
+    return 0;
+}
+int jots_ctx_reset_stats(jots_ctx_t c) { c->c->stats = Stats(); return 0; }
+
+// ---- operators --------------------------------------------------------------------------------
+jots_op_t jots_op_create(jots_ctx_t c, int sim_type, double dt, int scheme, int solver, int prec, double rel, double abs_, int max_iter,
+                         double nrel, double nabs, int nmax) {
+    JOTS_TRY
+    SolverSpec ls; ls.solver = solver; ls.prec = prec; ls.rel_tol = rel; ls.abs_tol = abs_; ls.max_iter = max_iter;
+    NewtonSpec nw; nw.rel_tol = nrel; nw.abs_tol = nabs; nw.max_iter = nmax;
+    if (solver < 0 || solver > 2) throw std::runtime_error("unknown solver id");
+    if (prec < 0 || prec > 1) throw std::runtime_error("unknown preconditioner id");
+    auto* h = new jots_op_s;
+    h->c = c->c; h->sim_type = sim_type;
+    if (!c->c->mat_state.p) { c->c->mat_state.alloc(c->c->n); c->c->zero(c->c->mat_state.p); }
+    if (sim_type == JOTS_LINEARIZED_UNSTEADY) h->own.reset(new LinearConductionOperator(c->c, ls, dt, scheme));
+    else if (sim_type == JOTS_NONLINEAR_UNSTEADY) h->own.reset(new NonlinearConductionOperator(c->c, ls, nw, dt, scheme));
+    else if (sim_type == JOTS_STEADY) h->own.reset(new SteadyConductionOperator(c->c, ls, nw));
+    else { delete h; throw std::runtime_error("unknown simulation type id"); }
+    h->it = h->own.get();
+    return h;
+    JOTS_CATCH_PTR
+}
+void jots_op_destroy(jots_op_t op) { delete op; }
+int jots_op_iterate(jots_op_t op, double* u, int loc, double* time) {
+    JOTS_TRY
+    Out o(op->c, u, loc, true);
+    if (time) op->it->time = *time;
+    op->it->Iterate(o.p);
+    if (time) *time = op->it->time;
+    o.finish();
+    return 0;
+    JOTS_CATCH_INT
+}
+
+namespace {
+struct OpAccess : JOTSIterator {  // reach the protected Mult / ImplicitSolve through the base
+    static void implicit(JOTSIterator* it, double dt, const double* u, double* k) { (it->*(&OpAccess::ImplicitSolve))(dt, u, k); }
+    static void mult(JOTSIterator* it, const double* u, double* k) { (it->*(&OpAccess::Mult))(u, k); }
+};
+}  // namespace
+
+int jots_op_implicit_solve(jots_op_t op, double dt, const double* u, double* k, int loc) {
+    JOTS_TRY
+    In i(op->c, u, loc); Out o(op->c, k, loc);
+    OpAccess::implicit(op->it, dt, i.p, o.p);
+    o.finish();
+    return 0;
+    JOTS_CATCH_INT
+}
+int jots_op_mult(jots_op_t op, const double* u, double* k, int loc) {
+    JOTS_TRY
+    In i(op->c, u, loc); Out o(op->c, k, loc);
+    OpAccess::mult(op->it, i.p, o.p);
+    o.finish();
+    return 0;
+    JOTS_CATCH_INT
+}
+int jots_op_process_mat_prop_update(jots_op_t op, int which) { JOTS_TRY op->it->ProcessMatPropUpdate(which); return 0; JOTS_CATCH_INT }
+int jots_op_update_neumann(jots_op_t op) { JOTS_TRY op->it->UpdateNeumann(); return 0; JOTS_CATCH_INT }
+int jots_op_get_neumann(jots_op_t op, double* b, int loc) {
+    JOTS_TRY Out o(op->c, b, loc); op->c->copy(op->it->b_vec.p, o.p); o.finish(); return 0; JOTS_CATCH_INT
+}
+
+// resolve a building-block form of an operator into something to run
+static void run_form(jots_op_t op, int form, const double* x, const double* state, double* y, bool diag) {
+    Ctx* c = op->c;
+    if (op->sim_type == JOTS_LINEARIZED_UNSTEADY) {
+        auto* L = static_cast<LinearConductionOperator*>(op->it);
+        if (state) c->set_mat_state(state);
+        FormSpec f;
+        if (form == JOTS_FORM_MASS) f = L->M_spec();
+        else if (form == JOTS_FORM_STIFFNESS) f = L->K_spec();
+        else if (form == JOTS_FORM_SYSTEM) f = L->A_spec();
+        else if (form == JOTS_FORM_RESIDUAL && !diag) { L->CalculateRHS(x, y); return; }
+        else throw std::runtime_error("form not available for this operator");
+        if (diag) c->diag_form(f, y); else c->apply_form(f, x, y);
+    } else if (op->sim_type == JOTS_NONLINEAR_UNSTEADY) {
+        auto* N = static_cast<NonlinearConductionOperator*>(op->it);
+        if (form == JOTS_FORM_SYSTEM) {
+            if (!state) throw std::runtime_error("the nonlinear Jacobian needs a state");
+            FormSpec f = N->jacobian_spec(state);
+            if (diag) c->diag_form(f, y); else c->apply_form(f, x, y);
+        } else if (form == JOTS_FORM_RESIDUAL && !diag) {
+            if (!state) throw std::runtime_error("the nonlinear residual needs u_n as state");
+            // R(k = x) with u_n = state
+            op->un.alloc(c->n);
+            c->copy(state, op->un.p);
+            N->set_un(op->un.p);
+            N->new_state(x);
+            N->mult(x, y);
+        } else if (form == JOTS_FORM_MASS) {
+            FormSpec f;
+            f.op = OP_LIN; f.cf = CF_CONST; f.cm = 1.0; f.ck = 0.0; f.m0 = 1.0; f.a0 = 0.0;
+            f.mask_in = f.mask_out = f.diag_one = true;
+            if (diag) c->diag_form(f, y); else c->apply_form(f, x, y);
+        } else throw std::runtime_error("form not available for this operator");
+    } else {
+        auto* S = static_cast<SteadyConductionOperator*>(op->it);
+        if (form == JOTS_FORM_SYSTEM) {
+            if (!state) throw std::runtime_error("the steady Jacobian needs a state");
+            FormOp* J = static_cast<FormOp*>(S->gradient(state));
+            if (diag) J->assemble_diag(y); else J->mult(x, y);
+        } else if (form == JOTS_FORM_RESIDUAL && !diag) S->mult(x, y);
+        else throw std::runtime_error("form not available for this operator");
+    }
+}
+
+int jots_op_form_apply(jots_op_t op, int form, const double* x, const double* state, double* y, int loc) {
+    JOTS_TRY
+    In ix(op->c, x, loc), is(op->c, state, loc); Out o(op->c, y, loc);
+    run_form(op, form, ix.p, is.p, o.p, false);
+    o.finish();
+    return 0;
+    JOTS_CATCH_INT
+}
+int jots_op_form_diagonal(jots_op_t op, int form, const double* state, double* d, int loc) {
+    JOTS_TRY
+    In is(op->c, state, loc); Out o(op->c, d, loc);
+    run_form(op, form, nullptr, is.p, o.p, true);
+    o.finish();
+    return 0;
+    JOTS_CATCH_INT
+}
+int jots_op_form_time(jots_op_t op, int form, const double* x, const double* state, double* y, int reps, double* ms) {
+    JOTS_TRY
+    Ctx* c = op->c;
+    cudaEvent_t e0, e1;
+    JOTS_CUDA(cudaEventCreate(&e0)); JOTS_CUDA(cudaEventCreate(&e1));
+    run_form(op, form, x, state, y, false);
+    c->sync();
+    JOTS_CUDA(cudaEventRecord(e0, c->stream));
+    for (int i = 0; i < reps; ++i) run_form(op, form, x, state, y, false);
+    JOTS_CUDA(cudaEventRecord(e1, c->stream));
+    JOTS_CUDA(cudaEventSynchronize(e1));
+    float t = 0;
+    JOTS_CUDA(cudaEventElapsedTime(&t, e0, e1));
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    if (ms) *ms = (double)t / (reps > 0 ? reps : 1);
+    return 0;
+    JOTS_CATCH_INT
+}
+
+// ---- driver -----------------------------------------------------------------------------------
+static void bind_views(jots_driver_s* h) {
+    h->ctx_view.c = h->d->ctx.get();
+    h->op_view.c = h->d->ctx.get();
+    h->op_view.it = h->d->it.get();
+    const std::string& st = h->d->cfg.sim_type;
+    h->op_view.sim_type = st == "Linearized_Unsteady" ? JOTS_LINEARIZED_UNSTEADY : st == "Nonlinear_Unsteady" ? JOTS_NONLINEAR_UNSTEADY : JOTS_STEADY;
+}
+jots_driver_t jots_driver_create(const char* ini, int device) {
+    JOTS_TRY
+    Config cfg(ini);
+    auto* h = new jots_driver_s;
+    h->d.reset(new JOTSDriver(cfg, device));
+    bind_views(h);
+    return h;
+    JOTS_CATCH_PTR
+}
+jots_driver_t jots_driver_create_on_mesh(const char* ini, jots_mesh_t mesh, int device) {
+    JOTS_TRY
+    Config cfg(ini);
+    auto* h = new jots_driver_s;
+    h->d.reset(new JOTSDriver(cfg, device, &mesh->m));
+    bind_views(h);
+    return h;
+    JOTS_CATCH_PTR
+}
+void jots_driver_destroy(jots_driver_t d) { delete d; }
+int jots_driver_run(jots_driver_t d, int max_steps, int* done) {
+    JOTS_TRY
+    int n = d->d->Run(max_steps);
+    if (done) *done = n;
+    return 0;
+    JOTS_CATCH_INT
+}
+int64_t jots_driver_size(jots_driver_t d) { return d->d->ctx->n; }
+int jots_driver_get_u(jots_driver_t d, double* u, int loc) {
+    JOTS_TRY
+    Ctx* c = d->d->ctx.get();
+    JOTS_CUDA(cudaMemcpyAsync(u, d->d->u.p, c->n * sizeof(double), loc == JOTS_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, c->stream));
+    c->sync();
+    return 0;
+    JOTS_CATCH_INT
+}
+int jots_driver_set_u(jots_driver_t d, const double* u, int loc) {
+    JOTS_TRY
+    Ctx* c = d->d->ctx.get();
+    JOTS_CUDA(cudaMemcpyAsync(d->d->u.p, u, c->n * sizeof(double), loc == JOTS_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, c->stream));
+    c->sync();
+    return 0;
+    JOTS_CATCH_INT
+}
+double jots_driver_time(jots_driver_t d) { return d->d->time; }
+jots_ctx_t jots_driver_ctx(jots_driver_t d) { return &d->ctx_view; }
+jots_op_t jots_driver_op(jots_driver_t d) { return &d->op_view; }
+int jots_driver_step_count(jots_driver_t d) { return d->d->it_num; }
+jots_space_t jots_driver_space(jots_driver_t d) {
+    JOTS_TRY auto* h = new jots_space_s; h->s = d->d->ctx->space; return h; JOTS_CATCH_PTR
+}
+
+}  // extern "C"

@@ -1,0 +1,256 @@
+#include "ctx.hpp"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+#include "basis.hpp"
+#include "halo.hpp"
+#include "launch.hpp"
+
+namespace jots {
+
+void cuda_check(cudaError_t e, const char* what, const char* file, int line) {
+    if (e == cudaSuccess) return;
+    throw CudaError(std::string("CUDA error: ") + cudaGetErrorString(e) + " in " + what + " (" + file + ":" + std::to_string(line) + ")");
+}
+
+void BCSpec::update(double t) {
+    // SinusoidalBC::UpdateCoeff: A sin(w t + phase) + shift (boundary_condition.cpp:65-75)
+    if (constant()) value = v[0];
+    else value = v[0] * std::sin(v[1] * t + v[2]) + v[3];
+}
+
+static void fill_tables(TablesRT& t, int dim, int p) {
+    std::memset(&t, 0, sizeof(t));
+    const int D = p + 1, Q = domain_quad_points(dim, p);
+    t.D = D; t.Q = Q; t.DZ = dim == 3 ? D : 1; t.QZ = dim == 3 ? Q : 1;
+    std::vector<double> nodes = gauss_lobatto_01(D), qx, qw, B, G, Bq, Gq;
+    gauss_legendre_01(Q, qx, qw);
+    lagrange_tab(nodes, qx, B, G);
+    lagrange_tab(qx, qx, Bq, Gq);
+    for (int i = 0; i < Q * D; ++i) { t.B[i] = B[i]; t.G[i] = G[i]; }
+    for (int i = 0; i < Q * Q; ++i) t.Gq[i] = Gq[i];
+    for (int i = 0; i < Q; ++i) t.W[i] = qw[i];
+    if (dim == 3) {
+        for (int i = 0; i < Q * D; ++i) { t.Bz[i] = B[i]; t.Gz[i] = G[i]; }
+        for (int i = 0; i < Q * Q; ++i) t.Gqz[i] = Gq[i];
+        for (int i = 0; i < Q; ++i) t.Wz[i] = qw[i];
+    } else {
+        t.Bz[0] = 1.0; t.Gz[0] = 0.0; t.Gqz[0] = 0.0; t.Wz[0] = 1.0;
+    }
+}
+
+Ctx::Ctx(const Space& s, int dev) : device(dev), space(s) {
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        throw CudaError("no CUDA device available: the conduction solve has no CPU fallback");
+    JOTS_CUDA(cudaSetDevice(dev));
+    JOTS_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    own_stream = true;
+    n = s.ndof; n_owned = s.ndof;
+    fill_tables(tabs, s.dim, s.p);
+    // geometry: affine elements only (every mesh the reference ships and the synthetic bricks)
+    const int dim = s.dim, nv = 1 << dim;
+    std::vector<double> geom((size_t)s.nelem * 10);
+    bool uniform = true;
+    for (int64_t el = 0; el < s.nelem; ++el) {
+        const double* X = &s.elem_corner[(size_t)el * nv * dim];
+        double J[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+        for (int a = 0; a < dim; ++a)
+            for (int i = 0; i < dim; ++i) J[i][a] = X[(1 << a) * dim + i] - X[i];
+        double scale = 0.0;
+        for (int a = 0; a < dim; ++a) for (int i = 0; i < dim; ++i) scale = std::max(scale, std::fabs(J[i][a]));
+        for (int c = 0; c < nv; ++c)
+            for (int i = 0; i < dim; ++i) {
+                double x = X[i];
+                for (int a = 0; a < dim; ++a) if ((c >> a) & 1) x += J[i][a];
+                if (std::fabs(x - X[c * dim + i]) > 1e-10 * scale)
+                    throw std::runtime_error("non-affine (general multilinear) elements are not supported by the device kernels yet");
+            }
+        const double det = J[0][0] * (J[1][1] * J[2][2] - J[1][2] * J[2][1]) - J[0][1] * (J[1][0] * J[2][2] - J[1][2] * J[2][0]) +
+                           J[0][2] * (J[1][0] * J[2][1] - J[1][1] * J[2][0]);
+        if (!(det > 0)) throw std::runtime_error("non-positive element Jacobian");
+        double* g = &geom[(size_t)el * 10];
+        // invJ[a][i] = d xi_a / d x_i
+        g[0] = (J[1][1] * J[2][2] - J[1][2] * J[2][1]) / det; g[1] = (J[0][2] * J[2][1] - J[0][1] * J[2][2]) / det; g[2] = (J[0][1] * J[1][2] - J[0][2] * J[1][1]) / det;
+        g[3] = (J[1][2] * J[2][0] - J[1][0] * J[2][2]) / det; g[4] = (J[0][0] * J[2][2] - J[0][2] * J[2][0]) / det; g[5] = (J[0][2] * J[1][0] - J[0][0] * J[1][2]) / det;
+        g[6] = (J[1][0] * J[2][1] - J[1][1] * J[2][0]) / det; g[7] = (J[0][1] * J[2][0] - J[0][0] * J[2][1]) / det; g[8] = (J[0][0] * J[1][1] - J[0][1] * J[1][0]) / det;
+        g[9] = det;
+        if (uniform && el > 0)
+            for (int i = 0; i < 10; ++i)
+                if (std::fabs(g[i] - geom[i]) > 1e-12 * std::max(std::fabs(geom[i]), std::fabs(geom[i < 9 ? 4 * (i / 3) : 9]))) { uniform = false; break; }
+    }
+    if (uniform && s.nelem > 0) { geom.resize(10); geom_stride = 0; }
+    d_geom.upload(geom);
+    d_gather.upload(s.gather);
+    d_gather_ess.upload(s.gather);
+    d_bdr_gather.upload(s.bdr_gather);
+    d_bdr_attr.upload(s.bdr_attr);
+    d_bdr_corner.upload(s.bdr_corner);
+    d_scal.alloc(64);
+    d_partial.alloc((size_t)DOT_MAX_BLOCKS * 4);
+    d_counter.alloc(1);
+    JOTS_CUDA(cudaMemset(d_counter.p, 0, sizeof(unsigned int)));
+    JOTS_CUDA(cudaMallocHost((void**)&h_scal, 64 * sizeof(double)));
+    std::vector<unsigned char> em((size_t)n, 0);
+    d_essmark.upload(em);
+    Poly one; one.n = 1; std::memset(one.c, 0, sizeof(one.c)); one.c[0] = 1.0;
+    mat.rho = one; mat.C = one; mat.k = one;
+}
+
+Ctx::~Ctx() {
+    cudaSetDevice(device);
+    if (h_scal) cudaFreeHost(h_scal);
+    if (own_stream && stream) cudaStreamDestroy(stream);
+    delete halo;
+}
+
+void Ctx::set_materials(const Poly& rho, const Poly& C, const Poly& k) {
+    mat.rho = rho; mat.C = C; mat.k = k;
+}
+
+void Ctx::set_bcs(const std::vector<BCSpec>& b) {
+    bcs = b;
+    // dbc_bdr[i] = 1 for essential BC i; marker index i <-> attribute i+1 (jots_iterator.cpp:12-30)
+    std::vector<int> attrs;
+    bc_dofs.assign(bcs.size(), {});
+    d_bc_dofs.clear();
+    d_bc_dofs.resize(bcs.size());
+    for (size_t i = 0; i < bcs.size(); ++i) {
+        std::vector<int> one{(int)i + 1};
+        space.essential_dofs(one, bc_dofs[i]);
+        d_bc_dofs[i].upload(bc_dofs[i]);
+        if (bcs[i].essential()) attrs.push_back((int)i + 1);
+    }
+    space.essential_dofs(attrs, ess);
+    d_ess.upload(ess);
+    std::vector<unsigned char> em((size_t)n, 0);
+    for (int d : ess) em[d] = 1;
+    d_essmark.upload(em);
+    std::vector<int> ge(space.gather);
+    for (auto& g : ge) if (em[g]) g = ~g;
+    d_gather_ess.upload(ge);
+    d_gattr.alloc(std::max<size_t>(bcs.size(), 1));
+}
+
+bool Ctx::any_flux() const {
+    for (auto& b : bcs) if (!b.essential() && b.value != 0.0) return true;
+    return false;
+}
+
+void Ctx::upload_flux_values() {
+    std::vector<double> g(std::max<size_t>(bcs.size(), 1), 0.0);
+    for (size_t i = 0; i < bcs.size(); ++i) g[i] = bcs[i].essential() ? 0.0 : bcs[i].value;
+    JOTS_CUDA(cudaMemcpyAsync(d_gattr.p, g.data(), g.size() * sizeof(double), cudaMemcpyHostToDevice, stream));
+    JOTS_CUDA(cudaStreamSynchronize(stream));
+}
+
+FormArgs Ctx::make_args(const FormSpec& f, const double* x, double* y, bool) const {
+    FormArgs a;
+    std::memset(&a, 0, sizeof(a));
+    a.gather = d_gather_ess.p;
+    a.geom = d_geom.p; a.geom_stride = geom_stride;
+    a.x = x; a.z = f.state; a.y = y;
+    a.nelem = (int)space.nelem;
+    a.mask_in = f.mask_in; a.mask_out = f.mask_out;
+    a.cm = f.cm; a.ck = f.ck; a.cb = f.cb; a.m0 = f.m0; a.a0 = f.a0; a.inv_rc = f.inv_rc;
+    a.mat = mat;
+    return a;
+}
+
+static void fill_face_tables(FaceArgs& fa, int p, int nq) {
+    const int D = p + 1;
+    std::vector<double> nodes = gauss_lobatto_01(D), qx, qw, B, G;
+    gauss_legendre_01(nq, qx, qw);
+    lagrange_tab(nodes, qx, B, G);
+    for (int i = 0; i < nq * D; ++i) fa.Bf[i] = B[i];
+    for (int i = 0; i < nq; ++i) { fa.Wf[i] = qw[i]; fa.xq[i] = qx[i]; }
+    fa.nq = nq;
+}
+
+static FaceArgs base_face_args(const Ctx& c, int nq) {
+    FaceArgs fa;
+    std::memset(&fa, 0, sizeof(fa));
+    fa.dim = c.space.dim; fa.D = c.space.D; fa.nfl = c.space.nfl; fa.nbdr = (int)c.space.nbdr;
+    fa.bdr_gather = c.d_bdr_gather.p; fa.bdr_corner = c.d_bdr_corner.p; fa.bdr_attr = c.d_bdr_attr.p;
+    fa.g_attr = c.d_gattr.p; fa.n_attr = (int)c.bcs.size();
+    fa.ess = c.d_essmark.p;
+    fa.mat = c.mat;
+    fa.scale = 1.0; fa.div_const = 1.0;
+    fill_face_tables(fa, c.space.p, nq);
+    return fa;
+}
+
+void Ctx::apply_form(const FormSpec& f, const double* x, double* y) {
+    zero(y);
+    FormArgs a = make_args(f, x, y, false);
+    int rc = launch_form_apply(space.dim, space.p, f.op, f.cf, a, tabs, stream);
+    if (rc) throw std::runtime_error("form (op=" + std::to_string(f.op) + ", cf=" + std::to_string(f.cf) + ") is not instantiated, rc=" + std::to_string(rc));
+    stats.kernel_launches += 2;
+    if (f.bdr_mass_scale != 0.0 && any_flux()) {
+        FaceArgs fa = base_face_args(*this, bdr_mass_quad_points(space.p));
+        fa.z = f.state; fa.x = x; fa.y = y; fa.mask_in = f.mask_in; fa.mask_out = f.mask_out; fa.scale = f.bdr_mass_scale;
+        launch_face(FACE_MASS_APPLY, fa, stream);
+        ++stats.kernel_launches;
+    }
+    if (halo) halo_sum_exchange(*this, y);
+    if (f.diag_one) { v_copy_idx(stream, (int)ess.size(), d_ess.p, x, y); stats.kernel_launches += !ess.empty(); }
+    JOTS_CUDA(cudaGetLastError());
+    ++stats.applies;
+}
+
+void Ctx::diag_form(const FormSpec& f, double* d) {
+    zero(d);
+    FormArgs a = make_args(f, nullptr, d, true);
+    a.mask_out = (f.mask_out || f.diag_one) ? 1 : 0;
+    int rc = launch_form_diag(f.op == OP_RES ? OP_LIN : f.op, f.cf, a, tabs, stream);
+    if (rc) throw std::runtime_error("diagonal of form (op=" + std::to_string(f.op) + ", cf=" + std::to_string(f.cf) + ") is not instantiated");
+    stats.kernel_launches += 2;
+    if (f.bdr_mass_scale != 0.0 && any_flux()) {
+        FaceArgs fa = base_face_args(*this, bdr_mass_quad_points(space.p));
+        fa.z = f.state; fa.y = d; fa.mask_out = a.mask_out; fa.scale = f.bdr_mass_scale;
+        launch_face(FACE_MASS_DIAG, fa, stream);
+        ++stats.kernel_launches;
+    }
+    if (halo) halo_sum_exchange(*this, d);
+    if (f.diag_one) { v_set_idx(stream, (int)ess.size(), d_ess.p, 1.0, d); stats.kernel_launches += !ess.empty(); }
+    JOTS_CUDA(cudaGetLastError());
+    ++stats.diag_assemblies;
+}
+
+void Ctx::neumann_vector(double div_const, const double* state, double* b, bool zero_first, double scale, bool mask_out) {
+    if (zero_first) zero(b);
+    FaceArgs fa = base_face_args(*this, bdr_lf_quad_points(space.p));
+    fa.z = state; fa.y = b; fa.div_const = div_const; fa.scale = scale; fa.mask_out = mask_out;
+    launch_face(FACE_LOAD, fa, stream);
+    ++stats.kernel_launches;
+    if (halo && zero_first) halo_sum_exchange(*this, b);
+    JOTS_CUDA(cudaGetLastError());
+}
+
+void Ctx::fetch_scalars(int nv, double* out) {
+    if (halo) halo_allreduce(*this, d_scal.p, nv);
+    JOTS_CUDA(cudaMemcpyAsync(h_scal, d_scal.p, nv * sizeof(double), cudaMemcpyDeviceToHost, stream));
+    JOTS_CUDA(cudaStreamSynchronize(stream));
+    for (int i = 0; i < nv; ++i) out[i] = h_scal[i];
+}
+
+void Ctx::dots(int nv, const double* const* a, const double* const* b, double* out) {
+    v_dots(stream, n_owned, nv, a, b, dot_scratch(), d_scal.p);
+    ++stats.kernel_launches; stats.dots += nv;
+    fetch_scalars(nv, out);
+}
+
+double Ctx::dot(const double* a, const double* b) {
+    double r;
+    const double* aa[1] = {a};
+    const double* bb[1] = {b};
+    dots(1, aa, bb, &r);
+    return r;
+}
+
+double Ctx::norm(const double* a) { return std::sqrt(dot(a, a)); }
+
+}  // namespace jots

@@ -1,0 +1,138 @@
+// Device context of the conduction solve: uploaded space tables, boundary-condition index sets,
+// material models, form application and the BLAS-1 helpers the solvers use.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "diag_face_host.hpp"
+#include "forms.hpp"
+#include "mesh.hpp"
+#include "vec.hpp"
+
+namespace jots {
+
+struct CudaError : std::runtime_error {
+    using std::runtime_error::runtime_error;
+};
+void cuda_check(cudaError_t e, const char* what, const char* file, int line);
+#define JOTS_CUDA(x) ::jots::cuda_check((x), #x, __FILE__, __LINE__)
+
+// simple owning device array
+template <class T>
+struct DArr {
+    T* p = nullptr;
+    size_t n = 0;
+    DArr() = default;
+    DArr(const DArr&) = delete;
+    DArr(DArr&& o) noexcept : p(o.p), n(o.n) { o.p = nullptr; o.n = 0; }
+    DArr& operator=(const DArr&) = delete;
+    ~DArr() { release(); }
+    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+    void alloc(size_t count) {
+        if (count == n && p) return;
+        release();
+        if (count) JOTS_CUDA(cudaMalloc((void**)&p, count * sizeof(T)));
+        n = count;
+    }
+    void upload(const std::vector<T>& h) {
+        alloc(h.size());
+        if (!h.empty()) JOTS_CUDA(cudaMemcpy(p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+    }
+};
+
+enum { BC_ISOTHERMAL = 0, BC_HEATFLUX = 1, BC_SIN_ISOTHERMAL = 2, BC_SIN_HEATFLUX = 3 };
+
+// BC value objects (/root/reference/src/boundary_condition.hpp:14-105, .cpp:49-75)
+struct BCSpec {
+    int kind = BC_HEATFLUX;
+    double v[4] = {0, 0, 0, 0};  // value | amp, angular freq, phase, vertical shift
+    double value = 0.0;          // current coefficient value (UpdateCoeff)
+    bool essential() const { return kind == BC_ISOTHERMAL || kind == BC_SIN_ISOTHERMAL; }
+    bool constant() const { return kind == BC_ISOTHERMAL || kind == BC_HEATFLUX; }
+    void update(double t);
+};
+
+// one matrix-free operator = one element form + optional boundary-mass term + essential handling
+struct FormSpec {
+    int op = OP_LIN, cf = CF_CONST;
+    double cm = 0, ck = 0, cb = 0, m0 = 1, a0 = 1, inv_rc = 1;
+    bool mask_in = false, mask_out = false;
+    bool diag_one = false;          // y[ess] = x[ess] (EliminateRowsCols / DIAG_ONE)
+    const double* state = nullptr;  // frozen state z
+    double bdr_mass_scale = 0.0;    // + scale * int_bdr (g/(rho C))' phi_i phi_j  (0 = absent)
+};
+
+struct Stats {
+    long long applies = 0, diag_assemblies = 0, krylov_iters = 0, newton_iters = 0, residual_evals = 0, steps = 0,
+              kernel_launches = 0, dots = 0;
+    double last_linear_norm = 0, last_newton_norm = 0;
+    int last_linear_converged = 1, last_newton_converged = 1, last_linear_iters = 0, last_newton_iters = 0;
+};
+
+struct Halo;  // multi-GPU interface exchange (halo.hpp)
+
+class Ctx {
+public:
+    Ctx(const Space& s, int device);
+    ~Ctx();
+
+    // --- static description
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    Space space;             // host copy (index sets, boundary tables)
+    int64_t n = 0;           // local vector length (L-vector)
+    int64_t n_owned = 0;     // leading entries owned by this rank (== n on one GPU)
+    TablesRT tabs;
+    MatSet mat;
+    std::vector<BCSpec> bcs;             // index i <-> boundary attribute i+1
+    std::vector<int> ess;                // sorted essential DOFs (GetEssentialTrueDofs)
+    std::vector<std::vector<int>> bc_dofs;  // per BC: DOFs of its boundary elements
+    Stats stats;
+    Halo* halo = nullptr;
+
+    // --- device tables
+    DArr<int> d_gather, d_gather_ess, d_bdr_gather, d_bdr_attr, d_ess;
+    std::vector<DArr<int>> d_bc_dofs;
+    DArr<double> d_geom, d_bdr_corner, d_gattr;
+    DArr<unsigned char> d_essmark;
+    int geom_stride = 10;
+    DArr<double> d_scal, d_partial;
+    DArr<double> mat_state;   // vector the nodal property polynomials were last evaluated on (UpdateMatProps)
+    void set_mat_state(const double* u) { mat_state.alloc(n); copy(u, mat_state.p); }
+    DArr<unsigned int> d_counter;
+    double* h_scal = nullptr;  // pinned
+
+    // --- setup
+    void set_materials(const Poly& rho, const Poly& C, const Poly& k);
+    void set_bcs(const std::vector<BCSpec>& b);
+
+    // --- forms
+    void apply_form(const FormSpec& f, const double* x, double* y);
+    void diag_form(const FormSpec& f, double* d);
+    // b_i = sum_faces int (g / divisor) phi_i; state != null -> divisor rho_h(state) C_h(state)
+    void neumann_vector(double div_const, const double* state, double* b, bool zero_first = true, double scale = 1.0,
+                        bool mask_out = false);
+    void upload_flux_values();   // g per attribute from the current BC values (essential -> 0)
+    bool any_flux() const;
+
+    // --- vectors
+    DotScratch dot_scratch() { return DotScratch{d_partial.p, d_counter.p}; }
+    double dot(const double* a, const double* b);
+    void dots(int nv, const double* const* a, const double* const* b, double* out);
+    void fetch_scalars(int nv, double* out);   // d_scal -> host (+ allreduce across ranks)
+    double norm(const double* a) ;
+    void zero(double* y) { JOTS_CUDA(cudaMemsetAsync(y, 0, n * sizeof(double), stream)); }
+    void copy(const double* x, double* y) { JOTS_CUDA(cudaMemcpyAsync(y, x, n * sizeof(double), cudaMemcpyDeviceToDevice, stream)); }
+    void zero_ess(double* y) { v_set_idx(stream, (int)ess.size(), d_ess.p, 0.0, y); stats.kernel_launches += !ess.empty(); }
+    void sync() { JOTS_CUDA(cudaStreamSynchronize(stream)); }
+
+    FormArgs make_args(const FormSpec& f, const double* x, double* y, bool for_diag) const;
+private:
+    bool own_stream = false;
+};
+
+}  // namespace jots

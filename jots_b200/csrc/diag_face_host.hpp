@@ -1,0 +1,35 @@
+// Host-visible plain structs shared with the loop-based kernels (no device code here).
+#pragma once
+#include "forms.hpp"
+
+namespace jots {
+
+struct TablesRT {
+    int D, Q, DZ, QZ;
+    double B[30], G[30], Gq[36], W[6];
+    double Bz[30], Gz[30], Gqz[36], Wz[6];
+};
+
+enum { FACE_LOAD = 0, FACE_MASS_APPLY = 1, FACE_MASS_DIAG = 2 };
+
+struct FaceArgs {
+    int dim, D, nq, nfl, nbdr;
+    const int* bdr_gather;      // [nbdr*nfl]
+    const double* bdr_corner;   // [nbdr*2^(dim-1)*dim]
+    const int* bdr_attr;        // [nbdr]
+    const double* g_attr;       // flux per attribute index (attr-1), 0 for unmapped/essential
+    int n_attr;
+    const unsigned char* ess;   // [ndof] essential marker (may be null)
+    const double* z;            // state for rho_h, C_h (null -> uniform: divide by div_const)
+    const double* x;            // FACE_MASS_APPLY input
+    double* y;
+    int mask_in, mask_out;
+    double scale;
+    double div_const;           // constant divisor rho*C (1 for the plain Neumann vector)
+    MatSet mat;
+    double Bf[25];              // [nq*D] basis at the face rule
+    double Wf[5];
+    double xq[5];               // 1-D rule points (for the surface Jacobian)
+};
+
+}  // namespace jots

@@ -1,0 +1,48 @@
+// Host shim for the hot-path callers of the reference's driver: the .ini key set and defaults of
+// Config (/root/reference/src/config_file.cpp:7-172) and the per-step order of JOTSDriver::Run
+// (/root/reference/src/jots_driver.cpp:568-725): UpdateAndApplyBCs -> UpdateMatProps -> Iteration.
+// Output, restart and preCICE stay with the reference's own driver.
+#pragma once
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "operators.hpp"
+
+namespace jots {
+
+struct Config {
+    explicit Config(const std::string& path);
+    std::string path, sim_type = "Unsteady", mesh_file = "mesh_name.mesh", time_scheme = "Euler_Implicit";
+    std::string solver = "FGMRES", prec = "Chebyshev";
+    bool use_restart = false, with_precice = false, using_time_integration = false, using_newton = false;
+    int fe_order = 1, serial_refine = 0, parallel_refine = 0, max_timesteps = 100, max_iter = 100, newton_max_iter = 0;
+    double initial_temp = 100.0, dt = 0.1, abs_tol = 1e-16, rel_tol = 1e-10, newton_abs_tol = 1e-16, newton_rel_tol = 1e-10;
+    std::map<std::string, std::vector<std::string>> mat_props;
+    std::map<int, std::vector<std::string>> bcs;
+};
+
+Poly parse_property(const std::vector<std::string>& info);
+BCSpec parse_bc(const std::vector<std::string>& info);
+
+class JOTSDriver {
+public:
+    // mesh == nullptr: read cfg.mesh_file (relative paths are taken as given) and refine
+    JOTSDriver(const Config& cfg, int device, const Mesh* mesh = nullptr);
+    void UpdateAndApplyBCs();
+    void UpdateMatProps(bool apply_changes);
+    void Iteration();
+    void Step();               // one pass of the Run() loop body
+    int Run(int max_steps);    // max_steps < 0: run to max_timesteps; returns the number of steps done
+    Config cfg;
+    std::unique_ptr<Ctx> ctx;
+    std::unique_ptr<JOTSIterator> it;
+    DArr<double> u;
+    int it_num = 0, max_timesteps = 0;
+    double time = 0.0, dt = 0.0;
+    bool initialized_bcs = false;
+    bool has_prop[3] = {false, false, false};
+};
+
+}  // namespace jots

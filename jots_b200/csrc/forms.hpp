@@ -1,0 +1,76 @@
+// Element "forms" of the conduction solve evaluated matrix-free on the device.
+//
+// Every domain integral the reference assembles into a sparse matrix or element vector
+// (a3, a6-a10, a13, a15) has the quadrature-point shape
+//
+//      y_i = sum_q w_q |J| [ F_q . grad phi_i  +  S_q phi_i ]
+//
+// with, for an input field x (value x_q, physical gradient gx) and a frozen state z (gradient gz):
+//
+//   OP_LIN : F = a1 gx                     S = m x_q
+//            MassIntegrator / DiffusionIntegrator of linear_conduction_operator.cpp:59,63 and
+//            nl_conduction_operator.cpp:189,200
+//   OP_JAC : F = a1 gx + a2 x_q gz         S = m x_q + 2 nb (gz.gx) + ndb |gz|^2 x_q
+//            JOTSNonlinearDiffusionIntegrator::AssembleElementGrad (jots_nlfis.cpp:24-40) and
+//            JOTSNonlinearConvectionIntegrator::AssembleElementGrad (jots_nlfis.cpp:83-95)
+//   OP_RES : F = a1 gz                     S = m x_q + nb |gz|^2
+//            ::AssembleElementVector of the same integrators (jots_nlfis.cpp:16-22, 75-81) plus the
+//            mass term of ReducedSystemOperatorR::Mult (nl_conduction_operator.cpp:70-79)
+//
+// The coefficients are *nodal fields interpolated to the quadrature points* (PolynomialProperty ->
+// GridFunctionCoefficient, material_property.cpp:31-49), ratios are ratios of interpolants
+// (nl_conduction_operator.cpp:92-163):
+//
+//   CF_CONST     : m = cm*m0, a1 = ck*a0
+//   CF_LINFIELDS : m = cm*rho_h*C_h, a1 = ck*k_h                     (linearized operator)
+//   CF_K         : m = cm*m0, a1 = ck*k_h*inv_rc, a2 = ck*k'_h*inv_rc   (rho, C uniform)
+//   CF_FULL      : m = cm, a1 = ck*alpha, a2 = ck*alpha', nb = cb*(-beta), ndb = cb*(-beta')
+#pragma once
+#include <cstdint>
+
+namespace jots {
+
+enum { OP_LIN = 0, OP_JAC = 1, OP_RES = 2 };
+enum { CF_CONST = 0, CF_LINFIELDS = 1, CF_K = 2, CF_FULL = 3 };
+
+constexpr int MAX_POLY = 8;
+
+// Uniform (n == 1) or Polynomial (n >= 2, highest power first) property
+struct Poly {
+    int n;
+    double c[MAX_POLY];
+};
+struct MatSet {
+    Poly rho, C, k;
+};
+
+struct FormArgs {
+    const int* gather;    // [nelem*nloc]; essential DOFs are stored as ~index (negative)
+    const double* geom;   // [nelem*10]: invJ[a][i] (9, row-major: a = reference axis) + detJ
+    int geom_stride;      // 10, or 0 when every element shares geom[0..9]
+    const double* x;      // input vector
+    const double* z;      // frozen state (coefficients + grad z); may be null for CF_CONST/OP_LIN
+    double* y;            // output, accumulated with atomics (caller zeroes it)
+    int nelem;
+    int mask_in;          // treat x as zero on essential DOFs (eliminated columns)
+    int mask_out;         // skip essential rows
+    double cm, ck, cb;
+    double m0, a0;        // CF_CONST
+    double inv_rc;        // CF_K
+    MatSet mat;
+};
+
+// 1-D tables; DZ = QZ = 1 turns the hex kernel into the quad kernel
+template <int D, int Q, int DZ, int QZ>
+struct Tables {
+    double B[Q * D];       // B[q*D+i] = l_i(x_q)
+    double G[Q * D];       // G[q*D+i] = l_i'(x_q)
+    double Gq[Q * Q];      // collocated derivative at the quadrature points
+    double W[Q];
+    double Bz[QZ * DZ];
+    double Gz[QZ * DZ];
+    double Gqz[QZ * QZ];
+    double Wz[QZ];
+};
+
+}  // namespace jots

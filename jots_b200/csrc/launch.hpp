@@ -1,0 +1,22 @@
+// Host-callable launchers of the element / face kernels (implemented in *.cu).
+#pragma once
+#include <cuda_runtime.h>
+
+#include "diag_face_host.hpp"
+#include "forms.hpp"
+
+namespace jots {
+
+
+// returns 0 on success, non-zero when the (shape, op, cf) combination is not instantiated
+int launch_form_apply(int dim, int p, int op, int cf, const FormArgs& a, const TablesRT& t, cudaStream_t st);
+int launch_form_diag(int op, int cf, const FormArgs& a, const TablesRT& t, cudaStream_t st);
+int launch_face(int mode, const FaceArgs& a, cudaStream_t st);
+
+// per-shape entry points (one translation unit each so they compile in parallel)
+#define JOTS_DECL_SHAPE(NAME) int launch_form_apply_##NAME(int op, int cf, const FormArgs& a, const TablesRT& t, cudaStream_t st);
+JOTS_DECL_SHAPE(h1) JOTS_DECL_SHAPE(h2) JOTS_DECL_SHAPE(h3) JOTS_DECL_SHAPE(h4)
+JOTS_DECL_SHAPE(q1) JOTS_DECL_SHAPE(q2) JOTS_DECL_SHAPE(q3) JOTS_DECL_SHAPE(q4)
+#undef JOTS_DECL_SHAPE
+
+}  // namespace jots

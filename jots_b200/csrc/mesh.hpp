@@ -1,0 +1,69 @@
+// Host-side mesh + H1 lattice space: the tables MFEM's Mesh / ParFiniteElementSpace hand to the
+// conduction operators in the reference (/root/reference/src/jots_driver.cpp:143-211):
+// element -> DOF gather table, element geometry, boundary faces with attributes, essential DOFs.
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+namespace jots {
+
+struct Mesh {
+    int dim = 0;
+    std::vector<double> verts;      // [nv*dim]
+    std::vector<int64_t> elems;     // [ne*2^dim]  MFEM local vertex order
+    std::vector<int> elem_attr;     // [ne]
+    std::vector<int64_t> bdr;       // [nb*2^(dim-1)]
+    std::vector<int> bdr_attr;      // [nb]
+    bool is_brick = false;          // structured hint (make_brick)
+    int64_t bn[3] = {0, 0, 0};
+    double bl[3] = {0, 0, 0};
+
+    int nvpe() const { return 1 << dim; }
+    int nvpf() const { return 1 << (dim - 1); }
+    int64_t n_elem() const { return (int64_t)elems.size() / nvpe(); }
+    int64_t n_bdr() const { return (int64_t)bdr.size() / nvpf(); }
+    int64_t n_verts() const { return (int64_t)verts.size() / dim; }
+    std::vector<int> bdr_attributes() const;  // sorted unique
+};
+
+// corner bits (a,b,c) -> MFEM local vertex id
+int corner_vertex(int dim, int a, int b, int c);
+
+Mesh read_mfem_mesh(const std::string& path);   // Mesh(file,1): fix_orientation=true
+Mesh make_brick(int64_t nx, int64_t ny, int64_t nz, double lx, double ly, double lz);
+Mesh make_rect(int64_t nx, int64_t ny, double lx, double ly, double x0, double y0);
+Mesh uniform_refine(const Mesh& m);             // Mesh::UniformRefinement
+int64_t fix_orientation(Mesh& m);
+
+// lattice numbering of (p+1)^dim nodes per element shared on vertices/edges/faces, numbered in
+// order of first appearance (elements in order, local nodes lexicographic, x fastest)
+void lattice_numbering(const Mesh& m, int p, std::vector<int64_t>& gather, int64_t& nnodes);
+void brick_lattice_numbering(int64_t nx, int64_t ny, int64_t nz, int p, std::vector<int64_t>& gather, int64_t& nnodes);
+
+void face_lattice_nodes(int dim, int p, int f, std::vector<int>& out);
+void face_vertices_local(int dim, int f, std::vector<int>& out);
+void locate_boundary_faces(const Mesh& m, std::vector<int64_t>& be, std::vector<int>& bf);
+
+struct Space {
+    int dim = 0, p = 0, D = 0, Q = 0, nloc = 0, nfl = 0;
+    int64_t nelem = 0, ndof = 0, nbdr = 0;
+    std::vector<int> gather;          // [nelem*nloc]
+    std::vector<double> elem_corner;  // [nelem*2^dim*dim] vertex coordinates in corner-bit order
+    std::vector<int64_t> bdr_elem;
+    std::vector<int> bdr_face, bdr_attr;
+    std::vector<int> bdr_gather;      // [nbdr*nfl]
+    std::vector<double> bdr_corner;   // [nbdr*2^(dim-1)*dim] face corners, lower free axis fastest
+    std::vector<int> attributes;      // sorted unique boundary attributes
+    std::vector<double> nodes;        // GL nodes on [0,1]
+    bool is_brick = false;
+    int64_t bn[3] = {0, 0, 0};
+    double bl[3] = {0, 0, 0};
+
+    void node_coordinates(std::vector<double>& out) const;  // [ndof*dim]
+    void essential_dofs(const std::vector<int>& attrs, std::vector<int>& out) const;  // sorted unique
+};
+
+Space make_space(const Mesh& m, int p);
+
+}  // namespace jots

@@ -1,0 +1,135 @@
+#include "vec.cuh"
+#include "vec.hpp"
+
+namespace jots {
+
+static inline int grid_for(int64_t n, int per_thread = 4) {
+    int64_t b = (n + (int64_t)VEC_THREADS * per_thread - 1) / ((int64_t)VEC_THREADS * per_thread);
+    if (b < 1) b = 1;
+    if (b > DOT_MAX_BLOCKS) b = DOT_MAX_BLOCKS;
+    return (int)b;
+}
+
+// w = a*x + b*y   (x, y may alias w)
+__global__ void k_waxpby(int64_t n, double a, const double* __restrict__ x, double b, const double* __restrict__ y, double* w) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) w[i] = a * x[i] + b * y[i];
+}
+__global__ void k_axpy(int64_t n, double a, const double* __restrict__ x, double* y) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) y[i] += a * x[i];
+}
+__global__ void k_scale(int64_t n, double a, const double* __restrict__ x, double* y) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) y[i] = a * x[i];
+}
+__global__ void k_mul(int64_t n, const double* __restrict__ d, const double* __restrict__ x, double* y) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) y[i] = d[i] * x[i];
+}
+// y = d * (x + c * r * d')  helpers for Chebyshev:  y = a*d*x + b*d*z
+__global__ void k_mul_waxpby(int64_t n, const double* __restrict__ d, double a, const double* __restrict__ x, double b,
+                             const double* __restrict__ z, double* y) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) y[i] = d[i] * (a * x[i] + b * z[i]);
+}
+__global__ void k_fill(int64_t n, double a, double* y) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) y[i] = a;
+}
+__global__ void k_rsqrt(int64_t n, const double* __restrict__ d, double* y) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) y[i] = 1.0 / sqrt(d[i]);
+}
+__global__ void k_recip(int64_t n, const double* __restrict__ d, double* y) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) y[i] = 1.0 / d[i];
+}
+// deterministic pseudo-random vector in [-1,1): splitmix64 of the global index
+__global__ void k_hash_unit(int64_t n, const int64_t* __restrict__ gidx, int64_t offset, double* y) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const uint64_t gi = (uint64_t)(gidx ? gidx[i] : i) + (uint64_t)offset + 1ull;
+        uint64_t z = gi * 0x9E3779B97F4A7C15ull;
+        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+        z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+        z = z ^ (z >> 31);
+        y[i] = (double)(z >> 11) * (2.0 / 9007199254740992.0) - 1.0;
+    }
+}
+__global__ void k_set_idx(int n, const int* __restrict__ idx, double v, double* y) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) y[idx[i]] = v;
+}
+__global__ void k_copy_idx(int n, const int* __restrict__ idx, const double* __restrict__ x, double* y) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) y[idx[i]] = x[idx[i]];
+}
+
+template <int NV>
+__global__ void __launch_bounds__(VEC_THREADS) k_dots(int64_t n, const double* __restrict__ a0, const double* __restrict__ b0,
+                                                       const double* __restrict__ a1, const double* __restrict__ b1,
+                                                       const double* __restrict__ a2, const double* __restrict__ b2,
+                                                       DotScratch s, double* result) {
+    double v[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) v[i] = 0.0;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        v[0] += a0[i] * b0[i];
+        if (NV > 1) v[1] += a1[i] * b1[i];
+        if (NV > 2) v[2] += a2[i] * b2[i];
+    }
+    grid_reduce<NV>(v, s, result);
+}
+
+// CG update fused: x += alpha d ; r -= alpha z ; (optional) zz = dinv*r ; result = (r, zz or r)
+__global__ void __launch_bounds__(VEC_THREADS) k_cg_update(int64_t n, int64_t n_owned, double alpha, const double* __restrict__ d,
+                                                            const double* Ad, double* x, double* r,
+                                                            const double* __restrict__ dinv, double* z, DotScratch s, double* result) {
+    double v[1] = {0.0};
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        x[i] += alpha * d[i];
+        const double ri = r[i] - alpha * Ad[i];
+        r[i] = ri;
+        double zi = ri;
+        if (dinv) { zi = dinv[i] * ri; z[i] = zi; }
+        if (i < n_owned) v[0] += ri * zi;
+    }
+    grid_reduce<1>(v, s, result);
+}
+
+void v_waxpby(cudaStream_t st, int64_t n, double a, const double* x, double b, const double* y, double* w) {
+    k_waxpby<<<grid_for(n), VEC_THREADS, 0, st>>>(n, a, x, b, y, w);
+}
+void v_axpy(cudaStream_t st, int64_t n, double a, const double* x, double* y) { k_axpy<<<grid_for(n), VEC_THREADS, 0, st>>>(n, a, x, y); }
+void v_scale(cudaStream_t st, int64_t n, double a, const double* x, double* y) { k_scale<<<grid_for(n), VEC_THREADS, 0, st>>>(n, a, x, y); }
+void v_mul(cudaStream_t st, int64_t n, const double* d, const double* x, double* y) { k_mul<<<grid_for(n), VEC_THREADS, 0, st>>>(n, d, x, y); }
+void v_mul_waxpby(cudaStream_t st, int64_t n, const double* d, double a, const double* x, double b, const double* z, double* y) {
+    k_mul_waxpby<<<grid_for(n), VEC_THREADS, 0, st>>>(n, d, a, x, b, z, y);
+}
+void v_fill(cudaStream_t st, int64_t n, double a, double* y) { k_fill<<<grid_for(n), VEC_THREADS, 0, st>>>(n, a, y); }
+void v_rsqrt(cudaStream_t st, int64_t n, const double* d, double* y) { k_rsqrt<<<grid_for(n), VEC_THREADS, 0, st>>>(n, d, y); }
+void v_recip(cudaStream_t st, int64_t n, const double* d, double* y) { k_recip<<<grid_for(n), VEC_THREADS, 0, st>>>(n, d, y); }
+void v_hash_unit(cudaStream_t st, int64_t n, const int64_t* gidx, int64_t offset, double* y) {
+    k_hash_unit<<<grid_for(n), VEC_THREADS, 0, st>>>(n, gidx, offset, y);
+}
+void v_set_idx(cudaStream_t st, int n, const int* idx, double v, double* y) {
+    if (n > 0) k_set_idx<<<(n + 255) / 256, 256, 0, st>>>(n, idx, v, y);
+}
+void v_copy_idx(cudaStream_t st, int n, const int* idx, const double* x, double* y) {
+    if (n > 0) k_copy_idx<<<(n + 255) / 256, 256, 0, st>>>(n, idx, x, y);
+}
+void v_dots(cudaStream_t st, int64_t n, int nv, const double* const* a, const double* const* b, DotScratch s, double* result) {
+    const int g = grid_for(n, 8);
+    if (nv == 1) k_dots<1><<<g, VEC_THREADS, 0, st>>>(n, a[0], b[0], nullptr, nullptr, nullptr, nullptr, s, result);
+    else if (nv == 2) k_dots<2><<<g, VEC_THREADS, 0, st>>>(n, a[0], b[0], a[1], b[1], nullptr, nullptr, s, result);
+    else k_dots<3><<<g, VEC_THREADS, 0, st>>>(n, a[0], b[0], a[1], b[1], a[2], b[2], s, result);
+}
+void v_cg_update(cudaStream_t st, int64_t n, int64_t n_owned, double alpha, const double* d, const double* Ad, double* x, double* r,
+                 const double* dinv, double* z, DotScratch s, double* result) {
+    k_cg_update<<<grid_for(n, 8), VEC_THREADS, 0, st>>>(n, n_owned, alpha, d, Ad, x, r, dinv, z, s, result);
+}
+
+}  // namespace jots

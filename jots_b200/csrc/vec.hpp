@@ -1,0 +1,26 @@
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+
+namespace jots {
+constexpr int VEC_THREADS = 256;
+constexpr int DOT_MAX_BLOCKS = 148 * 8;
+struct DotScratch {
+    double* partial;        // [DOT_MAX_BLOCKS * 4]
+    unsigned int* counter;  // zero-initialised ticket
+};
+void v_waxpby(cudaStream_t st, int64_t n, double a, const double* x, double b, const double* y, double* w);
+void v_axpy(cudaStream_t st, int64_t n, double a, const double* x, double* y);
+void v_scale(cudaStream_t st, int64_t n, double a, const double* x, double* y);
+void v_mul(cudaStream_t st, int64_t n, const double* d, const double* x, double* y);
+void v_mul_waxpby(cudaStream_t st, int64_t n, const double* d, double a, const double* x, double b, const double* z, double* y);
+void v_fill(cudaStream_t st, int64_t n, double a, double* y);
+void v_rsqrt(cudaStream_t st, int64_t n, const double* d, double* y);
+void v_recip(cudaStream_t st, int64_t n, const double* d, double* y);
+void v_hash_unit(cudaStream_t st, int64_t n, const int64_t* gidx, int64_t offset, double* y);
+void v_set_idx(cudaStream_t st, int n, const int* idx, double v, double* y);
+void v_copy_idx(cudaStream_t st, int n, const int* idx, const double* x, double* y);
+void v_dots(cudaStream_t st, int64_t n, int nv, const double* const* a, const double* const* b, DotScratch s, double* result);
+void v_cg_update(cudaStream_t st, int64_t n, int64_t n_owned, double alpha, const double* d, const double* Ad, double* x, double* r,
+                 const double* dinv, double* z, DotScratch s, double* result);
+}  // namespace jots

@@ -1,0 +1,407 @@
+"""ctypes binding of libjots_b200.so (declarations: include/jots_b200.h)."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+HOST, DEVICE = 0, 1
+UNIFORM, POLYNOMIAL = 0, 1
+BC_ISOTHERMAL, BC_HEATFLUX, BC_SIN_ISOTHERMAL, BC_SIN_HEATFLUX = 0, 1, 2, 3
+CG, GMRES, FGMRES = 0, 1, 2
+JACOBI, CHEBYSHEV = 0, 1
+EULER_IMPLICIT, EULER_EXPLICIT, RK4 = 0, 1, 2
+LINEARIZED_UNSTEADY, NONLINEAR_UNSTEADY, STEADY = 0, 1, 2
+DENSITY, SPECIFIC_HEAT, THERMAL_CONDUCTIVITY = 0, 1, 2
+FORM_MASS, FORM_STIFFNESS, FORM_SYSTEM, FORM_RESIDUAL = 0, 1, 2, 3
+
+
+class JotsError(RuntimeError):
+    pass
+
+
+_LIB = None
+_P = C.c_void_p
+_D = C.POINTER(C.c_double)
+_I32 = C.POINTER(C.c_int32)
+_I64 = C.POINTER(C.c_int64)
+
+
+def library_path():
+    return os.path.join(os.path.dirname(os.path.abspath(__file__)), "libjots_b200.so")
+
+
+def load_library():
+    """Load the CUDA library; fails loudly when it has not been built (no fallback)."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = library_path()
+    if not os.path.exists(path):
+        raise JotsError("libjots_b200.so is not built (run `python -c 'import __graft_entry__ as g; g.build()'` "
+                        "or `make -C jots_b200/csrc`); jots_b200 has no CPU fallback")
+    lib = C.CDLL(path)
+    sig = {
+        "jots_last_error": (C.c_char_p, []),
+        "jots_version": (C.c_char_p, []),
+        "jots_device_count": (C.c_int, []),
+        "jots_mesh_read": (_P, [C.c_char_p]),
+        "jots_mesh_brick": (_P, [C.c_int64] * 3 + [C.c_double] * 3),
+        "jots_mesh_rect": (_P, [C.c_int64] * 2 + [C.c_double] * 4),
+        "jots_mesh_refine": (_P, [_P]),
+        "jots_mesh_destroy": (None, [_P]),
+        "jots_mesh_info": (C.c_int, [_P, C.POINTER(C.c_int), _I64, _I64, _I64]),
+        "jots_mesh_copy": (C.c_int, [_P, _P, _P, _P, _P]),
+        "jots_space_create": (_P, [_P, C.c_int]),
+        "jots_space_destroy": (None, [_P]),
+        "jots_space_info": (C.c_int, [_P, C.POINTER(C.c_int), C.POINTER(C.c_int), _I64, _I64, _I64, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+        "jots_space_copy_gather": (C.c_int, [_P, _P]),
+        "jots_space_copy_bdr": (C.c_int, [_P, _P, _P, _P, _P]),
+        "jots_space_copy_nodes": (C.c_int, [_P, _P]),
+        "jots_space_essential_dofs": (C.c_int64, [_P, _P, C.c_int, _P]),
+        "jots_ctx_create": (_P, [_P, C.c_int]),
+        "jots_ctx_destroy": (None, [_P]),
+        "jots_ctx_size": (C.c_int64, [_P]),
+        "jots_ctx_set_stream": (C.c_int, [_P, _P]),
+        "jots_ctx_sync": (C.c_int, [_P]),
+        "jots_ctx_set_material": (C.c_int, [_P, C.c_int, C.c_int, _P, C.c_int]),
+        "jots_ctx_set_bcs": (C.c_int, [_P, C.c_int, _P, _P]),
+        "jots_ctx_essential_dofs": (C.c_int64, [_P, _P]),
+        "jots_ctx_update_bcs": (C.c_int, [_P, C.c_double]),
+        "jots_ctx_apply_dirichlet": (C.c_int, [_P, _P, C.c_int, C.c_int]),
+        "jots_ctx_set_material_state": (C.c_int, [_P, _P, C.c_int]),
+        "jots_ctx_stats": (C.c_int, [_P, _P, _P]),
+        "jots_ctx_reset_stats": (C.c_int, [_P]),
+        "jots_op_create": (_P, [_P, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int,
+                                C.c_double, C.c_double, C.c_int]),
+        "jots_op_destroy": (None, [_P]),
+        "jots_op_iterate": (C.c_int, [_P, _P, C.c_int, _D]),
+        "jots_op_implicit_solve": (C.c_int, [_P, C.c_double, _P, _P, C.c_int]),
+        "jots_op_mult": (C.c_int, [_P, _P, _P, C.c_int]),
+        "jots_op_process_mat_prop_update": (C.c_int, [_P, C.c_int]),
+        "jots_op_update_neumann": (C.c_int, [_P]),
+        "jots_op_get_neumann": (C.c_int, [_P, _P, C.c_int]),
+        "jots_op_form_apply": (C.c_int, [_P, C.c_int, _P, _P, _P, C.c_int]),
+        "jots_op_form_diagonal": (C.c_int, [_P, C.c_int, _P, _P, C.c_int]),
+        "jots_op_form_time": (C.c_int, [_P, C.c_int, _P, _P, _P, C.c_int, _D]),
+        "jots_driver_create": (_P, [C.c_char_p, C.c_int]),
+        "jots_driver_create_on_mesh": (_P, [C.c_char_p, _P, C.c_int]),
+        "jots_driver_destroy": (None, [_P]),
+        "jots_driver_run": (C.c_int, [_P, C.c_int, C.POINTER(C.c_int)]),
+        "jots_driver_size": (C.c_int64, [_P]),
+        "jots_driver_get_u": (C.c_int, [_P, _P, C.c_int]),
+        "jots_driver_set_u": (C.c_int, [_P, _P, C.c_int]),
+        "jots_driver_time": (C.c_double, [_P]),
+        "jots_driver_ctx": (_P, [_P]),
+        "jots_driver_op": (_P, [_P]),
+        "jots_driver_step_count": (C.c_int, [_P]),
+        "jots_driver_space": (_P, [_P]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    lib._jots_symbols = sorted(sig)
+    _LIB = lib
+    return lib
+
+
+def _err():
+    return load_library().jots_last_error().decode()
+
+
+def _chk(rc):
+    if rc != 0:
+        raise JotsError(_err())
+
+
+def _handle(h):
+    if not h:
+        raise JotsError(_err())
+    return h
+
+
+def _ptr(a):
+    """Pointer for a numpy array (host) / int (device address) / torch tensor (device) / None."""
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data_as(C.c_void_p)
+    if isinstance(a, int):
+        return C.c_void_p(a)
+    if hasattr(a, "data_ptr"):
+        return C.c_void_p(a.data_ptr())
+    raise TypeError(type(a))
+
+
+def _loc(*arrs):
+    loc = None
+    for a in arrs:
+        if a is None:
+            continue
+        l = HOST if isinstance(a, np.ndarray) else DEVICE
+        if loc is not None and l != loc:
+            raise JotsError("all vector arguments of one call must live in the same memory space")
+        loc = l
+    return HOST if loc is None else loc
+
+
+def _f64(a):
+    if isinstance(a, np.ndarray):
+        if a.dtype != np.float64 or not a.flags.c_contiguous:
+            raise JotsError("host vectors must be contiguous float64 arrays")
+    return a
+
+
+class Mesh:
+    def __init__(self, handle):
+        self._h = _handle(handle)
+
+    @classmethod
+    def read(cls, path):
+        return cls(load_library().jots_mesh_read(os.fsencode(path)))
+
+    @classmethod
+    def brick(cls, nx, ny, nz, lx, ly, lz):
+        return cls(load_library().jots_mesh_brick(nx, ny, nz, lx, ly, lz))
+
+    @classmethod
+    def rect(cls, nx, ny, lx, ly, x0=0.0, y0=0.0):
+        return cls(load_library().jots_mesh_rect(nx, ny, lx, ly, x0, y0))
+
+    def refine(self):
+        return Mesh(load_library().jots_mesh_refine(self._h))
+
+    def info(self):
+        dim = C.c_int()
+        ne, nb, nv = C.c_int64(), C.c_int64(), C.c_int64()
+        _chk(load_library().jots_mesh_info(self._h, dim, ne, nb, nv))
+        return dict(dim=dim.value, n_elem=ne.value, n_bdr=nb.value, n_verts=nv.value)
+
+    def arrays(self):
+        i = self.info()
+        dim = i["dim"]
+        verts = np.empty((i["n_verts"], dim))
+        elems = np.empty((i["n_elem"], 2 ** dim), dtype=np.int64)
+        bdr = np.empty((i["n_bdr"], 2 ** (dim - 1)), dtype=np.int64)
+        battr = np.empty(i["n_bdr"], dtype=np.int32)
+        _chk(load_library().jots_mesh_copy(self._h, _ptr(verts), _ptr(elems), _ptr(bdr), _ptr(battr)))
+        return verts, elems, bdr, battr
+
+    def __del__(self):
+        if getattr(self, "_h", None) and _LIB is not None:
+            _LIB.jots_mesh_destroy(self._h)
+            self._h = None
+
+
+class Space:
+    def __init__(self, mesh=None, order=1, handle=None):
+        self._h = _handle(handle if handle is not None else load_library().jots_space_create(mesh._h, order))
+        dim, p, dpe, dpf = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        ne, nd, nb = C.c_int64(), C.c_int64(), C.c_int64()
+        _chk(load_library().jots_space_info(self._h, dim, p, ne, nd, nb, dpe, dpf))
+        self.dim, self.order, self.n_elem, self.n_dof, self.n_bdr = dim.value, p.value, ne.value, nd.value, nb.value
+        self.dofs_per_elem, self.dofs_per_face = dpe.value, dpf.value
+
+    def gather(self):
+        g = np.empty((self.n_elem, self.dofs_per_elem), dtype=np.int32)
+        _chk(load_library().jots_space_copy_gather(self._h, _ptr(g)))
+        return g
+
+    def boundary(self):
+        bg = np.empty((self.n_bdr, self.dofs_per_face), dtype=np.int32)
+        ba = np.empty(self.n_bdr, dtype=np.int32)
+        be = np.empty(self.n_bdr, dtype=np.int64)
+        bf = np.empty(self.n_bdr, dtype=np.int32)
+        _chk(load_library().jots_space_copy_bdr(self._h, _ptr(bg), _ptr(ba), _ptr(be), _ptr(bf)))
+        return bg, ba, be, bf
+
+    def node_coordinates(self):
+        x = np.empty((self.n_dof, self.dim))
+        _chk(load_library().jots_space_copy_nodes(self._h, _ptr(x)))
+        return x
+
+    def essential_dofs(self, attrs):
+        a = np.asarray(list(attrs), dtype=np.int32)
+        n = load_library().jots_space_essential_dofs(self._h, _ptr(a), a.size, None)
+        if n < 0:
+            raise JotsError(_err())
+        out = np.empty(n, dtype=np.int32)
+        load_library().jots_space_essential_dofs(self._h, _ptr(a), a.size, _ptr(out))
+        return out
+
+    def __del__(self):
+        if getattr(self, "_h", None) and _LIB is not None:
+            _LIB.jots_space_destroy(self._h)
+            self._h = None
+
+
+_BC_KIND = {"Isothermal": BC_ISOTHERMAL, "HeatFlux": BC_HEATFLUX, "Sinusoidal_Isothermal": BC_SIN_ISOTHERMAL,
+            "Sinusoidal_HeatFlux": BC_SIN_HEATFLUX}
+
+
+class Context:
+    """Device context of one subdomain."""
+
+    def __init__(self, space=None, device=0, handle=None, owner=None):
+        self._owner = owner  # keeps a Driver alive for borrowed handles
+        self._borrowed = handle is not None
+        self._h = _handle(handle if handle is not None else load_library().jots_ctx_create(space._h, device))
+        self.n = load_library().jots_ctx_size(self._h)
+
+    def set_stream(self, stream):
+        _chk(load_library().jots_ctx_set_stream(self._h, C.c_void_p(int(stream))))
+
+    def sync(self):
+        _chk(load_library().jots_ctx_sync(self._h))
+
+    def set_material(self, which, spec):
+        """spec: ('Uniform', v) / ('Polynomial', c0, c1, ...) -- the .ini value split on commas."""
+        model = {"Uniform": UNIFORM, "Polynomial": POLYNOMIAL}.get(spec[0])
+        if model is None:
+            raise JotsError("Unknown/Invalid material model specified")
+        c = np.asarray([float(v) for v in spec[1:]], dtype=np.float64)
+        _chk(load_library().jots_ctx_set_material(self._h, which, model, _ptr(c), c.size))
+
+    def set_bcs(self, specs):
+        """specs[i] <-> boundary attribute i+1: ('Isothermal', v) / ('HeatFlux', v) / ('Sinusoidal_*', A, w, ph, s)."""
+        kinds = np.zeros(len(specs), dtype=np.int32)
+        params = np.zeros((len(specs), 4))
+        for i, s in enumerate(specs):
+            if s[0] not in _BC_KIND:
+                raise JotsError("Invalid/Unknown boundary condition specified: '%s'" % s[0])
+            kinds[i] = _BC_KIND[s[0]]
+            vals = [float(v) for v in s[1:]]
+            params[i, :len(vals)] = vals
+        _chk(load_library().jots_ctx_set_bcs(self._h, len(specs), _ptr(kinds), _ptr(params)))
+
+    def essential_dofs(self):
+        n = load_library().jots_ctx_essential_dofs(self._h, None)
+        out = np.empty(n, dtype=np.int32)
+        load_library().jots_ctx_essential_dofs(self._h, _ptr(out))
+        return out
+
+    def update_bcs(self, t):
+        _chk(load_library().jots_ctx_update_bcs(self._h, float(t)))
+
+    def apply_dirichlet(self, u, only_time_dependent=False):
+        _chk(load_library().jots_ctx_apply_dirichlet(self._h, _ptr(_f64(u)), _loc(u), int(only_time_dependent)))
+
+    def set_material_state(self, u):
+        _chk(load_library().jots_ctx_set_material_state(self._h, _ptr(_f64(u)), _loc(u)))
+
+    def stats(self):
+        out = np.zeros(12, dtype=np.int64)
+        norms = np.zeros(2)
+        _chk(load_library().jots_ctx_stats(self._h, _ptr(out), _ptr(norms)))
+        keys = ["applies", "diag_assemblies", "krylov_iters", "newton_iters", "residual_evals", "steps", "kernel_launches",
+                "dots", "last_linear_iters", "last_linear_converged", "last_newton_iters", "last_newton_converged"]
+        d = {k: int(v) for k, v in zip(keys, out)}
+        d["last_linear_norm"], d["last_newton_norm"] = float(norms[0]), float(norms[1])
+        return d
+
+    def reset_stats(self):
+        _chk(load_library().jots_ctx_reset_stats(self._h))
+
+    def __del__(self):
+        if getattr(self, "_h", None) and not self._borrowed and _LIB is not None:
+            _LIB.jots_ctx_destroy(self._h)
+        self._h = None
+
+
+class Operator:
+    """Linear / Nonlinear / Steady conduction operator (JOTSIterator + TimeDependentOperator)."""
+
+    def __init__(self, ctx, sim_type, dt=0.0, time_scheme=EULER_IMPLICIT, solver=FGMRES, prec=CHEBYSHEV,
+                 rel_tol=1e-10, abs_tol=1e-16, max_iter=100, newton_rel_tol=1e-10, newton_abs_tol=1e-16, newton_max_iter=0,
+                 handle=None, owner=None):
+        self.ctx = ctx
+        self._owner = owner
+        self._borrowed = handle is not None
+        if handle is not None:
+            self._h = _handle(handle)
+            return
+        self._h = _handle(load_library().jots_op_create(ctx._h, sim_type, dt, time_scheme, solver, prec, rel_tol, abs_tol,
+                                                        max_iter, newton_rel_tol, newton_abs_tol, newton_max_iter))
+
+    def iterate(self, u, time=0.0):
+        t = C.c_double(time)
+        _chk(load_library().jots_op_iterate(self._h, _ptr(_f64(u)), _loc(u), C.byref(t)))
+        return t.value
+
+    def implicit_solve(self, dt, u, k):
+        _chk(load_library().jots_op_implicit_solve(self._h, dt, _ptr(_f64(u)), _ptr(_f64(k)), _loc(u, k)))
+
+    def mult(self, u, k):
+        _chk(load_library().jots_op_mult(self._h, _ptr(_f64(u)), _ptr(_f64(k)), _loc(u, k)))
+
+    def process_mat_prop_update(self, which):
+        _chk(load_library().jots_op_process_mat_prop_update(self._h, which))
+
+    def update_neumann(self):
+        _chk(load_library().jots_op_update_neumann(self._h))
+
+    def neumann_vector(self):
+        b = np.empty(self.ctx.n)
+        _chk(load_library().jots_op_get_neumann(self._h, _ptr(b), HOST))
+        return b
+
+    def form_apply(self, form, x, y, state=None):
+        _chk(load_library().jots_op_form_apply(self._h, form, _ptr(_f64(x)), _ptr(state), _ptr(_f64(y)), _loc(x, state, y)))
+        return y
+
+    def form_diagonal(self, form, d, state=None):
+        _chk(load_library().jots_op_form_diagonal(self._h, form, _ptr(state), _ptr(_f64(d)), _loc(state, d)))
+        return d
+
+    def form_time(self, form, x_dev, y_dev, state_dev=None, reps=10):
+        ms = C.c_double()
+        _chk(load_library().jots_op_form_time(self._h, form, _ptr(x_dev), _ptr(state_dev), _ptr(y_dev), reps, C.byref(ms)))
+        return ms.value
+
+    def __del__(self):
+        if getattr(self, "_h", None) and not self._borrowed and _LIB is not None:
+            _LIB.jots_op_destroy(self._h)
+        self._h = None
+
+
+class Driver:
+    """Config + the hot-path part of JOTSDriver::Run."""
+
+    def __init__(self, ini_path, device=0, mesh=None):
+        lib = load_library()
+        if mesh is None:
+            self._h = _handle(lib.jots_driver_create(os.fsencode(ini_path), device))
+        else:
+            self._h = _handle(lib.jots_driver_create_on_mesh(os.fsencode(ini_path), mesh._h, device))
+        self.n = lib.jots_driver_size(self._h)
+        self.ctx = Context(handle=lib.jots_driver_ctx(self._h), owner=self)
+        self.op = Operator(self.ctx, None, handle=lib.jots_driver_op(self._h), owner=self)
+
+    def run(self, max_steps=-1):
+        done = C.c_int()
+        _chk(load_library().jots_driver_run(self._h, max_steps, C.byref(done)))
+        return done.value
+
+    def get_u(self, out=None):
+        u = np.empty(self.n) if out is None else out
+        _chk(load_library().jots_driver_get_u(self._h, _ptr(u), _loc(u)))
+        return u
+
+    def set_u(self, u):
+        _chk(load_library().jots_driver_set_u(self._h, _ptr(_f64(u)), _loc(u)))
+
+    @property
+    def time(self):
+        return load_library().jots_driver_time(self._h)
+
+    def space(self):
+        return Space(handle=load_library().jots_driver_space(self._h))
+
+    def __del__(self):
+        if getattr(self, "_h", None) and _LIB is not None:
+            self.ctx._h = None
+            self.op._h = None
+            _LIB.jots_driver_destroy(self._h)
+            self._h = None

@@ -17,7 +17,7 @@ Visualization_Freq=0
 """
 
 
-def _ini(sim, mesh, t0, props, bcs, time=True, newton=None, solver="FGMRES", prec="Chebyshev",
+def ini_text(sim, mesh, t0, props, bcs, time=True, newton=None, solver="FGMRES", prec="Chebyshev",
          steps=200, dt="1e-2", order=2, scheme="Euler_Implicit", refine=0):
     s = "[FiniteElementSetup]\nSimulation_Type=%s\nFE_Order=%d\nUse_Restart=No\nMesh_File=%s\n" % (sim, order, mesh)
     s += "Serial_Refine=%d\nParallel_Refine=0\nInitial_Temperature=%s\n\n[MaterialProperties]\n" % (refine, t0)
@@ -45,23 +45,23 @@ _BC_B2 = ["HeatFlux, 7.5e5", _HF0, _HF0, _HF0, _HF0, _HF0]
 # name -> dict(sim, mesh key, analytic name, eps, ini builder)
 CASES = {
     "Reinert_B1": dict(mesh="reinert", exact="reinert_b1", eps=1e-8,
-                       ini=lambda m, **kw: _ini("Linearized_Unsteady", m, 300, _CONST, _BC_B1, **kw)),
+                       ini=lambda m, **kw: ini_text("Linearized_Unsteady", m, 300, _CONST, _BC_B1, **kw)),
     "Reinert_B2": dict(mesh="reinert", exact="reinert_b2", eps=1e-8,
-                       ini=lambda m, **kw: _ini("Linearized_Unsteady", m, 300, _CONST, _BC_B2, **kw)),
+                       ini=lambda m, **kw: ini_text("Linearized_Unsteady", m, 300, _CONST, _BC_B2, **kw)),
     "Reinert_B3": dict(mesh="reinert", exact="reinert_b3", eps=1e-8,
-                       ini=lambda m, **kw: _ini("Linearized_Unsteady", m, 300, _B3, _BC_B2, **kw)),
+                       ini=lambda m, **kw: ini_text("Linearized_Unsteady", m, 300, _B3, _BC_B2, **kw)),
     "NL_Reinert_B1": dict(mesh="reinert", exact="reinert_b1", eps=1e-8,
-                          ini=lambda m, **kw: _ini("Nonlinear_Unsteady", m, 300, _CONST, _BC_B1, newton=100, **kw)),
+                          ini=lambda m, **kw: ini_text("Nonlinear_Unsteady", m, 300, _CONST, _BC_B1, newton=100, **kw)),
     "NL_Reinert_B2": dict(mesh="reinert", exact="reinert_b2", eps=1e-8,
-                          ini=lambda m, **kw: _ini("Nonlinear_Unsteady", m, 300, _CONST, _BC_B2, newton=100, **kw)),
+                          ini=lambda m, **kw: ini_text("Nonlinear_Unsteady", m, 300, _CONST, _BC_B2, newton=100, **kw)),
     "NL_Reinert_B3": dict(mesh="reinert", exact="reinert_b3", eps=1e-8,
-                          ini=lambda m, **kw: _ini("Nonlinear_Unsteady", m, 300, _B3, _BC_B2, newton=100, **kw)),
+                          ini=lambda m, **kw: ini_text("Nonlinear_Unsteady", m, 300, _B3, _BC_B2, newton=100, **kw)),
     "Danish_Model1": dict(mesh="danish", exact="danish_model1", eps=3e-5,
-                          ini=lambda m, **kw: _ini("Steady", m, 0.5, [("Thermal_Conductivity_k", "Polynomial, 50, 1")],
+                          ini=lambda m, **kw: ini_text("Steady", m, 0.5, [("Thermal_Conductivity_k", "Polynomial, 50, 1")],
                                                    ["Isothermal, 0", _HF0, _HF0, "Isothermal, 1", _HF0, _HF0],
                                                    time=False, newton=5000, solver="CG", **kw)),
     "Danish_Model1_Neumann": dict(mesh="danish", exact="danish_model1", eps=3e-5,
-                                  ini=lambda m, **kw: _ini("Steady", m, 0.5, [("Thermal_Conductivity_k", "Polynomial, 50, 1")],
+                                  ini=lambda m, **kw: ini_text("Steady", m, 0.5, [("Thermal_Conductivity_k", "Polynomial, 50, 1")],
                                                            ["Isothermal, 0", _HF0, _HF0, "HeatFlux, 26", _HF0, _HF0],
                                                            time=False, newton=5000, solver="CG", **kw)),
 }
@@ -71,9 +71,15 @@ BRICKS = {"reinert": (99, 1, 1, 0.01, 0.01, 0.01), "danish": (99, 1, 1, 1.0, 0.1
 REF_MESH = {"reinert": "examples/meshes/Reinert_1D_block.mesh", "danish": "examples/meshes/Danish_1D_bar.mesh"}
 
 
-def write_brick_mesh(path, nx, ny, nz, lx, ly, lz):
-    """Write an axis-aligned brick in 'MFEM mesh v1.0' format with the attribute convention of
-    examples/meshes/cube_25_L0p01.mesh (1=x0 2=y0 3=z0 4=x1 5=y1 6=z1)."""
+def _grade(t, g):
+    """monotone map of [0,1] onto itself; g = 0 is the identity"""
+    return t + g * t * (1.0 - t)
+
+
+def write_brick_mesh(path, nx, ny, nz, lx, ly, lz, grade=0.0, shear=0.0):
+    """Write a brick in 'MFEM mesh v1.0' format with the attribute convention of
+    examples/meshes/cube_25_L0p01.mesh (1=x0 2=y0 3=z0 4=x1 5=y1 6=z1).  grade != 0 makes the
+    element sizes vary (still affine per element); shear != 0 applies a global affine shear."""
     vx, vy = nx + 1, ny + 1
     vid = lambda i, j, k: i + vx * (j + vy * k)
     out = ["MFEM mesh v1.0", "", "dimension", "3", "", "elements", str(nx * ny * nz)]
@@ -102,12 +108,13 @@ def write_brick_mesh(path, nx, ny, nz, lx, ly, lz):
     for k in range(nz + 1):
         for j in range(ny + 1):
             for i in range(nx + 1):
-                out.append("%.17g %.17g %.17g" % (i * lx / nx, j * ly / ny, k * lz / nz))
+                x, y, z = lx * _grade(i / nx, grade), ly * _grade(j / ny, -grade), lz * _grade(k / nz, 0.5 * grade)
+                out.append("%.17g %.17g %.17g" % (x + shear * y + 0.5 * shear * z, y + 0.25 * shear * z, z))
     with open(path, "w") as f:
         f.write("\n".join(out) + "\n")
 
 
-def write_quad_mesh(path, nx, ny, lx, ly, y0=0.0):
+def write_quad_mesh(path, nx, ny, lx, ly, y0=0.0, grade=0.0, shear=0.0):
     """2-D rectangle, attributes 1=bottom 2=right 3=top 4=left (plate.mesh convention)."""
     vx = nx + 1
     vid = lambda i, j: i + vx * j
@@ -127,7 +134,8 @@ def write_quad_mesh(path, nx, ny, lx, ly, y0=0.0):
     out += ["", "vertices", str(vx * (ny + 1)), "2"]
     for j in range(ny + 1):
         for i in range(nx + 1):
-            out.append("%.17g %.17g" % (i * lx / nx, y0 + j * ly / ny))
+            x, y = lx * _grade(i / nx, grade), ly * _grade(j / ny, -grade)
+            out.append("%.17g %.17g" % (x + shear * y, y0 + y))
     with open(path, "w") as f:
         f.write("\n".join(out) + "\n")
 
