@@ -1,0 +1,325 @@
+// Register-slab element kernel for hexes with a diagonal metric (axis-aligned bricks, any axis
+// permutation) -- the fast path of the operator apply.
+//
+// The generic kernel (apply_generic.cuh) moves one shared-memory word per DFMA and is bound by the
+// 128 B/clk shared-memory port.  Here the contractions are regrouped so that almost all of them
+// run out of registers:
+//   phase 1  one thread per (element, i, j) nodal pencil: gather the L-vector DOFs, evaluate the
+//            nodal property polynomials in registers, contract along z with B and G, store the
+//            resulting 3x3 planes for each of the Q quadrature planes;
+//   phase 2  one thread per (element, quadrature plane qz): load the few planes, do every in-plane
+//            interpolation / derivative, the quadrature-point physics and the transposed in-plane
+//            contractions entirely in registers (about 1300 DFMA per thread for the Q2 Jacobian
+//            apply), store two 3x3 result planes;
+//   phase 3  one thread per (element, i, j): transposed z contraction, FP64 atomics to the L-vector.
+// Shared-memory traffic drops from ~4400 to ~600 words per Q2 element.
+#pragma once
+#include "coef.cuh"
+
+namespace jots {
+
+template <int D, int Q>
+struct SlabTables {
+    double B[Q * D], G[Q * D];     // B[q*D+i] = l_i(x_q), G = derivative
+    double BW[Q * D], GW[Q * D];   // rows scaled by the quadrature weight W[q]
+    double W[Q];
+};
+
+template <int OP, int CF> struct SlabCfg {
+    static constexpr bool X_GRAD = (OP != OP_RES);
+    static constexpr bool Z_GRAD = (OP != OP_LIN);
+    static constexpr int NF = CoefNF<CF, OP>::value;          // CF_CONST: 0, CF_K: 1 (2 for OP_JAC)
+    static constexpr int NP = 1 + (X_GRAD ? 1 : 0) + (Z_GRAD ? 2 : 0) + NF;
+    // plane ids
+    static constexpr int P_XB = 0;
+    static constexpr int P_XG = 1;                              // if X_GRAD
+    static constexpr int P_ZB = 1 + (X_GRAD ? 1 : 0);           // if Z_GRAD
+    static constexpr int P_ZG = P_ZB + 1;
+    static constexpr int P_F0 = 1 + (X_GRAD ? 1 : 0) + (Z_GRAD ? 2 : 0);
+};
+
+template <int D> struct PlaneStride { static constexpr int value = (D * D + 1) / 2 * 2 + (((D * D + 1) / 2) % 2 == 0 ? 2 : 0); };
+// D=2: 4 -> 4+2 = 6 ; D=3: 10 ; D=4: 16+2 = 18   (stride/2 odd => conflict-free 128-bit plane loads)
+
+template <int D, int Q, int NP> struct ElemStride {
+    static constexpr int PS = PlaneStride<D>::value;
+    static constexpr int raw = (NP + 2) * Q * PS;
+    static constexpr int value = raw + ((8 - raw % 16) + 16) % 16;   // == 8 (mod 16)
+};
+
+template <int D, int Q>
+__device__ __forceinline__ void xpass(const double (&in)[D * D], const double* tab, double (&out)[D * Q]) {
+#pragma unroll
+    for (int j = 0; j < D; ++j)
+#pragma unroll
+        for (int q = 0; q < Q; ++q) {
+            double s = tab[q * D] * in[j * D];
+#pragma unroll
+            for (int i = 1; i < D; ++i) s += tab[q * D + i] * in[j * D + i];
+            out[j * Q + q] = s;
+        }
+}
+template <int D, int Q>
+__device__ __forceinline__ void ypass(const double (&in)[D * Q], const double* tab, double (&out)[Q * Q]) {
+#pragma unroll
+    for (int qy = 0; qy < Q; ++qy)
+#pragma unroll
+        for (int qx = 0; qx < Q; ++qx) {
+            double s = tab[qy * D] * in[qx];
+#pragma unroll
+            for (int j = 1; j < D; ++j) s += tab[qy * D + j] * in[j * Q + qx];
+            out[qy * Q + qx] = s;
+        }
+}
+// out[j][qx] = sum_qy tab[qy][j] in[qy][qx]
+template <int D, int Q>
+__device__ __forceinline__ void ypassT(const double (&in)[Q * Q], const double* tab, double (&out)[D * Q]) {
+#pragma unroll
+    for (int j = 0; j < D; ++j)
+#pragma unroll
+        for (int qx = 0; qx < Q; ++qx) {
+            double s = tab[j] * in[qx];
+#pragma unroll
+            for (int qy = 1; qy < Q; ++qy) s += tab[qy * D + j] * in[qy * Q + qx];
+            out[j * Q + qx] = s;
+        }
+}
+// acc[j][i] += scale * sum_qx tab[qx][i] in[j][qx]
+template <int D, int Q>
+__device__ __forceinline__ void xpassT_acc(const double (&in)[D * Q], const double* tab, double scale, double (&acc)[D * D]) {
+#pragma unroll
+    for (int j = 0; j < D; ++j)
+#pragma unroll
+        for (int i = 0; i < D; ++i) {
+            double s = tab[i] * in[j * Q];
+#pragma unroll
+            for (int qx = 1; qx < Q; ++qx) s += tab[qx * D + i] * in[j * Q + qx];
+            acc[j * D + i] += scale * s;
+        }
+}
+
+template <int D, int PS>
+__device__ __forceinline__ void load_plane(const double* p, double (&out)[D * D]) {
+    const double2* p2 = reinterpret_cast<const double2*>(p);
+#pragma unroll
+    for (int m = 0; m < (D * D) / 2; ++m) { const double2 v = p2[m]; out[2 * m] = v.x; out[2 * m + 1] = v.y; }
+    if ((D * D) % 2) out[D * D - 1] = p[D * D - 1];
+}
+template <int D, int PS>
+__device__ __forceinline__ void store_plane(double* p, const double (&in)[D * D]) {
+    double2* p2 = reinterpret_cast<double2*>(p);
+#pragma unroll
+    for (int m = 0; m < (D * D) / 2; ++m) p2[m] = make_double2(in[2 * m], in[2 * m + 1]);
+    if ((D * D) % 2) p[D * D - 1] = in[D * D - 1];
+}
+
+template <int D, int Q, int OP, int CF, int E>
+__global__ void __launch_bounds__(E* Q) form_apply_slab_kernel(const FormArgs a, const SlabTables<D, Q> t) {
+    typedef SlabCfg<OP, CF> C;
+    constexpr int NF = C::NF, NFA = NF > 0 ? NF : 1, NP = C::NP;
+    constexpr int PS = PlaneStride<D>::value;
+    constexpr int ES = ElemStride<D, Q, NP>::value;
+    constexpr int ND = D * D * D, DD = D * D;
+    constexpr int T = E * Q;
+    extern __shared__ __align__(16) double smem[];
+    const int tid = threadIdx.x;
+    const int e0 = blockIdx.x * E;
+
+    // ---------------- phase 1: gather + z contraction --------------------------------------------
+    for (int item = tid; item < E * DD; item += T) {
+        const int el = item / DD, ij = item - el * DD;
+        const int e = e0 + el;
+        if (e >= a.nelem) continue;
+        double xr[D], zr[D], fr[NFA][D];
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+            const int g = a.gather[(size_t)e * ND + ij + DD * k];
+            const int idx = g < 0 ? ~g : g;
+            xr[k] = (g < 0 && a.mask_in) ? 0.0 : a.x[idx];
+            if (C::Z_GRAD || NF > 0) {
+                zr[k] = a.z[idx];
+                if (NF > 0) {
+                    double f[NFA];
+                    nodal_fields<CF, OP>(a.mat, zr[k], f);
+#pragma unroll
+                    for (int n = 0; n < NF; ++n) fr[n][k] = f[n];
+                }
+            }
+        }
+        double* base = smem + el * ES + ij;
+#pragma unroll
+        for (int qz = 0; qz < Q; ++qz) {
+            double s = 0.0, sg = 0.0, zs = 0.0, zg = 0.0;
+#pragma unroll
+            for (int k = 0; k < D; ++k) {
+                s += t.B[qz * D + k] * xr[k];
+                if (C::X_GRAD) sg += t.G[qz * D + k] * xr[k];
+                if (C::Z_GRAD) { zs += t.B[qz * D + k] * zr[k]; zg += t.G[qz * D + k] * zr[k]; }
+            }
+            base[(C::P_XB * Q + qz) * PS] = s;
+            if (C::X_GRAD) base[(C::P_XG * Q + qz) * PS] = sg;
+            if (C::Z_GRAD) { base[(C::P_ZB * Q + qz) * PS] = zs; base[(C::P_ZG * Q + qz) * PS] = zg; }
+#pragma unroll
+            for (int n = 0; n < NF; ++n) {
+                double fs = 0.0;
+#pragma unroll
+                for (int k = 0; k < D; ++k) fs += t.B[qz * D + k] * fr[n][k];
+                base[((C::P_F0 + n) * Q + qz) * PS] = fs;
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---------------- phase 2: one quadrature plane per thread, all in registers -----------------
+    {
+        const int el = tid / Q, qz = tid - el * Q;
+        int e = e0 + el;
+        if (e >= a.nelem) e = a.nelem - 1;
+        const double* gm = a.geom + (size_t)e * a.geom_stride;
+        const double gxx = gm[0] * gm[0] + gm[1] * gm[1] + gm[2] * gm[2];
+        const double gyy = gm[3] * gm[3] + gm[4] * gm[4] + gm[5] * gm[5];
+        const double gzz = gm[6] * gm[6] + gm[7] * gm[7] + gm[8] * gm[8];
+        const double wz = t.W[qz] * gm[9];
+        const double* pl = smem + el * ES + qz * PS;
+        auto plane = [&](int id) { return pl + id * Q * PS; };
+
+        double p9[DD], t12[D * Q], A[DD], Bp[DD];
+#pragma unroll
+        for (int i = 0; i < DD; ++i) { A[i] = 0.0; Bp[i] = 0.0; }
+
+        // coefficient planes: a1 (diffusion) and, for the Jacobian, a2 = ck * alpha'
+        double a1[Q * Q], a2x[Q * Q];
+        double a1c = 0.0;
+        if (CF == CF_CONST) a1c = a.ck * a.a0;
+        else {
+            load_plane<D, PS>(plane(C::P_F0), p9);
+            xpass<D, Q>(p9, t.B, t12);
+            ypass<D, Q>(t12, t.B, a1);
+            const double sc = a.ck * a.inv_rc;
+#pragma unroll
+            for (int q = 0; q < Q * Q; ++q) a1[q] *= sc;
+            if (OP == OP_JAC) {
+                load_plane<D, PS>(plane(C::P_F0 + 1), p9);
+                xpass<D, Q>(p9, t.B, t12);
+                ypass<D, Q>(t12, t.B, a2x);
+            }
+        }
+        // x: value, in-plane sources
+        double xB12[D * Q], xG12[D * Q], vy12[D * Q];
+        load_plane<D, PS>(plane(C::P_XB), p9);
+        xpass<D, Q>(p9, t.B, xB12);
+        if (C::X_GRAD) xpass<D, Q>(p9, t.G, xG12);
+        {
+            double xv[Q * Q];
+            ypass<D, Q>(xB12, t.B, xv);
+            if (OP == OP_JAC && CF != CF_CONST) {
+                const double sc = a.ck * a.inv_rc;
+#pragma unroll
+                for (int q = 0; q < Q * Q; ++q) a2x[q] *= sc * xv[q];
+            }
+            ypassT<D, Q>(xv, t.BW, vy12);   // mass term, scaled by c_m below
+        }
+        const double c_m = a.cm * (CF == CF_CONST || CF == CF_K ? a.m0 : 1.0) * wz;
+        double zB12[D * Q], zG12[D * Q];
+        if (C::Z_GRAD) {
+            load_plane<D, PS>(plane(C::P_ZB), p9);
+            xpass<D, Q>(p9, t.B, zB12);
+            xpass<D, Q>(p9, t.G, zG12);
+        }
+        // ---- x direction
+        {
+            double F[Q * Q];
+            if (OP == OP_RES) ypass<D, Q>(zG12, t.B, F);
+            else ypass<D, Q>(xG12, t.B, F);
+            if (CF == CF_CONST) {
+#pragma unroll
+                for (int q = 0; q < Q * Q; ++q) F[q] *= a1c;
+            } else {
+#pragma unroll
+                for (int q = 0; q < Q * Q; ++q) F[q] *= a1[q];
+                if (OP == OP_JAC) {
+                    double zd[Q * Q];
+                    ypass<D, Q>(zG12, t.B, zd);
+#pragma unroll
+                    for (int q = 0; q < Q * Q; ++q) F[q] += a2x[q] * zd[q];
+                }
+            }
+            ypassT<D, Q>(F, t.BW, t12);
+            xpassT_acc<D, Q>(t12, t.GW, wz * gxx, A);
+        }
+        // ---- y direction (+ mass)
+        {
+            double F[Q * Q];
+            if (OP == OP_RES) ypass<D, Q>(zB12, t.G, F);
+            else ypass<D, Q>(xB12, t.G, F);
+            if (CF == CF_CONST) {
+#pragma unroll
+                for (int q = 0; q < Q * Q; ++q) F[q] *= a1c;
+            } else {
+#pragma unroll
+                for (int q = 0; q < Q * Q; ++q) F[q] *= a1[q];
+                if (OP == OP_JAC) {
+                    double zd[Q * Q];
+                    ypass<D, Q>(zB12, t.G, zd);
+#pragma unroll
+                    for (int q = 0; q < Q * Q; ++q) F[q] += a2x[q] * zd[q];
+                }
+            }
+            ypassT<D, Q>(F, t.GW, t12);
+            const double cy = wz * gyy;
+#pragma unroll
+            for (int i = 0; i < D * Q; ++i) t12[i] = cy * t12[i] + c_m * vy12[i];
+            xpassT_acc<D, Q>(t12, t.BW, 1.0, A);
+        }
+        // ---- z direction
+        {
+            double F[Q * Q];
+            load_plane<D, PS>(plane(OP == OP_RES ? C::P_ZG : C::P_XG), p9);
+            xpass<D, Q>(p9, t.B, t12);
+            ypass<D, Q>(t12, t.B, F);
+            if (CF == CF_CONST) {
+#pragma unroll
+                for (int q = 0; q < Q * Q; ++q) F[q] *= a1c;
+            } else {
+#pragma unroll
+                for (int q = 0; q < Q * Q; ++q) F[q] *= a1[q];
+                if (OP == OP_JAC) {
+                    double zd[Q * Q];
+                    load_plane<D, PS>(plane(C::P_ZG), p9);
+                    xpass<D, Q>(p9, t.B, t12);
+                    ypass<D, Q>(t12, t.B, zd);
+#pragma unroll
+                    for (int q = 0; q < Q * Q; ++q) F[q] += a2x[q] * zd[q];
+                }
+            }
+            ypassT<D, Q>(F, t.BW, t12);
+            xpassT_acc<D, Q>(t12, t.BW, wz * gzz, Bp);
+        }
+        double* outp = smem + el * ES + (NP * Q + qz) * PS;
+        store_plane<D, PS>(outp, A);
+        store_plane<D, PS>(outp + Q * PS, Bp);
+    }
+    __syncthreads();
+
+    // ---------------- phase 3: transposed z contraction + scatter --------------------------------
+    for (int item = tid; item < E * DD; item += T) {
+        const int el = item / DD, ij = item - el * DD;
+        const int e = e0 + el;
+        if (e >= a.nelem) continue;
+        const double* base = smem + el * ES + NP * Q * PS + ij;
+        double Aq[Q], Bq[Q];
+#pragma unroll
+        for (int qz = 0; qz < Q; ++qz) { Aq[qz] = base[qz * PS]; Bq[qz] = base[(Q + qz) * PS]; }
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+            double s = 0.0;
+#pragma unroll
+            for (int qz = 0; qz < Q; ++qz) s += t.B[qz * D + k] * Aq[qz] + t.G[qz * D + k] * Bq[qz];
+            const int g = a.gather[(size_t)e * ND + ij + DD * k];
+            if (g >= 0) atomicAdd(a.y + g, s);
+            else if (!a.mask_out) atomicAdd(a.y + (~g), s);
+        }
+    }
+}
+
+}  // namespace jots

@@ -2,6 +2,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 #include "basis.hpp"
@@ -50,11 +51,13 @@ Ctx::Ctx(const Space& s, int dev) : device(dev), space(s) {
     JOTS_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
     own_stream = true;
     n = s.ndof; n_owned = s.ndof;
+    if (const char* ev = std::getenv("JOTS_DISABLE_SLAB")) use_slab = !(ev[0] == '1');
     fill_tables(tabs, s.dim, s.p);
     // geometry: affine elements only (every mesh the reference ships and the synthetic bricks)
     const int dim = s.dim, nv = 1 << dim;
     std::vector<double> geom((size_t)s.nelem * 10);
     bool uniform = true;
+    geom_diag = true;
     for (int64_t el = 0; el < s.nelem; ++el) {
         const double* X = &s.elem_corner[(size_t)el * nv * dim];
         double J[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
@@ -78,6 +81,13 @@ Ctx::Ctx(const Space& s, int dev) : device(dev), space(s) {
         g[3] = (J[1][2] * J[2][0] - J[1][0] * J[2][2]) / det; g[4] = (J[0][0] * J[2][2] - J[0][2] * J[2][0]) / det; g[5] = (J[0][2] * J[1][0] - J[0][0] * J[1][2]) / det;
         g[6] = (J[1][0] * J[2][1] - J[1][1] * J[2][0]) / det; g[7] = (J[0][1] * J[2][0] - J[0][0] * J[2][1]) / det; g[8] = (J[0][0] * J[1][1] - J[0][1] * J[1][0]) / det;
         g[9] = det;
+        {
+            // metric G = invJ invJ^T diagonal?
+            const double g01 = g[0] * g[3] + g[1] * g[4] + g[2] * g[5], g02 = g[0] * g[6] + g[1] * g[7] + g[2] * g[8],
+                         g12 = g[3] * g[6] + g[4] * g[7] + g[5] * g[8];
+            const double gs = g[0] * g[0] + g[1] * g[1] + g[2] * g[2] + g[3] * g[3] + g[4] * g[4] + g[5] * g[5] + g[6] * g[6] + g[7] * g[7] + g[8] * g[8];
+            if (std::fabs(g01) + std::fabs(g02) + std::fabs(g12) > 1e-13 * gs) geom_diag = false;
+        }
         if (uniform && el > 0)
             for (int i = 0; i < 10; ++i)
                 if (std::fabs(g[i] - geom[i]) > 1e-12 * std::max(std::fabs(geom[i]), std::fabs(geom[i < 9 ? 4 * (i / 3) : 9]))) { uniform = false; break; }
@@ -152,6 +162,7 @@ FormArgs Ctx::make_args(const FormSpec& f, const double* x, double* y, bool) con
     std::memset(&a, 0, sizeof(a));
     a.gather = d_gather_ess.p;
     a.geom = d_geom.p; a.geom_stride = geom_stride;
+    a.geom_diag = (geom_diag && use_slab) ? 1 : 0;
     a.x = x; a.z = f.state; a.y = y;
     a.nelem = (int)space.nelem;
     a.mask_in = f.mask_in; a.mask_out = f.mask_out;

@@ -100,6 +100,8 @@ public:
     DArr<double> d_geom, d_bdr_corner, d_gattr;
     DArr<unsigned char> d_essmark;
     int geom_stride = 10;
+    bool geom_diag = false;   // diagonal metric on every element
+    bool use_slab = true;     // JOTS_DISABLE_SLAB=1 forces the generic kernel
     DArr<double> d_scal, d_partial;
     DArr<double> mat_state;   // vector the nodal property polynomials were last evaluated on (UpdateMatProps)
     void set_mat_state(const double* u) { mat_state.alloc(n); copy(u, mat_state.p); }

@@ -6,6 +6,10 @@ namespace jots {
 
 int launch_form_apply(int dim, int p, int op, int cf, const FormArgs& a, const TablesRT& t, cudaStream_t st) {
     if (a.nelem <= 0) return 0;
+    if (dim == 3 && a.geom_diag) {
+        // fast path: register-slab kernel (axis-aligned hexes, CF_CONST / CF_K, Q1-Q2)
+        if (launch_form_apply_slab(p, op, cf, a, t, st) == 0) return 0;
+    }
     if (dim == 3) {
         switch (p) {
             case 1: return launch_form_apply_h1(op, cf, a, t, st);

@@ -1,0 +1,47 @@
+// Instantiations of the register-slab kernel (hexes, diagonal metric, CF_CONST / CF_K).
+#include "apply_slab.cuh"
+#include "diag_face_host.hpp"
+#include "launch.hpp"
+
+namespace jots {
+
+template <int D, int Q, int OP, int CF>
+static int launch_slab(const FormArgs& a, const TablesRT& r, cudaStream_t st) {
+    constexpr int E = 32;
+    typedef SlabCfg<OP, CF> C;
+    SlabTables<D, Q> t;
+    for (int q = 0; q < Q; ++q) {
+        t.W[q] = r.W[q];
+        for (int i = 0; i < D; ++i) {
+            t.B[q * D + i] = r.B[q * D + i]; t.G[q * D + i] = r.G[q * D + i];
+            t.BW[q * D + i] = r.W[q] * r.B[q * D + i]; t.GW[q * D + i] = r.W[q] * r.G[q * D + i];
+        }
+    }
+    const size_t smem = (size_t)E * ElemStride<D, Q, C::NP>::value * sizeof(double);
+    auto kern = form_apply_slab_kernel<D, Q, OP, CF, E>;
+    static bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        configured = true;
+    }
+    const int grid = (a.nelem + E - 1) / E;
+    kern<<<grid, E * Q, smem, st>>>(a, t);
+    return 0;
+}
+
+template <int D, int Q>
+static int dispatch(int op, int cf, const FormArgs& a, const TablesRT& t, cudaStream_t st) {
+#define CASE(OPV, CFV) if (op == OPV && cf == CFV) return launch_slab<D, Q, OPV, CFV>(a, t, st);
+    CASE(OP_LIN, CF_CONST) CASE(OP_LIN, CF_K) CASE(OP_JAC, CF_K) CASE(OP_RES, CF_CONST) CASE(OP_RES, CF_K)
+#undef CASE
+    return 1;
+}
+
+// returns 0 when launched, non-zero when this (order, op, cf) has no slab instantiation
+int launch_form_apply_slab(int p, int op, int cf, const FormArgs& a, const TablesRT& t, cudaStream_t st) {
+    if (p == 1) return dispatch<2, 3>(op, cf, a, t, st);
+    if (p == 2) return dispatch<3, 4>(op, cf, a, t, st);
+    return 1;
+}
+
+}  // namespace jots

@@ -125,9 +125,36 @@ def test_nonlinear_forms(J, tmp_path, dim, p, props):
     assert rel(dev.op.neumann_vector(), it.b_vec) < APPLY_TOL
 
 
-@pytest.mark.parametrize("dim,p", [(3, 2), (3, 3), (2, 2), (2, 1)])
-def test_steady_forms(J, tmp_path, dim, p):
-    dev, orc = build(J, tmp_path, "Steady", dim, p, "k", grade=0.4, shear=0.2, solver="CG")
+@pytest.mark.parametrize("p", [1, 2])
+@pytest.mark.parametrize("props", ["const", "k"])
+@pytest.mark.parametrize("sim", ["Linearized_Unsteady", "Nonlinear_Unsteady"])
+def test_axis_aligned_fast_path(J, tmp_path, sim, props, p):
+    """Axis-aligned (graded) bricks take the register-slab kernel: same checks as above."""
+    dev, orc = build(J, tmp_path, sim, 3, p, props, grade=0.6, shear=0.0, n=(5, 3, 4))
+    n = dev.n
+    state = smooth_state(orc)
+    x = rnd(n, 11)
+    it = orc.it
+    if sim == "Linearized_Unsteady":
+        orc.u = state.copy()
+        orc.update_mat_props(True)
+        for form, mat in ((J.FORM_MASS, it.M_mat), (J.FORM_STIFFNESS, it.K_mat), (J.FORM_SYSTEM, it.A_mat)):
+            y = dev.op.form_apply(form, x, np.empty(n), state=state)
+            assert rel(y, mat @ x) < APPLY_TOL, (form, rel(y, mat @ x))
+    else:
+        k = 50.0 * rnd(n, 12)
+        it.u_n = state
+        it.new_state(k)
+        r = dev.op.form_apply(J.FORM_RESIDUAL, k, np.empty(n), state=state)
+        assert rel(r, it.mult(k)) < APPLY_TOL
+        Jm = it.gradient(k)
+        y = dev.op.form_apply(J.FORM_SYSTEM, x, np.empty(n), state=state + it.dt * k)
+        assert rel(y, Jm @ x) < APPLY_TOL
+
+
+@pytest.mark.parametrize("dim,p,shear", [(3, 2, 0.2), (3, 2, 0.0), (3, 1, 0.0), (3, 3, 0.2), (2, 2, 0.2), (2, 1, 0.2)])
+def test_steady_forms(J, tmp_path, dim, p, shear):
+    dev, orc = build(J, tmp_path, "Steady", dim, p, "k", grade=0.4, shear=shear, solver="CG")
     n = dev.n
     u = smooth_state(orc)
     x = rnd(n, 4)
