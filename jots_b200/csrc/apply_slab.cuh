@@ -322,4 +322,301 @@ __global__ void __launch_bounds__(E* Q) form_apply_slab_kernel(const FormArgs a,
     }
 }
 
+// =================================================================================================
+// v2: two threads per quadrature plane.  Thread h = 0 owns the quadrature columns qx < Q/2, thread
+// h = 1 the mirrored columns Q-1-qx.  Gauss / Gauss-Lobatto points are symmetric about 1/2, so
+// B[Q-1-q][D-1-i] = B[q][i] and G[Q-1-q][D-1-i] = -G[q][i]: the mirrored thread runs the *same*
+// instruction stream with the same compile-time tables on the plane read with i reversed (the sign
+// of G cancels because every x-derivative is contracted with G again).  Registers per thread halve,
+// warps per SM double, no contraction is duplicated (for odd Q the middle column is shared, each
+// thread taking half its weight).
+template <int D, int Q>
+struct Slab2Tables {
+    double B[Q * D], G[Q * D];      // full tables (y / z passes)
+    double BW[Q * D], GW[Q * D];    // W[q] * row (transposed y pass)
+    double BWh[Q * D], GWh[Q * D];  // W[q] * row, middle column halved when Q is odd (transposed x pass)
+    double W[Q];
+};
+
+template <int D, int QC>
+__device__ __forceinline__ void xpassC(const double (&in)[D * D], const double* tab, double (&out)[D * QC]) {
+#pragma unroll
+    for (int j = 0; j < D; ++j)
+#pragma unroll
+        for (int c = 0; c < QC; ++c) {
+            double s = tab[c * D] * in[j * D];
+#pragma unroll
+            for (int i = 1; i < D; ++i) s += tab[c * D + i] * in[j * D + i];
+            out[j * QC + c] = s;
+        }
+}
+template <int D, int Q, int QC>
+__device__ __forceinline__ void ypassC(const double (&in)[D * QC], const double* tab, double (&out)[Q * QC]) {
+#pragma unroll
+    for (int qy = 0; qy < Q; ++qy)
+#pragma unroll
+        for (int c = 0; c < QC; ++c) {
+            double s = tab[qy * D] * in[c];
+#pragma unroll
+            for (int j = 1; j < D; ++j) s += tab[qy * D + j] * in[j * QC + c];
+            out[qy * QC + c] = s;
+        }
+}
+template <int D, int Q, int QC>
+__device__ __forceinline__ void ypassTC(const double (&in)[Q * QC], const double* tab, double (&out)[D * QC]) {
+#pragma unroll
+    for (int j = 0; j < D; ++j)
+#pragma unroll
+        for (int c = 0; c < QC; ++c) {
+            double s = tab[j] * in[c];
+#pragma unroll
+            for (int qy = 1; qy < Q; ++qy) s += tab[qy * D + j] * in[qy * QC + c];
+            out[j * QC + c] = s;
+        }
+}
+template <int D, int QC>
+__device__ __forceinline__ void xpassTC_acc(const double (&in)[D * QC], const double* tab, double scale, double (&acc)[D * D]) {
+#pragma unroll
+    for (int j = 0; j < D; ++j)
+#pragma unroll
+        for (int i = 0; i < D; ++i) {
+            double s = tab[i] * in[j * QC];
+#pragma unroll
+            for (int c = 1; c < QC; ++c) s += tab[c * D + i] * in[j * QC + c];
+            acc[j * D + i] += scale * s;
+        }
+}
+// reverse the i index of a D x D plane when flip is set (branch-free selects)
+template <int D>
+__device__ __forceinline__ void flip_plane(double (&p)[D * D], bool flip) {
+#pragma unroll
+    for (int j = 0; j < D; ++j)
+#pragma unroll
+        for (int i = 0; i < D / 2; ++i) {
+            const double lo = p[j * D + i], hi = p[j * D + D - 1 - i];
+            p[j * D + i] = flip ? hi : lo;
+            p[j * D + D - 1 - i] = flip ? lo : hi;
+        }
+}
+
+template <int D, int Q, int OP, int CF, int E, int T>
+__global__ void __launch_bounds__(T) form_apply_slab2_kernel(const FormArgs a, const Slab2Tables<D, Q> t) {
+    typedef SlabCfg<OP, CF> C;
+    constexpr int NF = C::NF, NFA = NF > 0 ? NF : 1, NP = C::NP;
+    constexpr int QC = (Q + 1) / 2;
+    constexpr int PS = PlaneStride<D>::value;
+    constexpr int NPT = NP + 4;                      // + A, Bp for each half
+    constexpr int ESraw = NPT * Q * PS;
+    constexpr int ES = ESraw + ((8 - ESraw % 16) + 16) % 16;
+    constexpr int ND = D * D * D, DD = D * D;
+    extern __shared__ __align__(16) double smem[];
+    const int tid = threadIdx.x;
+    const int e0 = blockIdx.x * E;
+
+    // ---------------- phase 1: gather + z contraction --------------------------------------------
+    for (int item = tid; item < E * DD; item += T) {
+        const int el = item / DD, ij = item - el * DD;
+        const int e = e0 + el;
+        if (e >= a.nelem) continue;
+        double xr[D], zr[D], fr[NFA][D];
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+            const int g = a.gather[(size_t)e * ND + ij + DD * k];
+            const int idx = g < 0 ? ~g : g;
+            xr[k] = (g < 0 && a.mask_in) ? 0.0 : a.x[idx];
+            if (C::Z_GRAD || NF > 0) {
+                zr[k] = a.z[idx];
+                if (NF > 0) {
+                    double f[NFA];
+                    nodal_fields<CF, OP>(a.mat, zr[k], f);
+#pragma unroll
+                    for (int n = 0; n < NF; ++n) fr[n][k] = f[n];
+                }
+            }
+        }
+        double* base = smem + el * ES + ij;
+#pragma unroll
+        for (int qz = 0; qz < Q; ++qz) {
+            double s = 0.0, sg = 0.0, zs = 0.0, zg = 0.0;
+#pragma unroll
+            for (int k = 0; k < D; ++k) {
+                s += t.B[qz * D + k] * xr[k];
+                if (C::X_GRAD) sg += t.G[qz * D + k] * xr[k];
+                if (C::Z_GRAD) { zs += t.B[qz * D + k] * zr[k]; zg += t.G[qz * D + k] * zr[k]; }
+            }
+            base[(C::P_XB * Q + qz) * PS] = s;
+            if (C::X_GRAD) base[(C::P_XG * Q + qz) * PS] = sg;
+            if (C::Z_GRAD) { base[(C::P_ZB * Q + qz) * PS] = zs; base[(C::P_ZG * Q + qz) * PS] = zg; }
+#pragma unroll
+            for (int n = 0; n < NF; ++n) {
+                double fs = 0.0;
+#pragma unroll
+                for (int k = 0; k < D; ++k) fs += t.B[qz * D + k] * fr[n][k];
+                base[((C::P_F0 + n) * Q + qz) * PS] = fs;
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---------------- phase 2: half a quadrature plane per thread --------------------------------
+    if (tid < E * Q * 2) {
+        const int el = tid / (2 * Q), r = tid - el * 2 * Q, qz = r >> 1;
+        const bool h = r & 1;
+        int e = e0 + el;
+        if (e >= a.nelem) e = a.nelem - 1;
+        const double* gm = a.geom + (size_t)e * a.geom_stride;
+        const double gxx = gm[0] * gm[0] + gm[1] * gm[1] + gm[2] * gm[2];
+        const double gyy = gm[3] * gm[3] + gm[4] * gm[4] + gm[5] * gm[5];
+        const double gzz = gm[6] * gm[6] + gm[7] * gm[7] + gm[8] * gm[8];
+        const double wz = t.W[qz] * gm[9];
+        const double* pl = smem + el * ES + qz * PS;
+        auto getp = [&](int id, double (&out)[DD]) { load_plane<D, PS>(pl + id * Q * PS, out); flip_plane<D>(out, h); };
+
+        double p9[DD], t6[D * QC], A[DD], Bp[DD];
+#pragma unroll
+        for (int i = 0; i < DD; ++i) { A[i] = 0.0; Bp[i] = 0.0; }
+        double a1[Q * QC], a2x[Q * QC];
+        double a1c = 0.0;
+        if (CF == CF_CONST) a1c = a.ck * a.a0;
+        else {
+            getp(C::P_F0, p9);
+            xpassC<D, QC>(p9, t.B, t6);
+            ypassC<D, Q, QC>(t6, t.B, a1);
+            const double sc = a.ck * a.inv_rc;
+#pragma unroll
+            for (int q = 0; q < Q * QC; ++q) a1[q] *= sc;
+            if (OP == OP_JAC) {
+                getp(C::P_F0 + 1, p9);
+                xpassC<D, QC>(p9, t.B, t6);
+                ypassC<D, Q, QC>(t6, t.B, a2x);
+            }
+        }
+        double xB6[D * QC], xG6[D * QC], vy6[D * QC];
+        getp(C::P_XB, p9);
+        xpassC<D, QC>(p9, t.B, xB6);
+        if (C::X_GRAD) xpassC<D, QC>(p9, t.G, xG6);
+        {
+            double xv[Q * QC];
+            ypassC<D, Q, QC>(xB6, t.B, xv);
+            if (OP == OP_JAC && CF != CF_CONST) {
+                const double sc = a.ck * a.inv_rc;
+#pragma unroll
+                for (int q = 0; q < Q * QC; ++q) a2x[q] *= sc * xv[q];
+            }
+            ypassTC<D, Q, QC>(xv, t.BW, vy6);
+        }
+        const double c_m = a.cm * (CF == CF_CONST || CF == CF_K ? a.m0 : 1.0) * wz;
+        double zB6[D * QC], zG6[D * QC];
+        if (C::Z_GRAD) {
+            getp(C::P_ZB, p9);
+            xpassC<D, QC>(p9, t.B, zB6);
+            xpassC<D, QC>(p9, t.G, zG6);
+        }
+        // ---- x direction (both G's carry the mirror sign: it cancels)
+        {
+            double F[Q * QC];
+            if (OP == OP_RES) ypassC<D, Q, QC>(zG6, t.B, F);
+            else ypassC<D, Q, QC>(xG6, t.B, F);
+            if (CF == CF_CONST) {
+#pragma unroll
+                for (int q = 0; q < Q * QC; ++q) F[q] *= a1c;
+            } else {
+#pragma unroll
+                for (int q = 0; q < Q * QC; ++q) F[q] *= a1[q];
+                if (OP == OP_JAC) {
+                    double zd[Q * QC];
+                    ypassC<D, Q, QC>(zG6, t.B, zd);
+#pragma unroll
+                    for (int q = 0; q < Q * QC; ++q) F[q] += a2x[q] * zd[q];
+                }
+            }
+            ypassTC<D, Q, QC>(F, t.BW, t6);
+            xpassTC_acc<D, QC>(t6, t.GWh, wz * gxx, A);
+        }
+        // ---- y direction (+ mass)
+        {
+            double F[Q * QC];
+            if (OP == OP_RES) ypassC<D, Q, QC>(zB6, t.G, F);
+            else ypassC<D, Q, QC>(xB6, t.G, F);
+            if (CF == CF_CONST) {
+#pragma unroll
+                for (int q = 0; q < Q * QC; ++q) F[q] *= a1c;
+            } else {
+#pragma unroll
+                for (int q = 0; q < Q * QC; ++q) F[q] *= a1[q];
+                if (OP == OP_JAC) {
+                    double zd[Q * QC];
+                    ypassC<D, Q, QC>(zB6, t.G, zd);
+#pragma unroll
+                    for (int q = 0; q < Q * QC; ++q) F[q] += a2x[q] * zd[q];
+                }
+            }
+            ypassTC<D, Q, QC>(F, t.GW, t6);
+            const double cy = wz * gyy;
+#pragma unroll
+            for (int i = 0; i < D * QC; ++i) t6[i] = cy * t6[i] + c_m * vy6[i];
+            xpassTC_acc<D, QC>(t6, t.BWh, 1.0, A);
+        }
+        // ---- z direction
+        {
+            double F[Q * QC];
+            getp(OP == OP_RES ? C::P_ZG : C::P_XG, p9);
+            xpassC<D, QC>(p9, t.B, t6);
+            ypassC<D, Q, QC>(t6, t.B, F);
+            if (CF == CF_CONST) {
+#pragma unroll
+                for (int q = 0; q < Q * QC; ++q) F[q] *= a1c;
+            } else {
+#pragma unroll
+                for (int q = 0; q < Q * QC; ++q) F[q] *= a1[q];
+                if (OP == OP_JAC) {
+                    double zd[Q * QC];
+                    getp(C::P_ZG, p9);
+                    xpassC<D, QC>(p9, t.B, t6);
+                    ypassC<D, Q, QC>(t6, t.B, zd);
+#pragma unroll
+                    for (int q = 0; q < Q * QC; ++q) F[q] += a2x[q] * zd[q];
+                }
+            }
+            ypassTC<D, Q, QC>(F, t.BW, t6);
+            xpassTC_acc<D, QC>(t6, t.BWh, wz * gzz, Bp);
+        }
+        flip_plane<D>(A, h);
+        flip_plane<D>(Bp, h);
+        double* outp = smem + el * ES + ((NP + (h ? 2 : 0)) * Q + qz) * PS;
+        store_plane<D, PS>(outp, A);
+        store_plane<D, PS>(outp + Q * PS, Bp);
+    }
+    __syncthreads();
+
+    // ---------------- phase 3: transposed z contraction + scatter --------------------------------
+    for (int item = tid; item < E * DD; item += T) {
+        const int el = item / DD, ij = item - el * DD;
+        const int e = e0 + el;
+        if (e >= a.nelem) continue;
+        const double* base = smem + el * ES + NP * Q * PS + ij;
+        double Aq[Q], Bq[Q];
+#pragma unroll
+        for (int qz = 0; qz < Q; ++qz) {
+            Aq[qz] = base[qz * PS] + base[(2 * Q + qz) * PS];
+            Bq[qz] = base[(Q + qz) * PS] + base[(3 * Q + qz) * PS];
+        }
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+            double s = 0.0;
+#pragma unroll
+            for (int qz = 0; qz < Q; ++qz) s += t.B[qz * D + k] * Aq[qz] + t.G[qz * D + k] * Bq[qz];
+            const int g = a.gather[(size_t)e * ND + ij + DD * k];
+            if (g >= 0) atomicAdd(a.y + g, s);
+            else if (!a.mask_out) atomicAdd(a.y + (~g), s);
+        }
+    }
+}
+
+template <int D, int Q, int NP> struct Elem2Stride {
+    static constexpr int PS = PlaneStride<D>::value;
+    static constexpr int raw = (NP + 4) * Q * PS;
+    static constexpr int value = raw + ((8 - raw % 16) + 16) % 16;
+};
+
 }  // namespace jots

@@ -1,4 +1,6 @@
 // Instantiations of the register-slab kernel (hexes, diagonal metric, CF_CONST / CF_K).
+#include <cstdlib>
+
 #include "apply_slab.cuh"
 #include "diag_face_host.hpp"
 #include "launch.hpp"
@@ -29,9 +31,43 @@ static int launch_slab(const FormArgs& a, const TablesRT& r, cudaStream_t st) {
     return 0;
 }
 
+template <int D, int Q, int OP, int CF>
+static int launch_slab2(const FormArgs& a, const TablesRT& r, cudaStream_t st) {
+    // E elements per block, 2*Q threads per element in phase 2, D*D threads per element in phases 1/3
+    constexpr int E = (Q == 4) ? 28 : 32;
+    constexpr int T = ((E * (2 * Q > D * D ? 2 * Q : D * D)) + 31) / 32 * 32;
+    typedef SlabCfg<OP, CF> C;
+    Slab2Tables<D, Q> t;
+    for (int q = 0; q < Q; ++q) {
+        t.W[q] = r.W[q];
+        const double half = (Q % 2 == 1 && q == Q / 2) ? 0.5 : 1.0;
+        for (int i = 0; i < D; ++i) {
+            t.B[q * D + i] = r.B[q * D + i]; t.G[q * D + i] = r.G[q * D + i];
+            t.BW[q * D + i] = r.W[q] * r.B[q * D + i]; t.GW[q * D + i] = r.W[q] * r.G[q * D + i];
+            t.BWh[q * D + i] = half * r.W[q] * r.B[q * D + i]; t.GWh[q * D + i] = half * r.W[q] * r.G[q * D + i];
+        }
+    }
+    const size_t smem = (size_t)E * Elem2Stride<D, Q, C::NP>::value * sizeof(double);
+    auto kern = form_apply_slab2_kernel<D, Q, OP, CF, E, T>;
+    static bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        configured = true;
+    }
+    const int grid = (a.nelem + E - 1) / E;
+    kern<<<grid, T, smem, st>>>(a, t);
+    return 0;
+}
+
+static int slab_variant() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("JOTS_SLAB_VARIANT"); v = e ? atoi(e) : 2; }
+    return v;
+}
+
 template <int D, int Q>
 static int dispatch(int op, int cf, const FormArgs& a, const TablesRT& t, cudaStream_t st) {
-#define CASE(OPV, CFV) if (op == OPV && cf == CFV) return launch_slab<D, Q, OPV, CFV>(a, t, st);
+#define CASE(OPV, CFV) if (op == OPV && cf == CFV) return slab_variant() == 1 ? launch_slab<D, Q, OPV, CFV>(a, t, st) : launch_slab2<D, Q, OPV, CFV>(a, t, st);
     CASE(OP_LIN, CF_CONST) CASE(OP_LIN, CF_K) CASE(OP_JAC, CF_K) CASE(OP_RES, CF_CONST) CASE(OP_RES, CF_K)
 #undef CASE
     return 1;
