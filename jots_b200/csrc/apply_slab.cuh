@@ -338,6 +338,16 @@ struct Slab2Tables {
     double W[Q];
 };
 
+// 64-bit shared-memory accesses: a half-warp must touch 16 distinct 8-byte slots.  Phase 1/3 lanes
+// run over (element, ij) items -> element stride == D*D (mod 16); phase 2 lanes over (element, qz,
+// h) -> plane stride chosen so that {qz*PS + el*ES} stay distinct (D=3: 10, D=2: 5).
+template <int D> struct Plane2Stride { static constexpr int value = D == 3 ? 10 : D == 2 ? 5 : D * D + 1; };
+template <int D, int Q, int NP> struct Elem2Stride {
+    static constexpr int PS = Plane2Stride<D>::value;
+    static constexpr int raw = (NP + 4) * Q * PS;
+    static constexpr int value = raw + (((D * D) % 16 - raw % 16) + 16) % 16;   // == D*D (mod 16)
+};
+
 template <int D, int QC>
 __device__ __forceinline__ void xpassC(const double (&in)[D * D], const double* tab, double (&out)[D * QC]) {
 #pragma unroll
@@ -404,10 +414,8 @@ __global__ void __launch_bounds__(T) form_apply_slab2_kernel(const FormArgs a, c
     typedef SlabCfg<OP, CF> C;
     constexpr int NF = C::NF, NFA = NF > 0 ? NF : 1, NP = C::NP;
     constexpr int QC = (Q + 1) / 2;
-    constexpr int PS = PlaneStride<D>::value;
-    constexpr int NPT = NP + 4;                      // + A, Bp for each half
-    constexpr int ESraw = NPT * Q * PS;
-    constexpr int ES = ESraw + ((8 - ESraw % 16) + 16) % 16;
+    constexpr int PS = Plane2Stride<D>::value;
+    constexpr int ES = Elem2Stride<D, Q, NP>::value;
     constexpr int ND = D * D * D, DD = D * D;
     extern __shared__ __align__(16) double smem[];
     const int tid = threadIdx.x;
@@ -470,7 +478,12 @@ __global__ void __launch_bounds__(T) form_apply_slab2_kernel(const FormArgs a, c
         const double gzz = gm[6] * gm[6] + gm[7] * gm[7] + gm[8] * gm[8];
         const double wz = t.W[qz] * gm[9];
         const double* pl = smem + el * ES + qz * PS;
-        auto getp = [&](int id, double (&out)[DD]) { load_plane<D, PS>(pl + id * Q * PS, out); flip_plane<D>(out, h); };
+        auto getp = [&](int id, double (&out)[DD]) {
+            const double* p = pl + id * Q * PS;
+#pragma unroll
+            for (int m = 0; m < DD; ++m) out[m] = p[m];
+            flip_plane<D>(out, h);
+        };
 
         double p9[DD], t6[D * QC], A[DD], Bp[DD];
 #pragma unroll
@@ -584,8 +597,8 @@ __global__ void __launch_bounds__(T) form_apply_slab2_kernel(const FormArgs a, c
         flip_plane<D>(A, h);
         flip_plane<D>(Bp, h);
         double* outp = smem + el * ES + ((NP + (h ? 2 : 0)) * Q + qz) * PS;
-        store_plane<D, PS>(outp, A);
-        store_plane<D, PS>(outp + Q * PS, Bp);
+#pragma unroll
+        for (int m = 0; m < DD; ++m) { outp[m] = A[m]; outp[Q * PS + m] = Bp[m]; }
     }
     __syncthreads();
 
@@ -613,10 +626,5 @@ __global__ void __launch_bounds__(T) form_apply_slab2_kernel(const FormArgs a, c
     }
 }
 
-template <int D, int Q, int NP> struct Elem2Stride {
-    static constexpr int PS = PlaneStride<D>::value;
-    static constexpr int raw = (NP + 4) * Q * PS;
-    static constexpr int value = raw + ((8 - raw % 16) + 16) % 16;
-};
 
 }  // namespace jots

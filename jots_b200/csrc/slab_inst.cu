@@ -31,10 +31,9 @@ static int launch_slab(const FormArgs& a, const TablesRT& r, cudaStream_t st) {
     return 0;
 }
 
-template <int D, int Q, int OP, int CF>
-static int launch_slab2(const FormArgs& a, const TablesRT& r, cudaStream_t st) {
+template <int D, int Q, int OP, int CF, int E>
+static int launch_slab2e(const FormArgs& a, const TablesRT& r, cudaStream_t st) {
     // E elements per block, 2*Q threads per element in phase 2, D*D threads per element in phases 1/3
-    constexpr int E = (Q == 4) ? 28 : 32;
     constexpr int T = ((E * (2 * Q > D * D ? 2 * Q : D * D)) + 31) / 32 * 32;
     typedef SlabCfg<OP, CF> C;
     Slab2Tables<D, Q> t;
@@ -57,6 +56,17 @@ static int launch_slab2(const FormArgs& a, const TablesRT& r, cudaStream_t st) {
     const int grid = (a.nelem + E - 1) / E;
     kern<<<grid, T, smem, st>>>(a, t);
     return 0;
+}
+
+static int slab_elems() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("JOTS_SLAB_ELEMS"); v = e ? atoi(e) : 14; }
+    return v;
+}
+template <int D, int Q, int OP, int CF>
+static int launch_slab2(const FormArgs& a, const TablesRT& r, cudaStream_t st) {
+    if constexpr (Q == 4) return slab_elems() == 28 ? launch_slab2e<D, Q, OP, CF, 28>(a, r, st) : launch_slab2e<D, Q, OP, CF, 14>(a, r, st);
+    else return launch_slab2e<D, Q, OP, CF, 32>(a, r, st);
 }
 
 static int slab_variant() {
