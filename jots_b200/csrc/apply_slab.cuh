@@ -627,4 +627,165 @@ __global__ void __launch_bounds__(T) form_apply_slab2_kernel(const FormArgs a, c
 }
 
 
+// =================================================================================================
+// Diagonal of an OP_LIN / OP_JAC form with the same three-phase structure: the diagonal of a
+// tensor-product form is a transposed interpolation with squared tables,
+//   d_i = sum_q w_q [ a1 sum_a g_aa (d_a phi_i)^2 + a2 phi_i sum_a g_aa d_a z d_a phi_i + m phi_i^2 ],
+// (d_x phi_i)^2 = G^2[qx][i1] B^2[qy][i2] B^2[qz][i3] etc.  Replaces the generic loop kernel (41 ms at
+// 17M DOFs) on axis-aligned hexes.
+template <int D, int Q>
+struct SlabDiagTables {
+    double B[Q * D], G[Q * D];
+    double B2W[Q * D], G2W[Q * D], BGW[Q * D];       // W[q] * B^2, W[q] * G^2, W[q] * B * G
+    double B2Wh[Q * D], G2Wh[Q * D], BGWh[Q * D];    // middle column halved when Q is odd
+    double B2[Q * D], G2[Q * D], BG[Q * D];          // unweighted (z direction; W[qz] is in wz)
+    double mB[D];                                    // sum_q W[q] B[q][i]^2
+    double W[Q];
+};
+
+template <int D, int Q, int OP, int CF, int E, int T>
+__global__ void __launch_bounds__(T) form_diag_slab2_kernel(const FormArgs a, const SlabDiagTables<D, Q> t) {
+    constexpr int NF = CoefNF<CF, OP>::value, NFA = NF > 0 ? NF : 1;
+    constexpr bool JAC = (OP == OP_JAC);
+    constexpr int NPI = NF + (JAC ? 2 : 0);          // input planes: fields, zB, zG
+    constexpr int P_ZB = NF, P_ZG = NF + 1;
+    constexpr int QC = (Q + 1) / 2;
+    constexpr int PS = Plane2Stride<D>::value;
+    constexpr int ES = Elem2Stride<D, Q, NPI + 2>::value;   // NPI + 6 planes
+    constexpr int ND = D * D * D, DD = D * D;
+    extern __shared__ __align__(16) double smem[];
+    const int tid = threadIdx.x;
+    const int e0 = blockIdx.x * E;
+
+    if (NPI > 0) {
+        for (int item = tid; item < E * DD; item += T) {
+            const int el = item / DD, ij = item - el * DD;
+            const int e = e0 + el;
+            if (e >= a.nelem) continue;
+            double zr[D], fr[NFA][D];
+#pragma unroll
+            for (int k = 0; k < D; ++k) {
+                const int g = a.gather[(size_t)e * ND + ij + DD * k];
+                zr[k] = a.z[g < 0 ? ~g : g];
+                double f[NFA];
+                nodal_fields<CF, OP>(a.mat, zr[k], f);
+#pragma unroll
+                for (int n = 0; n < NF; ++n) fr[n][k] = f[n];
+            }
+            double* base = smem + el * ES + ij;
+#pragma unroll
+            for (int qz = 0; qz < Q; ++qz) {
+                if (JAC) {
+                    double zs = 0.0, zg = 0.0;
+#pragma unroll
+                    for (int k = 0; k < D; ++k) { zs += t.B[qz * D + k] * zr[k]; zg += t.G[qz * D + k] * zr[k]; }
+                    base[(P_ZB * Q + qz) * PS] = zs; base[(P_ZG * Q + qz) * PS] = zg;
+                }
+#pragma unroll
+                for (int n = 0; n < NF; ++n) {
+                    double fs = 0.0;
+#pragma unroll
+                    for (int k = 0; k < D; ++k) fs += t.B[qz * D + k] * fr[n][k];
+                    base[(n * Q + qz) * PS] = fs;
+                }
+            }
+        }
+    }
+    __syncthreads();
+
+    if (tid < E * Q * 2) {
+        const int el = tid / (2 * Q), r = tid - el * 2 * Q, qz = r >> 1;
+        const bool h = r & 1;
+        int e = e0 + el;
+        if (e >= a.nelem) e = a.nelem - 1;
+        const double* gm = a.geom + (size_t)e * a.geom_stride;
+        const double gxx = gm[0] * gm[0] + gm[1] * gm[1] + gm[2] * gm[2];
+        const double gyy = gm[3] * gm[3] + gm[4] * gm[4] + gm[5] * gm[5];
+        const double gzz = gm[6] * gm[6] + gm[7] * gm[7] + gm[8] * gm[8];
+        const double wz = t.W[qz] * gm[9];
+        const double* pl = smem + el * ES + qz * PS;
+        auto getp = [&](int id, double (&out)[DD]) {
+            const double* p = pl + id * Q * PS;
+#pragma unroll
+            for (int m = 0; m < DD; ++m) out[m] = p[m];
+            flip_plane<D>(out, h);
+        };
+        double p9[DD], t6[D * QC], A[DD], Bz[DD], Cz[DD];
+#pragma unroll
+        for (int i = 0; i < DD; ++i) { A[i] = 0.0; Bz[i] = 0.0; Cz[i] = 0.0; }
+        double a1[Q * QC];
+        if (CF == CF_CONST) {
+#pragma unroll
+            for (int q = 0; q < Q * QC; ++q) a1[q] = a.ck * a.a0;
+        } else {
+            getp(0, p9);
+            xpassC<D, QC>(p9, t.B, t6);
+            ypassC<D, Q, QC>(t6, t.B, a1);
+            const double sc = a.ck * a.inv_rc;
+#pragma unroll
+            for (int q = 0; q < Q * QC; ++q) a1[q] *= sc;
+        }
+        ypassTC<D, Q, QC>(a1, t.B2W, t6);
+        xpassTC_acc<D, QC>(t6, t.G2Wh, wz * gxx, A);
+        xpassTC_acc<D, QC>(t6, t.B2Wh, wz * gzz, Bz);
+        ypassTC<D, Q, QC>(a1, t.G2W, t6);
+        xpassTC_acc<D, QC>(t6, t.B2Wh, wz * gyy, A);
+        if (JAC) {
+            double a2[Q * QC], zB6[D * QC], zG6[D * QC], F[Q * QC];
+            getp(1, p9);
+            xpassC<D, QC>(p9, t.B, t6);
+            ypassC<D, Q, QC>(t6, t.B, a2);
+            const double sc = a.ck * a.inv_rc;
+#pragma unroll
+            for (int q = 0; q < Q * QC; ++q) a2[q] *= sc;
+            getp(P_ZB, p9);
+            xpassC<D, QC>(p9, t.B, zB6);
+            xpassC<D, QC>(p9, t.G, zG6);
+            ypassC<D, Q, QC>(zG6, t.B, F);
+#pragma unroll
+            for (int q = 0; q < Q * QC; ++q) F[q] *= a2[q];
+            ypassTC<D, Q, QC>(F, t.B2W, t6);
+            xpassTC_acc<D, QC>(t6, t.BGWh, wz * gxx, A);
+            ypassC<D, Q, QC>(zB6, t.G, F);
+#pragma unroll
+            for (int q = 0; q < Q * QC; ++q) F[q] *= a2[q];
+            ypassTC<D, Q, QC>(F, t.BGW, t6);
+            xpassTC_acc<D, QC>(t6, t.B2Wh, wz * gyy, A);
+            getp(P_ZG, p9);
+            xpassC<D, QC>(p9, t.B, t6);
+            ypassC<D, Q, QC>(t6, t.B, F);
+#pragma unroll
+            for (int q = 0; q < Q * QC; ++q) F[q] *= a2[q];
+            ypassTC<D, Q, QC>(F, t.B2W, t6);
+            xpassTC_acc<D, QC>(t6, t.B2Wh, wz * gzz, Cz);
+        }
+        flip_plane<D>(A, h); flip_plane<D>(Bz, h); flip_plane<D>(Cz, h);
+        double* outp = smem + el * ES + ((NPI + (h ? 3 : 0)) * Q + qz) * PS;
+#pragma unroll
+        for (int m = 0; m < DD; ++m) { outp[m] = A[m]; outp[Q * PS + m] = Bz[m]; outp[2 * Q * PS + m] = Cz[m]; }
+    }
+    __syncthreads();
+
+    for (int item = tid; item < E * DD; item += T) {
+        const int el = item / DD, ij = item - el * DD;
+        const int e = e0 + el;
+        if (e >= a.nelem) continue;
+        const double* base = smem + el * ES + NPI * Q * PS + ij;
+        const double* gm = a.geom + (size_t)e * a.geom_stride;
+        const double mass = a.cm * (CF == CF_CONST || CF == CF_K ? a.m0 : 1.0) * gm[9] * t.mB[ij % D] * t.mB[ij / D];
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+            double s = mass * t.mB[k];
+#pragma unroll
+            for (int qz = 0; qz < Q; ++qz)
+                s += t.B2[qz * D + k] * (base[qz * PS] + base[(3 * Q + qz) * PS]) +
+                     t.G2[qz * D + k] * (base[(Q + qz) * PS] + base[(4 * Q + qz) * PS]) +
+                     t.BG[qz * D + k] * (base[(2 * Q + qz) * PS] + base[(5 * Q + qz) * PS]);
+            const int g = a.gather[(size_t)e * ND + ij + DD * k];
+            if (g >= 0) atomicAdd(a.y + g, s);
+            else if (!a.mask_out) atomicAdd(a.y + (~g), s);
+        }
+    }
+}
+
 }  // namespace jots

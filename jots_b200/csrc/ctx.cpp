@@ -216,7 +216,7 @@ void Ctx::diag_form(const FormSpec& f, double* d) {
     zero(d);
     FormArgs a = make_args(f, nullptr, d, true);
     a.mask_out = (f.mask_out || f.diag_one) ? 1 : 0;
-    int rc = launch_form_diag(f.op == OP_RES ? OP_LIN : f.op, f.cf, a, tabs, stream);
+    int rc = launch_form_diag(space.dim, space.p, f.op == OP_RES ? OP_LIN : f.op, f.cf, a, tabs, stream);
     if (rc) throw std::runtime_error("diagonal of form (op=" + std::to_string(f.op) + ", cf=" + std::to_string(f.cf) + ") is not instantiated");
     stats.kernel_launches += 2;
     if (f.bdr_mass_scale != 0.0 && any_flux()) {

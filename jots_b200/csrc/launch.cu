@@ -39,8 +39,9 @@ static int diag_one(const FormArgs& a, const TablesRT& t, cudaStream_t st) {
     return 0;
 }
 
-int launch_form_diag(int op, int cf, const FormArgs& a, const TablesRT& t, cudaStream_t st) {
+int launch_form_diag(int dim, int p, int op, int cf, const FormArgs& a, const TablesRT& t, cudaStream_t st) {
     if (a.nelem <= 0) return 0;
+    if (dim == 3 && a.geom_diag && launch_form_diag_slab(p, op, cf, a, t, st) == 0) return 0;
 #define CASE(OPV, CFV) if (op == OPV && cf == CFV) return diag_one<OPV, CFV>(a, t, st);
     CASE(OP_LIN, CF_CONST) CASE(OP_LIN, CF_LINFIELDS) CASE(OP_LIN, CF_K)
     CASE(OP_JAC, CF_K) CASE(OP_JAC, CF_FULL)

@@ -83,6 +83,51 @@ static int dispatch(int op, int cf, const FormArgs& a, const TablesRT& t, cudaSt
     return 1;
 }
 
+template <int D, int Q, int OP, int CF>
+static int launch_diag_slab(const FormArgs& a, const TablesRT& r, cudaStream_t st) {
+    constexpr int E = (Q == 4) ? 14 : 32;
+    constexpr int T = ((E * (2 * Q > D * D ? 2 * Q : D * D)) + 31) / 32 * 32;
+    constexpr int NF = CoefNF<CF, OP>::value;
+    constexpr int NPI = NF + (OP == OP_JAC ? 2 : 0);
+    SlabDiagTables<D, Q> t;
+    for (int i = 0; i < D; ++i) t.mB[i] = 0.0;
+    for (int q = 0; q < Q; ++q) {
+        t.W[q] = r.W[q];
+        const double half = (Q % 2 == 1 && q == Q / 2) ? 0.5 : 1.0;
+        for (int i = 0; i < D; ++i) {
+            const double b = r.B[q * D + i], g = r.G[q * D + i], w = r.W[q];
+            t.B[q * D + i] = b; t.G[q * D + i] = g;
+            t.B2[q * D + i] = b * b; t.G2[q * D + i] = g * g; t.BG[q * D + i] = b * g;
+            t.B2W[q * D + i] = w * b * b; t.G2W[q * D + i] = w * g * g; t.BGW[q * D + i] = w * b * g;
+            t.B2Wh[q * D + i] = half * w * b * b; t.G2Wh[q * D + i] = half * w * g * g; t.BGWh[q * D + i] = half * w * b * g;
+            t.mB[i] += w * b * b;
+        }
+    }
+    const size_t smem = (size_t)E * Elem2Stride<D, Q, NPI + 2>::value * sizeof(double);
+    auto kern = form_diag_slab2_kernel<D, Q, OP, CF, E, T>;
+    static bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        configured = true;
+    }
+    kern<<<(a.nelem + E - 1) / E, T, smem, st>>>(a, t);
+    return 0;
+}
+
+template <int D, int Q>
+static int dispatch_diag(int op, int cf, const FormArgs& a, const TablesRT& t, cudaStream_t st) {
+#define CASE(OPV, CFV) if (op == OPV && cf == CFV) return launch_diag_slab<D, Q, OPV, CFV>(a, t, st);
+    CASE(OP_LIN, CF_CONST) CASE(OP_LIN, CF_K) CASE(OP_JAC, CF_K)
+#undef CASE
+    return 1;
+}
+
+int launch_form_diag_slab(int p, int op, int cf, const FormArgs& a, const TablesRT& t, cudaStream_t st) {
+    if (p == 1) return dispatch_diag<2, 3>(op, cf, a, t, st);
+    if (p == 2) return dispatch_diag<3, 4>(op, cf, a, t, st);
+    return 1;
+}
+
 // returns 0 when launched, non-zero when this (order, op, cf) has no slab instantiation
 int launch_form_apply_slab(int p, int op, int cf, const FormArgs& a, const TablesRT& t, cudaStream_t st) {
     if (p == 1) return dispatch<2, 3>(op, cf, a, t, st);

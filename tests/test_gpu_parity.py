@@ -141,6 +141,9 @@ def test_axis_aligned_fast_path(J, tmp_path, sim, props, p):
         for form, mat in ((J.FORM_MASS, it.M_mat), (J.FORM_STIFFNESS, it.K_mat), (J.FORM_SYSTEM, it.A_mat)):
             y = dev.op.form_apply(form, x, np.empty(n), state=state)
             assert rel(y, mat @ x) < APPLY_TOL, (form, rel(y, mat @ x))
+            if form != J.FORM_STIFFNESS:
+                d = dev.op.form_diagonal(form, np.empty(n), state=state)
+                assert rel(d, mat.diagonal()) < APPLY_TOL, (form, rel(d, mat.diagonal()))
     else:
         k = 50.0 * rnd(n, 12)
         it.u_n = state
@@ -150,6 +153,8 @@ def test_axis_aligned_fast_path(J, tmp_path, sim, props, p):
         Jm = it.gradient(k)
         y = dev.op.form_apply(J.FORM_SYSTEM, x, np.empty(n), state=state + it.dt * k)
         assert rel(y, Jm @ x) < APPLY_TOL
+        d = dev.op.form_diagonal(J.FORM_SYSTEM, np.empty(n), state=state + it.dt * k)
+        assert rel(d, Jm.diagonal()) < APPLY_TOL, rel(d, Jm.diagonal())
 
 
 @pytest.mark.parametrize("dim,p,shear", [(3, 2, 0.2), (3, 2, 0.0), (3, 1, 0.0), (3, 3, 0.2), (2, 2, 0.2), (2, 1, 0.2)])
