@@ -102,9 +102,9 @@ def run_reference(args):
         cpu_oracle_run(args.order, args.solver, args.prec, max(2, n // 2), 1)
     r = cpu_oracle_run(args.order, args.solver, args.prec, n, args.steps)
     line = {"impl": "reference", "metric": METRIC, "value": r["gdofs"], "unit": "GDOF/s", "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": 1e3 * r["time"] / max(r["steps"], 1), "higher_is_better": True, "scaling": "strong",
+            "warmup": args.warmup, "ms_per_step": 1e3 * r["time"] / max(r["steps"], 1), "higher_is_better": True, "scaling": args.scaling,
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload_config(args, 1),
+            "config": workload_config(args, max(1, args.gpus)),
             "steps_per_s": r["steps_per_s"],
             "cpu_baseline": {"value": r["gdofs"], "unit": "GDOF/s", "cores": 1, "kind": "port",
                              "sample": "same physics on a %d^3-element Q%d brick (%d DOFs), %d steps; NumPy/SciPy restatement, "
@@ -113,13 +113,34 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def box_dims(world):
+    d = [1, 1, 1]
+    r, a = world, 0
+    while r > 1:
+        d[a % 3] *= 2
+        r //= 2
+        a += 1
+    return d
+
+
+def global_brick(args, world):
+    """elements per direction of the global brick: fixed (strong) or n per GPU in every direction (weak)"""
+    if args.scaling == "strong" or world == 1:
+        return [args.n, args.n, args.n]
+    return [args.n * k for k in box_dims(world)]
+
+
 def workload_config(args, world):
-    nd = (args.n * args.order + 1) ** 3
-    return {"workload": "configs[3]: synthetic refined brick, %d^3 Q%d hexes, %d DOFs, nonlinear unsteady (backward Euler, "
-                        "dt=1e-2), k(T)=0.09T-17, Newton + %s/%s rel 1e-10" % (args.n, args.order, nd, args.solver, args.prec),
-            "n_elem_per_dir": args.n, "order": args.order, "n_dof": nd, "solver": args.solver, "preconditioner": args.prec,
-            "parallelism": "1 subdomain per GPU" if world > 1 else "single GPU",
-            "l2_policy": "vectors (136 MB each at N=128) exceed the 126 MB L2; no explicit flush"}
+    ne = global_brick(args, world)
+    nd = 1
+    for k in ne:
+        nd *= k * args.order + 1
+    return {"workload": "configs[3]: synthetic refined brick, %dx%dx%d Q%d hexes, %d DOFs, nonlinear unsteady (backward Euler, "
+                        "dt=1e-2), k(T)=0.09T-17, Newton + %s/%s rel 1e-10" % (ne[0], ne[1], ne[2], args.order, nd, args.solver, args.prec),
+            "n_elem": ne, "order": args.order, "n_dof": nd, "solver": args.solver, "preconditioner": args.prec,
+            "parallelism": ("box partition %s, 1 subdomain per GPU, NCCL interface sum-exchange + scalar all-reduce" % "x".join(map(str, box_dims(world))))
+                           if world > 1 else "single GPU",
+            "l2_policy": "vectors (136 MB each at 128^3 elements per GPU) exceed the 126 MB L2; no explicit flush"}
 
 
 def main():
@@ -135,6 +156,8 @@ def main():
     ap.add_argument("--cpu-n", type=int, default=12, help="elements per direction of the CPU-baseline sample")
     ap.add_argument("--apply-reps", type=int, default=20)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="N>1: weak = --n elements per direction per GPU, strong = --n for the global brick")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -162,8 +185,15 @@ def main():
     tmp = tempfile.mkdtemp()
     ini = os.path.join(tmp, "bench.ini")
     write_ini(ini, args.order, args.solver, args.prec, 10 ** 9)
-    mesh = J.Mesh.brick(args.n, args.n, args.n, 0.01, 0.01, 0.01)
-    drv = J.Driver(ini, local, mesh=mesh)
+    ne = global_brick(args, world)
+    mesh = J.Mesh.brick(ne[0], ne[1], ne[2], 0.01 * ne[0] / args.n, 0.01 * ne[1] / args.n, 0.01 * ne[2] / args.n)
+    comm = None
+    if world > 1:
+        uid = [J.Comm.unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        comm = J.Comm(uid[0], rank, world, local)
+    drv = J.Driver(ini, local, mesh=mesh, comm=comm)
+    del mesh
     stream = torch.cuda.current_stream()
     drv.ctx.set_stream(stream.cuda_stream)
     ndof = drv.n
@@ -187,7 +217,7 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t[0])
     iters = int(t[1])
-    total_dof = ndof * world   # replicas until the interface exchange lands
+    total_dof = workload_config(args, world)["n_dof"]
     value = total_dof * iters / (ms * 1e-3) / 1e9
 
     # ---- end to end through the C ABI with host buffers ---------------------------------------------
@@ -230,7 +260,7 @@ def main():
     if rank != 0:
         return
     line = {"metric": METRIC, "value": value, "unit": "GDOF/s", "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "config": workload_config(args, world),
             "steps_per_s": K / (ms * 1e-3), "krylov_iters": iters, "newton_iters": st["newton_iters"],
             "apply_gdofs": ndof / (apply_ms * 1e-3) / 1e9, "apply_ms": apply_ms, "residual_ms": res_ms,

@@ -32,6 +32,8 @@ typedef struct jots_space_s* jots_space_t;   /* host H1 space tables (mfem::ParF
 typedef struct jots_ctx_s* jots_ctx_t;       /* device context of one subdomain */
 typedef struct jots_op_s* jots_op_t;         /* one conduction operator (JOTSIterator) */
 typedef struct jots_driver_s* jots_driver_t; /* hot-path callers of JOTSDriver */
+typedef struct jots_part_s* jots_part_t;     /* one subdomain of a partitioned space (ParMesh role) */
+typedef struct jots_comm_s* jots_comm_t;     /* NCCL communicator, one rank per GPU */
 
 enum { JOTS_HOST = 0, JOTS_DEVICE = 1 };
 enum { JOTS_UNIFORM = 0, JOTS_POLYNOMIAL = 1 };                      /* src/option_structure.hpp:25-37 */
@@ -117,9 +119,28 @@ int jots_op_form_diagonal(jots_op_t op, int form, const double* state, double* d
 int jots_op_form_time(jots_op_t op, int form, const double* x_dev, const double* state_dev, double* y_dev,
                       int reps, double* ms_per_apply);
 
+/* ---- multi-GPU: one subdomain per GPU (ParMesh(comm, mesh), src/jots_driver.cpp:178) ------------- */
+/* deterministic partition built redundantly on every rank; dims = {px,py,pz} or NULL (automatic box
+   partition of bricks, recursive coordinate bisection otherwise) */
+jots_part_t jots_partition_create(jots_mesh_t mesh, jots_space_t global_space, int nranks, int rank, const int32_t* dims);
+void jots_partition_destroy(jots_part_t p);
+int jots_partition_info(jots_part_t p, int64_t* n_local, int64_t* n_owned, int64_t* n_global, int64_t* n_elem,
+                        int* n_neighbors, int64_t* n_shared);
+jots_space_t jots_partition_space(jots_part_t p);                     /* local space, owned DOFs first */
+int jots_partition_copy(jots_part_t p, int64_t* global_id, int64_t* local_elems);
+int64_t jots_partition_neighbor(jots_part_t p, int i, int* rank, int32_t* local_idx); /* shared DOFs, ascending global id */
+int64_t jots_partition_reduction(jots_part_t p, int32_t* red_dof, int32_t* red_ptr, int32_t* red_src);
+int jots_comm_unique_id(char out[128]);                               /* rank 0, then broadcast by the caller */
+jots_comm_t jots_comm_create(const char id[128], int rank, int nranks, int device);
+void jots_comm_destroy(jots_comm_t c);
+jots_ctx_t jots_ctx_create_part(jots_part_t p, int device, jots_comm_t comm);
+
 /* ---- driver shim: Config + the hot-path part of JOTSDriver::Run (src/jots_driver.cpp:568-725) --- */
 jots_driver_t jots_driver_create(const char* ini_path, int device);
 jots_driver_t jots_driver_create_on_mesh(const char* ini_path, jots_mesh_t mesh, int device);
+/* collective over the communicator: every rank passes the same global mesh (or NULL: read Mesh_File) */
+jots_driver_t jots_driver_create_dist(const char* ini_path, jots_mesh_t mesh, int device, jots_comm_t comm);
+int jots_driver_copy_global_ids(jots_driver_t d, int64_t* global_id, int64_t* n_owned);
 void jots_driver_destroy(jots_driver_t d);
 int jots_driver_run(jots_driver_t d, int max_steps, int* steps_done);  /* max_steps < 0: to Max_Timesteps */
 int64_t jots_driver_size(jots_driver_t d);

@@ -21,6 +21,8 @@ struct jots_op_s {
     JOTSIterator* it = nullptr;
     DArr<double> un;  // u_n copy for residual building blocks
 };
+struct jots_comm_s { Comm* c = nullptr; };
+struct jots_part_s { Partition p; };
 struct jots_driver_s { std::unique_ptr<JOTSDriver> d; jots_ctx_s ctx_view; jots_op_s op_view; };
 
 static thread_local std::string g_err;
@@ -375,6 +377,63 @@ int jots_op_form_time(jots_op_t op, int form, const double* x, const double* sta
     JOTS_CATCH_INT
 }
 
+// ---- partition / communicator -----------------------------------------------------------------
+jots_part_t jots_partition_create(jots_mesh_t mesh, jots_space_t global, int nranks, int rank, const int32_t* dims) {
+    JOTS_TRY
+    std::vector<int> er;
+    int d[3] = {0, 0, 0};
+    if (dims) { d[0] = dims[0]; d[1] = dims[1]; d[2] = dims[2]; }
+    partition_elements(mesh->m, nranks, dims ? d : nullptr, er);
+    auto* h = new jots_part_s;
+    h->p = make_partition(global->s, er, nranks, rank);
+    return h;
+    JOTS_CATCH_PTR
+}
+void jots_partition_destroy(jots_part_t p) { delete p; }
+int jots_partition_info(jots_part_t p, int64_t* n_local, int64_t* n_owned, int64_t* n_global, int64_t* n_elem, int* n_nbr, int64_t* n_shared) {
+    if (n_local) *n_local = p->p.n_local;
+    if (n_owned) *n_owned = p->p.n_owned;
+    if (n_global) *n_global = p->p.n_global;
+    if (n_elem) *n_elem = (int64_t)p->p.local_elems.size();
+    if (n_nbr) *n_nbr = (int)p->p.nbr_rank.size();
+    if (n_shared) *n_shared = (int64_t)p->p.red_dof.size();
+    return 0;
+}
+jots_space_t jots_partition_space(jots_part_t p) {
+    JOTS_TRY auto* h = new jots_space_s; h->s = p->p.local; return h; JOTS_CATCH_PTR
+}
+int jots_partition_copy(jots_part_t p, int64_t* global_id, int64_t* local_elems) {
+    if (global_id) std::memcpy(global_id, p->p.global_id.data(), p->p.global_id.size() * sizeof(int64_t));
+    if (local_elems) std::memcpy(local_elems, p->p.local_elems.data(), p->p.local_elems.size() * sizeof(int64_t));
+    return 0;
+}
+int64_t jots_partition_neighbor(jots_part_t p, int i, int* rank, int32_t* local_idx) {
+    if (i < 0 || i >= (int)p->p.nbr_rank.size()) { g_err = "neighbour index out of range"; return -1; }
+    if (rank) *rank = p->p.nbr_rank[i];
+    if (local_idx) std::memcpy(local_idx, p->p.nbr_dofs[i].data(), p->p.nbr_dofs[i].size() * sizeof(int));
+    return (int64_t)p->p.nbr_dofs[i].size();
+}
+int64_t jots_partition_reduction(jots_part_t p, int32_t* red_dof, int32_t* red_ptr, int32_t* red_src) {
+    const Partition& P = p->p;
+    if (red_dof) std::memcpy(red_dof, P.red_dof.data(), P.red_dof.size() * sizeof(int));
+    if (red_ptr) std::memcpy(red_ptr, P.red_ptr.data(), P.red_ptr.size() * sizeof(int));
+    if (red_src) std::memcpy(red_src, P.red_src.data(), P.red_src.size() * sizeof(int));
+    return (int64_t)P.red_src.size();
+}
+int jots_comm_unique_id(char out[128]) { JOTS_TRY comm_unique_id(out); return 0; JOTS_CATCH_INT }
+jots_comm_t jots_comm_create(const char id[128], int rank, int nranks, int device) {
+    JOTS_TRY auto* h = new jots_comm_s; h->c = comm_create(id, rank, nranks, device); return h; JOTS_CATCH_PTR
+}
+void jots_comm_destroy(jots_comm_t c) { if (c) { comm_destroy(c->c); delete c; } }
+jots_ctx_t jots_ctx_create_part(jots_part_t p, int device, jots_comm_t comm) {
+    JOTS_TRY
+    auto* h = new jots_ctx_s;
+    h->own.reset(new Ctx(p->p, device, comm ? comm->c : nullptr));
+    h->c = h->own.get();
+    return h;
+    JOTS_CATCH_PTR
+}
+
 // ---- driver -----------------------------------------------------------------------------------
 static void bind_views(jots_driver_s* h) {
     h->ctx_view.c = h->d->ctx.get();
@@ -400,6 +459,24 @@ jots_driver_t jots_driver_create_on_mesh(const char* ini, jots_mesh_t mesh, int 
     bind_views(h);
     return h;
     JOTS_CATCH_PTR
+}
+jots_driver_t jots_driver_create_dist(const char* ini, jots_mesh_t mesh, int device, jots_comm_t comm) {
+    JOTS_TRY
+    Config cfg(ini);
+    auto* h = new jots_driver_s;
+    h->d.reset(new JOTSDriver(cfg, device, mesh ? &mesh->m : nullptr, comm ? comm->c : nullptr));
+    bind_views(h);
+    return h;
+    JOTS_CATCH_PTR
+}
+int jots_driver_copy_global_ids(jots_driver_t d, int64_t* out, int64_t* n_owned) {
+    JOTS_TRY
+    Ctx* c = d->d->ctx.get();
+    if (d->d->part) std::memcpy(out, d->d->part->global_id.data(), c->n * sizeof(int64_t));
+    else for (int64_t i = 0; i < c->n; ++i) out[i] = i;
+    if (n_owned) *n_owned = c->n_owned;
+    return 0;
+    JOTS_CATCH_INT
 }
 void jots_driver_destroy(jots_driver_t d) { delete d; }
 int jots_driver_run(jots_driver_t d, int max_steps, int* done) {

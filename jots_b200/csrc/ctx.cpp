@@ -8,6 +8,7 @@
 #include "basis.hpp"
 #include "halo.hpp"
 #include "launch.hpp"
+#include "partition.hpp"
 
 namespace jots {
 
@@ -42,7 +43,15 @@ static void fill_tables(TablesRT& t, int dim, int p) {
     }
 }
 
-Ctx::Ctx(const Space& s, int dev) : device(dev), space(s) {
+Ctx::Ctx(const Space& s, int dev) : device(dev), space(s) { init(s, dev); }
+
+Ctx::Ctx(const Partition& p, int dev, Comm* comm) : device(dev), space(p.local) {
+    init(p.local, dev);
+    n_owned = p.n_owned;
+    if (comm) halo = halo_create(p, comm);
+}
+
+void Ctx::init(const Space& s, int dev) {
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev == 0)
@@ -114,7 +123,7 @@ Ctx::~Ctx() {
     cudaSetDevice(device);
     if (h_scal) cudaFreeHost(h_scal);
     if (own_stream && stream) cudaStreamDestroy(stream);
-    delete halo;
+    halo_destroy(halo);
 }
 
 void Ctx::set_materials(const Poly& rho, const Poly& C, const Poly& k) {
@@ -237,7 +246,10 @@ void Ctx::neumann_vector(double div_const, const double* state, double* b, bool 
     fa.z = state; fa.y = b; fa.div_const = div_const; fa.scale = scale; fa.mask_out = mask_out;
     launch_face(FACE_LOAD, fa, stream);
     ++stats.kernel_launches;
-    if (halo && zero_first) halo_sum_exchange(*this, b);
+    if (halo) {
+        if (!zero_first) throw std::runtime_error("accumulating Neumann assembly is not available on partitioned contexts");
+        halo_sum_exchange(*this, b);
+    }
     JOTS_CUDA(cudaGetLastError());
 }
 

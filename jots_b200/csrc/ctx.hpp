@@ -68,7 +68,7 @@ struct FormSpec {
 
 struct Stats {
     long long applies = 0, diag_assemblies = 0, krylov_iters = 0, newton_iters = 0, residual_evals = 0, steps = 0,
-              kernel_launches = 0, dots = 0;
+              kernel_launches = 0, dots = 0, halo_exchanges = 0;
     double last_linear_norm = 0, last_newton_norm = 0;
     int last_linear_converged = 1, last_newton_converged = 1, last_linear_iters = 0, last_newton_iters = 0;
 };
@@ -78,6 +78,8 @@ struct Halo;  // multi-GPU interface exchange (halo.hpp)
 class Ctx {
 public:
     Ctx(const Space& s, int device);
+    // one subdomain of a partitioned space; comm may be null (no exchange: testing only)
+    Ctx(const struct Partition& p, int device, struct Comm* comm);
     ~Ctx();
 
     // --- static description
@@ -134,6 +136,7 @@ public:
 
     FormArgs make_args(const FormSpec& f, const double* x, double* y, bool for_diag) const;
 private:
+    void init(const Space& s, int dev);
     bool own_stream = false;
 };
 

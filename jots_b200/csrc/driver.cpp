@@ -5,6 +5,8 @@
 #include <fstream>
 #include <sstream>
 
+#include "halo.hpp"
+
 namespace jots {
 
 static std::string trim(const std::string& s) {
@@ -144,7 +146,7 @@ static int map_label(const std::string& s, const std::vector<std::pair<std::stri
     throw std::runtime_error(std::string("unknown ") + what + ": '" + s + "'");
 }
 
-JOTSDriver::JOTSDriver(const Config& cfg_, int device, const Mesh* mesh_in) : cfg(cfg_) {
+JOTSDriver::JOTSDriver(const Config& cfg_, int device, const Mesh* mesh_in, Comm* comm) : cfg(cfg_) {
     if (cfg.with_precice || cfg.use_restart)
         throw std::runtime_error("preCICE / restart configurations are handled by the reference's own driver (out of scope)");
     Mesh mesh;
@@ -154,7 +156,13 @@ JOTSDriver::JOTSDriver(const Config& cfg_, int device, const Mesh* mesh_in) : cf
         for (int i = 0; i < cfg.serial_refine + cfg.parallel_refine; ++i) mesh = uniform_refine(mesh);
     }
     Space space = make_space(mesh, cfg.fe_order);
-    ctx.reset(new Ctx(space, device));
+    if (comm && comm_size(comm) > 1) {
+        // ParMesh(comm, mesh): one subdomain per rank (jots_driver.cpp:178)
+        std::vector<int> elem_rank;
+        partition_elements(mesh, comm_size(comm), nullptr, elem_rank);
+        part.reset(new Partition(make_partition(space, elem_rank, comm_size(comm), comm_rank(comm))));
+        ctx.reset(new Ctx(*part, device, comm));
+    } else ctx.reset(new Ctx(space, device));
     // material properties
     Poly one; one.n = 1; for (double& v : one.c) v = 0.0; one.c[0] = 1.0;
     Poly props[3] = {one, one, one};

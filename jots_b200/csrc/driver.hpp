@@ -9,6 +9,7 @@
 #include <vector>
 
 #include "operators.hpp"
+#include "partition.hpp"
 
 namespace jots {
 
@@ -29,7 +30,8 @@ BCSpec parse_bc(const std::vector<std::string>& info);
 class JOTSDriver {
 public:
     // mesh == nullptr: read cfg.mesh_file (relative paths are taken as given) and refine
-    JOTSDriver(const Config& cfg, int device, const Mesh* mesh = nullptr);
+    JOTSDriver(const Config& cfg, int device, const Mesh* mesh = nullptr, struct Comm* comm = nullptr);
+    std::unique_ptr<struct Partition> part;   // subdomain (multi-GPU runs)
     void UpdateAndApplyBCs();
     void UpdateMatProps(bool apply_changes);
     void Iteration();

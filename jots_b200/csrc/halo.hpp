@@ -7,6 +7,15 @@
 namespace jots {
 class Ctx;
 struct Halo;
+struct Comm;
+struct Partition;
+void comm_unique_id(char out[128]);
+Comm* comm_create(const char id[128], int rank, int nranks, int device);
+void comm_destroy(Comm* c);
+int comm_rank(const Comm* c);
+int comm_size(const Comm* c);
+Halo* halo_create(const Partition& P, Comm* comm);
+void halo_destroy(Halo* h);
 void halo_sum_exchange(Ctx& c, double* y);
 void halo_allreduce(Ctx& c, double* d_vals, int nv);
 const int64_t* halo_global_index(Ctx& c);  // device array: local DOF -> global DOF

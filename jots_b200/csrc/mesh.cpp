@@ -470,6 +470,14 @@ void Space::node_coordinates(std::vector<double>& out) const {
 
 void Space::essential_dofs(const std::vector<int>& attrs, std::vector<int>& out) const {
     out.clear();
+    if (has_attr_dofs) {
+        for (size_t ai = 0; ai < attributes.size(); ++ai)
+            if (std::find(attrs.begin(), attrs.end(), attributes[ai]) != attrs.end())
+                out.insert(out.end(), attr_dofs[ai].begin(), attr_dofs[ai].end());
+        std::sort(out.begin(), out.end());
+        out.erase(std::unique(out.begin(), out.end()), out.end());
+        return;
+    }
     for (int64_t b = 0; b < nbdr; ++b) {
         if (std::find(attrs.begin(), attrs.end(), bdr_attr[b]) == attrs.end()) continue;
         for (int i = 0; i < nfl; ++i) out.push_back(bdr_gather[b * nfl + i]);

@@ -59,6 +59,9 @@ struct Space {
     bool is_brick = false;
     int64_t bn[3] = {0, 0, 0};
     double bl[3] = {0, 0, 0};
+    // subdomain spaces: DOFs of the GLOBAL boundary elements of attribute attributes[i] (local ids)
+    bool has_attr_dofs = false;
+    std::vector<std::vector<int>> attr_dofs;
 
     void node_coordinates(std::vector<double>& out) const;  // [ndof*dim]
     void essential_dofs(const std::vector<int>& attrs, std::vector<int>& out) const;  // sorted unique

@@ -153,7 +153,7 @@ NonlinearConductionOperator::NonlinearConductionOperator(Ctx* ctx, const SolverS
     }
     lin_solver = make_solver();
     newton.rel_tol = nw.rel_tol; newton.abs_tol = nw.abs_tol; newton.max_iter = nw.max_iter; newton.print = nw.print;
-    z.alloc(c->n); tmp.alloc(c->n);
+    z.alloc(c->n); tmp.alloc(c->n); tmp2.alloc(c->n);
     // unit mass, FormSystemMatrix -> eliminated (:189-192)
     FormSpec ms;
     ms.op = OP_LIN; ms.cf = CF_CONST; ms.cm = 1.0; ms.ck = 0.0; ms.m0 = 1.0; ms.a0 = 0.0;
@@ -181,7 +181,13 @@ void NonlinearConductionOperator::mult(const double* k, double* y) {
     else f.cf = CF_FULL;
     c->apply_form(f, k, y);
     if (has_BN) {
-        if (c->any_flux()) c->neumann_vector(1.0, z.p, y, false, -1.0, true);
+        if (c->any_flux()) {
+            // boundary part of BN(z): int (g / (rho_h C_h)) phi_i (jots_nlfis.cpp:51-54), assembled and
+            // interface-summed on its own, then subtracted
+            c->neumann_vector(1.0, z.p, tmp2.p, true, 1.0, true);
+            v_axpy(c->stream, c->n, -1.0, tmp2.p, y);
+            ++c->stats.kernel_launches;
+        }
     } else {
         v_axpy(c->stream, c->n, -1.0, b_vec.p, y);
         ++c->stats.kernel_launches;
@@ -202,8 +208,13 @@ void NonlinearConductionOperator::A_mult(const double* zz, double* y) {
     else if (!has_BN) { f.cf = CF_K; f.inv_rc = inv_rc; }
     else f.cf = CF_FULL;
     c->apply_form(f, tmp.p, y);
-    if (has_BN) { if (c->any_flux()) c->neumann_vector(1.0, z.p, y, false, 1.0, true); }
-    else { v_axpy(c->stream, c->n, 1.0, b_vec.p, y); ++c->stats.kernel_launches; }
+    if (has_BN) {
+        if (c->any_flux()) {
+            c->neumann_vector(1.0, z.p, tmp2.p, true, 1.0, true);
+            v_axpy(c->stream, c->n, 1.0, tmp2.p, y);
+            ++c->stats.kernel_launches;
+        }
+    } else { v_axpy(c->stream, c->n, 1.0, b_vec.p, y); ++c->stats.kernel_launches; }
 }
 
 FormSpec NonlinearConductionOperator::jacobian_spec(const double* zz) {

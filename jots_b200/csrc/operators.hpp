@@ -91,7 +91,7 @@ private:
     Newton newton;
     std::unique_ptr<FormOp> J_op, M_op;
     const double* u_n = nullptr;
-    DArr<double> z, tmp;
+    DArr<double> z, tmp, tmp2;
     double inv_rc = 1.0;
 };
 

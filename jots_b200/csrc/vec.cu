@@ -66,6 +66,23 @@ __global__ void k_copy_idx(int n, const int* __restrict__ idx, const double* __r
     if (i < n) y[idx[i]] = x[idx[i]];
 }
 
+// interface exchange helpers
+__global__ void k_pack(int n, const int* __restrict__ idx, const double* __restrict__ y, double* out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = y[idx[i]];
+}
+// canonical-order sum of the contributions of every sharing rank (ascending rank; -1 = own value)
+__global__ void k_reduce_shared(int n, const int* __restrict__ dof, const int* __restrict__ ptr, const int* __restrict__ src,
+                                const double* __restrict__ recv, double* y) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int d = dof[i];
+    const double own = y[d];
+    double acc = 0.0;
+    for (int k = ptr[i]; k < ptr[i + 1]; ++k) { const int s = src[k]; acc += s < 0 ? own : recv[s]; }
+    y[d] = acc;
+}
+
 template <int NV>
 __global__ void __launch_bounds__(VEC_THREADS) k_dots(int64_t n, const double* __restrict__ a0, const double* __restrict__ b0,
                                                        const double* __restrict__ a1, const double* __restrict__ b1,
@@ -120,6 +137,12 @@ void v_set_idx(cudaStream_t st, int n, const int* idx, double v, double* y) {
 }
 void v_copy_idx(cudaStream_t st, int n, const int* idx, const double* x, double* y) {
     if (n > 0) k_copy_idx<<<(n + 255) / 256, 256, 0, st>>>(n, idx, x, y);
+}
+void v_pack(cudaStream_t st, int n, const int* idx, const double* y, double* out) {
+    if (n > 0) k_pack<<<(n + 255) / 256, 256, 0, st>>>(n, idx, y, out);
+}
+void v_reduce_shared(cudaStream_t st, int n, const int* dof, const int* ptr, const int* src, const double* recv, double* y) {
+    if (n > 0) k_reduce_shared<<<(n + 255) / 256, 256, 0, st>>>(n, dof, ptr, src, recv, y);
 }
 void v_dots(cudaStream_t st, int64_t n, int nv, const double* const* a, const double* const* b, DotScratch s, double* result) {
     const int g = grid_for(n, 8);

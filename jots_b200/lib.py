@@ -85,6 +85,19 @@ def load_library():
         "jots_op_form_apply": (C.c_int, [_P, C.c_int, _P, _P, _P, C.c_int]),
         "jots_op_form_diagonal": (C.c_int, [_P, C.c_int, _P, _P, C.c_int]),
         "jots_op_form_time": (C.c_int, [_P, C.c_int, _P, _P, _P, C.c_int, _D]),
+        "jots_partition_create": (_P, [_P, _P, C.c_int, C.c_int, _P]),
+        "jots_partition_destroy": (None, [_P]),
+        "jots_partition_info": (C.c_int, [_P, _I64, _I64, _I64, _I64, C.POINTER(C.c_int), _I64]),
+        "jots_partition_space": (_P, [_P]),
+        "jots_partition_copy": (C.c_int, [_P, _P, _P]),
+        "jots_partition_neighbor": (C.c_int64, [_P, C.c_int, C.POINTER(C.c_int), _P]),
+        "jots_partition_reduction": (C.c_int64, [_P, _P, _P, _P]),
+        "jots_comm_unique_id": (C.c_int, [C.c_char_p]),
+        "jots_comm_create": (_P, [C.c_char_p, C.c_int, C.c_int, C.c_int]),
+        "jots_comm_destroy": (None, [_P]),
+        "jots_ctx_create_part": (_P, [_P, C.c_int, _P]),
+        "jots_driver_create_dist": (_P, [C.c_char_p, _P, C.c_int, _P]),
+        "jots_driver_copy_global_ids": (C.c_int, [_P, _P, _I64]),
         "jots_driver_create": (_P, [C.c_char_p, C.c_int]),
         "jots_driver_create_on_mesh": (_P, [C.c_char_p, _P, C.c_int]),
         "jots_driver_destroy": (None, [_P]),
@@ -366,12 +379,80 @@ class Operator:
         self._h = None
 
 
+class Partition:
+    """One subdomain of a partitioned space (host-side index sets only)."""
+
+    def __init__(self, mesh, space, nranks, rank, dims=None):
+        d = None if dims is None else np.asarray(dims, dtype=np.int32)
+        self._h = _handle(load_library().jots_partition_create(mesh._h, space._h, nranks, rank, _ptr(d)))
+        nl, no, ng, ne, ns = C.c_int64(), C.c_int64(), C.c_int64(), C.c_int64(), C.c_int64()
+        nn = C.c_int()
+        _chk(load_library().jots_partition_info(self._h, nl, no, ng, ne, nn, ns))
+        self.n_local, self.n_owned, self.n_global, self.n_elem = nl.value, no.value, ng.value, ne.value
+        self.n_neighbors, self.n_shared = nn.value, ns.value
+        self.rank, self.nranks = rank, nranks
+
+    def space(self):
+        return Space(handle=load_library().jots_partition_space(self._h))
+
+    def global_ids(self):
+        g = np.empty(self.n_local, dtype=np.int64)
+        e = np.empty(self.n_elem, dtype=np.int64)
+        _chk(load_library().jots_partition_copy(self._h, _ptr(g), _ptr(e)))
+        return g, e
+
+    def neighbors(self):
+        out = []
+        for i in range(self.n_neighbors):
+            r = C.c_int()
+            n = load_library().jots_partition_neighbor(self._h, i, C.byref(r), None)
+            idx = np.empty(n, dtype=np.int32)
+            load_library().jots_partition_neighbor(self._h, i, C.byref(r), _ptr(idx))
+            out.append((r.value, idx))
+        return out
+
+    def reduction(self):
+        n = load_library().jots_partition_reduction(self._h, None, None, None)
+        dof = np.empty(self.n_shared, dtype=np.int32)
+        ptr = np.empty(self.n_shared + 1, dtype=np.int32)
+        src = np.empty(n, dtype=np.int32)
+        load_library().jots_partition_reduction(self._h, _ptr(dof), _ptr(ptr), _ptr(src))
+        return dof, ptr, src
+
+    def __del__(self):
+        if getattr(self, "_h", None) and _LIB is not None:
+            _LIB.jots_partition_destroy(self._h)
+            self._h = None
+
+
+class Comm:
+    """NCCL communicator, one rank per GPU.  ``Comm.unique_id()`` on rank 0, broadcast by the caller."""
+
+    @staticmethod
+    def unique_id():
+        buf = C.create_string_buffer(128)
+        _chk(load_library().jots_comm_unique_id(buf))
+        return buf.raw
+
+    def __init__(self, uid, rank, nranks, device):
+        self._h = _handle(load_library().jots_comm_create(uid, rank, nranks, device))
+        self.rank, self.nranks = rank, nranks
+
+    def __del__(self):
+        if getattr(self, "_h", None) and _LIB is not None:
+            _LIB.jots_comm_destroy(self._h)
+            self._h = None
+
+
 class Driver:
     """Config + the hot-path part of JOTSDriver::Run."""
 
-    def __init__(self, ini_path, device=0, mesh=None):
+    def __init__(self, ini_path, device=0, mesh=None, comm=None):
         lib = load_library()
-        if mesh is None:
+        self._comm = comm
+        if comm is not None:
+            self._h = _handle(lib.jots_driver_create_dist(os.fsencode(ini_path), mesh._h if mesh is not None else None, device, comm._h))
+        elif mesh is None:
             self._h = _handle(lib.jots_driver_create(os.fsencode(ini_path), device))
         else:
             self._h = _handle(lib.jots_driver_create_on_mesh(os.fsencode(ini_path), mesh._h, device))
@@ -395,6 +476,13 @@ class Driver:
     @property
     def time(self):
         return load_library().jots_driver_time(self._h)
+
+    def global_ids(self):
+        """(global DOF id of every local entry, number of leading owned entries)."""
+        g = np.empty(self.n, dtype=np.int64)
+        no = C.c_int64()
+        _chk(load_library().jots_driver_copy_global_ids(self._h, _ptr(g), C.byref(no)))
+        return g, no.value
 
     def space(self):
         return Space(handle=load_library().jots_driver_space(self._h))
