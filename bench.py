@@ -149,7 +149,7 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
-    ap.add_argument("--n", type=int, default=128, help="elements per direction of the synthetic brick")
+    ap.add_argument("--elems", dest="n", type=int, default=128, help="elements per direction of the synthetic brick")
     ap.add_argument("--order", type=int, default=2)
     ap.add_argument("--solver", default="CG")
     ap.add_argument("--prec", default="Jacobi")
@@ -257,8 +257,14 @@ def main():
     alg_bytes = 24.0 * ndof
     achieved = alg_bytes / (apply_ms * 1e-3) / 1e9
 
+    def finish():
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+
     if rank != 0:
-        return
+        del drv, comm
+        return finish()
     line = {"metric": METRIC, "value": value, "unit": "GDOF/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "config": workload_config(args, world),
@@ -278,9 +284,9 @@ def main():
                                 "sample": "same physics on a %d^3-element Q%d brick (%d DOFs), 2 steps, %.1f s; NumPy/SciPy "
                                           "restatement of the reference's assemble+SpMV algorithm" % (args.cpu_n, args.order, r["ndof"], r["time"]),
                                 "steps_per_s": r["steps_per_s"]}
-    print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+    print(json.dumps(line), flush=True)
+    del drv, comm
+    finish()
 
 
 if __name__ == "__main__":
