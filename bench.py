@@ -181,6 +181,12 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    t_start = time.perf_counter()
+
+    def trace(msg):
+        if os.environ.get("JOTS_BENCH_TRACE"):
+            print("[bench rank %d %.1fs] %s" % (rank, time.perf_counter() - t_start, msg), file=sys.stderr, flush=True)
+
     W, K = args.warmup, args.steps
     tmp = tempfile.mkdtemp()
     ini = os.path.join(tmp, "bench.ini")
@@ -192,8 +198,10 @@ def main():
         uid = [J.Comm.unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)
         comm = J.Comm(uid[0], rank, world, local)
+    trace("mesh + communicator ready")
     drv = J.Driver(ini, local, mesh=mesh, comm=comm)
     del mesh
+    trace("driver ready (n_local = %d)" % drv.n)
     stream = torch.cuda.current_stream()
     drv.ctx.set_stream(stream.cuda_stream)
     ndof = drv.n
@@ -201,6 +209,7 @@ def main():
     # ---- device-resident timing ---------------------------------------------------------------
     for _ in range(W):
         drv.run(1)
+        trace("warm-up step done")
     barrier()
     drv.ctx.reset_stats()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -220,6 +229,7 @@ def main():
     total_dof = workload_config(args, world)["n_dof"]
     value = total_dof * iters / (ms * 1e-3) / 1e9
 
+    trace("timed steps done: %.1f ms" % ms)
     # ---- end to end through the C ABI with host buffers ---------------------------------------------
     u_host = torch.empty(ndof, dtype=torch.float64).pin_memory().numpy()
     drv.get_u(u_host)
@@ -239,6 +249,7 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = total_dof * int(t[1]) / float(t[0]) / 1e9
 
+    trace("e2e done")
     # ---- dominant kernel: Jacobian-vector apply -------------------------------------------------------
     x = torch.empty(ndof, dtype=torch.float64, device="cuda").uniform_(-1.0, 1.0)
     y = torch.empty_like(x)
