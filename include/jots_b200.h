@@ -67,6 +67,14 @@ int jots_mesh_copy(jots_mesh_t m, double* verts, int64_t* elems, int64_t* bdr, i
 
 /* ---- space: H1_FECollection + ParFiniteElementSpace (src/jots_driver.cpp:194-196) ------------- */
 jots_space_t jots_space_create(jots_mesh_t m, int order);
+/* the same space from tables the caller already holds (ParFiniteElementSpace::GetElementDofs /
+   GetBdrElementDofs + vertex coordinates): gather[n_elem][(p+1)^dim] in lexicographic local order (x
+   fastest), element corners [n_elem][2^dim][dim] in corner-bit order, boundary faces with their
+   (p+1)^(dim-1) DOFs (lower free axis fastest), 2^(dim-1) corners and attribute */
+jots_space_t jots_space_create_from_tables(int dim, int order, int64_t n_elem, int64_t n_dof, const int32_t* gather,
+                                           const double* elem_corners, int64_t n_bdr, const int32_t* bdr_gather,
+                                           const double* bdr_corners, const int32_t* bdr_attr);
+int jots_space_copy_corners(jots_space_t s, double* elem_corners, double* bdr_corners);
 void jots_space_destroy(jots_space_t s);
 int jots_space_info(jots_space_t s, int* dim, int* order, int64_t* n_elem, int64_t* n_dof, int64_t* n_bdr,
                     int* dofs_per_elem, int* dofs_per_face);

@@ -1,6 +1,7 @@
 // extern "C" boundary of libjots_b200.so (declarations and reference citations: include/jots_b200.h)
 #include "../../include/jots_b200.h"
 
+#include <algorithm>
 #include <cstring>
 #include <exception>
 #include <string>
@@ -113,6 +114,44 @@ int jots_mesh_copy(jots_mesh_t m, double* verts, int64_t* elems, int64_t* bdr, i
 // ---- space ------------------------------------------------------------------------------------
 jots_space_t jots_space_create(jots_mesh_t m, int order) {
     JOTS_TRY auto* h = new jots_space_s; h->s = make_space(m->m, order); return h; JOTS_CATCH_PTR
+}
+jots_space_t jots_space_create_from_tables(int dim, int order, int64_t n_elem, int64_t n_dof, const int32_t* gather,
+                                           const double* elem_corners, int64_t n_bdr, const int32_t* bdr_gather,
+                                           const double* bdr_corners, const int32_t* bdr_attr) {
+    JOTS_TRY
+    if (dim != 2 && dim != 3) throw std::runtime_error("only 2-D / 3-D spaces are supported");
+    if (order < 1 || order > 4) throw std::runtime_error("FE_Order must be 1..4");
+    auto* h = new jots_space_s;
+    Space& S = h->s;
+    S.dim = dim; S.p = order; S.D = order + 1; S.Q = dim == 3 ? order + 2 : order + 1;
+    S.nloc = 1; for (int a = 0; a < dim; ++a) S.nloc *= S.D;
+    S.nfl = S.nloc / S.D;
+    S.nelem = n_elem; S.ndof = n_dof; S.nbdr = n_bdr;
+    const int nv = 1 << dim, nfv = 1 << (dim - 1);
+    S.gather.assign(gather, gather + n_elem * S.nloc);
+    for (int g : S.gather) if (g < 0 || g >= n_dof) { delete h; throw std::runtime_error("gather table entry out of range"); }
+    S.elem_corner.assign(elem_corners, elem_corners + n_elem * nv * dim);
+    S.bdr_gather.assign(bdr_gather, bdr_gather + n_bdr * S.nfl);
+    S.bdr_corner.assign(bdr_corners, bdr_corners + n_bdr * nfv * dim);
+    S.bdr_attr.assign(bdr_attr, bdr_attr + n_bdr);
+    S.bdr_elem.assign(n_bdr, -1); S.bdr_face.assign(n_bdr, -1);
+    S.attributes = S.bdr_attr;
+    std::sort(S.attributes.begin(), S.attributes.end());
+    S.attributes.erase(std::unique(S.attributes.begin(), S.attributes.end()), S.attributes.end());
+    {
+        // GL nodes for node_coordinates()
+        Mesh dummy = dim == 3 ? make_brick(1, 1, 1, 1, 1, 1) : make_rect(1, 1, 1, 1, 0, 0);
+        S.nodes = make_space(dummy, order).nodes;
+    }
+    return h;
+    JOTS_CATCH_PTR
+}
+int jots_space_copy_corners(jots_space_t s, double* elem_corners, double* bdr_corners) {
+    JOTS_TRY
+    if (elem_corners) std::memcpy(elem_corners, s->s.elem_corner.data(), s->s.elem_corner.size() * sizeof(double));
+    if (bdr_corners) std::memcpy(bdr_corners, s->s.bdr_corner.data(), s->s.bdr_corner.size() * sizeof(double));
+    return 0;
+    JOTS_CATCH_INT
 }
 void jots_space_destroy(jots_space_t s) { delete s; }
 int jots_space_info(jots_space_t s, int* dim, int* order, int64_t* ne, int64_t* nd, int64_t* nb, int* dpe, int* dpf) {

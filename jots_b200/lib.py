@@ -22,6 +22,7 @@ class JotsError(RuntimeError):
 
 
 _LIB = None
+_NOHANDLE = object()
 _P = C.c_void_p
 _D = C.POINTER(C.c_double)
 _I32 = C.POINTER(C.c_int32)
@@ -55,6 +56,8 @@ def load_library():
         "jots_mesh_copy": (C.c_int, [_P, _P, _P, _P, _P]),
         "jots_space_create": (_P, [_P, C.c_int]),
         "jots_space_destroy": (None, [_P]),
+        "jots_space_create_from_tables": (_P, [C.c_int, C.c_int, C.c_int64, C.c_int64, _P, _P, C.c_int64, _P, _P, _P]),
+        "jots_space_copy_corners": (C.c_int, [_P, _P, _P]),
         "jots_space_info": (C.c_int, [_P, C.POINTER(C.c_int), C.POINTER(C.c_int), _I64, _I64, _I64, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
         "jots_space_copy_gather": (C.c_int, [_P, _P]),
         "jots_space_copy_bdr": (C.c_int, [_P, _P, _P, _P, _P]),
@@ -209,13 +212,30 @@ class Mesh:
 
 
 class Space:
-    def __init__(self, mesh=None, order=1, handle=None):
-        self._h = _handle(handle if handle is not None else load_library().jots_space_create(mesh._h, order))
+    def __init__(self, mesh=None, order=1, handle=_NOHANDLE):
+        self._h = _handle(load_library().jots_space_create(mesh._h, order) if handle is _NOHANDLE else handle)
         dim, p, dpe, dpf = C.c_int(), C.c_int(), C.c_int(), C.c_int()
         ne, nd, nb = C.c_int64(), C.c_int64(), C.c_int64()
         _chk(load_library().jots_space_info(self._h, dim, p, ne, nd, nb, dpe, dpf))
         self.dim, self.order, self.n_elem, self.n_dof, self.n_bdr = dim.value, p.value, ne.value, nd.value, nb.value
         self.dofs_per_elem, self.dofs_per_face = dpe.value, dpf.value
+
+    @classmethod
+    def from_tables(cls, dim, order, n_dof, gather, elem_corners, bdr_gather, bdr_corners, bdr_attr):
+        gather = np.ascontiguousarray(gather, dtype=np.int32)
+        ec = np.ascontiguousarray(elem_corners, dtype=np.float64)
+        bg = np.ascontiguousarray(bdr_gather, dtype=np.int32)
+        bc = np.ascontiguousarray(bdr_corners, dtype=np.float64)
+        ba = np.ascontiguousarray(bdr_attr, dtype=np.int32)
+        h = load_library().jots_space_create_from_tables(dim, order, gather.shape[0], n_dof, _ptr(gather), _ptr(ec), ba.size,
+                                                         _ptr(bg), _ptr(bc), _ptr(ba))
+        return cls(handle=h)
+
+    def corners(self):
+        ec = np.empty((self.n_elem, 2 ** self.dim, self.dim))
+        bc = np.empty((self.n_bdr, 2 ** (self.dim - 1), self.dim))
+        _chk(load_library().jots_space_copy_corners(self._h, _ptr(ec), _ptr(bc)))
+        return ec, bc
 
     def gather(self):
         g = np.empty((self.n_elem, self.dofs_per_elem), dtype=np.int32)

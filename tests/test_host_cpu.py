@@ -82,6 +82,20 @@ def test_shipped_meshes(name):
         assert (sp.essential_dofs([1]) == osp.essential_dofs([1])).all()
 
 
+def test_space_from_caller_tables_round_trip():
+    """jots_space_create_from_tables: the drop-in entry for a caller that already holds MFEM's tables."""
+    sp = J.Space(J.Mesh.brick(3, 2, 2, 1.0, 0.5, 0.25), 2)
+    ec, bc = sp.corners()
+    bg, ba, _, _ = sp.boundary()
+    sp2 = J.Space.from_tables(3, 2, sp.n_dof, sp.gather(), ec, bg, bc, ba)
+    assert (sp2.n_dof, sp2.n_elem, sp2.n_bdr) == (sp.n_dof, sp.n_elem, sp.n_bdr)
+    assert (sp2.gather() == sp.gather()).all()
+    assert (sp2.essential_dofs([1, 4]) == sp.essential_dofs([1, 4])).all()
+    assert np.abs(sp2.node_coordinates() - sp.node_coordinates()).max() < 1e-15
+    with pytest.raises(J.JotsError, match="out of range"):
+        J.Space.from_tables(3, 2, 5, sp.gather(), ec, bg, bc, ba)
+
+
 def _emulated_exchange(parts, vals):
     """pairwise exchange + canonical-order reduction, as halo_sum_exchange does on the device"""
     recv = []
