@@ -788,4 +788,315 @@ __global__ void __launch_bounds__(T) form_diag_slab2_kernel(const FormArgs a, co
     }
 }
 
+// =================================================================================================
+// v3: persistent, software-pipelined version of v2.  Each block loops over tiles; while it computes
+// tile i (phase 2, FP64 bound) the L-vector values of tile i+1 and the gather rows of tile i+2 are in
+// flight as cp.async copies into shared-memory staging buffers, so no warp waits on a global load
+// (the long-scoreboard stalls that took 35 % of v2's issue slots).  The two result planes of each
+// half-plane thread alias the input planes of the same (element, qz) -- both threads of the pair are
+// adjacent lanes of one warp, a __syncwarp() orders their last read before the first write -- which
+// keeps four 128-thread blocks (16 warps) resident per SM.
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(s), "l"(gsrc));
+}
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(s), "l"(gsrc));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+template <int D, int Q, int NP> struct Elem3Stride {
+    static constexpr int PS = Plane2Stride<D>::value;
+    static constexpr int NPA = NP > 4 ? NP : 4;                       // room for the 4 aliased result planes
+    static constexpr int raw = NPA * Q * PS;
+    static constexpr int value = raw + (((D * D) % 16 - raw % 16) + 16) % 16;   // == D*D (mod 16)
+};
+template <int D, int Q, int NP, int E> struct Slab3Smem {
+    static constexpr int ND = D * D * D;
+    static constexpr size_t planes = (size_t)E * Elem3Stride<D, Q, NP>::value * sizeof(double);
+    static constexpr size_t stage = (size_t)2 * 2 * E * ND * sizeof(double);
+    static constexpr size_t idx = (size_t)3 * E * ND * sizeof(int);
+    static constexpr size_t total = planes + stage + idx;
+};
+
+template <int D, int Q, int OP, int CF, int E, int T>
+__global__ void __launch_bounds__(T) form_apply_slab3_kernel(const FormArgs a, const Slab2Tables<D, Q> t) {
+    typedef SlabCfg<OP, CF> C;
+    constexpr int NF = C::NF, NFA = NF > 0 ? NF : 1, NP = C::NP;
+    constexpr int QC = (Q + 1) / 2;
+    constexpr int PS = Plane2Stride<D>::value;
+    constexpr int ES = Elem3Stride<D, Q, NP>::value;
+    constexpr int ND = D * D * D, DD = D * D;
+    constexpr bool NEED_Z = C::Z_GRAD || NF > 0;
+    extern __shared__ __align__(16) double smem[];
+    double* planes = smem;
+    double* stage = smem + (size_t)E * ES;                                  // [2][2][E*ND]
+    int* idxbuf = reinterpret_cast<int*>(stage + (size_t)2 * 2 * E * ND);   // [3][E*ND]
+    const int tid = threadIdx.x;
+    const int ntiles = (a.nelem + E - 1) / E;
+    const int nmine = blockIdx.x < ntiles ? (ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+    auto tile_of = [&](int i) { return (int)blockIdx.x + i * (int)gridDim.x; };
+    auto nvalid = [&](int tile) { const int r = a.nelem - tile * E; return r < E ? r : E; };
+    // gather rows of tile i -> idxbuf[i % 3]
+    auto issue_idx = [&](int i) {
+        if (i < nmine) {
+            const int tile = tile_of(i), n = nvalid(tile) * ND;
+            const int* src = a.gather + (size_t)tile * E * ND;
+            int* dst = idxbuf + (i % 3) * E * ND;
+            for (int m = tid; m < n; m += T) cp_async4(dst + m, src + m);
+        }
+        cp_async_commit();
+    };
+    // L-vector values of tile i (indices already in shared memory) -> stage[i % 2]
+    auto issue_vals = [&](int i) {
+        if (i < nmine) {
+            const int n = nvalid(tile_of(i)) * ND;
+            const int* ix = idxbuf + (i % 3) * E * ND;
+            double* sx = stage + (size_t)(i % 2) * 2 * E * ND;
+            double* sz = sx + E * ND;
+            for (int m = tid; m < n; m += T) {
+                const int g = ix[m];
+                const int idx = g < 0 ? ~g : g;
+                cp_async8(sx + m, a.x + idx);
+                if (NEED_Z) cp_async8(sz + m, a.z + idx);
+            }
+        }
+        cp_async_commit();
+    };
+
+    issue_idx(0);
+    issue_idx(1);
+    cp_async_wait<1>();
+    __syncthreads();
+    issue_vals(0);
+
+    // geometry of a uniform mesh is loop invariant
+    double gxx = 0, gyy = 0, gzz = 0, det = 0;
+    if (a.geom_stride == 0) {
+        const double* gm = a.geom;
+        gxx = gm[0] * gm[0] + gm[1] * gm[1] + gm[2] * gm[2];
+        gyy = gm[3] * gm[3] + gm[4] * gm[4] + gm[5] * gm[5];
+        gzz = gm[6] * gm[6] + gm[7] * gm[7] + gm[8] * gm[8];
+        det = gm[9];
+    }
+
+    for (int it = 0; it < nmine; ++it) {
+        const int tile = tile_of(it), e0 = tile * E, nv = nvalid(tile);
+        issue_idx(it + 2);
+        cp_async_wait<1>();          // values of tile it and gather rows of tile it+1 have landed
+        __syncthreads();
+        issue_vals(it + 1);
+        const int* ix = idxbuf + (it % 3) * E * ND;
+        const double* sx = stage + (size_t)(it % 2) * 2 * E * ND;
+        const double* sz = sx + E * ND;
+
+        // ---------------- phase 1: z contraction from the staged values ---------------------------
+        for (int item = tid; item < nv * DD; item += T) {
+            const int el = item / DD, ij = item - el * DD;
+            double xr[D], zr[D], fr[NFA][D];
+#pragma unroll
+            for (int k = 0; k < D; ++k) {
+                const int m = el * ND + ij + DD * k;
+                const int g = ix[m];
+                xr[k] = (g < 0 && a.mask_in) ? 0.0 : sx[m];
+                if (NEED_Z) {
+                    zr[k] = sz[m];
+                    if (NF > 0) {
+                        double f[NFA];
+                        nodal_fields<CF, OP>(a.mat, zr[k], f);
+#pragma unroll
+                        for (int n = 0; n < NF; ++n) fr[n][k] = f[n];
+                    }
+                }
+            }
+            double* base = planes + el * ES + ij;
+#pragma unroll
+            for (int qz = 0; qz < Q; ++qz) {
+                double s = 0.0, sg = 0.0, zs = 0.0, zg = 0.0;
+#pragma unroll
+                for (int k = 0; k < D; ++k) {
+                    s += t.B[qz * D + k] * xr[k];
+                    if (C::X_GRAD) sg += t.G[qz * D + k] * xr[k];
+                    if (C::Z_GRAD) { zs += t.B[qz * D + k] * zr[k]; zg += t.G[qz * D + k] * zr[k]; }
+                }
+                base[(C::P_XB * Q + qz) * PS] = s;
+                if (C::X_GRAD) base[(C::P_XG * Q + qz) * PS] = sg;
+                if (C::Z_GRAD) { base[(C::P_ZB * Q + qz) * PS] = zs; base[(C::P_ZG * Q + qz) * PS] = zg; }
+#pragma unroll
+                for (int n = 0; n < NF; ++n) {
+                    double fs = 0.0;
+#pragma unroll
+                    for (int k = 0; k < D; ++k) fs += t.B[qz * D + k] * fr[n][k];
+                    base[((C::P_F0 + n) * Q + qz) * PS] = fs;
+                }
+            }
+        }
+        __syncthreads();
+
+        // ---------------- phase 2: half a quadrature plane per thread ----------------------------
+        const unsigned p2mask = __ballot_sync(0xffffffffu, tid < E * Q * 2);
+        if (tid < E * Q * 2) {
+            const int el = tid / (2 * Q), r = tid - el * 2 * Q, qz = r >> 1;
+            const bool h = r & 1;
+            if (a.geom_stride != 0) {
+                int e = e0 + el;
+                if (e >= a.nelem) e = a.nelem - 1;
+                const double* gm = a.geom + (size_t)e * a.geom_stride;
+                gxx = gm[0] * gm[0] + gm[1] * gm[1] + gm[2] * gm[2];
+                gyy = gm[3] * gm[3] + gm[4] * gm[4] + gm[5] * gm[5];
+                gzz = gm[6] * gm[6] + gm[7] * gm[7] + gm[8] * gm[8];
+                det = gm[9];
+            }
+            const double wz = t.W[qz] * det;
+            double* pl = planes + el * ES + qz * PS;
+            auto getp = [&](int id, double (&out)[DD]) {
+                const double* p = pl + id * Q * PS;
+#pragma unroll
+                for (int m = 0; m < DD; ++m) out[m] = p[m];
+                flip_plane<D>(out, h);
+            };
+            double p9[DD], t6[D * QC], A[DD], Bp[DD];
+#pragma unroll
+            for (int i = 0; i < DD; ++i) { A[i] = 0.0; Bp[i] = 0.0; }
+            double a1[Q * QC], a2x[Q * QC];
+            double a1c = 0.0;
+            if (CF == CF_CONST) a1c = a.ck * a.a0;
+            else {
+                getp(C::P_F0, p9);
+                xpassC<D, QC>(p9, t.B, t6);
+                ypassC<D, Q, QC>(t6, t.B, a1);
+                const double sc = a.ck * a.inv_rc;
+#pragma unroll
+                for (int q = 0; q < Q * QC; ++q) a1[q] *= sc;
+                if (OP == OP_JAC) {
+                    getp(C::P_F0 + 1, p9);
+                    xpassC<D, QC>(p9, t.B, t6);
+                    ypassC<D, Q, QC>(t6, t.B, a2x);
+                }
+            }
+            double xB6[D * QC], xG6[D * QC], vy6[D * QC];
+            getp(C::P_XB, p9);
+            xpassC<D, QC>(p9, t.B, xB6);
+            if (C::X_GRAD) xpassC<D, QC>(p9, t.G, xG6);
+            {
+                double xv[Q * QC];
+                ypassC<D, Q, QC>(xB6, t.B, xv);
+                if (OP == OP_JAC && CF != CF_CONST) {
+                    const double sc = a.ck * a.inv_rc;
+#pragma unroll
+                    for (int q = 0; q < Q * QC; ++q) a2x[q] *= sc * xv[q];
+                }
+                ypassTC<D, Q, QC>(xv, t.BW, vy6);
+            }
+            const double c_m = a.cm * (CF == CF_CONST || CF == CF_K ? a.m0 : 1.0) * wz;
+            double zB6[D * QC], zG6[D * QC];
+            if (C::Z_GRAD) {
+                getp(C::P_ZB, p9);
+                xpassC<D, QC>(p9, t.B, zB6);
+                xpassC<D, QC>(p9, t.G, zG6);
+            }
+            {   // x direction (both G's carry the mirror sign: it cancels)
+                double F[Q * QC];
+                if (OP == OP_RES) ypassC<D, Q, QC>(zG6, t.B, F);
+                else ypassC<D, Q, QC>(xG6, t.B, F);
+                if (CF == CF_CONST) {
+#pragma unroll
+                    for (int q = 0; q < Q * QC; ++q) F[q] *= a1c;
+                } else {
+#pragma unroll
+                    for (int q = 0; q < Q * QC; ++q) F[q] *= a1[q];
+                    if (OP == OP_JAC) {
+                        double zd[Q * QC];
+                        ypassC<D, Q, QC>(zG6, t.B, zd);
+#pragma unroll
+                        for (int q = 0; q < Q * QC; ++q) F[q] += a2x[q] * zd[q];
+                    }
+                }
+                ypassTC<D, Q, QC>(F, t.BW, t6);
+                xpassTC_acc<D, QC>(t6, t.GWh, wz * gxx, A);
+            }
+            {   // y direction (+ mass)
+                double F[Q * QC];
+                if (OP == OP_RES) ypassC<D, Q, QC>(zB6, t.G, F);
+                else ypassC<D, Q, QC>(xB6, t.G, F);
+                if (CF == CF_CONST) {
+#pragma unroll
+                    for (int q = 0; q < Q * QC; ++q) F[q] *= a1c;
+                } else {
+#pragma unroll
+                    for (int q = 0; q < Q * QC; ++q) F[q] *= a1[q];
+                    if (OP == OP_JAC) {
+                        double zd[Q * QC];
+                        ypassC<D, Q, QC>(zB6, t.G, zd);
+#pragma unroll
+                        for (int q = 0; q < Q * QC; ++q) F[q] += a2x[q] * zd[q];
+                    }
+                }
+                ypassTC<D, Q, QC>(F, t.GW, t6);
+                const double cy = wz * gyy;
+#pragma unroll
+                for (int i = 0; i < D * QC; ++i) t6[i] = cy * t6[i] + c_m * vy6[i];
+                xpassTC_acc<D, QC>(t6, t.BWh, 1.0, A);
+            }
+            {   // z direction
+                double F[Q * QC];
+                getp(OP == OP_RES ? C::P_ZG : C::P_XG, p9);
+                xpassC<D, QC>(p9, t.B, t6);
+                ypassC<D, Q, QC>(t6, t.B, F);
+                if (CF == CF_CONST) {
+#pragma unroll
+                    for (int q = 0; q < Q * QC; ++q) F[q] *= a1c;
+                } else {
+#pragma unroll
+                    for (int q = 0; q < Q * QC; ++q) F[q] *= a1[q];
+                    if (OP == OP_JAC) {
+                        double zd[Q * QC];
+                        getp(C::P_ZG, p9);
+                        xpassC<D, QC>(p9, t.B, t6);
+                        ypassC<D, Q, QC>(t6, t.B, zd);
+#pragma unroll
+                        for (int q = 0; q < Q * QC; ++q) F[q] += a2x[q] * zd[q];
+                    }
+                }
+                ypassTC<D, Q, QC>(F, t.BW, t6);
+                xpassTC_acc<D, QC>(t6, t.BWh, wz * gzz, Bp);
+            }
+            flip_plane<D>(A, h);
+            flip_plane<D>(Bp, h);
+            // result planes alias input planes [0..3][qz] of this (element, qz): only this thread pair
+            // (adjacent lanes) ever touches them
+            __syncwarp(p2mask);
+            double* outp = pl + (h ? 2 : 0) * Q * PS;
+#pragma unroll
+            for (int m = 0; m < DD; ++m) { outp[m] = A[m]; outp[Q * PS + m] = Bp[m]; }
+        }
+        __syncthreads();
+
+        // ---------------- phase 3: transposed z contraction + scatter ----------------------------
+        for (int item = tid; item < nv * DD; item += T) {
+            const int el = item / DD, ij = item - el * DD;
+            const double* base = planes + el * ES + ij;
+            double Aq[Q], Bq[Q];
+#pragma unroll
+            for (int qz = 0; qz < Q; ++qz) {
+                Aq[qz] = base[qz * PS] + base[(2 * Q + qz) * PS];
+                Bq[qz] = base[(Q + qz) * PS] + base[(3 * Q + qz) * PS];
+            }
+#pragma unroll
+            for (int k = 0; k < D; ++k) {
+                double s = 0.0;
+#pragma unroll
+                for (int qz = 0; qz < Q; ++qz) s += t.B[qz * D + k] * Aq[qz] + t.G[qz * D + k] * Bq[qz];
+                const int g = ix[el * ND + ij + DD * k];
+                if (g >= 0) atomicAdd(a.y + g, s);
+                else if (!a.mask_out) atomicAdd(a.y + (~g), s);
+            }
+        }
+        __syncthreads();
+    }
+    cp_async_wait<0>();
+}
+
 }  // namespace jots

@@ -58,6 +58,41 @@ static int launch_slab2e(const FormArgs& a, const TablesRT& r, cudaStream_t st) 
     return 0;
 }
 
+template <int D, int Q, int OP, int CF, int E>
+static int launch_slab3e(const FormArgs& a, const TablesRT& r, cudaStream_t st) {
+    constexpr int T = ((E * (2 * Q > D * D ? 2 * Q : D * D)) + 31) / 32 * 32;
+    typedef SlabCfg<OP, CF> C;
+    Slab2Tables<D, Q> t;
+    for (int q = 0; q < Q; ++q) {
+        t.W[q] = r.W[q];
+        const double half = (Q % 2 == 1 && q == Q / 2) ? 0.5 : 1.0;
+        for (int i = 0; i < D; ++i) {
+            t.B[q * D + i] = r.B[q * D + i]; t.G[q * D + i] = r.G[q * D + i];
+            t.BW[q * D + i] = r.W[q] * r.B[q * D + i]; t.GW[q * D + i] = r.W[q] * r.G[q * D + i];
+            t.BWh[q * D + i] = half * r.W[q] * r.B[q * D + i]; t.GWh[q * D + i] = half * r.W[q] * r.G[q * D + i];
+        }
+    }
+    const size_t smem = Slab3Smem<D, Q, C::NP, E>::total;
+    auto kern = form_apply_slab3_kernel<D, Q, OP, CF, E, T>;
+    static int grid_max = 0;
+    if (!grid_max) {
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        int dev = 0, sms = 148, per_sm = 1;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, T, smem);
+        grid_max = sms * (per_sm > 0 ? per_sm : 1);
+    }
+    const int ntiles = (a.nelem + E - 1) / E;
+    kern<<<ntiles < grid_max ? ntiles : grid_max, T, smem, st>>>(a, t);
+    return 0;
+}
+template <int D, int Q, int OP, int CF>
+static int launch_slab3(const FormArgs& a, const TablesRT& r, cudaStream_t st) {
+    if constexpr (Q == 4) return launch_slab3e<D, Q, OP, CF, 14>(a, r, st);
+    else return launch_slab3e<D, Q, OP, CF, 32>(a, r, st);
+}
+
 static int slab_elems() {
     static int v = -1;
     if (v < 0) { const char* e = getenv("JOTS_SLAB_ELEMS"); v = e ? atoi(e) : 14; }
@@ -71,13 +106,13 @@ static int launch_slab2(const FormArgs& a, const TablesRT& r, cudaStream_t st) {
 
 static int slab_variant() {
     static int v = -1;
-    if (v < 0) { const char* e = getenv("JOTS_SLAB_VARIANT"); v = e ? atoi(e) : 2; }
+    if (v < 0) { const char* e = getenv("JOTS_SLAB_VARIANT"); v = e ? atoi(e) : 3; }
     return v;
 }
 
 template <int D, int Q>
 static int dispatch(int op, int cf, const FormArgs& a, const TablesRT& t, cudaStream_t st) {
-#define CASE(OPV, CFV) if (op == OPV && cf == CFV) return slab_variant() == 1 ? launch_slab<D, Q, OPV, CFV>(a, t, st) : launch_slab2<D, Q, OPV, CFV>(a, t, st);
+#define CASE(OPV, CFV) if (op == OPV && cf == CFV) return slab_variant() == 1 ? launch_slab<D, Q, OPV, CFV>(a, t, st) : slab_variant() == 2 ? launch_slab2<D, Q, OPV, CFV>(a, t, st) : launch_slab3<D, Q, OPV, CFV>(a, t, st);
     CASE(OP_LIN, CF_CONST) CASE(OP_LIN, CF_K) CASE(OP_JAC, CF_K) CASE(OP_RES, CF_CONST) CASE(OP_RES, CF_K)
 #undef CASE
     return 1;
