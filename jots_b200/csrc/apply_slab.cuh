@@ -907,7 +907,7 @@ __global__ void __launch_bounds__(T) form_apply_slab3_kernel(const FormArgs a, c
                         double f[NFA];
                         nodal_fields<CF, OP>(a.mat, zr[k], f);
 #pragma unroll
-                        for (int n = 0; n < NF; ++n) fr[n][k] = f[n];
+                        for (int n = 0; n < NF; ++n) fr[n][k] = (a.ck * a.inv_rc) * f[n];
                     }
                 }
             }
@@ -967,9 +967,6 @@ __global__ void __launch_bounds__(T) form_apply_slab3_kernel(const FormArgs a, c
                 getp(C::P_F0, p9);
                 xpassC<D, QC>(p9, t.B, t6);
                 ypassC<D, Q, QC>(t6, t.B, a1);
-                const double sc = a.ck * a.inv_rc;
-#pragma unroll
-                for (int q = 0; q < Q * QC; ++q) a1[q] *= sc;
                 if (OP == OP_JAC) {
                     getp(C::P_F0 + 1, p9);
                     xpassC<D, QC>(p9, t.B, t6);
@@ -984,9 +981,8 @@ __global__ void __launch_bounds__(T) form_apply_slab3_kernel(const FormArgs a, c
                 double xv[Q * QC];
                 ypassC<D, Q, QC>(xB6, t.B, xv);
                 if (OP == OP_JAC && CF != CF_CONST) {
-                    const double sc = a.ck * a.inv_rc;
 #pragma unroll
-                    for (int q = 0; q < Q * QC; ++q) a2x[q] *= sc * xv[q];
+                    for (int q = 0; q < Q * QC; ++q) a2x[q] *= xv[q];
                 }
                 ypassTC<D, Q, QC>(xv, t.BW, vy6);
             }
@@ -1068,9 +1064,10 @@ __global__ void __launch_bounds__(T) form_apply_slab3_kernel(const FormArgs a, c
             // result planes alias input planes [0..3][qz] of this (element, qz): only this thread pair
             // (adjacent lanes) ever touches them
             __syncwarp(p2mask);
-            double* outp = pl + (h ? 2 : 0) * Q * PS;
+            // A -> plane h, Bp -> plane 2 + h: the pair's stores differ by Q*PS == 8 (mod 16) 8-byte slots
+            double* outp = pl + (h ? 1 : 0) * Q * PS;
 #pragma unroll
-            for (int m = 0; m < DD; ++m) { outp[m] = A[m]; outp[Q * PS + m] = Bp[m]; }
+            for (int m = 0; m < DD; ++m) { outp[m] = A[m]; outp[2 * Q * PS + m] = Bp[m]; }
         }
         __syncthreads();
 
@@ -1081,8 +1078,8 @@ __global__ void __launch_bounds__(T) form_apply_slab3_kernel(const FormArgs a, c
             double Aq[Q], Bq[Q];
 #pragma unroll
             for (int qz = 0; qz < Q; ++qz) {
-                Aq[qz] = base[qz * PS] + base[(2 * Q + qz) * PS];
-                Bq[qz] = base[(Q + qz) * PS] + base[(3 * Q + qz) * PS];
+                Aq[qz] = base[qz * PS] + base[(Q + qz) * PS];
+                Bq[qz] = base[(2 * Q + qz) * PS] + base[(3 * Q + qz) * PS];
             }
 #pragma unroll
             for (int k = 0; k < D; ++k) {
