@@ -341,7 +341,7 @@ struct Slab2Tables {
 // 64-bit shared-memory accesses: a half-warp must touch 16 distinct 8-byte slots.  Phase 1/3 lanes
 // run over (element, ij) items -> element stride == D*D (mod 16); phase 2 lanes over (element, qz,
 // h) -> plane stride chosen so that {qz*PS + el*ES} stay distinct (D=3: 10, D=2: 5).
-template <int D> struct Plane2Stride { static constexpr int value = D == 3 ? 10 : D == 2 ? 5 : D * D + 1; };
+template <int D> struct Plane2Stride { static constexpr int value = D == 3 ? 10 : D == 2 ? 5 : 17; };
 template <int D, int Q, int NP> struct Elem2Stride {
     static constexpr int PS = Plane2Stride<D>::value;
     static constexpr int raw = (NP + 4) * Q * PS;

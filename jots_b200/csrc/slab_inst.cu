@@ -60,7 +60,8 @@ static int launch_slab2e(const FormArgs& a, const TablesRT& r, cudaStream_t st) 
 
 template <int D, int Q, int OP, int CF, int E>
 static int launch_slab3e(const FormArgs& a, const TablesRT& r, cudaStream_t st) {
-    constexpr int T = ((E * (2 * Q > D * D ? 2 * Q : D * D)) + 31) / 32 * 32;
+    // thread count follows phase 2 (2Q threads per element); phases 1/3 read shared memory and loop
+    constexpr int T = (E * 2 * Q + 31) / 32 * 32;
     typedef SlabCfg<OP, CF> C;
     Slab2Tables<D, Q> t;
     for (int q = 0; q < Q; ++q) {
@@ -90,6 +91,7 @@ static int launch_slab3e(const FormArgs& a, const TablesRT& r, cudaStream_t st) 
 template <int D, int Q, int OP, int CF>
 static int launch_slab3(const FormArgs& a, const TablesRT& r, cudaStream_t st) {
     if constexpr (Q == 4) return launch_slab3e<D, Q, OP, CF, 14>(a, r, st);
+    else if constexpr (Q == 5) return launch_slab3e<D, Q, OP, CF, 12>(a, r, st);
     else return launch_slab3e<D, Q, OP, CF, 32>(a, r, st);
 }
 
@@ -112,7 +114,14 @@ static int slab_variant() {
 
 template <int D, int Q>
 static int dispatch(int op, int cf, const FormArgs& a, const TablesRT& t, cudaStream_t st) {
-#define CASE(OPV, CFV) if (op == OPV && cf == CFV) return slab_variant() == 1 ? launch_slab<D, Q, OPV, CFV>(a, t, st) : slab_variant() == 2 ? launch_slab2<D, Q, OPV, CFV>(a, t, st) : launch_slab3<D, Q, OPV, CFV>(a, t, st);
+#define CASE(OPV, CFV)                                                                              \
+    if (op == OPV && cf == CFV) {                                                                   \
+        if constexpr (Q < 5) {                                                                      \
+            if (slab_variant() == 1) return launch_slab<D, Q, OPV, CFV>(a, t, st);                   \
+            if (slab_variant() == 2) return launch_slab2<D, Q, OPV, CFV>(a, t, st);                  \
+        }                                                                                           \
+        return launch_slab3<D, Q, OPV, CFV>(a, t, st);                                              \
+    }
     CASE(OP_LIN, CF_CONST) CASE(OP_LIN, CF_K) CASE(OP_JAC, CF_K) CASE(OP_RES, CF_CONST) CASE(OP_RES, CF_K)
 #undef CASE
     return 1;
@@ -167,6 +176,7 @@ int launch_form_diag_slab(int p, int op, int cf, const FormArgs& a, const Tables
 int launch_form_apply_slab(int p, int op, int cf, const FormArgs& a, const TablesRT& t, cudaStream_t st) {
     if (p == 1) return dispatch<2, 3>(op, cf, a, t, st);
     if (p == 2) return dispatch<3, 4>(op, cf, a, t, st);
+    if (p == 3) return dispatch<4, 5>(op, cf, a, t, st);
     return 1;
 }
 

@@ -125,7 +125,7 @@ def test_nonlinear_forms(J, tmp_path, dim, p, props):
     assert rel(dev.op.neumann_vector(), it.b_vec) < APPLY_TOL
 
 
-@pytest.mark.parametrize("p", [1, 2])
+@pytest.mark.parametrize("p", [1, 2, 3])
 @pytest.mark.parametrize("props", ["const", "k"])
 @pytest.mark.parametrize("sim", ["Linearized_Unsteady", "Nonlinear_Unsteady"])
 def test_axis_aligned_fast_path(J, tmp_path, sim, props, p):
