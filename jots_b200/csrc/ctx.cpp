@@ -276,4 +276,12 @@ double Ctx::dot(const double* a, const double* b) {
 
 double Ctx::norm(const double* a) { return std::sqrt(dot(a, a)); }
 
+double Ctx::max_local(const double* a) {
+    v_max(stream, n, a, dot_scratch(), d_scal.p);
+    ++stats.kernel_launches;
+    JOTS_CUDA(cudaMemcpyAsync(h_scal, d_scal.p, sizeof(double), cudaMemcpyDeviceToHost, stream));
+    JOTS_CUDA(cudaStreamSynchronize(stream));
+    return h_scal[0];
+}
+
 }  // namespace jots

@@ -129,6 +129,7 @@ public:
     void dots(int nv, const double* const* a, const double* const* b, double* out);
     void fetch_scalars(int nv, double* out);   // d_scal -> host (+ allreduce across ranks)
     double norm(const double* a) ;
+    double max_local(const double* a);   // rank-local maximum, as Vector::Max() in the reference
     void zero(double* y) { JOTS_CUDA(cudaMemsetAsync(y, 0, n * sizeof(double), stream)); }
     void copy(const double* x, double* y) { JOTS_CUDA(cudaMemcpyAsync(y, x, n * sizeof(double), cudaMemcpyDeviceToDevice, stream)); }
     void zero_ess(double* y) { v_set_idx(stream, (int)ess.size(), d_ess.p, 0.0, y); stats.kernel_launches += !ess.empty(); }

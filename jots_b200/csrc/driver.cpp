@@ -248,6 +248,8 @@ void JOTSDriver::Step() {
     UpdateAndApplyBCs();
     UpdateMatProps(true);
     Iteration();
+    // PostprocessIteration: blow-up check on the rank-local maximum (jots_driver.cpp:739-743)
+    if (check_blowup && ctx->max_local(u.p) > 1e10) throw std::runtime_error("JOTS has blown up");
 }
 
 int JOTSDriver::Run(int max_steps) {

@@ -44,6 +44,7 @@ public:
     int it_num = 0, max_timesteps = 0;
     double time = 0.0, dt = 0.0;
     bool initialized_bcs = false;
+    bool check_blowup = true;
     bool has_prop[3] = {false, false, false};
 };
 

@@ -117,6 +117,38 @@ __global__ void __launch_bounds__(VEC_THREADS) k_cg_update(int64_t n, int64_t n_
     grid_reduce<1>(v, s, result);
 }
 
+// max over a vector (JOTSDriver::PostprocessIteration blow-up check, jots_driver.cpp:739): per-block
+// maxima, final maximum by the last block to finish
+__global__ void __launch_bounds__(VEC_THREADS) k_max(int64_t n, const double* __restrict__ x, DotScratch s, double* result) {
+    __shared__ double sh[VEC_THREADS / 32];
+    __shared__ bool last;
+    double v = -1.7976931348623157e308;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) v = fmax(v, x[i]);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    if (lane == 0) sh[wid] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < VEC_THREADS / 32; ++w) v = fmax(v, sh[w]);
+        s.partial[blockIdx.x] = v;
+        __threadfence();
+        last = (atomicAdd(s.counter, 1u) == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (last && threadIdx.x == 0) {
+        __threadfence();
+        double m = s.partial[0];
+        for (int b = 1; b < (int)gridDim.x; ++b) m = fmax(m, s.partial[b]);
+        *result = m;
+        *s.counter = 0u;
+    }
+}
+void v_max(cudaStream_t st, int64_t n, const double* x, DotScratch s, double* result) {
+    k_max<<<grid_for(n, 8), VEC_THREADS, 0, st>>>(n, x, s, result);
+}
+
 void v_waxpby(cudaStream_t st, int64_t n, double a, const double* x, double b, const double* y, double* w) {
     k_waxpby<<<grid_for(n), VEC_THREADS, 0, st>>>(n, a, x, b, y, w);
 }

@@ -22,6 +22,7 @@ void v_set_idx(cudaStream_t st, int n, const int* idx, double v, double* y);
 void v_copy_idx(cudaStream_t st, int n, const int* idx, const double* x, double* y);
 void v_pack(cudaStream_t st, int n, const int* idx, const double* y, double* out);
 void v_reduce_shared(cudaStream_t st, int n, const int* dof, const int* ptr, const int* src, const double* recv, double* y);
+void v_max(cudaStream_t st, int64_t n, const double* x, DotScratch s, double* result);
 void v_dots(cudaStream_t st, int64_t n, int nv, const double* const* a, const double* const* b, DotScratch s, double* result);
 void v_cg_update(cudaStream_t st, int64_t n, int64_t n_owned, double alpha, const double* d, const double* Ad, double* x, double* r,
                  const double* dinv, double* z, DotScratch s, double* result);

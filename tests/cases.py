@@ -114,8 +114,9 @@ def write_brick_mesh(path, nx, ny, nz, lx, ly, lz, grade=0.0, shear=0.0):
         f.write("\n".join(out) + "\n")
 
 
-def write_quad_mesh(path, nx, ny, lx, ly, y0=0.0, grade=0.0, shear=0.0):
-    """2-D rectangle, attributes 1=bottom 2=right 3=top 4=left (plate.mesh convention)."""
+def write_quad_mesh(path, nx, ny, lx, ly, y0=0.0, grade=0.0, shear=0.0, attrs=(1, 2, 3, 4)):
+    """2-D rectangle; attrs = attributes of (bottom, right, top, left): (1, 2, 3, 4) is the plate.mesh
+    convention, (1, 3, 1, 2) the bar.mesh one (1 = long sides, 2 = x0, 3 = x1)."""
     vx = nx + 1
     vid = lambda i, j: i + vx * j
     out = ["MFEM mesh v1.0", "", "dimension", "2", "", "elements", str(nx * ny)]
@@ -124,11 +125,11 @@ def write_quad_mesh(path, nx, ny, lx, ly, y0=0.0, grade=0.0, shear=0.0):
             out.append("1 3 %d %d %d %d" % (vid(i, j), vid(i + 1, j), vid(i + 1, j + 1), vid(i, j + 1)))
     b = []
     for i in range(nx):
-        b.append((1, [vid(i, 0), vid(i + 1, 0)]))
-        b.append((3, [vid(i + 1, ny), vid(i, ny)]))
+        b.append((attrs[0], [vid(i, 0), vid(i + 1, 0)]))
+        b.append((attrs[2], [vid(i + 1, ny), vid(i, ny)]))
     for j in range(ny):
-        b.append((2, [vid(nx, j), vid(nx, j + 1)]))
-        b.append((4, [vid(0, j + 1), vid(0, j)]))
+        b.append((attrs[1], [vid(nx, j), vid(nx, j + 1)]))
+        b.append((attrs[3], [vid(0, j + 1), vid(0, j)]))
     out += ["", "boundary", str(len(b))]
     out += ["%d 1 %d %d" % (a, v[0], v[1]) for a, v in b]
     out += ["", "vertices", str(vx * (ny + 1)), "2"]

@@ -248,3 +248,64 @@ def test_errors_are_reported_not_fatal(J, tmp_path):
     bad.write_text("[FiniteElementSetup]\nMesh_File=/nonexistent.mesh\n[MaterialProperties]\n[BoundaryConditions]\n")
     with pytest.raises(J.JotsError):
         J.Driver(str(bad))
+
+
+# ---- the shipped 2-D example configurations, restated on regenerated meshes --------------------------
+_EX = {
+    # examples/steady_heat/Heated_Plate/Heated_Plate.ini: [NewtonSolverSettings] is commented out ->
+    # newton_max_iter = 0 -> zero Newton iterations; "on" = section enabled
+    "Heated_Plate_steady_as_shipped": dict(sim="Steady", order=2, mesh=("plate", 12, 6), t0=310, newton=None, time=False,
+        props=[("Thermal_Conductivity_k", "Uniform, 100")], bcs=["Isothermal, 310", HF0, "Isothermal, 300", HF0]),
+    "Heated_Plate_steady_newton_on": dict(sim="Steady", order=2, mesh=("plate", 12, 6), t0=310, newton=20, time=False,
+        props=[("Thermal_Conductivity_k", "Uniform, 100")], bcs=["Isothermal, 310", HF0, "Isothermal, 300", HF0]),
+    # examples/linearized_unsteady_heat/Sinusoidal_Isothermal_Heated_Bar (Q1, bar.mesh, 3 attributes)
+    "Sinusoidal_Isothermal_Heated_Bar": dict(sim="Linearized_Unsteady", order=1, mesh=("bar", 40, 4), t0=300, steps=60, dt="0.001",
+        props=[("Density_rho", "Uniform, 0.1"), ("Specific_Heat_C", "Uniform, 1000"), ("Thermal_Conductivity_k", "Uniform, 100")],
+        bcs=[HF0, "Isothermal, 300", "Sinusoidal_Isothermal, 5, 6.283185307, 0, 300"]),
+    "Sinusoidal_HeatFlux_Heated_Bar": dict(sim="Linearized_Unsteady", order=1, mesh=("bar", 40, 4), t0=300, steps=60, dt="0.001",
+        props=[("Density_rho", "Uniform, 0.1"), ("Specific_Heat_C", "Uniform, 1000"), ("Thermal_Conductivity_k", "Uniform, 100")],
+        bcs=[HF0, "Isothermal, 300", "Sinusoidal_HeatFlux, 1000, 6.283185307, 0, 0"]),
+    # examples/linearized_unsteady_heat/Quiescent_IC_HeatFlux: explicit Euler, Max_Timesteps=5e6 is not
+    # an int -> boost falls back to the default 100 steps
+    "Quiescent_IC_HeatFlux": dict(sim="Linearized_Unsteady", order=2, mesh=("plate", 8, 4), t0=300, steps="5e6", dt="1e-7",
+        scheme="Euler_Explicit", props=[("Density_rho", "Uniform, 1"), ("Specific_Heat_C", "Uniform, 1"), ("Thermal_Conductivity_k", "Uniform, 0.5")],
+        bcs=[HF0, HF0, HF0, HF0]),
+}
+
+
+@pytest.mark.parametrize("name", sorted(_EX))
+def test_shipped_2d_example_configs(J, tmp_path, name):
+    from oracle import jots as OJ
+    c = _EX[name]
+    mesh = str(tmp_path / "m.mesh")
+    kind, nx, ny = c["mesh"]
+    if kind == "plate":
+        write_quad_mesh(mesh, nx, ny, 1.0, 0.25, y0=-0.25)
+    else:
+        write_quad_mesh(mesh, nx, ny, 1.0, 0.1, attrs=(1, 3, 1, 2))
+    txt = ini_text(c["sim"], mesh, c["t0"], c["props"], c["bcs"], time=c.get("time", True), newton=c.get("newton"),
+                   steps=1, dt=c.get("dt", "1e-2"), order=c["order"], scheme=c.get("scheme", "Euler_Implicit"))
+    txt = txt.replace("Max_Timesteps=1\n", "Max_Timesteps=%s\n" % c.get("steps", 1))
+    ini = str(tmp_path / "c.ini")
+    with open(ini, "w") as f:
+        f.write(txt)
+    dev = J.Driver(ini)
+    orc = OJ.JOTSDriver(OJ.Config(ini))
+    n_dev = dev.run()
+    u_ref = orc.run()
+    assert n_dev == orc.it.stats["steps"]
+    if name == "Quiescent_IC_HeatFlux":
+        assert n_dev == 100
+    if name == "Heated_Plate_steady_as_shipped":
+        assert dev.ctx.stats()["newton_iters"] == 0
+    assert rel(dev.get_u(), u_ref) < FIELD_TOL
+
+
+def test_blow_up_is_reported_like_the_reference(J, tmp_path):
+    """An unstable explicit run trips the u.Max() > 1e10 check of PostprocessIteration
+    (jots_driver.cpp:739-743): an error status on our side, MFEM_ABORT in the reference."""
+    dev, orc = build(J, tmp_path, "Linearized_Unsteady", 2, 2, "const", scheme="Euler_Explicit", dt="1e-1", steps=400, n=(6, 4, 1))
+    with pytest.raises(J.JotsError, match="blown up"):
+        dev.run()
+    with pytest.raises(RuntimeError, match="blown up"):
+        orc.run()
