@@ -260,6 +260,16 @@ void Ctx::fetch_scalars(int nv, double* out) {
     for (int i = 0; i < nv; ++i) out[i] = h_scal[i];
 }
 
+void Ctx::allreduce_scalars(double* d_vals, int nv) {
+    if (halo) halo_allreduce(*this, d_vals, nv);
+}
+
+void Ctx::copy_scalars(int nv, double* out) {
+    JOTS_CUDA(cudaMemcpyAsync(h_scal, d_scal.p, nv * sizeof(double), cudaMemcpyDeviceToHost, stream));
+    JOTS_CUDA(cudaStreamSynchronize(stream));
+    for (int i = 0; i < nv; ++i) out[i] = h_scal[i];
+}
+
 void Ctx::dots(int nv, const double* const* a, const double* const* b, double* out) {
     v_dots(stream, n_owned, nv, a, b, dot_scratch(), d_scal.p);
     ++stats.kernel_launches; stats.dots += nv;

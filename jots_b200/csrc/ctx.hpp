@@ -128,6 +128,8 @@ public:
     double dot(const double* a, const double* b);
     void dots(int nv, const double* const* a, const double* const* b, double* out);
     void fetch_scalars(int nv, double* out);   // d_scal -> host (+ allreduce across ranks)
+    void allreduce_scalars(double* d_vals, int nv);   // stream-ordered all-reduce of device scalars (no-op on one GPU)
+    void copy_scalars(int nv, double* out);            // d_scal[0..nv) -> host, one synchronisation
     double norm(const double* a) ;
     double max_local(const double* a);   // rank-local maximum, as Vector::Max() in the reference
     void zero(double* y) { JOTS_CUDA(cudaMemsetAsync(y, 0, n * sizeof(double), stream)); }

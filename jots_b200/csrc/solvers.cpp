@@ -106,9 +106,11 @@ void ChebyshevPrec::mult(const double* r, double* z) {
     v_scale(c->stream, n, coef[order], rs, u);
     c->stats.kernel_launches += 2;
     for (int i = order - 1; i >= 0; --i) {
-        ahat(u, au, tmp);
-        v_waxpby(c->stream, n, 1.0, au, coef[i], rs, u);
-        ++c->stats.kernel_launches;
+        // u = ds * A (ds * u) + c_i * rs
+        v_mul(c->stream, n, ds.p, u, tmp);
+        A->mult(tmp, au);
+        v_mul_axpby(c->stream, n, ds.p, 1.0, au, coef[i], rs, u);
+        c->stats.kernel_launches += 2;
     }
     v_mul(c->stream, n, ds.p, u, z);
     ++c->stats.kernel_launches;
@@ -215,7 +217,7 @@ void Krylov::gmres(const double* b, double* x, bool flexible) {
     double beta = c->norm(r);
     const double final_norm = std::max(rel_tol * beta, abs_tol);
     if (beta <= final_norm) { info.converged = true; info.final_norm = beta; return; }
-    std::vector<double> H((size_t)(m + 1) * m, 0.0), s(m + 1, 0.0), cs(m + 1, 0.0), sn(m + 1, 0.0), yv(m + 1, 0.0);
+    std::vector<double> H((size_t)(m + 1) * m, 0.0), s(m + 1, 0.0), cs(m + 1, 0.0), sn(m + 1, 0.0), yv(m + 2, 0.0);
     auto Hh = [&](int i, int j) -> double& { return H[(size_t)i * m + j]; };
     auto update = [&](int k) {
         for (int i = 0; i <= k; ++i) yv[i] = s[i];
@@ -235,12 +237,18 @@ void Krylov::gmres(const double* b, double* x, bool flexible) {
         while (i < m && j <= max_iter) {
             if (flexible) { P(V(i), Z(i)); apply(Z(i), r); }
             else { apply(V(i), tmp); P(tmp, r); }
-            for (int k = 0; k <= i; ++k) {
-                Hh(k, i) = c->dot(r, V(k));
-                v_axpy(st, n, -Hh(k, i), V(k), r);
+            // modified Gram-Schmidt, device-chained: step k subtracts the previous projection and forms
+            // the next inner product in one pass; the i+2 scalars come back in a single copy
+            for (int k = 0; k <= i + 1; ++k) {
+                v_mgs_step(st, n, c->n_owned, r, k > 0 ? V(k - 1) : nullptr, k > 0 ? c->d_scal.p + (k - 1) : nullptr,
+                           k <= i ? V(k) : nullptr, c->dot_scratch(), c->d_scal.p + k);
                 ++c->stats.kernel_launches;
+                c->allreduce_scalars(c->d_scal.p + k, 1);
             }
-            Hh(i + 1, i) = c->norm(r);
+            c->copy_scalars(i + 2, yv.data());
+            c->stats.dots += i + 2;
+            for (int k = 0; k <= i; ++k) Hh(k, i) = yv[k];
+            Hh(i + 1, i) = std::sqrt(yv[i + 1]);
             v_scale(st, n, 1.0 / Hh(i + 1, i), r, V(i + 1));
             ++c->stats.kernel_launches;
             for (int k = 0; k < i; ++k) app_rot(Hh(k, i), Hh(k + 1, i), cs[k], sn[k]);

@@ -149,6 +149,37 @@ void v_max(cudaStream_t st, int64_t n, const double* x, DotScratch s, double* re
     k_max<<<grid_for(n, 8), VEC_THREADS, 0, st>>>(n, x, s, result);
 }
 
+// one modified Gram-Schmidt step without a host round trip:
+//   r -= (*hprev) * Vprev   (skipped when Vprev == nullptr)
+//   *result = (r, Vk) over the owned entries, or (r, r) when Vk == nullptr
+// hprev is the device scalar the previous step produced (already all-reduced on multi-GPU runs).
+__global__ void __launch_bounds__(VEC_THREADS) k_mgs_step(int64_t n, int64_t n_owned, double* r, const double* __restrict__ Vprev,
+                                                           const double* __restrict__ hprev, const double* __restrict__ Vk,
+                                                           DotScratch s, double* result) {
+    double v[1] = {0.0};
+    const double h = Vprev ? *hprev : 0.0;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        double ri = r[i];
+        if (Vprev) { ri -= h * Vprev[i]; r[i] = ri; }
+        if (i < n_owned) v[0] += ri * (Vk ? Vk[i] : ri);
+    }
+    grid_reduce<1>(v, s, result);
+}
+void v_mgs_step(cudaStream_t st, int64_t n, int64_t n_owned, double* r, const double* Vprev, const double* hprev, const double* Vk,
+                DotScratch s, double* result) {
+    k_mgs_step<<<grid_for(n, 8), VEC_THREADS, 0, st>>>(n, n_owned, r, Vprev, hprev, Vk, s, result);
+}
+// y = d * x * a + b * z   (Chebyshev Horner step: u = ds * (A t) + c_i * rs)
+__global__ void k_mul_axpby(int64_t n, const double* __restrict__ d, double a, const double* __restrict__ x, double b,
+                            const double* __restrict__ z, double* y) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) y[i] = a * d[i] * x[i] + b * z[i];
+}
+void v_mul_axpby(cudaStream_t st, int64_t n, const double* d, double a, const double* x, double b, const double* z, double* y) {
+    k_mul_axpby<<<grid_for(n), VEC_THREADS, 0, st>>>(n, d, a, x, b, z, y);
+}
+
 void v_waxpby(cudaStream_t st, int64_t n, double a, const double* x, double b, const double* y, double* w) {
     k_waxpby<<<grid_for(n), VEC_THREADS, 0, st>>>(n, a, x, b, y, w);
 }
