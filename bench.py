@@ -295,6 +295,13 @@ def main():
     peak = float(peaks.get("hbm_gbs", 6650.0))
     alg_bytes = 24.0 * ndof
     achieved = alg_bytes / (apply_ms * 1e-3) / 1e9
+    # dram__bytes_read + dram__bytes_write of the same kernel from the committed ncu --set full capture
+    traffic, fp64_pct = None, None
+    tr_path = os.path.join(ROOT, "profiles", "traffic_jac_q2_n128.json")
+    if os.path.exists(tr_path) and args.order == 2 and args.n == 128:
+        tr = json.load(open(tr_path))
+        if tr.get("n_dof") == ndof:
+            traffic, fp64_pct = tr["dram_bytes_per_launch"], tr.get("fp64_pipe_active_pct")
 
     def finish():
         if world > 1:
@@ -314,7 +321,12 @@ def main():
                     "ms_per_step": 1e3 * e2e_s / K},
             "gpu_launches": st["kernel_launches"],
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "form_apply_kernel<OP_JAC,CF_K> (Jacobian-vector apply, 24 B/DOF algorithmic)",
+                         "traffic": traffic, "algorithmic_bytes": alg_bytes,
+                         "kernel": "form_apply_slab3_kernel<OP_JAC,CF_K> (Jacobian-vector apply, 24 B/DOF algorithmic; incl. the "
+                                   "memset of y and the essential-row fix-up launches)",
+                         "note": "this kernel is FP64-pipe bound (about 740 FP64 instructions per DOF against 24 B/DOF), not HBM "
+                                 "bound: see fp64_pipe_active_pct (ncu) and DESIGN.md 5.1",
+                         "fp64_pipe_active_pct": fp64_pct,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6.65 TB/s",
                          "frac_of_8TBs_spec": achieved / 8000.0}}
     if not args.no_cpu and world == 1:
