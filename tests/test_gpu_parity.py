@@ -211,6 +211,20 @@ def test_explicit_paths(J, tmp_path, sim, scheme):
 
 
 @pytest.mark.parametrize("name", sorted(CASES))
+def test_reference_regressions_against_committed_golden_fields(J, tmp_path, name):
+    """Device field vs the committed oracle fixture (tests/golden/regressions.npz, made by
+    tests/golden/make_golden.py) for all eight regression configurations: <= 1e-8 relative l2."""
+    import os
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "regressions.npz"))
+    dev = J.Driver(make_case(name, tmp_path))
+    dev.run()
+    assert rel(dev.get_u(), gold[name]) < FIELD_TOL
+    st = dev.ctx.stats()
+    assert st["steps"] == gold[name + "__stats"][0]
+    assert abs(st["newton_iters"] - gold[name + "__stats"][1]) <= 2
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
 def test_reference_regressions(J, tmp_path, name):
     """The reference's own regression cases: device field vs the oracle's (<= 1e-8 relative l2) and
     vs the analytic solution with the reference's error functional and tolerance."""

@@ -32,3 +32,12 @@ def test_oracle_on_shipped_mesh_files(name, tmp_path):
     """Same pins on the reference's own mesh files (Pointwise vertex order, un-structured numbering)."""
     err, drv = _run(name, tmp_path, use_ref=True)
     assert np.isfinite(err) and err <= CASES[name]["eps"], (name, err)
+
+
+@pytest.mark.parametrize("name", ["Reinert_B1", "Danish_Model1_Neumann"])
+def test_committed_golden_fields_are_the_oracle_output(name, tmp_path):
+    """tests/golden/regressions.npz (the fixture the GPU tests compare against) is reproducible."""
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "regressions.npz"))
+    ini = make_case(name, tmp_path)
+    u = OJ.JOTSDriver(OJ.Config(ini)).run()
+    assert np.linalg.norm(u - gold[name]) <= 1e-12 * np.linalg.norm(gold[name])
