@@ -168,6 +168,13 @@ __global__ void __launch_bounds__(Q* Q* NE) form_apply_kernel(const FormArgs a, 
 #pragma unroll
         for (int n = 0; n < NF; ++n) f[n] = fq[n][qz];
         const QCoef c = qpoint_coef<CF, OP>(a, f);
+        if (a.geomq) {
+            // general multilinear element: geometric factors of this quadrature point
+            const double* g = a.geomq + ((size_t)e * (Q * Q * QZ) + tx + Q * (ty + Q * qz)) * 10;
+#pragma unroll
+            for (int i = 0; i < 9; ++i) iJ[i] = g[i];
+            detJ = g[9];
+        }
         const double w = t.W[tx] * t.W[ty] * t.Wz[qz] * detJ;
         double px[3] = {0, 0, 0}, pz[3] = {0, 0, 0};
         if (NEED_GX) {

@@ -62,11 +62,22 @@ void Ctx::init(const Space& s, int dev) {
     n = s.ndof; n_owned = s.ndof;
     if (const char* ev = std::getenv("JOTS_DISABLE_SLAB")) use_slab = !(ev[0] == '1');
     fill_tables(tabs, s.dim, s.p);
-    // geometry: affine elements only (every mesh the reference ships and the synthetic bricks)
+    // geometry: affine elements get one record each (one shared record when all are identical);
+    // general multilinear meshes get a record per quadrature point (d_geomq)
     const int dim = s.dim, nv = 1 << dim;
     std::vector<double> geom((size_t)s.nelem * 10);
-    bool uniform = true;
+    bool uniform = true, affine = true;
     geom_diag = true;
+    auto record = [](const double J[3][3], double* g) {
+        const double det = J[0][0] * (J[1][1] * J[2][2] - J[1][2] * J[2][1]) - J[0][1] * (J[1][0] * J[2][2] - J[1][2] * J[2][0]) +
+                           J[0][2] * (J[1][0] * J[2][1] - J[1][1] * J[2][0]);
+        if (!(det > 0)) throw std::runtime_error("non-positive element Jacobian");
+        // invJ[a][i] = d xi_a / d x_i
+        g[0] = (J[1][1] * J[2][2] - J[1][2] * J[2][1]) / det; g[1] = (J[0][2] * J[2][1] - J[0][1] * J[2][2]) / det; g[2] = (J[0][1] * J[1][2] - J[0][2] * J[1][1]) / det;
+        g[3] = (J[1][2] * J[2][0] - J[1][0] * J[2][2]) / det; g[4] = (J[0][0] * J[2][2] - J[0][2] * J[2][0]) / det; g[5] = (J[0][2] * J[1][0] - J[0][0] * J[1][2]) / det;
+        g[6] = (J[1][0] * J[2][1] - J[1][1] * J[2][0]) / det; g[7] = (J[0][1] * J[2][0] - J[0][0] * J[2][1]) / det; g[8] = (J[0][0] * J[1][1] - J[0][1] * J[1][0]) / det;
+        g[9] = det;
+    };
     for (int64_t el = 0; el < s.nelem; ++el) {
         const double* X = &s.elem_corner[(size_t)el * nv * dim];
         double J[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
@@ -74,22 +85,14 @@ void Ctx::init(const Space& s, int dev) {
             for (int i = 0; i < dim; ++i) J[i][a] = X[(1 << a) * dim + i] - X[i];
         double scale = 0.0;
         for (int a = 0; a < dim; ++a) for (int i = 0; i < dim; ++i) scale = std::max(scale, std::fabs(J[i][a]));
-        for (int c = 0; c < nv; ++c)
+        for (int c = 0; c < nv && affine; ++c)
             for (int i = 0; i < dim; ++i) {
                 double x = X[i];
                 for (int a = 0; a < dim; ++a) if ((c >> a) & 1) x += J[i][a];
-                if (std::fabs(x - X[c * dim + i]) > 1e-10 * scale)
-                    throw std::runtime_error("non-affine (general multilinear) elements are not supported by the device kernels yet");
+                if (std::fabs(x - X[c * dim + i]) > 1e-10 * scale) { affine = false; break; }
             }
-        const double det = J[0][0] * (J[1][1] * J[2][2] - J[1][2] * J[2][1]) - J[0][1] * (J[1][0] * J[2][2] - J[1][2] * J[2][0]) +
-                           J[0][2] * (J[1][0] * J[2][1] - J[1][1] * J[2][0]);
-        if (!(det > 0)) throw std::runtime_error("non-positive element Jacobian");
         double* g = &geom[(size_t)el * 10];
-        // invJ[a][i] = d xi_a / d x_i
-        g[0] = (J[1][1] * J[2][2] - J[1][2] * J[2][1]) / det; g[1] = (J[0][2] * J[2][1] - J[0][1] * J[2][2]) / det; g[2] = (J[0][1] * J[1][2] - J[0][2] * J[1][1]) / det;
-        g[3] = (J[1][2] * J[2][0] - J[1][0] * J[2][2]) / det; g[4] = (J[0][0] * J[2][2] - J[0][2] * J[2][0]) / det; g[5] = (J[0][2] * J[1][0] - J[0][0] * J[1][2]) / det;
-        g[6] = (J[1][0] * J[2][1] - J[1][1] * J[2][0]) / det; g[7] = (J[0][1] * J[2][0] - J[0][0] * J[2][1]) / det; g[8] = (J[0][0] * J[1][1] - J[0][1] * J[1][0]) / det;
-        g[9] = det;
+        record(J, g);
         {
             // metric G = invJ invJ^T diagonal?
             const double g01 = g[0] * g[3] + g[1] * g[4] + g[2] * g[5], g02 = g[0] * g[6] + g[1] * g[7] + g[2] * g[8],
@@ -100,6 +103,32 @@ void Ctx::init(const Space& s, int dev) {
         if (uniform && el > 0)
             for (int i = 0; i < 10; ++i)
                 if (std::fabs(g[i] - geom[i]) > 1e-12 * std::max(std::fabs(geom[i]), std::fabs(geom[i < 9 ? 4 * (i / 3) : 9]))) { uniform = false; break; }
+    }
+    if (!affine) {
+        // Jacobian of the multilinear map at every quadrature point (the oracle / MFEM evaluate the
+        // same map: ElementTransformation of a d-linear element)
+        uniform = false; geom_diag = false;
+        const int Q = tabs.Q, QZ = tabs.QZ, NQ = Q * Q * QZ;
+        std::vector<double> qx, qw;
+        gauss_legendre_01(Q, qx, qw);
+        std::vector<double> gq((size_t)s.nelem * NQ * 10);
+        for (int64_t el = 0; el < s.nelem; ++el) {
+            const double* X = &s.elem_corner[(size_t)el * nv * dim];
+            for (int q = 0; q < NQ; ++q) {
+                const double xi[3] = {qx[q % Q], qx[(q / Q) % Q], dim == 3 ? qx[q / (Q * Q)] : 0.0};
+                double J[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 1}};
+                if (dim == 2) { J[2][2] = 1.0; }
+                else J[2][2] = 0.0;
+                for (int c = 0; c < nv; ++c)
+                    for (int a = 0; a < dim; ++a) {
+                        double dn = ((c >> a) & 1) ? 1.0 : -1.0;
+                        for (int b = 0; b < dim; ++b) if (b != a) dn *= ((c >> b) & 1) ? xi[b] : 1.0 - xi[b];
+                        for (int i = 0; i < dim; ++i) J[i][a] += dn * X[c * dim + i];
+                    }
+                record(J, &gq[((size_t)el * NQ + q) * 10]);
+            }
+        }
+        d_geomq.upload(gq);
     }
     if (uniform && s.nelem > 0) { geom.resize(10); geom_stride = 0; }
     d_geom.upload(geom);
@@ -172,6 +201,7 @@ FormArgs Ctx::make_args(const FormSpec& f, const double* x, double* y, bool) con
     a.gather = d_gather_ess.p;
     a.geom = d_geom.p; a.geom_stride = geom_stride;
     a.geom_diag = (geom_diag && use_slab) ? 1 : 0;
+    a.geomq = d_geomq.p;
     a.x = x; a.z = f.state; a.y = y;
     a.nelem = (int)space.nelem;
     a.mask_in = f.mask_in; a.mask_out = f.mask_out;

@@ -99,7 +99,7 @@ public:
     // --- device tables
     DArr<int> d_gather, d_gather_ess, d_bdr_gather, d_bdr_attr, d_ess;
     std::vector<DArr<int>> d_bc_dofs;
-    DArr<double> d_geom, d_bdr_corner, d_gattr;
+    DArr<double> d_geom, d_geomq, d_bdr_corner, d_gattr;
     DArr<unsigned char> d_essmark;
     int geom_stride = 10;
     bool geom_diag = false;   // diagonal metric on every element

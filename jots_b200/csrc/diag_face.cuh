@@ -20,12 +20,8 @@ __global__ void __launch_bounds__(128) form_diag_kernel(const FormArgs a, const 
     extern __shared__ double smem[];
     double* zn = smem;                 // [ND]
     double* fn = zn + ND;              // [NFA][ND]
-    double* qd = fn + NFA * ND;        // [5][NQ]: wm, wa1, wr0, wr1, wr2
+    double* qd = fn + NFA * ND;        // [11][NQ]: wm, wa1, wr0, wr1, wr2, metric g00 g01 g02 g11 g12 g22
     for (int e = blockIdx.x; e < a.nelem; e += gridDim.x) {
-        const double* g = a.geom + (size_t)e * a.geom_stride;
-        double iJ[9];
-        for (int i = 0; i < 9; ++i) iJ[i] = g[i];
-        const double detJ = g[9];
         __syncthreads();
         for (int l = threadIdx.x; l < ND; l += blockDim.x) {
             const int gg = a.gather[(size_t)e * ND + l];
@@ -42,6 +38,10 @@ __global__ void __launch_bounds__(128) form_diag_kernel(const FormArgs a, const 
         __syncthreads();
         for (int q = threadIdx.x; q < NQ; q += blockDim.x) {
             const int q0 = q % Q, q1 = (q / Q) % Q, q2 = q / (Q * Q);
+            const double* g = a.geomq ? a.geomq + ((size_t)e * NQ + q) * 10 : a.geom + (size_t)e * a.geom_stride;
+            double iJ[9];
+            for (int i = 0; i < 9; ++i) iJ[i] = g[i];
+            const double detJ = g[9];
             double f[NFA];
             for (int n = 0; n < NFA; ++n) f[n] = 0.0;
             double gr[3] = {0, 0, 0};
@@ -68,15 +68,12 @@ __global__ void __launch_bounds__(128) form_diag_kernel(const FormArgs a, const 
             qd[1 * NQ + q] = w * c.a1;
             for (int aa = 0; aa < 3; ++aa)
                 qd[(2 + aa) * NQ + q] = cr * (iJ[3 * aa + 0] * pz[0] + iJ[3 * aa + 1] * pz[1] + iJ[3 * aa + 2] * pz[2]);
-        }
-        __syncthreads();
-        double gm[6];  // metric g_ab = sum_i iJ[a][i] iJ[b][i]: 00 01 02 11 12 22
-        {
-            int n = 0;
+            int n = 5;
             for (int aa = 0; aa < 3; ++aa)
                 for (int bb = aa; bb < 3; ++bb)
-                    gm[n++] = iJ[3 * aa] * iJ[3 * bb] + iJ[3 * aa + 1] * iJ[3 * bb + 1] + iJ[3 * aa + 2] * iJ[3 * bb + 2];
+                    qd[(n++) * NQ + q] = iJ[3 * aa] * iJ[3 * bb] + iJ[3 * aa + 1] * iJ[3 * bb + 1] + iJ[3 * aa + 2] * iJ[3 * bb + 2];
         }
+        __syncthreads();
         for (int l = threadIdx.x; l < ND; l += blockDim.x) {
             const int gg = a.gather[(size_t)e * ND + l];
             if (gg < 0 && a.mask_out) continue;
@@ -87,8 +84,8 @@ __global__ void __launch_bounds__(128) form_diag_kernel(const FormArgs a, const 
                 const double b0 = t.B[q0 * D + i0], b1 = t.B[q1 * D + i1], b2 = t.Bz[q2 * DZ + i2];
                 const double phi = b0 * b1 * b2;
                 const double d0 = t.G[q0 * D + i0] * b1 * b2, d1 = b0 * t.G[q1 * D + i1] * b2, d2 = b0 * b1 * t.Gz[q2 * DZ + i2];
-                const double gg2 = gm[0] * d0 * d0 + gm[3] * d1 * d1 + gm[5] * d2 * d2 +
-                                   2.0 * (gm[1] * d0 * d1 + gm[2] * d0 * d2 + gm[4] * d1 * d2);
+                const double gg2 = qd[5 * NQ + q] * d0 * d0 + qd[8 * NQ + q] * d1 * d1 + qd[10 * NQ + q] * d2 * d2 +
+                                   2.0 * (qd[6 * NQ + q] * d0 * d1 + qd[7 * NQ + q] * d0 * d2 + qd[9 * NQ + q] * d1 * d2);
                 d += qd[1 * NQ + q] * gg2 + qd[0 * NQ + q] * phi * phi;
                 if (OP == OP_JAC) d += phi * (qd[2 * NQ + q] * d0 + qd[3 * NQ + q] * d1 + qd[4 * NQ + q] * d2);
             }

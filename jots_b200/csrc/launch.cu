@@ -33,7 +33,7 @@ static int diag_one(const FormArgs& a, const TablesRT& t, cudaStream_t st) {
     constexpr int NF = CoefNF<CF, OP>::value;
     constexpr int NFA = NF > 0 ? NF : 1;
     const int ND = t.D * t.D * t.DZ, NQ = t.Q * t.Q * t.QZ;
-    const size_t smem = (size_t)(ND * (1 + NFA) + 5 * NQ) * sizeof(double);
+    const size_t smem = (size_t)(ND * (1 + NFA) + 11 * NQ) * sizeof(double);
     int grid = a.nelem < 148 * 64 ? a.nelem : 148 * 64;
     form_diag_kernel<OP, CF><<<grid, 128, smem, st>>>(a, t);
     return 0;

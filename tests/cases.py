@@ -76,7 +76,14 @@ def _grade(t, g):
     return t + g * t * (1.0 - t)
 
 
-def write_brick_mesh(path, nx, ny, nz, lx, ly, lz, grade=0.0, shear=0.0):
+def _jit(i, j, k, comp, amp):
+    """deterministic pseudo-random offset in [-amp, amp]"""
+    h = (i * 73856093) ^ (j * 19349663) ^ (k * 83492791) ^ (comp * 2654435761)
+    h = (h * 0x9E3779B1) & 0xFFFFFFFF
+    return amp * (2.0 * (h / 4294967295.0) - 1.0)
+
+
+def write_brick_mesh(path, nx, ny, nz, lx, ly, lz, grade=0.0, shear=0.0, jitter=0.0):
     """Write a brick in 'MFEM mesh v1.0' format with the attribute convention of
     examples/meshes/cube_25_L0p01.mesh (1=x0 2=y0 3=z0 4=x1 5=y1 6=z1).  grade != 0 makes the
     element sizes vary (still affine per element); shear != 0 applies a global affine shear."""
@@ -109,12 +116,14 @@ def write_brick_mesh(path, nx, ny, nz, lx, ly, lz, grade=0.0, shear=0.0):
         for j in range(ny + 1):
             for i in range(nx + 1):
                 x, y, z = lx * _grade(i / nx, grade), ly * _grade(j / ny, -grade), lz * _grade(k / nz, 0.5 * grade)
+                if jitter and 0 < i < nx and 0 < j < ny and 0 < k < nz:   # interior vertices: general trilinear hexes
+                    x += _jit(i, j, k, 0, jitter * lx / nx); y += _jit(i, j, k, 1, jitter * ly / ny); z += _jit(i, j, k, 2, jitter * lz / nz)
                 out.append("%.17g %.17g %.17g" % (x + shear * y + 0.5 * shear * z, y + 0.25 * shear * z, z))
     with open(path, "w") as f:
         f.write("\n".join(out) + "\n")
 
 
-def write_quad_mesh(path, nx, ny, lx, ly, y0=0.0, grade=0.0, shear=0.0, attrs=(1, 2, 3, 4)):
+def write_quad_mesh(path, nx, ny, lx, ly, y0=0.0, grade=0.0, shear=0.0, attrs=(1, 2, 3, 4), jitter=0.0):
     """2-D rectangle; attrs = attributes of (bottom, right, top, left): (1, 2, 3, 4) is the plate.mesh
     convention, (1, 3, 1, 2) the bar.mesh one (1 = long sides, 2 = x0, 3 = x1)."""
     vx = nx + 1
@@ -136,6 +145,8 @@ def write_quad_mesh(path, nx, ny, lx, ly, y0=0.0, grade=0.0, shear=0.0, attrs=(1
     for j in range(ny + 1):
         for i in range(nx + 1):
             x, y = lx * _grade(i / nx, grade), ly * _grade(j / ny, -grade)
+            if jitter and 0 < i < nx and 0 < j < ny:
+                x += _jit(i, j, 0, 0, jitter * lx / nx); y += _jit(i, j, 0, 1, jitter * ly / ny)
             out.append("%.17g %.17g" % (x + shear * y, y0 + y))
     with open(path, "w") as f:
         f.write("\n".join(out) + "\n")

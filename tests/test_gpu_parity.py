@@ -40,15 +40,15 @@ PROPS = {
 
 
 def build(J, tmp_path, sim, dim, p, props, bcs=None, grade=0.0, shear=0.0, solver="FGMRES", prec="Chebyshev", n=(3, 2, 2),
-          newton=None, scheme="Euler_Implicit", dt="1e-2", t0=300, steps=3):
+          newton=None, scheme="Euler_Implicit", dt="1e-2", t0=300, steps=3, jitter=0.0):
     """Write mesh + ini, build the device driver and the oracle driver on them."""
     from oracle import jots as OJ
     mesh = str(tmp_path / "m.mesh")
     if dim == 3:
-        write_brick_mesh(mesh, n[0], n[1], n[2], 0.01, 0.02, 0.015, grade=grade, shear=shear)
+        write_brick_mesh(mesh, n[0], n[1], n[2], 0.01, 0.02, 0.015, grade=grade, shear=shear, jitter=jitter)
         nb = 6
     else:
-        write_quad_mesh(mesh, n[0] + 1, n[1] + 1, 0.02, 0.01, grade=grade, shear=shear)
+        write_quad_mesh(mesh, n[0] + 1, n[1] + 1, 0.02, 0.01, grade=grade, shear=shear, jitter=jitter)
         nb = 4
     if bcs is None:
         bcs = ["HeatFlux, 7.5e5", "Isothermal, 350"] + [HF0] * (nb - 3) + ["HeatFlux, -2e5"]
@@ -323,3 +323,28 @@ def test_blow_up_is_reported_like_the_reference(J, tmp_path):
         dev.run()
     with pytest.raises(RuntimeError, match="blown up"):
         orc.run()
+
+
+@pytest.mark.parametrize("dim,p", [(3, 1), (3, 2), (3, 3), (2, 2), (2, 3)])
+@pytest.mark.parametrize("props", ["k", "full"])
+def test_general_multilinear_elements(J, tmp_path, dim, p, props):
+    """Non-affine (jittered) hexes / quads: per-quadrature-point Jacobians of the multilinear map."""
+    dev, orc = build(J, tmp_path, "Nonlinear_Unsteady", dim, p, props, grade=0.3, shear=0.2, jitter=0.2, n=(4, 3, 3), steps=2)
+    n = dev.n
+    un = smooth_state(orc)
+    k = 50.0 * rnd(n, 21)
+    x = rnd(n, 22)
+    it = orc.it
+    it.u_n = un
+    it.new_state(k)
+    r = dev.op.form_apply(J.FORM_RESIDUAL, k, np.empty(n), state=un)
+    assert rel(r, it.mult(k)) < APPLY_TOL
+    Jm = it.gradient(k)
+    z = un + it.dt * k
+    y = dev.op.form_apply(J.FORM_SYSTEM, x, np.empty(n), state=z)
+    assert rel(y, Jm @ x) < APPLY_TOL
+    d = dev.op.form_diagonal(J.FORM_SYSTEM, np.empty(n), state=z)
+    assert rel(d, Jm.diagonal()) < APPLY_TOL
+    assert rel(dev.op.neumann_vector(), it.b_vec) < APPLY_TOL
+    assert dev.run() == 2
+    assert rel(dev.get_u(), orc.run()) < FIELD_TOL
