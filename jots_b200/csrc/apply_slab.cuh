@@ -807,11 +807,20 @@ __device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
 
+// v3 shared-memory layout (found by exhaustive search for conflict-free 64-bit accesses of a half-warp):
+//   plane (id, qz) of an element starts at id*PSET + qz*PS; elements are ES apart.
+//   MIRROR: thread h=1 reads the planes with i reversed through its address (no register selects).
+template <int D, int Q> struct Slab3Layout {   // D = 2: no conflict-free mirrored layout exists, keep selects
+    static constexpr int PS = 5, PAD = 0, ESM = 4; static constexpr bool MIRROR = false;
+};
+template <> struct Slab3Layout<3, 4> { static constexpr int PS = 12, PAD = 2, ESM = 9; static constexpr bool MIRROR = true; };
+template <> struct Slab3Layout<4, 5> { static constexpr int PS = 17, PAD = 0, ESM = 0; static constexpr bool MIRROR = false; };  // mirrored addressing spills at 255 registers
 template <int D, int Q, int NP> struct Elem3Stride {
-    static constexpr int PS = Plane2Stride<D>::value;
+    static constexpr int PS = Slab3Layout<D, Q>::PS;
+    static constexpr int PSET = Q * PS + Slab3Layout<D, Q>::PAD;
     static constexpr int NPA = NP > 4 ? NP : 4;                       // room for the 4 aliased result planes
-    static constexpr int raw = NPA * Q * PS;
-    static constexpr int value = raw + (((D * D) % 16 - raw % 16) + 16) % 16;   // == D*D (mod 16)
+    static constexpr int raw = NPA * PSET;
+    static constexpr int value = raw + ((Slab3Layout<D, Q>::ESM - raw % 16) + 16) % 16;
 };
 template <int D, int Q, int NP, int E> struct Slab3Smem {
     static constexpr int ND = D * D * D;
@@ -826,8 +835,9 @@ __global__ void __launch_bounds__(T) form_apply_slab3_kernel(const FormArgs a, c
     typedef SlabCfg<OP, CF> C;
     constexpr int NF = C::NF, NFA = NF > 0 ? NF : 1, NP = C::NP;
     constexpr int QC = (Q + 1) / 2;
-    constexpr int PS = Plane2Stride<D>::value;
+    constexpr int PS = Elem3Stride<D, Q, NP>::PS, PSET = Elem3Stride<D, Q, NP>::PSET;
     constexpr int ES = Elem3Stride<D, Q, NP>::value;
+    constexpr bool MIRROR = Slab3Layout<D, Q>::MIRROR;
     constexpr int ND = D * D * D, DD = D * D;
     constexpr bool NEED_Z = C::Z_GRAD || NF > 0;
     extern __shared__ __align__(16) double smem[];
@@ -845,6 +855,7 @@ __global__ void __launch_bounds__(T) form_apply_slab3_kernel(const FormArgs a, c
             const int tile = tile_of(i), n = nvalid(tile) * ND;
             const int* src = a.gather + (size_t)tile * E * ND;
             int* dst = idxbuf + (i % 3) * E * ND;
+#pragma unroll 1
             for (int m = tid; m < n; m += T) cp_async4(dst + m, src + m);
         }
         cp_async_commit();
@@ -856,6 +867,7 @@ __global__ void __launch_bounds__(T) form_apply_slab3_kernel(const FormArgs a, c
             const int* ix = idxbuf + (i % 3) * E * ND;
             double* sx = stage + (size_t)(i % 2) * 2 * E * ND;
             double* sz = sx + E * ND;
+#pragma unroll 1
             for (int m = tid; m < n; m += T) {
                 const int g = ix[m];
                 const int idx = g < 0 ? ~g : g;
@@ -893,6 +905,7 @@ __global__ void __launch_bounds__(T) form_apply_slab3_kernel(const FormArgs a, c
         const double* sz = sx + E * ND;
 
         // ---------------- phase 1: z contraction from the staged values ---------------------------
+#pragma unroll 1
         for (int item = tid; item < nv * DD; item += T) {
             const int el = item / DD, ij = item - el * DD;
             double xr[D], zr[D], fr[NFA][D];
@@ -921,15 +934,15 @@ __global__ void __launch_bounds__(T) form_apply_slab3_kernel(const FormArgs a, c
                     if (C::X_GRAD) sg += t.G[qz * D + k] * xr[k];
                     if (C::Z_GRAD) { zs += t.B[qz * D + k] * zr[k]; zg += t.G[qz * D + k] * zr[k]; }
                 }
-                base[(C::P_XB * Q + qz) * PS] = s;
-                if (C::X_GRAD) base[(C::P_XG * Q + qz) * PS] = sg;
-                if (C::Z_GRAD) { base[(C::P_ZB * Q + qz) * PS] = zs; base[(C::P_ZG * Q + qz) * PS] = zg; }
+                base[C::P_XB * PSET + qz * PS] = s;
+                if (C::X_GRAD) base[C::P_XG * PSET + qz * PS] = sg;
+                if (C::Z_GRAD) { base[C::P_ZB * PSET + qz * PS] = zs; base[C::P_ZG * PSET + qz * PS] = zg; }
 #pragma unroll
                 for (int n = 0; n < NF; ++n) {
                     double fs = 0.0;
 #pragma unroll
                     for (int k = 0; k < D; ++k) fs += t.B[qz * D + k] * fr[n][k];
-                    base[((C::P_F0 + n) * Q + qz) * PS] = fs;
+                    base[(C::P_F0 + n) * PSET + qz * PS] = fs;
                 }
             }
         }
@@ -951,11 +964,21 @@ __global__ void __launch_bounds__(T) form_apply_slab3_kernel(const FormArgs a, c
             }
             const double wz = t.W[qz] * det;
             double* pl = planes + el * ES + qz * PS;
-            auto getp = [&](int id, double (&out)[DD]) {
-                const double* p = pl + id * Q * PS;
+            int mo[D];   // mirrored column offsets of the h = 1 thread
 #pragma unroll
-                for (int m = 0; m < DD; ++m) out[m] = p[m];
-                flip_plane<D>(out, h);
+            for (int i = 0; i < D; ++i) mo[i] = (MIRROR && h) ? D - 1 - i : i;
+            auto getp = [&](int id, double (&out)[DD]) {
+                const double* p = pl + id * PSET;
+                if (MIRROR) {
+#pragma unroll
+                    for (int jj = 0; jj < D; ++jj)
+#pragma unroll
+                        for (int i = 0; i < D; ++i) out[jj * D + i] = p[jj * D + mo[i]];
+                } else {
+#pragma unroll
+                    for (int m = 0; m < DD; ++m) out[m] = p[m];
+                    flip_plane<D>(out, h);
+                }
             };
             double p9[DD], t6[D * QC], A[DD], Bp[DD];
 #pragma unroll
@@ -1064,22 +1087,23 @@ __global__ void __launch_bounds__(T) form_apply_slab3_kernel(const FormArgs a, c
             // result planes alias input planes [0..3][qz] of this (element, qz): only this thread pair
             // (adjacent lanes) ever touches them
             __syncwarp(p2mask);
-            // A -> plane h, Bp -> plane 2 + h: the pair's stores differ by Q*PS == 8 (mod 16) 8-byte slots
-            double* outp = pl + (h ? 1 : 0) * Q * PS;
+            // A -> plane h, Bp -> plane 2 + h (layout chosen so that the pair's stores do not collide)
+            double* outp = pl + (h ? 1 : 0) * PSET;
 #pragma unroll
-            for (int m = 0; m < DD; ++m) { outp[m] = A[m]; outp[2 * Q * PS + m] = Bp[m]; }
+            for (int m = 0; m < DD; ++m) { outp[m] = A[m]; outp[2 * PSET + m] = Bp[m]; }
         }
         __syncthreads();
 
         // ---------------- phase 3: transposed z contraction + scatter ----------------------------
+#pragma unroll 1
         for (int item = tid; item < nv * DD; item += T) {
             const int el = item / DD, ij = item - el * DD;
             const double* base = planes + el * ES + ij;
             double Aq[Q], Bq[Q];
 #pragma unroll
             for (int qz = 0; qz < Q; ++qz) {
-                Aq[qz] = base[qz * PS] + base[(Q + qz) * PS];
-                Bq[qz] = base[(2 * Q + qz) * PS] + base[(3 * Q + qz) * PS];
+                Aq[qz] = base[qz * PS] + base[PSET + qz * PS];
+                Bq[qz] = base[2 * PSET + qz * PS] + base[3 * PSET + qz * PS];
             }
 #pragma unroll
             for (int k = 0; k < D; ++k) {
