@@ -87,7 +87,13 @@ def cpu_port_run(order, n, steps, threads=0):
         subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle", "c")], stdout=subprocess.DEVNULL)
     cmd = [CPU_BIN, str(n), str(n), str(n), "0.01", "0.01", "0.01", str(order), "1e-2", str(steps), "8000", "500", "300",
            "7.5e5", "300", "1e-10", "1e-16", "100", "1e-10", "100", str(threads), "2", "0.09", "-17"]
-    r = json.loads(subprocess.check_output(cmd).decode())
+    try:
+        out = subprocess.check_output(cmd)
+    except (subprocess.CalledProcessError, OSError):
+        # binary built on another CPU generation: rebuild on this host and retry once
+        subprocess.check_call(["make", "-B", "-C", os.path.join(ROOT, "oracle", "c")], stdout=subprocess.DEVNULL)
+        out = subprocess.check_output(cmd)
+    r = json.loads(out.decode())
     r["gdofs"] = r["ndof"] * r["krylov_iters"] / r["time"] / 1e9
     r["steps_per_s"] = r["steps"] / r["time"]
     return r
