@@ -188,7 +188,7 @@ def main():
     ap.add_argument("--solver", default="CG")
     ap.add_argument("--prec", default="Jacobi")
     ap.add_argument("--cpu-n", type=int, default=40, help="elements per direction of the CPU-baseline sample")
-    ap.add_argument("--apply-reps", type=int, default=20)
+    ap.add_argument("--apply-reps", type=int, default=100, help="timed operator applies (after 20 warm-up applies)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="N>1: weak = --n elements per direction per GPU, strong = --n for the global brick")
@@ -290,8 +290,7 @@ def main():
     z = torch.empty_like(x)
     drv.get_u(z)
     torch.cuda.synchronize()
-    for _ in range(3):
-        drv.op.form_time(J.FORM_SYSTEM, x, y, state_dev=z, reps=2)
+    drv.op.form_time(J.FORM_SYSTEM, x, y, state_dev=z, reps=min(20, max(2, args.apply_reps)))   # warm-up applies
     apply_ms = drv.op.form_time(J.FORM_SYSTEM, x, y, state_dev=z, reps=args.apply_reps)
     res_ms = drv.op.form_time(J.FORM_RESIDUAL, x, y, state_dev=z, reps=max(2, args.apply_reps // 4))
     peaks = {}
