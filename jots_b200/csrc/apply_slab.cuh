@@ -7,10 +7,10 @@
 //   phase 1  one thread per (element, i, j) nodal pencil: gather the L-vector DOFs, evaluate the
 //            nodal property polynomials in registers, contract along z with B and G, store the
 //            resulting 3x3 planes for each of the Q quadrature planes;
-//   phase 2  one thread per (element, quadrature plane qz): load the few planes, do every in-plane
-//            interpolation / derivative, the quadrature-point physics and the transposed in-plane
-//            contractions entirely in registers (about 1300 DFMA per thread for the Q2 Jacobian
-//            apply), store two 3x3 result planes;
+//   phase 2  two mirrored threads per (element, quadrature plane qz): load the few planes, do every
+//            in-plane interpolation / derivative, the quadrature-point physics and the transposed
+//            in-plane contractions entirely in registers (about 800 FP64 instructions per thread for
+//            the Q2 Jacobian apply), store two 3x3 result planes;
 //   phase 3  one thread per (element, i, j): transposed z contraction, FP64 atomics to the L-vector.
 // Shared-memory traffic drops from ~4400 to ~600 words per Q2 element.
 #pragma once
@@ -111,215 +111,6 @@ __device__ __forceinline__ void store_plane(double* p, const double (&in)[D * D]
 #pragma unroll
     for (int m = 0; m < (D * D) / 2; ++m) p2[m] = make_double2(in[2 * m], in[2 * m + 1]);
     if ((D * D) % 2) p[D * D - 1] = in[D * D - 1];
-}
-
-template <int D, int Q, int OP, int CF, int E>
-__global__ void __launch_bounds__(E* Q) form_apply_slab_kernel(const FormArgs a, const SlabTables<D, Q> t) {
-    typedef SlabCfg<OP, CF> C;
-    constexpr int NF = C::NF, NFA = NF > 0 ? NF : 1, NP = C::NP;
-    constexpr int PS = PlaneStride<D>::value;
-    constexpr int ES = ElemStride<D, Q, NP>::value;
-    constexpr int ND = D * D * D, DD = D * D;
-    constexpr int T = E * Q;
-    extern __shared__ __align__(16) double smem[];
-    const int tid = threadIdx.x;
-    const int e0 = blockIdx.x * E;
-
-    // ---------------- phase 1: gather + z contraction --------------------------------------------
-    for (int item = tid; item < E * DD; item += T) {
-        const int el = item / DD, ij = item - el * DD;
-        const int e = e0 + el;
-        if (e >= a.nelem) continue;
-        double xr[D], zr[D], fr[NFA][D];
-#pragma unroll
-        for (int k = 0; k < D; ++k) {
-            const int g = a.gather[(size_t)e * ND + ij + DD * k];
-            const int idx = g < 0 ? ~g : g;
-            xr[k] = (g < 0 && a.mask_in) ? 0.0 : a.x[idx];
-            if (C::Z_GRAD || NF > 0) {
-                zr[k] = a.z[idx];
-                if (NF > 0) {
-                    double f[NFA];
-                    nodal_fields<CF, OP>(a.mat, zr[k], f);
-#pragma unroll
-                    for (int n = 0; n < NF; ++n) fr[n][k] = f[n];
-                }
-            }
-        }
-        double* base = smem + el * ES + ij;
-#pragma unroll
-        for (int qz = 0; qz < Q; ++qz) {
-            double s = 0.0, sg = 0.0, zs = 0.0, zg = 0.0;
-#pragma unroll
-            for (int k = 0; k < D; ++k) {
-                s += t.B[qz * D + k] * xr[k];
-                if (C::X_GRAD) sg += t.G[qz * D + k] * xr[k];
-                if (C::Z_GRAD) { zs += t.B[qz * D + k] * zr[k]; zg += t.G[qz * D + k] * zr[k]; }
-            }
-            base[(C::P_XB * Q + qz) * PS] = s;
-            if (C::X_GRAD) base[(C::P_XG * Q + qz) * PS] = sg;
-            if (C::Z_GRAD) { base[(C::P_ZB * Q + qz) * PS] = zs; base[(C::P_ZG * Q + qz) * PS] = zg; }
-#pragma unroll
-            for (int n = 0; n < NF; ++n) {
-                double fs = 0.0;
-#pragma unroll
-                for (int k = 0; k < D; ++k) fs += t.B[qz * D + k] * fr[n][k];
-                base[((C::P_F0 + n) * Q + qz) * PS] = fs;
-            }
-        }
-    }
-    __syncthreads();
-
-    // ---------------- phase 2: one quadrature plane per thread, all in registers -----------------
-    {
-        const int el = tid / Q, qz = tid - el * Q;
-        int e = e0 + el;
-        if (e >= a.nelem) e = a.nelem - 1;
-        const double* gm = a.geom + (size_t)e * a.geom_stride;
-        const double gxx = gm[0] * gm[0] + gm[1] * gm[1] + gm[2] * gm[2];
-        const double gyy = gm[3] * gm[3] + gm[4] * gm[4] + gm[5] * gm[5];
-        const double gzz = gm[6] * gm[6] + gm[7] * gm[7] + gm[8] * gm[8];
-        const double wz = t.W[qz] * gm[9];
-        const double* pl = smem + el * ES + qz * PS;
-        auto plane = [&](int id) { return pl + id * Q * PS; };
-
-        double p9[DD], t12[D * Q], A[DD], Bp[DD];
-#pragma unroll
-        for (int i = 0; i < DD; ++i) { A[i] = 0.0; Bp[i] = 0.0; }
-
-        // coefficient planes: a1 (diffusion) and, for the Jacobian, a2 = ck * alpha'
-        double a1[Q * Q], a2x[Q * Q];
-        double a1c = 0.0;
-        if (CF == CF_CONST) a1c = a.ck * a.a0;
-        else {
-            load_plane<D, PS>(plane(C::P_F0), p9);
-            xpass<D, Q>(p9, t.B, t12);
-            ypass<D, Q>(t12, t.B, a1);
-            const double sc = a.ck * a.inv_rc;
-#pragma unroll
-            for (int q = 0; q < Q * Q; ++q) a1[q] *= sc;
-            if (OP == OP_JAC) {
-                load_plane<D, PS>(plane(C::P_F0 + 1), p9);
-                xpass<D, Q>(p9, t.B, t12);
-                ypass<D, Q>(t12, t.B, a2x);
-            }
-        }
-        // x: value, in-plane sources
-        double xB12[D * Q], xG12[D * Q], vy12[D * Q];
-        load_plane<D, PS>(plane(C::P_XB), p9);
-        xpass<D, Q>(p9, t.B, xB12);
-        if (C::X_GRAD) xpass<D, Q>(p9, t.G, xG12);
-        {
-            double xv[Q * Q];
-            ypass<D, Q>(xB12, t.B, xv);
-            if (OP == OP_JAC && CF != CF_CONST) {
-                const double sc = a.ck * a.inv_rc;
-#pragma unroll
-                for (int q = 0; q < Q * Q; ++q) a2x[q] *= sc * xv[q];
-            }
-            ypassT<D, Q>(xv, t.BW, vy12);   // mass term, scaled by c_m below
-        }
-        const double c_m = a.cm * (CF == CF_CONST || CF == CF_K ? a.m0 : 1.0) * wz;
-        double zB12[D * Q], zG12[D * Q];
-        if (C::Z_GRAD) {
-            load_plane<D, PS>(plane(C::P_ZB), p9);
-            xpass<D, Q>(p9, t.B, zB12);
-            xpass<D, Q>(p9, t.G, zG12);
-        }
-        // ---- x direction
-        {
-            double F[Q * Q];
-            if (OP == OP_RES) ypass<D, Q>(zG12, t.B, F);
-            else ypass<D, Q>(xG12, t.B, F);
-            if (CF == CF_CONST) {
-#pragma unroll
-                for (int q = 0; q < Q * Q; ++q) F[q] *= a1c;
-            } else {
-#pragma unroll
-                for (int q = 0; q < Q * Q; ++q) F[q] *= a1[q];
-                if (OP == OP_JAC) {
-                    double zd[Q * Q];
-                    ypass<D, Q>(zG12, t.B, zd);
-#pragma unroll
-                    for (int q = 0; q < Q * Q; ++q) F[q] += a2x[q] * zd[q];
-                }
-            }
-            ypassT<D, Q>(F, t.BW, t12);
-            xpassT_acc<D, Q>(t12, t.GW, wz * gxx, A);
-        }
-        // ---- y direction (+ mass)
-        {
-            double F[Q * Q];
-            if (OP == OP_RES) ypass<D, Q>(zB12, t.G, F);
-            else ypass<D, Q>(xB12, t.G, F);
-            if (CF == CF_CONST) {
-#pragma unroll
-                for (int q = 0; q < Q * Q; ++q) F[q] *= a1c;
-            } else {
-#pragma unroll
-                for (int q = 0; q < Q * Q; ++q) F[q] *= a1[q];
-                if (OP == OP_JAC) {
-                    double zd[Q * Q];
-                    ypass<D, Q>(zB12, t.G, zd);
-#pragma unroll
-                    for (int q = 0; q < Q * Q; ++q) F[q] += a2x[q] * zd[q];
-                }
-            }
-            ypassT<D, Q>(F, t.GW, t12);
-            const double cy = wz * gyy;
-#pragma unroll
-            for (int i = 0; i < D * Q; ++i) t12[i] = cy * t12[i] + c_m * vy12[i];
-            xpassT_acc<D, Q>(t12, t.BW, 1.0, A);
-        }
-        // ---- z direction
-        {
-            double F[Q * Q];
-            load_plane<D, PS>(plane(OP == OP_RES ? C::P_ZG : C::P_XG), p9);
-            xpass<D, Q>(p9, t.B, t12);
-            ypass<D, Q>(t12, t.B, F);
-            if (CF == CF_CONST) {
-#pragma unroll
-                for (int q = 0; q < Q * Q; ++q) F[q] *= a1c;
-            } else {
-#pragma unroll
-                for (int q = 0; q < Q * Q; ++q) F[q] *= a1[q];
-                if (OP == OP_JAC) {
-                    double zd[Q * Q];
-                    load_plane<D, PS>(plane(C::P_ZG), p9);
-                    xpass<D, Q>(p9, t.B, t12);
-                    ypass<D, Q>(t12, t.B, zd);
-#pragma unroll
-                    for (int q = 0; q < Q * Q; ++q) F[q] += a2x[q] * zd[q];
-                }
-            }
-            ypassT<D, Q>(F, t.BW, t12);
-            xpassT_acc<D, Q>(t12, t.BW, wz * gzz, Bp);
-        }
-        double* outp = smem + el * ES + (NP * Q + qz) * PS;
-        store_plane<D, PS>(outp, A);
-        store_plane<D, PS>(outp + Q * PS, Bp);
-    }
-    __syncthreads();
-
-    // ---------------- phase 3: transposed z contraction + scatter --------------------------------
-    for (int item = tid; item < E * DD; item += T) {
-        const int el = item / DD, ij = item - el * DD;
-        const int e = e0 + el;
-        if (e >= a.nelem) continue;
-        const double* base = smem + el * ES + NP * Q * PS + ij;
-        double Aq[Q], Bq[Q];
-#pragma unroll
-        for (int qz = 0; qz < Q; ++qz) { Aq[qz] = base[qz * PS]; Bq[qz] = base[(Q + qz) * PS]; }
-#pragma unroll
-        for (int k = 0; k < D; ++k) {
-            double s = 0.0;
-#pragma unroll
-            for (int qz = 0; qz < Q; ++qz) s += t.B[qz * D + k] * Aq[qz] + t.G[qz * D + k] * Bq[qz];
-            const int g = a.gather[(size_t)e * ND + ij + DD * k];
-            if (g >= 0) atomicAdd(a.y + g, s);
-            else if (!a.mask_out) atomicAdd(a.y + (~g), s);
-        }
-    }
 }
 
 // =================================================================================================
@@ -718,12 +509,26 @@ __global__ void __launch_bounds__(T) form_diag_slab2_kernel(const FormArgs a, co
 #pragma unroll
             for (int q = 0; q < Q * QC; ++q) a1[q] = a.ck * a.a0;
         } else {
-            getp(0, p9);
+            getp(CF == CF_LINFIELDS ? 2 : 0, p9);
             xpassC<D, QC>(p9, t.B, t6);
             ypassC<D, Q, QC>(t6, t.B, a1);
-            const double sc = a.ck * a.inv_rc;
+            const double sc = CF == CF_LINFIELDS ? a.ck : a.ck * a.inv_rc;
 #pragma unroll
             for (int q = 0; q < Q * QC; ++q) a1[q] *= sc;
+        }
+        if (CF == CF_LINFIELDS) {
+            // mass diagonal with the interpolated rho_h * C_h
+            double mq[Q * QC], cq[Q * QC];
+            getp(0, p9);
+            xpassC<D, QC>(p9, t.B, t6);
+            ypassC<D, Q, QC>(t6, t.B, mq);
+            getp(1, p9);
+            xpassC<D, QC>(p9, t.B, t6);
+            ypassC<D, Q, QC>(t6, t.B, cq);
+#pragma unroll
+            for (int q = 0; q < Q * QC; ++q) mq[q] *= cq[q];
+            ypassTC<D, Q, QC>(mq, t.B2W, t6);
+            xpassTC_acc<D, QC>(t6, t.B2Wh, a.cm * wz, A);
         }
         ypassTC<D, Q, QC>(a1, t.B2W, t6);
         xpassTC_acc<D, QC>(t6, t.G2Wh, wz * gxx, A);
@@ -772,7 +577,7 @@ __global__ void __launch_bounds__(T) form_diag_slab2_kernel(const FormArgs a, co
         if (e >= a.nelem) continue;
         const double* base = smem + el * ES + NPI * Q * PS + ij;
         const double* gm = a.geom + (size_t)e * a.geom_stride;
-        const double mass = a.cm * (CF == CF_CONST || CF == CF_K ? a.m0 : 1.0) * gm[9] * t.mB[ij % D] * t.mB[ij / D];
+        const double mass = (CF == CF_LINFIELDS ? 0.0 : a.cm * a.m0) * gm[9] * t.mB[ij % D] * t.mB[ij / D];
 #pragma unroll
         for (int k = 0; k < D; ++k) {
             double s = mass * t.mB[k];
@@ -920,7 +725,8 @@ __global__ void __launch_bounds__(T) form_apply_slab3_kernel(const FormArgs a, c
                         double f[NFA];
                         nodal_fields<CF, OP>(a.mat, zr[k], f);
 #pragma unroll
-                        for (int n = 0; n < NF; ++n) fr[n][k] = (a.ck * a.inv_rc) * f[n];
+                        for (int n = 0; n < NF; ++n)
+                            fr[n][k] = CF == CF_K ? (a.ck * a.inv_rc) * f[n] : (n == 2 ? a.ck * f[n] : f[n]);   // CF_LINFIELDS: rho, C, ck*k
                     }
                 }
             }
@@ -987,9 +793,22 @@ __global__ void __launch_bounds__(T) form_apply_slab3_kernel(const FormArgs a, c
             double a1c = 0.0;
             if (CF == CF_CONST) a1c = a.ck * a.a0;
             else {
-                getp(C::P_F0, p9);
+                getp(C::P_F0 + (CF == CF_LINFIELDS ? 2 : 0), p9);
                 xpassC<D, QC>(p9, t.B, t6);
                 ypassC<D, Q, QC>(t6, t.B, a1);
+                if (CF == CF_LINFIELDS) {
+                    // mass coefficient rho_h * C_h at the quadrature points (ProductCoefficient of two
+                    // interpolated fields, linear_conduction_operator.cpp:20,59) -> a2x
+                    double cq[Q * QC];
+                    getp(C::P_F0, p9);
+                    xpassC<D, QC>(p9, t.B, t6);
+                    ypassC<D, Q, QC>(t6, t.B, a2x);
+                    getp(C::P_F0 + 1, p9);
+                    xpassC<D, QC>(p9, t.B, t6);
+                    ypassC<D, Q, QC>(t6, t.B, cq);
+#pragma unroll
+                    for (int q = 0; q < Q * QC; ++q) a2x[q] *= cq[q];
+                }
                 if (OP == OP_JAC) {
                     getp(C::P_F0 + 1, p9);
                     xpassC<D, QC>(p9, t.B, t6);
@@ -1006,6 +825,10 @@ __global__ void __launch_bounds__(T) form_apply_slab3_kernel(const FormArgs a, c
                 if (OP == OP_JAC && CF != CF_CONST) {
 #pragma unroll
                     for (int q = 0; q < Q * QC; ++q) a2x[q] *= xv[q];
+                }
+                if (CF == CF_LINFIELDS) {
+#pragma unroll
+                    for (int q = 0; q < Q * QC; ++q) xv[q] *= a2x[q];
                 }
                 ypassTC<D, Q, QC>(xv, t.BW, vy6);
             }

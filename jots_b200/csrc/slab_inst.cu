@@ -7,30 +7,6 @@
 
 namespace jots {
 
-template <int D, int Q, int OP, int CF>
-static int launch_slab(const FormArgs& a, const TablesRT& r, cudaStream_t st) {
-    constexpr int E = 32;
-    typedef SlabCfg<OP, CF> C;
-    SlabTables<D, Q> t;
-    for (int q = 0; q < Q; ++q) {
-        t.W[q] = r.W[q];
-        for (int i = 0; i < D; ++i) {
-            t.B[q * D + i] = r.B[q * D + i]; t.G[q * D + i] = r.G[q * D + i];
-            t.BW[q * D + i] = r.W[q] * r.B[q * D + i]; t.GW[q * D + i] = r.W[q] * r.G[q * D + i];
-        }
-    }
-    const size_t smem = (size_t)E * ElemStride<D, Q, C::NP>::value * sizeof(double);
-    auto kern = form_apply_slab_kernel<D, Q, OP, CF, E>;
-    static bool configured = false;
-    if (!configured) {
-        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        configured = true;
-    }
-    const int grid = (a.nelem + E - 1) / E;
-    kern<<<grid, E * Q, smem, st>>>(a, t);
-    return 0;
-}
-
 template <int D, int Q, int OP, int CF, int E>
 static int launch_slab2e(const FormArgs& a, const TablesRT& r, cudaStream_t st) {
     // E elements per block, 2*Q threads per element in phase 2, D*D threads per element in phases 1/3
@@ -117,13 +93,14 @@ static int dispatch(int op, int cf, const FormArgs& a, const TablesRT& t, cudaSt
 #define CASE(OPV, CFV)                                                                              \
     if (op == OPV && cf == CFV) {                                                                   \
         if constexpr (Q < 5) {                                                                      \
-            if (slab_variant() == 1) return launch_slab<D, Q, OPV, CFV>(a, t, st);                   \
             if (slab_variant() == 2) return launch_slab2<D, Q, OPV, CFV>(a, t, st);                  \
         }                                                                                           \
         return launch_slab3<D, Q, OPV, CFV>(a, t, st);                                              \
     }
     CASE(OP_LIN, CF_CONST) CASE(OP_LIN, CF_K) CASE(OP_JAC, CF_K) CASE(OP_RES, CF_CONST) CASE(OP_RES, CF_K)
 #undef CASE
+    // rho(T) / C(T) in the linearized operator: pipelined kernel only
+    if (op == OP_LIN && cf == CF_LINFIELDS) return launch_slab3<D, Q, OP_LIN, CF_LINFIELDS>(a, t, st);
     return 1;
 }
 
@@ -161,7 +138,7 @@ static int launch_diag_slab(const FormArgs& a, const TablesRT& r, cudaStream_t s
 template <int D, int Q>
 static int dispatch_diag(int op, int cf, const FormArgs& a, const TablesRT& t, cudaStream_t st) {
 #define CASE(OPV, CFV) if (op == OPV && cf == CFV) return launch_diag_slab<D, Q, OPV, CFV>(a, t, st);
-    CASE(OP_LIN, CF_CONST) CASE(OP_LIN, CF_K) CASE(OP_JAC, CF_K)
+    CASE(OP_LIN, CF_CONST) CASE(OP_LIN, CF_K) CASE(OP_JAC, CF_K) CASE(OP_LIN, CF_LINFIELDS)
 #undef CASE
     return 1;
 }

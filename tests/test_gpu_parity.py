@@ -126,7 +126,7 @@ def test_nonlinear_forms(J, tmp_path, dim, p, props):
 
 
 @pytest.mark.parametrize("p", [1, 2, 3])
-@pytest.mark.parametrize("props", ["const", "k"])
+@pytest.mark.parametrize("props", ["const", "k", "full"])
 @pytest.mark.parametrize("sim", ["Linearized_Unsteady", "Nonlinear_Unsteady"])
 def test_axis_aligned_fast_path(J, tmp_path, sim, props, p):
     """Axis-aligned (graded) bricks take the register-slab kernel: same checks as above."""
