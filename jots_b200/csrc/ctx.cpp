@@ -61,6 +61,7 @@ void Ctx::init(const Space& s, int dev) {
     own_stream = true;
     n = s.ndof; n_owned = s.ndof;
     if (const char* ev = std::getenv("JOTS_DISABLE_SLAB")) use_slab = !(ev[0] == '1');
+    if (const char* ev = std::getenv("JOTS_OVERLAP_HALO")) overlap_halo = (ev[0] == '1');
     fill_tables(tabs, s.dim, s.p);
     // geometry: affine elements get one record each (one shared record when all are identical);
     // general multilinear meshes get a record per quadrature point (d_geomq)
@@ -236,7 +237,28 @@ static FaceArgs base_face_args(const Ctx& c, int nq) {
 void Ctx::apply_form(const FormSpec& f, const double* x, double* y) {
     zero(y);
     FormArgs a = make_args(f, x, y, false);
-    int rc = launch_form_apply(space.dim, space.p, f.op, f.cf, a, tabs, stream);
+    const int64_t n_if = (halo && overlap_halo && !(f.bdr_mass_scale != 0.0 && any_flux())) ? halo_interface_elems(*this) : 0;
+    bool overlapped = false;
+    int rc;
+    if (n_if > 0 && n_if < space.nelem) {
+        // interface elements first, their exchange overlaps the interior elements
+        FormArgs ai = a;
+        ai.nelem = (int)n_if;
+        rc = launch_form_apply(space.dim, space.p, f.op, f.cf, ai, tabs, stream);
+        if (!rc) {
+            halo_exchange_begin(*this, y);
+            FormArgs ar = a;
+            ar.gather = a.gather + (size_t)n_if * space.nloc;
+            ar.geom = a.geom + (size_t)n_if * a.geom_stride;
+            if (a.geomq) ar.geomq = a.geomq + (size_t)n_if * (tabs.Q * tabs.Q * tabs.QZ) * 10;
+            ar.nelem = (int)(space.nelem - n_if);
+            ar.nonpersistent = 1;   // blocks retire continuously, so the high-priority exchange kernels get SMs
+            rc = launch_form_apply(space.dim, space.p, f.op, f.cf, ar, tabs, stream);
+            halo_exchange_end(*this);
+            overlapped = true;
+            ++stats.kernel_launches;
+        }
+    } else rc = launch_form_apply(space.dim, space.p, f.op, f.cf, a, tabs, stream);
     if (rc) throw std::runtime_error("form (op=" + std::to_string(f.op) + ", cf=" + std::to_string(f.cf) + ") is not instantiated, rc=" + std::to_string(rc));
     stats.kernel_launches += 2;
     if (f.bdr_mass_scale != 0.0 && any_flux()) {
@@ -245,7 +267,7 @@ void Ctx::apply_form(const FormSpec& f, const double* x, double* y) {
         launch_face(FACE_MASS_APPLY, fa, stream);
         ++stats.kernel_launches;
     }
-    if (halo) halo_sum_exchange(*this, y);
+    if (halo && !overlapped) halo_sum_exchange(*this, y);
     if (f.diag_one) { v_copy_idx(stream, (int)ess.size(), d_ess.p, x, y); stats.kernel_launches += !ess.empty(); }
     JOTS_CUDA(cudaGetLastError());
     ++stats.applies;

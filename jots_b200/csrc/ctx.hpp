@@ -104,6 +104,8 @@ public:
     int geom_stride = 10;
     bool geom_diag = false;   // diagonal metric on every element
     bool use_slab = true;     // JOTS_DISABLE_SLAB=1 forces the generic kernel
+    bool overlap_halo = false; // JOTS_OVERLAP_HALO=1: exchange the interface elements' sums while the interior
+                               // elements run (measured neutral at 2 GPUs, so off by default)
     DArr<double> d_scal, d_partial;
     DArr<double> mat_state;   // vector the nodal property polynomials were last evaluated on (UpdateMatProps)
     void set_mat_state(const double* u) { mat_state.alloc(n); copy(u, mat_state.p); }

@@ -49,6 +49,7 @@ struct FormArgs {
     const double* geom;   // [nelem*10]: invJ[a][i] (9, row-major: a = reference axis) + detJ
     int geom_stride;      // 10, or 0 when every element shares geom[0..9]
     int geom_diag;        // metric invJ invJ^T is diagonal on every element (axis-aligned bricks)
+    int nonpersistent;    // prefer the non-persistent kernel variant (lets a concurrent communication kernel in)
     const double* geomq;  // non-affine (general multilinear) meshes: [nelem][NQ][10] per quadrature point, else null
     const double* x;      // input vector
     const double* z;      // frozen state (coefficients + grad z); may be null for CF_CONST/OP_LIN

@@ -93,7 +93,7 @@ static int dispatch(int op, int cf, const FormArgs& a, const TablesRT& t, cudaSt
 #define CASE(OPV, CFV)                                                                              \
     if (op == OPV && cf == CFV) {                                                                   \
         if constexpr (Q < 5) {                                                                      \
-            if (slab_variant() == 2) return launch_slab2<D, Q, OPV, CFV>(a, t, st);                  \
+            if (slab_variant() == 2 || a.nonpersistent) return launch_slab2<D, Q, OPV, CFV>(a, t, st); \
         }                                                                                           \
         return launch_slab3<D, Q, OPV, CFV>(a, t, st);                                              \
     }
