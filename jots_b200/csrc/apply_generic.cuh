@@ -263,6 +263,7 @@ __global__ void __launch_bounds__(Q* Q* NE) form_apply_kernel(const FormArgs a, 
             const int g = gi[k];
             if (g >= 0) atomicAdd(a.y + g, s);
             else if (!a.mask_out) atomicAdd(a.y + (~g), s);
+                else if (a.diag_one) a.y[~g] = a.x[~g];   // every writer stores the same value
         }
     }
 }

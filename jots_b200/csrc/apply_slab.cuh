@@ -413,6 +413,7 @@ __global__ void __launch_bounds__(T) form_apply_slab2_kernel(const FormArgs a, c
             const int g = a.gather[(size_t)e * ND + ij + DD * k];
             if (g >= 0) atomicAdd(a.y + g, s);
             else if (!a.mask_out) atomicAdd(a.y + (~g), s);
+                else if (a.diag_one) a.y[~g] = a.x[~g];   // every writer stores the same value
         }
     }
 }
@@ -589,6 +590,7 @@ __global__ void __launch_bounds__(T) form_diag_slab2_kernel(const FormArgs a, co
             const int g = a.gather[(size_t)e * ND + ij + DD * k];
             if (g >= 0) atomicAdd(a.y + g, s);
             else if (!a.mask_out) atomicAdd(a.y + (~g), s);
+                else if (a.diag_one) a.y[~g] = a.x[~g];   // every writer stores the same value
         }
     }
 }
@@ -936,6 +938,7 @@ __global__ void __launch_bounds__(T) form_apply_slab3_kernel(const FormArgs a, c
                 const int g = ix[el * ND + ij + DD * k];
                 if (g >= 0) atomicAdd(a.y + g, s);
                 else if (!a.mask_out) atomicAdd(a.y + (~g), s);
+                else if (a.diag_one) a.y[~g] = a.x[~g];   // every writer stores the same value
             }
         }
         __syncthreads();

@@ -196,7 +196,7 @@ void Ctx::upload_flux_values() {
     JOTS_CUDA(cudaStreamSynchronize(stream));
 }
 
-FormArgs Ctx::make_args(const FormSpec& f, const double* x, double* y, bool) const {
+FormArgs Ctx::make_args(const FormSpec& f, const double* x, double* y, bool for_diag) const {
     FormArgs a;
     std::memset(&a, 0, sizeof(a));
     a.gather = d_gather_ess.p;
@@ -206,6 +206,7 @@ FormArgs Ctx::make_args(const FormSpec& f, const double* x, double* y, bool) con
     a.x = x; a.z = f.state; a.y = y;
     a.nelem = (int)space.nelem;
     a.mask_in = f.mask_in; a.mask_out = f.mask_out;
+    a.diag_one = (f.diag_one && f.mask_out && !halo && !for_diag) ? 1 : 0;   // multi-GPU: after the interface sum
     a.cm = f.cm; a.ck = f.ck; a.cb = f.cb; a.m0 = f.m0; a.a0 = f.a0; a.inv_rc = f.inv_rc;
     a.mat = mat;
     return a;
@@ -268,7 +269,7 @@ void Ctx::apply_form(const FormSpec& f, const double* x, double* y) {
         ++stats.kernel_launches;
     }
     if (halo && !overlapped) halo_sum_exchange(*this, y);
-    if (f.diag_one) { v_copy_idx(stream, (int)ess.size(), d_ess.p, x, y); stats.kernel_launches += !ess.empty(); }
+    if (f.diag_one && !a.diag_one) { v_copy_idx(stream, (int)ess.size(), d_ess.p, x, y); stats.kernel_launches += !ess.empty(); }
     JOTS_CUDA(cudaGetLastError());
     ++stats.applies;
 }

@@ -57,6 +57,7 @@ struct FormArgs {
     int nelem;
     int mask_in;          // treat x as zero on essential DOFs (eliminated columns)
     int mask_out;         // skip essential rows
+    int diag_one;         // with mask_out: write y = x on essential rows from the kernel (unit diagonal)
     double cm, ck, cb;
     double m0, a0;        // CF_CONST
     double inv_rc;        // CF_K

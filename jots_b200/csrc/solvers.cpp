@@ -102,9 +102,8 @@ void ChebyshevPrec::mult(const double* r, double* z) {
     // z = ds * (c0 + c1 Ahat + c2 Ahat^2) (ds * r), Horner
     const int64_t n = c->n;
     double* rs = t0.p; double* u = t1.p; double* au = t2.p; double* tmp = t3.p;
-    v_mul(c->stream, n, ds.p, r, rs);
-    v_scale(c->stream, n, coef[order], rs, u);
-    c->stats.kernel_launches += 2;
+    v_mul2(c->stream, n, ds.p, r, coef[order], rs, u);
+    ++c->stats.kernel_launches;
     for (int i = order - 1; i >= 0; --i) {
         // u = ds * A (ds * u) + c_i * rs
         v_mul(c->stream, n, ds.p, u, tmp);

@@ -180,6 +180,18 @@ void v_mul_axpby(cudaStream_t st, int64_t n, const double* d, double a, const do
     k_mul_axpby<<<grid_for(n), VEC_THREADS, 0, st>>>(n, d, a, x, b, z, y);
 }
 
+// y1 = d * x ; y2 = c * y1   (first step of the Chebyshev Horner recurrence)
+__global__ void k_mul2(int64_t n, const double* __restrict__ d, const double* __restrict__ x, double c, double* y1, double* y2) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const double v = d[i] * x[i];
+        y1[i] = v; y2[i] = c * v;
+    }
+}
+void v_mul2(cudaStream_t st, int64_t n, const double* d, const double* x, double c, double* y1, double* y2) {
+    k_mul2<<<grid_for(n), VEC_THREADS, 0, st>>>(n, d, x, c, y1, y2);
+}
+
 void v_waxpby(cudaStream_t st, int64_t n, double a, const double* x, double b, const double* y, double* w) {
     k_waxpby<<<grid_for(n), VEC_THREADS, 0, st>>>(n, a, x, b, y, w);
 }

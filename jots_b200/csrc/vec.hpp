@@ -26,6 +26,7 @@ void v_max(cudaStream_t st, int64_t n, const double* x, DotScratch s, double* re
 void v_mgs_step(cudaStream_t st, int64_t n, int64_t n_owned, double* r, const double* Vprev, const double* hprev, const double* Vk,
                 DotScratch s, double* result);
 void v_mul_axpby(cudaStream_t st, int64_t n, const double* d, double a, const double* x, double b, const double* z, double* y);
+void v_mul2(cudaStream_t st, int64_t n, const double* d, const double* x, double c, double* y1, double* y2);
 void v_dots(cudaStream_t st, int64_t n, int nv, const double* const* a, const double* const* b, DotScratch s, double* result);
 void v_cg_update(cudaStream_t st, int64_t n, int64_t n_owned, double alpha, const double* d, const double* Ad, double* x, double* r,
                  const double* dinv, double* z, DotScratch s, double* result);
