@@ -1,11 +1,33 @@
 // Instantiations of the register-slab kernel (hexes, diagonal metric, CF_CONST / CF_K).
 #include <cstdlib>
+#include <mutex>
 
 #include "apply_slab.cuh"
 #include "diag_face_host.hpp"
 #include "launch.hpp"
 
 namespace jots {
+
+// cudaFuncSetAttribute / occupancy are per device: configure every kernel once per device (several
+// contexts of one process may sit on different GPUs, one host thread each)
+struct PerDevice {
+    std::mutex m;
+    int grid_max[64] = {0};
+    template <class K>
+    int get(K kern, int threads, size_t smem) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        std::lock_guard<std::mutex> lock(m);
+        if (!grid_max[dev]) {
+            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            int sms = 148, per_sm = 1;
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem);
+            grid_max[dev] = sms * (per_sm > 0 ? per_sm : 1);
+        }
+        return grid_max[dev];
+    }
+};
 
 template <int D, int Q, int OP, int CF, int E>
 static int launch_slab2e(const FormArgs& a, const TablesRT& r, cudaStream_t st) {
@@ -24,11 +46,8 @@ static int launch_slab2e(const FormArgs& a, const TablesRT& r, cudaStream_t st) 
     }
     const size_t smem = (size_t)E * Elem2Stride<D, Q, C::NP>::value * sizeof(double);
     auto kern = form_apply_slab2_kernel<D, Q, OP, CF, E, T>;
-    static bool configured = false;
-    if (!configured) {
-        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        configured = true;
-    }
+    static PerDevice pd;
+    pd.get(kern, T, smem);
     const int grid = (a.nelem + E - 1) / E;
     kern<<<grid, T, smem, st>>>(a, t);
     return 0;
@@ -51,15 +70,8 @@ static int launch_slab3e(const FormArgs& a, const TablesRT& r, cudaStream_t st) 
     }
     const size_t smem = Slab3Smem<D, Q, C::NP, E>::total;
     auto kern = form_apply_slab3_kernel<D, Q, OP, CF, E, T>;
-    static int grid_max = 0;
-    if (!grid_max) {
-        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        int dev = 0, sms = 148, per_sm = 1;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, T, smem);
-        grid_max = sms * (per_sm > 0 ? per_sm : 1);
-    }
+    static PerDevice pd;
+    const int grid_max = pd.get(kern, T, smem);
     const int ntiles = (a.nelem + E - 1) / E;
     kern<<<ntiles < grid_max ? ntiles : grid_max, T, smem, st>>>(a, t);
     return 0;
@@ -126,11 +138,8 @@ static int launch_diag_slab(const FormArgs& a, const TablesRT& r, cudaStream_t s
     }
     const size_t smem = (size_t)E * Elem2Stride<D, Q, NPI + 2>::value * sizeof(double);
     auto kern = form_diag_slab2_kernel<D, Q, OP, CF, E, T>;
-    static bool configured = false;
-    if (!configured) {
-        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        configured = true;
-    }
+    static PerDevice pd;
+    pd.get(kern, T, smem);
     kern<<<(a.nelem + E - 1) / E, T, smem, st>>>(a, t);
     return 0;
 }
