@@ -728,7 +728,7 @@ __global__ void __launch_bounds__(T) form_apply_slab3_kernel(const FormArgs a, c
                         nodal_fields<CF, OP>(a.mat, zr[k], f);
 #pragma unroll
                         for (int n = 0; n < NF; ++n)
-                            fr[n][k] = CF == CF_K ? (a.ck * a.inv_rc) * f[n] : (n == 2 ? a.ck * f[n] : f[n]);   // CF_LINFIELDS: rho, C, ck*k
+                            fr[n][k] = CF == CF_K ? (a.ck * a.inv_rc) * f[n] : (CF == CF_LINFIELDS && n == 2) ? a.ck * f[n] : f[n];
                     }
                 }
             }
@@ -791,121 +791,224 @@ __global__ void __launch_bounds__(T) form_apply_slab3_kernel(const FormArgs a, c
             double p9[DD], t6[D * QC], A[DD], Bp[DD];
 #pragma unroll
             for (int i = 0; i < DD; ++i) { A[i] = 0.0; Bp[i] = 0.0; }
-            double a1[Q * QC], a2x[Q * QC];
-            double a1c = 0.0;
-            if (CF == CF_CONST) a1c = a.ck * a.a0;
-            else {
-                getp(C::P_F0 + (CF == CF_LINFIELDS ? 2 : 0), p9);
-                xpassC<D, QC>(p9, t.B, t6);
-                ypassC<D, Q, QC>(t6, t.B, a1);
-                if (CF == CF_LINFIELDS) {
-                    // mass coefficient rho_h * C_h at the quadrature points (ProductCoefficient of two
-                    // interpolated fields, linear_conduction_operator.cpp:20,59) -> a2x
-                    double cq[Q * QC];
-                    getp(C::P_F0, p9);
+            if constexpr (CF == CF_FULL) {
+                // rho(T) and/or C(T): alpha, alpha', -beta, -beta' of nl_conduction_operator.cpp:92-163 from the
+                // eight interpolated nodal fields (k, k', rho, rho', rho'', C, C', C''), with 1/rho and 1/C
+                // formed once per quadrature point
+                constexpr int NQH = Q * QC;
+                auto field = [&](int n, double (&out)[NQH]) {
+                    getp(C::P_F0 + n, p9);
                     xpassC<D, QC>(p9, t.B, t6);
-                    ypassC<D, Q, QC>(t6, t.B, a2x);
-                    getp(C::P_F0 + 1, p9);
-                    xpassC<D, QC>(p9, t.B, t6);
-                    ypassC<D, Q, QC>(t6, t.B, cq);
+                    ypassC<D, Q, QC>(t6, t.B, out);
+                };
+                double a1[NQH], a2[NQH], nb[NQH], ndb[NQH];
+                {
+                    double ir[NQH], ic[NQH], sr[NQH], sc[NQH], tmpq[NQH];
+                    field(2, ir); field(5, ic);
 #pragma unroll
-                    for (int q = 0; q < Q * QC; ++q) a2x[q] *= cq[q];
+                    for (int q = 0; q < NQH; ++q) { ir[q] = 1.0 / ir[q]; ic[q] = 1.0 / ic[q]; }
+                    field(3, sr); field(6, sc);
+#pragma unroll
+                    for (int q = 0; q < NQH; ++q) { sr[q] *= ir[q]; sc[q] *= ic[q]; }
+                    if (OP == OP_JAC) {
+                        // inner = irc (-C''/C + 2 sC sR + 2 sC^2 - rho''/rho + 2 sR^2)
+                        field(4, tmpq);
+#pragma unroll
+                        for (int q = 0; q < NQH; ++q) ndb[q] = 2.0 * (sc[q] * sr[q] + sc[q] * sc[q] + sr[q] * sr[q]) - tmpq[q] * ir[q];
+                        field(7, tmpq);
+#pragma unroll
+                        for (int q = 0; q < NQH; ++q) ndb[q] -= tmpq[q] * ic[q];
+                    }
+                    field(0, a1);   // k
+#pragma unroll
+                    for (int q = 0; q < NQH; ++q) {
+                        const double irc = ir[q] * ic[q], sum = sr[q] + sc[q], kq = a1[q];
+                        a1[q] = a.ck * kq * irc;
+                        nb[q] = a.cb * kq * irc * sum;                         // cb * (-beta)
+                        if (OP == OP_JAC) {
+                            ndb[q] = kq * irc * ndb[q];                        // k * inner
+                            a2[q] = kq * sum;                                  // finished below with k'
+                            sr[q] = irc; sc[q] = sum;
+                        }
+                    }
+                    if (OP == OP_JAC) {
+                        field(1, tmpq);   // k'
+#pragma unroll
+                        for (int q = 0; q < NQH; ++q) {
+                            const double irc = sr[q], sum = sc[q];
+                            a2[q] = a.ck * irc * (tmpq[q] - a2[q]);              // ck * alpha'
+                            ndb[q] = a.cb * (tmpq[q] * irc * sum - ndb[q]);      // cb * (-beta') = -cb (k' t + k inner), t = -irc sum
+                        }
+                    }
                 }
+                double xB6[D * QC], xG6[D * QC], zB6[D * QC], zG6[D * QC], S[NQH];
+                getp(C::P_XB, p9);
+                xpassC<D, QC>(p9, t.B, xB6);
+                if (C::X_GRAD) xpassC<D, QC>(p9, t.G, xG6);
+                ypassC<D, Q, QC>(xB6, t.B, S);                                   // x at the quadrature points
                 if (OP == OP_JAC) {
-                    getp(C::P_F0 + 1, p9);
-                    xpassC<D, QC>(p9, t.B, t6);
-                    ypassC<D, Q, QC>(t6, t.B, a2x);
-                }
-            }
-            double xB6[D * QC], xG6[D * QC], vy6[D * QC];
-            getp(C::P_XB, p9);
-            xpassC<D, QC>(p9, t.B, xB6);
-            if (C::X_GRAD) xpassC<D, QC>(p9, t.G, xG6);
-            {
-                double xv[Q * QC];
-                ypassC<D, Q, QC>(xB6, t.B, xv);
-                if (OP == OP_JAC && CF != CF_CONST) {
 #pragma unroll
-                    for (int q = 0; q < Q * QC; ++q) a2x[q] *= xv[q];
+                    for (int q = 0; q < NQH; ++q) { a2[q] *= S[q]; ndb[q] *= S[q]; }   // alpha' x, (-beta') x
                 }
-                if (CF == CF_LINFIELDS) {
 #pragma unroll
-                    for (int q = 0; q < Q * QC; ++q) xv[q] *= a2x[q];
-                }
-                ypassTC<D, Q, QC>(xv, t.BW, vy6);
-            }
-            const double c_m = a.cm * (CF == CF_CONST || CF == CF_K ? a.m0 : 1.0) * wz;
-            double zB6[D * QC], zG6[D * QC];
-            if (C::Z_GRAD) {
+                for (int q = 0; q < NQH; ++q) S[q] *= a.cm;
                 getp(C::P_ZB, p9);
                 xpassC<D, QC>(p9, t.B, zB6);
                 xpassC<D, QC>(p9, t.G, zG6);
-            }
-            {   // x direction (both G's carry the mirror sign: it cancels)
-                double F[Q * QC];
-                if (OP == OP_RES) ypassC<D, Q, QC>(zG6, t.B, F);
-                else ypassC<D, Q, QC>(xG6, t.B, F);
-                if (CF == CF_CONST) {
-#pragma unroll
-                    for (int q = 0; q < Q * QC; ++q) F[q] *= a1c;
-                } else {
-#pragma unroll
-                    for (int q = 0; q < Q * QC; ++q) F[q] *= a1[q];
-                    if (OP == OP_JAC) {
-                        double zd[Q * QC];
-                        ypassC<D, Q, QC>(zG6, t.B, zd);
-#pragma unroll
-                        for (int q = 0; q < Q * QC; ++q) F[q] += a2x[q] * zd[q];
-                    }
-                }
-                ypassTC<D, Q, QC>(F, t.BW, t6);
-                xpassTC_acc<D, QC>(t6, t.GWh, wz * gxx, A);
-            }
-            {   // y direction (+ mass)
-                double F[Q * QC];
-                if (OP == OP_RES) ypassC<D, Q, QC>(zB6, t.G, F);
-                else ypassC<D, Q, QC>(xB6, t.G, F);
-                if (CF == CF_CONST) {
-#pragma unroll
-                    for (int q = 0; q < Q * QC; ++q) F[q] *= a1c;
-                } else {
-#pragma unroll
-                    for (int q = 0; q < Q * QC; ++q) F[q] *= a1[q];
-                    if (OP == OP_JAC) {
-                        double zd[Q * QC];
-                        ypassC<D, Q, QC>(zB6, t.G, zd);
-#pragma unroll
-                        for (int q = 0; q < Q * QC; ++q) F[q] += a2x[q] * zd[q];
-                    }
-                }
-                ypassTC<D, Q, QC>(F, t.GW, t6);
-                const double cy = wz * gyy;
-#pragma unroll
-                for (int i = 0; i < D * QC; ++i) t6[i] = cy * t6[i] + c_m * vy6[i];
-                xpassTC_acc<D, QC>(t6, t.BWh, 1.0, A);
-            }
-            {   // z direction
-                double F[Q * QC];
-                getp(OP == OP_RES ? C::P_ZG : C::P_XG, p9);
-                xpassC<D, QC>(p9, t.B, t6);
-                ypassC<D, Q, QC>(t6, t.B, F);
-                if (CF == CF_CONST) {
-#pragma unroll
-                    for (int q = 0; q < Q * QC; ++q) F[q] *= a1c;
-                } else {
-#pragma unroll
-                    for (int q = 0; q < Q * QC; ++q) F[q] *= a1[q];
-                    if (OP == OP_JAC) {
-                        double zd[Q * QC];
+                // one direction at a time: F_d = a1 xd + (alpha' x) zd (Jacobian) | a1 zd (residual);
+                // S += g_dd (2 nb zd xd + (-beta') x zd^2) | g_dd nb zd^2
+                auto direction = [&](int dir, const double* tabX, const double* tabY, const double* tabXT, const double* tabYT, double gdd,
+                                     double (&acc)[DD]) {
+                    double F[NQH], zd[NQH];
+                    if (dir == 2) {
                         getp(C::P_ZG, p9);
                         xpassC<D, QC>(p9, t.B, t6);
                         ypassC<D, Q, QC>(t6, t.B, zd);
+                        if (OP == OP_JAC) {
+                            getp(C::P_XG, p9);
+                            xpassC<D, QC>(p9, t.B, t6);
+                            ypassC<D, Q, QC>(t6, t.B, F);
+                        }
+                    } else {
+                        ypassC<D, Q, QC>(dir == 0 ? zG6 : zB6, tabY, zd);
+                        if (OP == OP_JAC) ypassC<D, Q, QC>(dir == 0 ? xG6 : xB6, tabY, F);
+                    }
+                    (void)tabX;
 #pragma unroll
-                        for (int q = 0; q < Q * QC; ++q) F[q] += a2x[q] * zd[q];
+                    for (int q = 0; q < NQH; ++q) {
+                        if (OP == OP_JAC) {
+                            S[q] += gdd * zd[q] * (2.0 * nb[q] * F[q] + ndb[q] * zd[q]);
+                            F[q] = a1[q] * F[q] + a2[q] * zd[q];
+                        } else {
+                            S[q] += gdd * nb[q] * zd[q] * zd[q];
+                            F[q] = a1[q] * zd[q];
+                        }
+                    }
+                    ypassTC<D, Q, QC>(F, tabYT, t6);
+                    xpassTC_acc<D, QC>(t6, tabXT, wz * gdd, acc);
+                };
+                direction(0, t.G, t.B, t.GWh, t.BW, gxx, A);
+                direction(1, t.B, t.G, t.BWh, t.GW, gyy, A);
+                direction(2, t.B, t.B, t.BWh, t.BW, gzz, Bp);
+                ypassTC<D, Q, QC>(S, t.BW, t6);
+                xpassTC_acc<D, QC>(t6, t.BWh, wz, A);
+            } else {
+                double a1[Q * QC], a2x[Q * QC];
+                double a1c = 0.0;
+                if (CF == CF_CONST) a1c = a.ck * a.a0;
+                else {
+                    getp(C::P_F0 + (CF == CF_LINFIELDS ? 2 : 0), p9);
+                    xpassC<D, QC>(p9, t.B, t6);
+                    ypassC<D, Q, QC>(t6, t.B, a1);
+                    if (CF == CF_LINFIELDS) {
+                        // mass coefficient rho_h * C_h at the quadrature points (ProductCoefficient of two
+                        // interpolated fields, linear_conduction_operator.cpp:20,59) -> a2x
+                        double cq[Q * QC];
+                        getp(C::P_F0, p9);
+                        xpassC<D, QC>(p9, t.B, t6);
+                        ypassC<D, Q, QC>(t6, t.B, a2x);
+                        getp(C::P_F0 + 1, p9);
+                        xpassC<D, QC>(p9, t.B, t6);
+                        ypassC<D, Q, QC>(t6, t.B, cq);
+    #pragma unroll
+                        for (int q = 0; q < Q * QC; ++q) a2x[q] *= cq[q];
+                    }
+                    if (OP == OP_JAC) {
+                        getp(C::P_F0 + 1, p9);
+                        xpassC<D, QC>(p9, t.B, t6);
+                        ypassC<D, Q, QC>(t6, t.B, a2x);
                     }
                 }
-                ypassTC<D, Q, QC>(F, t.BW, t6);
-                xpassTC_acc<D, QC>(t6, t.BWh, wz * gzz, Bp);
+                double xB6[D * QC], xG6[D * QC], vy6[D * QC];
+                getp(C::P_XB, p9);
+                xpassC<D, QC>(p9, t.B, xB6);
+                if (C::X_GRAD) xpassC<D, QC>(p9, t.G, xG6);
+                {
+                    double xv[Q * QC];
+                    ypassC<D, Q, QC>(xB6, t.B, xv);
+                    if (OP == OP_JAC && CF != CF_CONST) {
+    #pragma unroll
+                        for (int q = 0; q < Q * QC; ++q) a2x[q] *= xv[q];
+                    }
+                    if (CF == CF_LINFIELDS) {
+    #pragma unroll
+                        for (int q = 0; q < Q * QC; ++q) xv[q] *= a2x[q];
+                    }
+                    ypassTC<D, Q, QC>(xv, t.BW, vy6);
+                }
+                const double c_m = a.cm * (CF == CF_CONST || CF == CF_K ? a.m0 : 1.0) * wz;
+                double zB6[D * QC], zG6[D * QC];
+                if (C::Z_GRAD) {
+                    getp(C::P_ZB, p9);
+                    xpassC<D, QC>(p9, t.B, zB6);
+                    xpassC<D, QC>(p9, t.G, zG6);
+                }
+                {   // x direction (both G's carry the mirror sign: it cancels)
+                    double F[Q * QC];
+                    if (OP == OP_RES) ypassC<D, Q, QC>(zG6, t.B, F);
+                    else ypassC<D, Q, QC>(xG6, t.B, F);
+                    if (CF == CF_CONST) {
+    #pragma unroll
+                        for (int q = 0; q < Q * QC; ++q) F[q] *= a1c;
+                    } else {
+    #pragma unroll
+                        for (int q = 0; q < Q * QC; ++q) F[q] *= a1[q];
+                        if (OP == OP_JAC) {
+                            double zd[Q * QC];
+                            ypassC<D, Q, QC>(zG6, t.B, zd);
+    #pragma unroll
+                            for (int q = 0; q < Q * QC; ++q) F[q] += a2x[q] * zd[q];
+                        }
+                    }
+                    ypassTC<D, Q, QC>(F, t.BW, t6);
+                    xpassTC_acc<D, QC>(t6, t.GWh, wz * gxx, A);
+                }
+                {   // y direction (+ mass)
+                    double F[Q * QC];
+                    if (OP == OP_RES) ypassC<D, Q, QC>(zB6, t.G, F);
+                    else ypassC<D, Q, QC>(xB6, t.G, F);
+                    if (CF == CF_CONST) {
+    #pragma unroll
+                        for (int q = 0; q < Q * QC; ++q) F[q] *= a1c;
+                    } else {
+    #pragma unroll
+                        for (int q = 0; q < Q * QC; ++q) F[q] *= a1[q];
+                        if (OP == OP_JAC) {
+                            double zd[Q * QC];
+                            ypassC<D, Q, QC>(zB6, t.G, zd);
+    #pragma unroll
+                            for (int q = 0; q < Q * QC; ++q) F[q] += a2x[q] * zd[q];
+                        }
+                    }
+                    ypassTC<D, Q, QC>(F, t.GW, t6);
+                    const double cy = wz * gyy;
+    #pragma unroll
+                    for (int i = 0; i < D * QC; ++i) t6[i] = cy * t6[i] + c_m * vy6[i];
+                    xpassTC_acc<D, QC>(t6, t.BWh, 1.0, A);
+                }
+                {   // z direction
+                    double F[Q * QC];
+                    getp(OP == OP_RES ? C::P_ZG : C::P_XG, p9);
+                    xpassC<D, QC>(p9, t.B, t6);
+                    ypassC<D, Q, QC>(t6, t.B, F);
+                    if (CF == CF_CONST) {
+    #pragma unroll
+                        for (int q = 0; q < Q * QC; ++q) F[q] *= a1c;
+                    } else {
+    #pragma unroll
+                        for (int q = 0; q < Q * QC; ++q) F[q] *= a1[q];
+                        if (OP == OP_JAC) {
+                            double zd[Q * QC];
+                            getp(C::P_ZG, p9);
+                            xpassC<D, QC>(p9, t.B, t6);
+                            ypassC<D, Q, QC>(t6, t.B, zd);
+    #pragma unroll
+                            for (int q = 0; q < Q * QC; ++q) F[q] += a2x[q] * zd[q];
+                        }
+                    }
+                    ypassTC<D, Q, QC>(F, t.BW, t6);
+                    xpassTC_acc<D, QC>(t6, t.BWh, wz * gzz, Bp);
+                }
             }
             flip_plane<D>(A, h);
             flip_plane<D>(Bp, h);

@@ -111,8 +111,12 @@ static int dispatch(int op, int cf, const FormArgs& a, const TablesRT& t, cudaSt
     }
     CASE(OP_LIN, CF_CONST) CASE(OP_LIN, CF_K) CASE(OP_JAC, CF_K) CASE(OP_RES, CF_CONST) CASE(OP_RES, CF_K)
 #undef CASE
-    // rho(T) / C(T) in the linearized operator: pipelined kernel only
+    // rho(T) / C(T): pipelined kernel only
     if (op == OP_LIN && cf == CF_LINFIELDS) return launch_slab3<D, Q, OP_LIN, CF_LINFIELDS>(a, t, st);
+    if constexpr (Q < 5) {
+        if (op == OP_JAC && cf == CF_FULL) return launch_slab3<D, Q, OP_JAC, CF_FULL>(a, t, st);
+        if (op == OP_RES && cf == CF_FULL) return launch_slab3<D, Q, OP_RES, CF_FULL>(a, t, st);
+    }
     return 1;
 }
 
