@@ -32,10 +32,16 @@ BCS = ["HeatFlux, 7.5e5", "HeatFlux, 0", "HeatFlux, 0", "Isothermal, 300", "Heat
 METRIC = "Krylov GDOF/s (N_dof x Krylov iterations / solve time), nonlinear unsteady implicit step, Q2 hex"
 
 
+PROPS_B = [("Density_rho", "Uniform, 8000"), ("Specific_Heat_C", "Polynomial, 4.5, -850"),
+           ("Thermal_Conductivity_k", "Polynomial, 0.09, -17")]   # SURVEY.md 8d variant B: C(T) exercises the BN terms
+VARIANT = {"A": PROPS, "B": PROPS_B}
+_variant = "A"
+
+
 def write_ini(path, order, solver, prec, steps):
     from cases import ini_text
     with open(path, "w") as f:
-        f.write(ini_text("Nonlinear_Unsteady", "synthetic-brick", 300, PROPS, BCS, newton=100, solver=solver, prec=prec,
+        f.write(ini_text("Nonlinear_Unsteady", "synthetic-brick", 300, VARIANT[_variant], BCS, newton=100, solver=solver, prec=prec,
                          steps=steps, order=order))
 
 
@@ -170,7 +176,8 @@ def workload_config(args, world):
     for k in ne:
         nd *= k * args.order + 1
     return {"workload": "configs[3]: synthetic refined brick, %dx%dx%d Q%d hexes, %d DOFs, nonlinear unsteady (backward Euler, "
-                        "dt=1e-2), k(T)=0.09T-17, Newton + %s/%s rel 1e-10" % (ne[0], ne[1], ne[2], args.order, nd, args.solver, args.prec),
+                        "dt=1e-2), k(T)=0.09T-17%s, Newton + %s/%s rel 1e-10" % (ne[0], ne[1], ne[2], args.order, nd,
+                                                                                    ", C(T)=4.5T-850" if args.variant == "B" else "", args.solver, args.prec),
             "n_elem": ne, "order": args.order, "n_dof": nd, "solver": args.solver, "preconditioner": args.prec,
             "parallelism": ("box partition %s, 1 subdomain per GPU, NCCL interface sum-exchange + scalar all-reduce" % "x".join(map(str, box_dims(world))))
                            if world > 1 else "single GPU",
@@ -190,9 +197,12 @@ def main():
     ap.add_argument("--cpu-n", type=int, default=40, help="elements per direction of the CPU-baseline sample")
     ap.add_argument("--apply-reps", type=int, default=100, help="timed operator applies (after 20 warm-up applies)")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--variant", default="A", choices=["A", "B"], help="B: C(T) = 4.5 T - 850 as well (FGMRES recommended)")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="N>1: weak = --n elements per direction per GPU, strong = --n for the global brick")
     args = ap.parse_args()
+    global _variant
+    _variant = args.variant
     if args.impl == "reference":
         return run_reference(args)
 
@@ -334,7 +344,7 @@ def main():
                          "fp64_pipe_active_pct": fp64_pct,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6.65 TB/s",
                          "frac_of_8TBs_spec": achieved / 8000.0}}
-    if not args.no_cpu and world == 1:
+    if not args.no_cpu and world == 1 and args.variant == "A":
         if args.solver == "CG" and args.prec == "Jacobi":
             line["cpu_baseline"] = cpu_baseline_entry(cpu_port_run(args.order, args.cpu_n, 2), args.cpu_n, args.order)
         else:
