@@ -791,11 +791,13 @@ __global__ void __launch_bounds__(T) form_apply_slab3_kernel(const FormArgs a, c
             double p9[DD], t6[D * QC], A[DD], Bp[DD];
 #pragma unroll
             for (int i = 0; i < DD; ++i) { A[i] = 0.0; Bp[i] = 0.0; }
-            if constexpr (CF == CF_FULL) {
+            if constexpr (CF == CF_FULL || CF == CF_FULLC) {
                 // rho(T) and/or C(T): alpha, alpha', -beta, -beta' of nl_conduction_operator.cpp:92-163 from the
-                // eight interpolated nodal fields (k, k', rho, rho', rho'', C, C', C''), with 1/rho and 1/C
-                // formed once per quadrature point
+                // interpolated nodal fields (k, k', rho, rho', rho'', C, C', C''; CF_FULLC: uniform rho, five
+                // fields), with 1/rho and 1/C formed once per quadrature point
                 constexpr int NQH = Q * QC;
+                constexpr bool RHO = (CF == CF_FULL);
+                constexpr int F_K = 0, F_DK = 1, F_R = 2, F_DR = 3, F_D2R = 4, F_C = RHO ? 5 : 2, F_DC = RHO ? 6 : 3, F_D2C = RHO ? 7 : 4;
                 auto field = [&](int n, double (&out)[NQH]) {
                     getp(C::P_F0 + n, p9);
                     xpassC<D, QC>(p9, t.B, t6);
@@ -804,22 +806,27 @@ __global__ void __launch_bounds__(T) form_apply_slab3_kernel(const FormArgs a, c
                 double a1[NQH], a2[NQH], nb[NQH], ndb[NQH];
                 {
                     double ir[NQH], ic[NQH], sr[NQH], sc[NQH], tmpq[NQH];
-                    field(2, ir); field(5, ic);
+                    const double ir0 = 1.0 / a.mat.rho.c[0];
+                    field(F_C, ic);
+                    if (RHO) field(F_R, ir);
 #pragma unroll
-                    for (int q = 0; q < NQH; ++q) { ir[q] = 1.0 / ir[q]; ic[q] = 1.0 / ic[q]; }
-                    field(3, sr); field(6, sc);
+                    for (int q = 0; q < NQH; ++q) { ir[q] = RHO ? 1.0 / ir[q] : ir0; ic[q] = 1.0 / ic[q]; }
+                    field(F_DC, sc);
+                    if (RHO) field(F_DR, sr);
 #pragma unroll
-                    for (int q = 0; q < NQH; ++q) { sr[q] *= ir[q]; sc[q] *= ic[q]; }
+                    for (int q = 0; q < NQH; ++q) { sr[q] = RHO ? sr[q] * ir[q] : 0.0; sc[q] *= ic[q]; }
                     if (OP == OP_JAC) {
                         // inner = irc (-C''/C + 2 sC sR + 2 sC^2 - rho''/rho + 2 sR^2)
-                        field(4, tmpq);
+                        field(F_D2C, tmpq);
 #pragma unroll
-                        for (int q = 0; q < NQH; ++q) ndb[q] = 2.0 * (sc[q] * sr[q] + sc[q] * sc[q] + sr[q] * sr[q]) - tmpq[q] * ir[q];
-                        field(7, tmpq);
+                        for (int q = 0; q < NQH; ++q) ndb[q] = 2.0 * (sc[q] * sr[q] + sc[q] * sc[q] + sr[q] * sr[q]) - tmpq[q] * ic[q];
+                        if (RHO) {
+                            field(F_D2R, tmpq);
 #pragma unroll
-                        for (int q = 0; q < NQH; ++q) ndb[q] -= tmpq[q] * ic[q];
+                            for (int q = 0; q < NQH; ++q) ndb[q] -= tmpq[q] * ir[q];
+                        }
                     }
-                    field(0, a1);   // k
+                    field(F_K, a1);
 #pragma unroll
                     for (int q = 0; q < NQH; ++q) {
                         const double irc = ir[q] * ic[q], sum = sr[q] + sc[q], kq = a1[q];
@@ -832,7 +839,7 @@ __global__ void __launch_bounds__(T) form_apply_slab3_kernel(const FormArgs a, c
                         }
                     }
                     if (OP == OP_JAC) {
-                        field(1, tmpq);   // k'
+                        field(F_DK, tmpq);
 #pragma unroll
                         for (int q = 0; q < NQH; ++q) {
                             const double irc = sr[q], sum = sc[q];

@@ -45,6 +45,7 @@ template <> struct CoefNF<CF_K, OP_LIN> { static constexpr int value = 1; };
 template <> struct CoefNF<CF_K, OP_RES> { static constexpr int value = 1; };
 template <> struct CoefNF<CF_K, OP_JAC> { static constexpr int value = 2; };
 template <int OP> struct CoefNF<CF_FULL, OP> { static constexpr int value = 8; };
+template <int OP> struct CoefNF<CF_FULLC, OP> { static constexpr int value = 5; };
 
 // nodal fields to interpolate, from the nodal state value u
 template <int CF, int OP>
@@ -54,6 +55,9 @@ __device__ __forceinline__ void nodal_fields(const MatSet& mat, double u, double
     } else if (CF == CF_K) {
         f[0] = poly_val(mat.k, u);
         if (OP == OP_JAC) f[1] = poly_d1(mat.k, u);
+    } else if (CF == CF_FULLC) {
+        f[0] = poly_val(mat.k, u); f[1] = poly_d1(mat.k, u);
+        f[2] = poly_val(mat.C, u); f[3] = poly_d1(mat.C, u); f[4] = poly_d2(mat.C, u);
     } else if (CF == CF_FULL) {
         f[0] = poly_val(mat.k, u); f[1] = poly_d1(mat.k, u);
         f[2] = poly_val(mat.rho, u); f[3] = poly_d1(mat.rho, u); f[4] = poly_d2(mat.rho, u);

@@ -31,7 +31,8 @@
 namespace jots {
 
 enum { OP_LIN = 0, OP_JAC = 1, OP_RES = 2 };
-enum { CF_CONST = 0, CF_LINFIELDS = 1, CF_K = 2, CF_FULL = 3 };
+enum { CF_CONST = 0, CF_LINFIELDS = 1, CF_K = 2, CF_FULL = 3,
+       CF_FULLC = 4 };   // CF_FULL with a uniform density (slab kernel only, chosen at launch): k, k', C, C', C''
 
 constexpr int MAX_POLY = 8;
 

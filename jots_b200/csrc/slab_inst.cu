@@ -114,8 +114,11 @@ static int dispatch(int op, int cf, const FormArgs& a, const TablesRT& t, cudaSt
     // rho(T) / C(T): pipelined kernel only
     if (op == OP_LIN && cf == CF_LINFIELDS) return launch_slab3<D, Q, OP_LIN, CF_LINFIELDS>(a, t, st);
     if constexpr (Q < 5) {
-        if (op == OP_JAC && cf == CF_FULL) return launch_slab3<D, Q, OP_JAC, CF_FULL>(a, t, st);
-        if (op == OP_RES && cf == CF_FULL) return launch_slab3<D, Q, OP_RES, CF_FULL>(a, t, st);
+        const bool rho_uniform = a.mat.rho.n == 1;   // five property fields instead of eight
+        if (op == OP_JAC && cf == CF_FULL)
+            return rho_uniform ? launch_slab3<D, Q, OP_JAC, CF_FULLC>(a, t, st) : launch_slab3<D, Q, OP_JAC, CF_FULL>(a, t, st);
+        if (op == OP_RES && cf == CF_FULL)
+            return rho_uniform ? launch_slab3<D, Q, OP_RES, CF_FULLC>(a, t, st) : launch_slab3<D, Q, OP_RES, CF_FULL>(a, t, st);
     }
     return 1;
 }
