@@ -5,38 +5,36 @@
 
 namespace jots {
 
-// PolynomialProperty::UpdateCoeff / UpdateDCoeff / UpdateD2Coeff arithmetic
-// (/root/reference/src/material_property.cpp:36-81): sum_i c_i u^(n-1-i), powers by repeated
-// multiplication, highest power first.  Uniform (n == 1): value c_0, derivatives 0.
-__device__ __forceinline__ double poly_val(const Poly& P, double u) {
-    if (P.n == 1) return P.c[0];
-    double z1 = 0.0;
-    for (int i = 0; i < P.n; ++i) {
-        double z2 = 1.0;
-        for (int j = 0; j < P.n - i - 1; ++j) z2 *= u;
-        z1 += z2 * P.c[i];
+// PolynomialProperty (/root/reference/src/material_property.cpp:36-81): value, first and second derivative
+// of sum_i c_i u^(n-1-i) (coefficients highest power first).  The reference forms every power by repeated
+// multiplication (O(n^2) products); here one Horner sweep yields all three (3 FMA per coefficient, no
+// per-degree code) -- same polynomial, results equal to within a few ulp.  Uniform (n == 1): value c_0,
+// derivatives 0.  n is uniform across the grid, so the loop does not diverge.
+__device__ __forceinline__ void poly_eval(const Poly& P, double u, double& val, double& d1, double& d2) {
+    double p = P.c[0], dp = 0.0, ddp = 0.0;
+#pragma unroll 1
+    for (int i = 1; i < P.n; ++i) {
+        ddp = ddp * u + dp;
+        dp = dp * u + p;
+        p = p * u + P.c[i];
     }
-    return z1;
+    val = p; d1 = dp; d2 = 2.0 * ddp;
+}
+__device__ __forceinline__ double poly_val(const Poly& P, double u) {
+    double p = P.c[0];
+#pragma unroll 1
+    for (int i = 1; i < P.n; ++i) p = p * u + P.c[i];
+    return p;
 }
 __device__ __forceinline__ double poly_d1(const Poly& P, double u) {
-    if (P.n == 1) return 0.0;
-    double z1 = 0.0;
-    for (int i = 0; i < P.n - 1; ++i) {
-        double z2 = (double)(P.n - 1 - i);
-        for (int j = 0; j < P.n - i - 2; ++j) z2 *= u;
-        z1 += z2 * P.c[i];
-    }
-    return z1;
+    double v, d1, d2;
+    poly_eval(P, u, v, d1, d2);
+    return d1;
 }
 __device__ __forceinline__ double poly_d2(const Poly& P, double u) {
-    if (P.n == 1) return 0.0;
-    double z1 = 0.0;
-    for (int i = 0; i < P.n - 2; ++i) {
-        double z2 = (double)((P.n - 1 - i) * (P.n - 2 - i));
-        for (int j = 0; j < P.n - i - 3; ++j) z2 *= u;
-        z1 += z2 * P.c[i];
-    }
-    return z1;
+    double v, d1, d2;
+    poly_eval(P, u, v, d1, d2);
+    return d2;
 }
 
 template <int CF, int OP> struct CoefNF { static constexpr int value = 0; };
@@ -50,18 +48,19 @@ template <int OP> struct CoefNF<CF_FULLC, OP> { static constexpr int value = 5; 
 // nodal fields to interpolate, from the nodal state value u
 template <int CF, int OP>
 __device__ __forceinline__ void nodal_fields(const MatSet& mat, double u, double* f) {
+    double v, d1, d2;
     if (CF == CF_LINFIELDS) {
         f[0] = poly_val(mat.rho, u); f[1] = poly_val(mat.C, u); f[2] = poly_val(mat.k, u);
     } else if (CF == CF_K) {
-        f[0] = poly_val(mat.k, u);
-        if (OP == OP_JAC) f[1] = poly_d1(mat.k, u);
+        if (OP == OP_JAC) { poly_eval(mat.k, u, v, d1, d2); f[0] = v; f[1] = d1; }
+        else f[0] = poly_val(mat.k, u);
     } else if (CF == CF_FULLC) {
-        f[0] = poly_val(mat.k, u); f[1] = poly_d1(mat.k, u);
-        f[2] = poly_val(mat.C, u); f[3] = poly_d1(mat.C, u); f[4] = poly_d2(mat.C, u);
+        poly_eval(mat.k, u, v, d1, d2); f[0] = v; f[1] = d1;
+        poly_eval(mat.C, u, v, d1, d2); f[2] = v; f[3] = d1; f[4] = d2;
     } else if (CF == CF_FULL) {
-        f[0] = poly_val(mat.k, u); f[1] = poly_d1(mat.k, u);
-        f[2] = poly_val(mat.rho, u); f[3] = poly_d1(mat.rho, u); f[4] = poly_d2(mat.rho, u);
-        f[5] = poly_val(mat.C, u); f[6] = poly_d1(mat.C, u); f[7] = poly_d2(mat.C, u);
+        poly_eval(mat.k, u, v, d1, d2); f[0] = v; f[1] = d1;
+        poly_eval(mat.rho, u, v, d1, d2); f[2] = v; f[3] = d1; f[4] = d2;
+        poly_eval(mat.C, u, v, d1, d2); f[5] = v; f[6] = d1; f[7] = d2;
     }
 }
 
