@@ -64,6 +64,7 @@ jots_mesh_t jots_mesh_refine(jots_mesh_t m);                        /* UniformRe
 void jots_mesh_destroy(jots_mesh_t m);
 int jots_mesh_info(jots_mesh_t m, int* dim, int64_t* n_elem, int64_t* n_bdr, int64_t* n_verts);
 int jots_mesh_copy(jots_mesh_t m, double* verts, int64_t* elems, int64_t* bdr, int32_t* bdr_attr);
+int jots_mesh_set_vertices(jots_mesh_t m, const double* verts);     /* Mesh::SetVertices: new coordinates [n_verts*dim], same topology */
 
 /* ---- space: H1_FECollection + ParFiniteElementSpace (src/jots_driver.cpp:194-196) ------------- */
 jots_space_t jots_space_create(jots_mesh_t m, int order);
@@ -83,6 +84,13 @@ int jots_space_copy_bdr(jots_space_t s, int32_t* bdr_gather, int32_t* bdr_attr, 
 int jots_space_copy_nodes(jots_space_t s, double* xyz);             /* [n_dof*dim] */
 /* GetEssentialTrueDofs (src/jots_iterator.cpp:30): returns the count, fills out[] when non-NULL */
 int64_t jots_space_essential_dofs(jots_space_t s, const int32_t* attrs, int n_attrs, int32_t* out);
+/* Row-structured tiles of the TMA element kernel (apply_slab4.cuh), exposed so that the index contract can be
+   checked bit-exactly on the host: runs of at most tile_elems elements with contiguous DOF rows; one record per
+   tile = {int32 e0, nv, any_ess, pad; int32 base[D*D (+1 if odd)]; uint64 ess_bits[D*D]}.  Returns the number of
+   tiles (0: the space has no row structure, the gather-table kernel is used), -1 on error; *record_bytes = size
+   of one record; fills out[] (n_tiles*record_bytes) when non-NULL. */
+int64_t jots_space_rowtiles(jots_space_t s, const int32_t* ess, int64_t n_ess, int tile_elems, double min_fill,
+                            int* record_bytes, unsigned char* out);
 
 /* ---- device context ----------------------------------------------------------------------------- */
 jots_ctx_t jots_ctx_create(jots_space_t s, int device);
@@ -102,6 +110,7 @@ int jots_ctx_set_material_state(jots_ctx_t c, const double* u, int loc); /* Upda
 /* counters: applies, diag assemblies, krylov iters, newton iters, residual evals, steps,
    kernel launches, dots, last linear iters, last linear converged, last newton iters, last newton converged */
 int jots_ctx_stats(jots_ctx_t c, int64_t out[12], double norms[2]);
+int64_t jots_ctx_rowtile_applies(jots_ctx_t c);   /* operator applies that ran the row-structured (TMA) element kernel */
 int jots_ctx_reset_stats(jots_ctx_t c);
 
 /* ---- operators (JOTSIterator + TimeDependentOperator) ------------------------------------------- */

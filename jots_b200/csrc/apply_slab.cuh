@@ -637,11 +637,277 @@ template <int D, int Q, int NP, int E> struct Slab3Smem {
     static constexpr size_t total = planes + stage + idx;
 };
 
+// Phase 2 of the pipelined slab kernels: one thread owns half a quadrature plane (element, qz, h) and keeps every
+// in-plane contraction and the quadrature-point physics in registers.  pl points at plane (id 0, qz) of the
+// element; plane id sits at pl + id*PSET.  The two result planes alias input planes 0..3 of the same (element,
+// qz): only this thread pair (adjacent lanes) ever touches them, __syncwarp orders last read before first write.
+template <int D, int Q, int OP, int CF, int PSET, bool MIRROR>
+__device__ __forceinline__ void slab_phase2(const FormArgs& a, const Slab2Tables<D, Q>& t, double* pl, const bool h,
+                                            const double wz, const double gxx, const double gyy, const double gzz,
+                                            const unsigned p2mask) {
+    typedef SlabCfg<OP, CF> C;
+    constexpr int QC = (Q + 1) / 2;
+    constexpr int DD = D * D;
+    int mo[D];   // mirrored column offsets of the h = 1 thread
+#pragma unroll
+    for (int i = 0; i < D; ++i) mo[i] = (MIRROR && h) ? D - 1 - i : i;
+    auto getp = [&](int id, double (&out)[DD]) {
+        const double* p = pl + id * PSET;
+        if (MIRROR) {
+#pragma unroll
+            for (int jj = 0; jj < D; ++jj)
+#pragma unroll
+                for (int i = 0; i < D; ++i) out[jj * D + i] = p[jj * D + mo[i]];
+        } else {
+#pragma unroll
+            for (int m = 0; m < DD; ++m) out[m] = p[m];
+            flip_plane<D>(out, h);
+        }
+    };
+    double p9[DD], t6[D * QC], A[DD], Bp[DD];
+#pragma unroll
+    for (int i = 0; i < DD; ++i) { A[i] = 0.0; Bp[i] = 0.0; }
+    if constexpr (CF == CF_FULL || CF == CF_FULLC) {
+        // rho(T) and/or C(T): alpha, alpha', -beta, -beta' of nl_conduction_operator.cpp:92-163 from the
+        // interpolated nodal fields (k, k', rho, rho', rho'', C, C', C''; CF_FULLC: uniform rho, five
+        // fields), with 1/rho and 1/C formed once per quadrature point
+        constexpr int NQH = Q * QC;
+        constexpr bool RHO = (CF == CF_FULL);
+        constexpr int F_K = 0, F_DK = 1, F_R = 2, F_DR = 3, F_D2R = 4, F_C = RHO ? 5 : 2, F_DC = RHO ? 6 : 3, F_D2C = RHO ? 7 : 4;
+        auto field = [&](int n, double (&out)[NQH]) {
+            getp(C::P_F0 + n, p9);
+            xpassC<D, QC>(p9, t.B, t6);
+            ypassC<D, Q, QC>(t6, t.B, out);
+        };
+        double a1[NQH], a2[NQH], nb[NQH], ndb[NQH];
+        {
+            double ir[NQH], ic[NQH], sr[NQH], sc[NQH], tmpq[NQH];
+            const double ir0 = 1.0 / a.mat.rho.c[0];
+            field(F_C, ic);
+            if (RHO) field(F_R, ir);
+#pragma unroll
+            for (int q = 0; q < NQH; ++q) { ir[q] = RHO ? 1.0 / ir[q] : ir0; ic[q] = 1.0 / ic[q]; }
+            field(F_DC, sc);
+            if (RHO) field(F_DR, sr);
+#pragma unroll
+            for (int q = 0; q < NQH; ++q) { sr[q] = RHO ? sr[q] * ir[q] : 0.0; sc[q] *= ic[q]; }
+            if (OP == OP_JAC) {
+                // inner = irc (-C''/C + 2 sC sR + 2 sC^2 - rho''/rho + 2 sR^2)
+                field(F_D2C, tmpq);
+#pragma unroll
+                for (int q = 0; q < NQH; ++q) ndb[q] = 2.0 * (sc[q] * sr[q] + sc[q] * sc[q] + sr[q] * sr[q]) - tmpq[q] * ic[q];
+                if (RHO) {
+                    field(F_D2R, tmpq);
+#pragma unroll
+                    for (int q = 0; q < NQH; ++q) ndb[q] -= tmpq[q] * ir[q];
+                }
+            }
+            field(F_K, a1);
+#pragma unroll
+            for (int q = 0; q < NQH; ++q) {
+                const double irc = ir[q] * ic[q], sum = sr[q] + sc[q], kq = a1[q];
+                a1[q] = a.ck * kq * irc;
+                nb[q] = a.cb * kq * irc * sum;                         // cb * (-beta)
+                if (OP == OP_JAC) {
+                    ndb[q] = kq * irc * ndb[q];                        // k * inner
+                    a2[q] = kq * sum;                                  // finished below with k'
+                    sr[q] = irc; sc[q] = sum;
+                }
+            }
+            if (OP == OP_JAC) {
+                field(F_DK, tmpq);
+#pragma unroll
+                for (int q = 0; q < NQH; ++q) {
+                    const double irc = sr[q], sum = sc[q];
+                    a2[q] = a.ck * irc * (tmpq[q] - a2[q]);              // ck * alpha'
+                    ndb[q] = a.cb * (tmpq[q] * irc * sum - ndb[q]);      // cb * (-beta') = -cb (k' t + k inner), t = -irc sum
+                }
+            }
+        }
+        double xB6[D * QC], xG6[D * QC], zB6[D * QC], zG6[D * QC], S[NQH];
+        getp(C::P_XB, p9);
+        xpassC<D, QC>(p9, t.B, xB6);
+        if (C::X_GRAD) xpassC<D, QC>(p9, t.G, xG6);
+        ypassC<D, Q, QC>(xB6, t.B, S);                                   // x at the quadrature points
+        if (OP == OP_JAC) {
+#pragma unroll
+            for (int q = 0; q < NQH; ++q) { a2[q] *= S[q]; ndb[q] *= S[q]; }   // alpha' x, (-beta') x
+        }
+#pragma unroll
+        for (int q = 0; q < NQH; ++q) S[q] *= a.cm;
+        getp(C::P_ZB, p9);
+        xpassC<D, QC>(p9, t.B, zB6);
+        xpassC<D, QC>(p9, t.G, zG6);
+        // one direction at a time: F_d = a1 xd + (alpha' x) zd (Jacobian) | a1 zd (residual);
+        // S += g_dd (2 nb zd xd + (-beta') x zd^2) | g_dd nb zd^2
+        auto direction = [&](int dir, const double* tabX, const double* tabY, const double* tabXT, const double* tabYT, double gdd,
+                             double (&acc)[DD]) {
+            double F[NQH], zd[NQH];
+            if (dir == 2) {
+                getp(C::P_ZG, p9);
+                xpassC<D, QC>(p9, t.B, t6);
+                ypassC<D, Q, QC>(t6, t.B, zd);
+                if (OP == OP_JAC) {
+                    getp(C::P_XG, p9);
+                    xpassC<D, QC>(p9, t.B, t6);
+                    ypassC<D, Q, QC>(t6, t.B, F);
+                }
+            } else {
+                ypassC<D, Q, QC>(dir == 0 ? zG6 : zB6, tabY, zd);
+                if (OP == OP_JAC) ypassC<D, Q, QC>(dir == 0 ? xG6 : xB6, tabY, F);
+            }
+            (void)tabX;
+#pragma unroll
+            for (int q = 0; q < NQH; ++q) {
+                if (OP == OP_JAC) {
+                    S[q] += gdd * zd[q] * (2.0 * nb[q] * F[q] + ndb[q] * zd[q]);
+                    F[q] = a1[q] * F[q] + a2[q] * zd[q];
+                } else {
+                    S[q] += gdd * nb[q] * zd[q] * zd[q];
+                    F[q] = a1[q] * zd[q];
+                }
+            }
+            ypassTC<D, Q, QC>(F, tabYT, t6);
+            xpassTC_acc<D, QC>(t6, tabXT, wz * gdd, acc);
+        };
+        direction(0, t.G, t.B, t.GWh, t.BW, gxx, A);
+        direction(1, t.B, t.G, t.BWh, t.GW, gyy, A);
+        direction(2, t.B, t.B, t.BWh, t.BW, gzz, Bp);
+        ypassTC<D, Q, QC>(S, t.BW, t6);
+        xpassTC_acc<D, QC>(t6, t.BWh, wz, A);
+    } else {
+        double a1[Q * QC], a2x[Q * QC];
+        double a1c = 0.0;
+        if (CF == CF_CONST) a1c = a.ck * a.a0;
+        else {
+            getp(C::P_F0 + (CF == CF_LINFIELDS ? 2 : 0), p9);
+            xpassC<D, QC>(p9, t.B, t6);
+            ypassC<D, Q, QC>(t6, t.B, a1);
+            if (CF == CF_LINFIELDS) {
+                // mass coefficient rho_h * C_h at the quadrature points (ProductCoefficient of two
+                // interpolated fields, linear_conduction_operator.cpp:20,59) -> a2x
+                double cq[Q * QC];
+                getp(C::P_F0, p9);
+                xpassC<D, QC>(p9, t.B, t6);
+                ypassC<D, Q, QC>(t6, t.B, a2x);
+                getp(C::P_F0 + 1, p9);
+                xpassC<D, QC>(p9, t.B, t6);
+                ypassC<D, Q, QC>(t6, t.B, cq);
+    #pragma unroll
+                for (int q = 0; q < Q * QC; ++q) a2x[q] *= cq[q];
+            }
+            if (OP == OP_JAC) {
+                getp(C::P_F0 + 1, p9);
+                xpassC<D, QC>(p9, t.B, t6);
+                ypassC<D, Q, QC>(t6, t.B, a2x);
+            }
+        }
+        double xB6[D * QC], xG6[D * QC], vy6[D * QC];
+        getp(C::P_XB, p9);
+        xpassC<D, QC>(p9, t.B, xB6);
+        if (C::X_GRAD) xpassC<D, QC>(p9, t.G, xG6);
+        {
+            double xv[Q * QC];
+            ypassC<D, Q, QC>(xB6, t.B, xv);
+            if (OP == OP_JAC && CF != CF_CONST) {
+    #pragma unroll
+                for (int q = 0; q < Q * QC; ++q) a2x[q] *= xv[q];
+            }
+            if (CF == CF_LINFIELDS) {
+    #pragma unroll
+                for (int q = 0; q < Q * QC; ++q) xv[q] *= a2x[q];
+            }
+            ypassTC<D, Q, QC>(xv, t.BW, vy6);
+        }
+        const double c_m = a.cm * (CF == CF_CONST || CF == CF_K ? a.m0 : 1.0) * wz;
+        double zB6[D * QC], zG6[D * QC];
+        if (C::Z_GRAD) {
+            getp(C::P_ZB, p9);
+            xpassC<D, QC>(p9, t.B, zB6);
+            xpassC<D, QC>(p9, t.G, zG6);
+        }
+        {   // x direction (both G's carry the mirror sign: it cancels)
+            double F[Q * QC];
+            if (OP == OP_RES) ypassC<D, Q, QC>(zG6, t.B, F);
+            else ypassC<D, Q, QC>(xG6, t.B, F);
+            if (CF == CF_CONST) {
+    #pragma unroll
+                for (int q = 0; q < Q * QC; ++q) F[q] *= a1c;
+            } else {
+    #pragma unroll
+                for (int q = 0; q < Q * QC; ++q) F[q] *= a1[q];
+                if (OP == OP_JAC) {
+                    double zd[Q * QC];
+                    ypassC<D, Q, QC>(zG6, t.B, zd);
+    #pragma unroll
+                    for (int q = 0; q < Q * QC; ++q) F[q] += a2x[q] * zd[q];
+                }
+            }
+            ypassTC<D, Q, QC>(F, t.BW, t6);
+            xpassTC_acc<D, QC>(t6, t.GWh, wz * gxx, A);
+        }
+        {   // y direction (+ mass)
+            double F[Q * QC];
+            if (OP == OP_RES) ypassC<D, Q, QC>(zB6, t.G, F);
+            else ypassC<D, Q, QC>(xB6, t.G, F);
+            if (CF == CF_CONST) {
+    #pragma unroll
+                for (int q = 0; q < Q * QC; ++q) F[q] *= a1c;
+            } else {
+    #pragma unroll
+                for (int q = 0; q < Q * QC; ++q) F[q] *= a1[q];
+                if (OP == OP_JAC) {
+                    double zd[Q * QC];
+                    ypassC<D, Q, QC>(zB6, t.G, zd);
+    #pragma unroll
+                    for (int q = 0; q < Q * QC; ++q) F[q] += a2x[q] * zd[q];
+                }
+            }
+            ypassTC<D, Q, QC>(F, t.GW, t6);
+            const double cy = wz * gyy;
+    #pragma unroll
+            for (int i = 0; i < D * QC; ++i) t6[i] = cy * t6[i] + c_m * vy6[i];
+            xpassTC_acc<D, QC>(t6, t.BWh, 1.0, A);
+        }
+        {   // z direction
+            double F[Q * QC];
+            getp(OP == OP_RES ? C::P_ZG : C::P_XG, p9);
+            xpassC<D, QC>(p9, t.B, t6);
+            ypassC<D, Q, QC>(t6, t.B, F);
+            if (CF == CF_CONST) {
+    #pragma unroll
+                for (int q = 0; q < Q * QC; ++q) F[q] *= a1c;
+            } else {
+    #pragma unroll
+                for (int q = 0; q < Q * QC; ++q) F[q] *= a1[q];
+                if (OP == OP_JAC) {
+                    double zd[Q * QC];
+                    getp(C::P_ZG, p9);
+                    xpassC<D, QC>(p9, t.B, t6);
+                    ypassC<D, Q, QC>(t6, t.B, zd);
+    #pragma unroll
+                    for (int q = 0; q < Q * QC; ++q) F[q] += a2x[q] * zd[q];
+                }
+            }
+            ypassTC<D, Q, QC>(F, t.BW, t6);
+            xpassTC_acc<D, QC>(t6, t.BWh, wz * gzz, Bp);
+        }
+    }
+    flip_plane<D>(A, h);
+    flip_plane<D>(Bp, h);
+    // result planes alias input planes [0..3][qz] of this (element, qz): only this thread pair
+    // (adjacent lanes) ever touches them
+    __syncwarp(p2mask);
+    // A -> plane h, Bp -> plane 2 + h (layout chosen so that the pair's stores do not collide)
+    double* outp = pl + (h ? 1 : 0) * PSET;
+#pragma unroll
+    for (int m = 0; m < DD; ++m) { outp[m] = A[m]; outp[2 * PSET + m] = Bp[m]; }
+}
+
 template <int D, int Q, int OP, int CF, int E, int T>
 __global__ void __launch_bounds__(T) form_apply_slab3_kernel(const FormArgs a, const Slab2Tables<D, Q> t) {
     typedef SlabCfg<OP, CF> C;
     constexpr int NF = C::NF, NFA = NF > 0 ? NF : 1, NP = C::NP;
-    constexpr int QC = (Q + 1) / 2;
     constexpr int PS = Elem3Stride<D, Q, NP>::PS, PSET = Elem3Stride<D, Q, NP>::PSET;
     constexpr int ES = Elem3Stride<D, Q, NP>::value;
     constexpr bool MIRROR = Slab3Layout<D, Q>::MIRROR;
@@ -772,260 +1038,7 @@ __global__ void __launch_bounds__(T) form_apply_slab3_kernel(const FormArgs a, c
             }
             const double wz = t.W[qz] * det;
             double* pl = planes + el * ES + qz * PS;
-            int mo[D];   // mirrored column offsets of the h = 1 thread
-#pragma unroll
-            for (int i = 0; i < D; ++i) mo[i] = (MIRROR && h) ? D - 1 - i : i;
-            auto getp = [&](int id, double (&out)[DD]) {
-                const double* p = pl + id * PSET;
-                if (MIRROR) {
-#pragma unroll
-                    for (int jj = 0; jj < D; ++jj)
-#pragma unroll
-                        for (int i = 0; i < D; ++i) out[jj * D + i] = p[jj * D + mo[i]];
-                } else {
-#pragma unroll
-                    for (int m = 0; m < DD; ++m) out[m] = p[m];
-                    flip_plane<D>(out, h);
-                }
-            };
-            double p9[DD], t6[D * QC], A[DD], Bp[DD];
-#pragma unroll
-            for (int i = 0; i < DD; ++i) { A[i] = 0.0; Bp[i] = 0.0; }
-            if constexpr (CF == CF_FULL || CF == CF_FULLC) {
-                // rho(T) and/or C(T): alpha, alpha', -beta, -beta' of nl_conduction_operator.cpp:92-163 from the
-                // interpolated nodal fields (k, k', rho, rho', rho'', C, C', C''; CF_FULLC: uniform rho, five
-                // fields), with 1/rho and 1/C formed once per quadrature point
-                constexpr int NQH = Q * QC;
-                constexpr bool RHO = (CF == CF_FULL);
-                constexpr int F_K = 0, F_DK = 1, F_R = 2, F_DR = 3, F_D2R = 4, F_C = RHO ? 5 : 2, F_DC = RHO ? 6 : 3, F_D2C = RHO ? 7 : 4;
-                auto field = [&](int n, double (&out)[NQH]) {
-                    getp(C::P_F0 + n, p9);
-                    xpassC<D, QC>(p9, t.B, t6);
-                    ypassC<D, Q, QC>(t6, t.B, out);
-                };
-                double a1[NQH], a2[NQH], nb[NQH], ndb[NQH];
-                {
-                    double ir[NQH], ic[NQH], sr[NQH], sc[NQH], tmpq[NQH];
-                    const double ir0 = 1.0 / a.mat.rho.c[0];
-                    field(F_C, ic);
-                    if (RHO) field(F_R, ir);
-#pragma unroll
-                    for (int q = 0; q < NQH; ++q) { ir[q] = RHO ? 1.0 / ir[q] : ir0; ic[q] = 1.0 / ic[q]; }
-                    field(F_DC, sc);
-                    if (RHO) field(F_DR, sr);
-#pragma unroll
-                    for (int q = 0; q < NQH; ++q) { sr[q] = RHO ? sr[q] * ir[q] : 0.0; sc[q] *= ic[q]; }
-                    if (OP == OP_JAC) {
-                        // inner = irc (-C''/C + 2 sC sR + 2 sC^2 - rho''/rho + 2 sR^2)
-                        field(F_D2C, tmpq);
-#pragma unroll
-                        for (int q = 0; q < NQH; ++q) ndb[q] = 2.0 * (sc[q] * sr[q] + sc[q] * sc[q] + sr[q] * sr[q]) - tmpq[q] * ic[q];
-                        if (RHO) {
-                            field(F_D2R, tmpq);
-#pragma unroll
-                            for (int q = 0; q < NQH; ++q) ndb[q] -= tmpq[q] * ir[q];
-                        }
-                    }
-                    field(F_K, a1);
-#pragma unroll
-                    for (int q = 0; q < NQH; ++q) {
-                        const double irc = ir[q] * ic[q], sum = sr[q] + sc[q], kq = a1[q];
-                        a1[q] = a.ck * kq * irc;
-                        nb[q] = a.cb * kq * irc * sum;                         // cb * (-beta)
-                        if (OP == OP_JAC) {
-                            ndb[q] = kq * irc * ndb[q];                        // k * inner
-                            a2[q] = kq * sum;                                  // finished below with k'
-                            sr[q] = irc; sc[q] = sum;
-                        }
-                    }
-                    if (OP == OP_JAC) {
-                        field(F_DK, tmpq);
-#pragma unroll
-                        for (int q = 0; q < NQH; ++q) {
-                            const double irc = sr[q], sum = sc[q];
-                            a2[q] = a.ck * irc * (tmpq[q] - a2[q]);              // ck * alpha'
-                            ndb[q] = a.cb * (tmpq[q] * irc * sum - ndb[q]);      // cb * (-beta') = -cb (k' t + k inner), t = -irc sum
-                        }
-                    }
-                }
-                double xB6[D * QC], xG6[D * QC], zB6[D * QC], zG6[D * QC], S[NQH];
-                getp(C::P_XB, p9);
-                xpassC<D, QC>(p9, t.B, xB6);
-                if (C::X_GRAD) xpassC<D, QC>(p9, t.G, xG6);
-                ypassC<D, Q, QC>(xB6, t.B, S);                                   // x at the quadrature points
-                if (OP == OP_JAC) {
-#pragma unroll
-                    for (int q = 0; q < NQH; ++q) { a2[q] *= S[q]; ndb[q] *= S[q]; }   // alpha' x, (-beta') x
-                }
-#pragma unroll
-                for (int q = 0; q < NQH; ++q) S[q] *= a.cm;
-                getp(C::P_ZB, p9);
-                xpassC<D, QC>(p9, t.B, zB6);
-                xpassC<D, QC>(p9, t.G, zG6);
-                // one direction at a time: F_d = a1 xd + (alpha' x) zd (Jacobian) | a1 zd (residual);
-                // S += g_dd (2 nb zd xd + (-beta') x zd^2) | g_dd nb zd^2
-                auto direction = [&](int dir, const double* tabX, const double* tabY, const double* tabXT, const double* tabYT, double gdd,
-                                     double (&acc)[DD]) {
-                    double F[NQH], zd[NQH];
-                    if (dir == 2) {
-                        getp(C::P_ZG, p9);
-                        xpassC<D, QC>(p9, t.B, t6);
-                        ypassC<D, Q, QC>(t6, t.B, zd);
-                        if (OP == OP_JAC) {
-                            getp(C::P_XG, p9);
-                            xpassC<D, QC>(p9, t.B, t6);
-                            ypassC<D, Q, QC>(t6, t.B, F);
-                        }
-                    } else {
-                        ypassC<D, Q, QC>(dir == 0 ? zG6 : zB6, tabY, zd);
-                        if (OP == OP_JAC) ypassC<D, Q, QC>(dir == 0 ? xG6 : xB6, tabY, F);
-                    }
-                    (void)tabX;
-#pragma unroll
-                    for (int q = 0; q < NQH; ++q) {
-                        if (OP == OP_JAC) {
-                            S[q] += gdd * zd[q] * (2.0 * nb[q] * F[q] + ndb[q] * zd[q]);
-                            F[q] = a1[q] * F[q] + a2[q] * zd[q];
-                        } else {
-                            S[q] += gdd * nb[q] * zd[q] * zd[q];
-                            F[q] = a1[q] * zd[q];
-                        }
-                    }
-                    ypassTC<D, Q, QC>(F, tabYT, t6);
-                    xpassTC_acc<D, QC>(t6, tabXT, wz * gdd, acc);
-                };
-                direction(0, t.G, t.B, t.GWh, t.BW, gxx, A);
-                direction(1, t.B, t.G, t.BWh, t.GW, gyy, A);
-                direction(2, t.B, t.B, t.BWh, t.BW, gzz, Bp);
-                ypassTC<D, Q, QC>(S, t.BW, t6);
-                xpassTC_acc<D, QC>(t6, t.BWh, wz, A);
-            } else {
-                double a1[Q * QC], a2x[Q * QC];
-                double a1c = 0.0;
-                if (CF == CF_CONST) a1c = a.ck * a.a0;
-                else {
-                    getp(C::P_F0 + (CF == CF_LINFIELDS ? 2 : 0), p9);
-                    xpassC<D, QC>(p9, t.B, t6);
-                    ypassC<D, Q, QC>(t6, t.B, a1);
-                    if (CF == CF_LINFIELDS) {
-                        // mass coefficient rho_h * C_h at the quadrature points (ProductCoefficient of two
-                        // interpolated fields, linear_conduction_operator.cpp:20,59) -> a2x
-                        double cq[Q * QC];
-                        getp(C::P_F0, p9);
-                        xpassC<D, QC>(p9, t.B, t6);
-                        ypassC<D, Q, QC>(t6, t.B, a2x);
-                        getp(C::P_F0 + 1, p9);
-                        xpassC<D, QC>(p9, t.B, t6);
-                        ypassC<D, Q, QC>(t6, t.B, cq);
-    #pragma unroll
-                        for (int q = 0; q < Q * QC; ++q) a2x[q] *= cq[q];
-                    }
-                    if (OP == OP_JAC) {
-                        getp(C::P_F0 + 1, p9);
-                        xpassC<D, QC>(p9, t.B, t6);
-                        ypassC<D, Q, QC>(t6, t.B, a2x);
-                    }
-                }
-                double xB6[D * QC], xG6[D * QC], vy6[D * QC];
-                getp(C::P_XB, p9);
-                xpassC<D, QC>(p9, t.B, xB6);
-                if (C::X_GRAD) xpassC<D, QC>(p9, t.G, xG6);
-                {
-                    double xv[Q * QC];
-                    ypassC<D, Q, QC>(xB6, t.B, xv);
-                    if (OP == OP_JAC && CF != CF_CONST) {
-    #pragma unroll
-                        for (int q = 0; q < Q * QC; ++q) a2x[q] *= xv[q];
-                    }
-                    if (CF == CF_LINFIELDS) {
-    #pragma unroll
-                        for (int q = 0; q < Q * QC; ++q) xv[q] *= a2x[q];
-                    }
-                    ypassTC<D, Q, QC>(xv, t.BW, vy6);
-                }
-                const double c_m = a.cm * (CF == CF_CONST || CF == CF_K ? a.m0 : 1.0) * wz;
-                double zB6[D * QC], zG6[D * QC];
-                if (C::Z_GRAD) {
-                    getp(C::P_ZB, p9);
-                    xpassC<D, QC>(p9, t.B, zB6);
-                    xpassC<D, QC>(p9, t.G, zG6);
-                }
-                {   // x direction (both G's carry the mirror sign: it cancels)
-                    double F[Q * QC];
-                    if (OP == OP_RES) ypassC<D, Q, QC>(zG6, t.B, F);
-                    else ypassC<D, Q, QC>(xG6, t.B, F);
-                    if (CF == CF_CONST) {
-    #pragma unroll
-                        for (int q = 0; q < Q * QC; ++q) F[q] *= a1c;
-                    } else {
-    #pragma unroll
-                        for (int q = 0; q < Q * QC; ++q) F[q] *= a1[q];
-                        if (OP == OP_JAC) {
-                            double zd[Q * QC];
-                            ypassC<D, Q, QC>(zG6, t.B, zd);
-    #pragma unroll
-                            for (int q = 0; q < Q * QC; ++q) F[q] += a2x[q] * zd[q];
-                        }
-                    }
-                    ypassTC<D, Q, QC>(F, t.BW, t6);
-                    xpassTC_acc<D, QC>(t6, t.GWh, wz * gxx, A);
-                }
-                {   // y direction (+ mass)
-                    double F[Q * QC];
-                    if (OP == OP_RES) ypassC<D, Q, QC>(zB6, t.G, F);
-                    else ypassC<D, Q, QC>(xB6, t.G, F);
-                    if (CF == CF_CONST) {
-    #pragma unroll
-                        for (int q = 0; q < Q * QC; ++q) F[q] *= a1c;
-                    } else {
-    #pragma unroll
-                        for (int q = 0; q < Q * QC; ++q) F[q] *= a1[q];
-                        if (OP == OP_JAC) {
-                            double zd[Q * QC];
-                            ypassC<D, Q, QC>(zB6, t.G, zd);
-    #pragma unroll
-                            for (int q = 0; q < Q * QC; ++q) F[q] += a2x[q] * zd[q];
-                        }
-                    }
-                    ypassTC<D, Q, QC>(F, t.GW, t6);
-                    const double cy = wz * gyy;
-    #pragma unroll
-                    for (int i = 0; i < D * QC; ++i) t6[i] = cy * t6[i] + c_m * vy6[i];
-                    xpassTC_acc<D, QC>(t6, t.BWh, 1.0, A);
-                }
-                {   // z direction
-                    double F[Q * QC];
-                    getp(OP == OP_RES ? C::P_ZG : C::P_XG, p9);
-                    xpassC<D, QC>(p9, t.B, t6);
-                    ypassC<D, Q, QC>(t6, t.B, F);
-                    if (CF == CF_CONST) {
-    #pragma unroll
-                        for (int q = 0; q < Q * QC; ++q) F[q] *= a1c;
-                    } else {
-    #pragma unroll
-                        for (int q = 0; q < Q * QC; ++q) F[q] *= a1[q];
-                        if (OP == OP_JAC) {
-                            double zd[Q * QC];
-                            getp(C::P_ZG, p9);
-                            xpassC<D, QC>(p9, t.B, t6);
-                            ypassC<D, Q, QC>(t6, t.B, zd);
-    #pragma unroll
-                            for (int q = 0; q < Q * QC; ++q) F[q] += a2x[q] * zd[q];
-                        }
-                    }
-                    ypassTC<D, Q, QC>(F, t.BW, t6);
-                    xpassTC_acc<D, QC>(t6, t.BWh, wz * gzz, Bp);
-                }
-            }
-            flip_plane<D>(A, h);
-            flip_plane<D>(Bp, h);
-            // result planes alias input planes [0..3][qz] of this (element, qz): only this thread pair
-            // (adjacent lanes) ever touches them
-            __syncwarp(p2mask);
-            // A -> plane h, Bp -> plane 2 + h (layout chosen so that the pair's stores do not collide)
-            double* outp = pl + (h ? 1 : 0) * PSET;
-#pragma unroll
-            for (int m = 0; m < DD; ++m) { outp[m] = A[m]; outp[2 * PSET + m] = Bp[m]; }
+            slab_phase2<D, Q, OP, CF, PSET, MIRROR>(a, t, pl, h, wz, gxx, gyy, gzz, p2mask);
         }
         __syncthreads();
 

@@ -110,6 +110,13 @@ int jots_mesh_copy(jots_mesh_t m, double* verts, int64_t* elems, int64_t* bdr, i
     return 0;
     JOTS_CATCH_INT
 }
+int jots_mesh_set_vertices(jots_mesh_t m, const double* verts) {
+    JOTS_TRY
+    if (!verts) throw std::runtime_error("jots_mesh_set_vertices: null coordinates");
+    std::memcpy(m->m.verts.data(), verts, m->m.verts.size() * sizeof(double));
+    return 0;
+    JOTS_CATCH_INT
+}
 
 // ---- space ------------------------------------------------------------------------------------
 jots_space_t jots_space_create(jots_mesh_t m, int order) {
@@ -197,6 +204,18 @@ int64_t jots_space_essential_dofs(jots_space_t s, const int32_t* attrs, int n_at
     } catch (const std::exception& ex) { fail(ex); return -1; }
 }
 
+int64_t jots_space_rowtiles(jots_space_t s, const int32_t* ess, int64_t n_ess, int tile_elems, double min_fill,
+                            int* record_bytes, unsigned char* out) {
+    try {
+        std::vector<int> e(ess, ess + n_ess);
+        std::vector<unsigned char> tab;
+        const int64_t nt = make_rowtiles(s->s, e, tile_elems, min_fill, tab);
+        if (record_bytes) *record_bytes = nt > 0 ? (int)(tab.size() / (size_t)nt) : 0;
+        if (out && nt > 0) std::memcpy(out, tab.data(), tab.size());
+        return nt;
+    } catch (const std::exception& ex) { fail(ex); return -1; }
+}
+
 // ---- context ----------------------------------------------------------------------------------
 jots_ctx_t jots_ctx_create(jots_space_t s, int device) {
     JOTS_TRY
@@ -275,6 +294,7 @@ int jots_ctx_stats(jots_ctx_t c, int64_t out[12], double norms[2]) {
     if (norms) { norms[0] = s.last_linear_norm; norms[1] = s.last_newton_norm; }
     return 0;
 }
+int64_t jots_ctx_rowtile_applies(jots_ctx_t c) { return c->c->stats.rowtile_applies; }
 int jots_ctx_reset_stats(jots_ctx_t c) { c->c->stats = Stats(); return 0; }
 
 // ---- operators --------------------------------------------------------------------------------

@@ -62,6 +62,7 @@ void Ctx::init(const Space& s, int dev) {
     n = s.ndof; n_owned = s.ndof;
     if (const char* ev = std::getenv("JOTS_DISABLE_SLAB")) use_slab = !(ev[0] == '1');
     if (const char* ev = std::getenv("JOTS_OVERLAP_HALO")) overlap_halo = (ev[0] == '1');
+    if (const char* ev = std::getenv("JOTS_SLAB_VARIANT")) slab_variant = std::atoi(ev);
     fill_tables(tabs, s.dim, s.p);
     // geometry: affine elements get one record each (one shared record when all are identical);
     // general multilinear meshes get a record per quadrature point (d_geomq)
@@ -182,6 +183,23 @@ void Ctx::set_bcs(const std::vector<BCSpec>& b) {
     for (auto& g : ge) if (em[g]) g = ~g;
     d_gather_ess.upload(ge);
     d_gattr.alloc(std::max<size_t>(bcs.size(), 1));
+    build_rowtiles();
+}
+
+// Row-structured tiles of apply_slab4.cuh (make_rowtiles, mesh.cpp): all-or-nothing, rebuilt with the essential set
+void Ctx::build_rowtiles() {
+    d_rowtiles.release();
+    n_rowtiles = 0;
+    if (space.dim != 3 || !geom_diag || !use_slab || slab_variant < 4 || space.nelem == 0) return;
+    const int E = slab4_tile_elems(space.p);
+    if (E <= 0) return;
+    std::vector<unsigned char> tab;
+    // JOTS_SLAB_VARIANT=5 keeps short tiles too (tests on small bricks)
+    const int64_t nt = make_rowtiles(space, ess, E, slab_variant == 4 ? 0.75 : 0.0, tab);
+    if (nt <= 0) return;
+    d_rowtiles.upload(tab);
+    n_rowtiles = (int)nt;
+    rowtile_elems = E;
 }
 
 bool Ctx::any_flux() const {
@@ -209,6 +227,10 @@ FormArgs Ctx::make_args(const FormSpec& f, const double* x, double* y, bool for_
     a.diag_one = (f.diag_one && f.mask_out && !halo && !for_diag) ? 1 : 0;   // multi-GPU: after the interface sum
     a.cm = f.cm; a.ck = f.ck; a.cb = f.cb; a.m0 = f.m0; a.a0 = f.a0; a.inv_rc = f.inv_rc;
     a.mat = mat;
+    a.rowtiles = (n_rowtiles > 0 && !for_diag) ? d_rowtiles.p : nullptr;
+    a.n_rowtiles = n_rowtiles;
+    a.rowtile_elems = rowtile_elems;
+    a.nvec = n;
     return a;
 }
 
@@ -243,6 +265,7 @@ void Ctx::apply_form(const FormSpec& f, const double* x, double* y) {
     int rc;
     if (n_if > 0 && n_if < space.nelem) {
         // interface elements first, their exchange overlaps the interior elements
+        a.rowtiles = nullptr; a.n_rowtiles = 0;   // element sub-ranges: gather-table kernels only
         FormArgs ai = a;
         ai.nelem = (int)n_if;
         rc = launch_form_apply(space.dim, space.p, f.op, f.cf, ai, tabs, stream);
@@ -259,7 +282,12 @@ void Ctx::apply_form(const FormSpec& f, const double* x, double* y) {
             overlapped = true;
             ++stats.kernel_launches;
         }
-    } else rc = launch_form_apply(space.dim, space.p, f.op, f.cf, a, tabs, stream);
+    } else {
+        // bricks: row-structured TMA kernel (no gather table); otherwise / when not instantiated the gather-table kernels
+        rc = (a.rowtiles && a.geom_diag && space.dim == 3) ? launch_form_apply_slab4(space.p, f.op, f.cf, a, tabs, stream) : 1;
+        if (!rc) ++stats.rowtile_applies;
+        else rc = launch_form_apply(space.dim, space.p, f.op, f.cf, a, tabs, stream);
+    }
     if (rc) throw std::runtime_error("form (op=" + std::to_string(f.op) + ", cf=" + std::to_string(f.cf) + ") is not instantiated, rc=" + std::to_string(rc));
     stats.kernel_launches += 2;
     if (f.bdr_mass_scale != 0.0 && any_flux()) {

@@ -68,7 +68,7 @@ struct FormSpec {
 
 struct Stats {
     long long applies = 0, diag_assemblies = 0, krylov_iters = 0, newton_iters = 0, residual_evals = 0, steps = 0,
-              kernel_launches = 0, dots = 0, halo_exchanges = 0;
+              kernel_launches = 0, dots = 0, halo_exchanges = 0, rowtile_applies = 0;
     double last_linear_norm = 0, last_newton_norm = 0;
     int last_linear_converged = 1, last_newton_converged = 1, last_linear_iters = 0, last_newton_iters = 0;
 };
@@ -101,6 +101,10 @@ public:
     std::vector<DArr<int>> d_bc_dofs;
     DArr<double> d_geom, d_geomq, d_bdr_corner, d_gattr;
     DArr<unsigned char> d_essmark;
+    DArr<unsigned char> d_rowtiles;   // RowTile<D> table of the row-structured slab kernel (empty: not applicable)
+    int n_rowtiles = 0, rowtile_elems = 0;
+    int slab_variant = 3;             // JOTS_SLAB_VARIANT: 2 non-persistent, 3 pipelined gather-table kernel, 4 row-structured (TMA)
+    void build_rowtiles();            // from space.gather + essential marks; all-or-nothing
     int geom_stride = 10;
     bool geom_diag = false;   // diagonal metric on every element
     bool use_slab = true;     // JOTS_DISABLE_SLAB=1 forces the generic kernel

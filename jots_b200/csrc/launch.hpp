@@ -11,6 +11,8 @@ namespace jots {
 // returns 0 on success, non-zero when the (shape, op, cf) combination is not instantiated
 int launch_form_apply(int dim, int p, int op, int cf, const FormArgs& a, const TablesRT& t, cudaStream_t st);
 int launch_form_apply_slab(int p, int op, int cf, const FormArgs& a, const TablesRT& t, cudaStream_t st);
+int launch_form_apply_slab4(int p, int op, int cf, const FormArgs& a, const TablesRT& t, cudaStream_t st);
+int slab4_tile_elems(int p);   // elements per RowTile for order p (0: none)
 int launch_form_diag_slab(int p, int op, int cf, const FormArgs& a, const TablesRT& t, cudaStream_t st);
 int launch_form_diag(int dim, int p, int op, int cf, const FormArgs& a, const TablesRT& t, cudaStream_t st);
 int launch_face(int mode, const FaceArgs& a, cudaStream_t st);

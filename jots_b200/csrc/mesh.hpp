@@ -69,4 +69,11 @@ struct Space {
 
 Space make_space(const Mesh& m, int p);
 
+// Row-structured tiles (RowTile<D> records of forms.hpp, apply_slab4.cuh): greedy segmentation of the element order
+// into runs of at most E elements in which DOF (i, j, k) of the m-th element is base[k*D + j] + p*m + i (contiguous
+// rows along the fastest lattice axis).  Returns the number of tiles, or 0 when some element is not even a run of
+// length one (file meshes numbered in first-appearance order, subdomains with owned-first numbering) or when the
+// tiles are on average less than min_fill full.  ess: sorted essential DOFs (one bit per row node in the record).
+int64_t make_rowtiles(const Space& s, const std::vector<int>& ess, int E, double min_fill, std::vector<unsigned char>& tab);
+
 }  // namespace jots

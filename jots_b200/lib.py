@@ -54,6 +54,7 @@ def load_library():
         "jots_mesh_destroy": (None, [_P]),
         "jots_mesh_info": (C.c_int, [_P, C.POINTER(C.c_int), _I64, _I64, _I64]),
         "jots_mesh_copy": (C.c_int, [_P, _P, _P, _P, _P]),
+        "jots_mesh_set_vertices": (C.c_int, [_P, _P]),
         "jots_space_create": (_P, [_P, C.c_int]),
         "jots_space_destroy": (None, [_P]),
         "jots_space_create_from_tables": (_P, [C.c_int, C.c_int, C.c_int64, C.c_int64, _P, _P, C.c_int64, _P, _P, _P]),
@@ -63,6 +64,7 @@ def load_library():
         "jots_space_copy_bdr": (C.c_int, [_P, _P, _P, _P, _P]),
         "jots_space_copy_nodes": (C.c_int, [_P, _P]),
         "jots_space_essential_dofs": (C.c_int64, [_P, _P, C.c_int, _P]),
+        "jots_space_rowtiles": (C.c_int64, [_P, _P, C.c_int64, C.c_int, C.c_double, _P, _P]),
         "jots_ctx_create": (_P, [_P, C.c_int]),
         "jots_ctx_destroy": (None, [_P]),
         "jots_ctx_size": (C.c_int64, [_P]),
@@ -76,6 +78,7 @@ def load_library():
         "jots_ctx_set_material_state": (C.c_int, [_P, _P, C.c_int]),
         "jots_ctx_stats": (C.c_int, [_P, _P, _P]),
         "jots_ctx_reset_stats": (C.c_int, [_P]),
+        "jots_ctx_rowtile_applies": (C.c_int64, [_P]),
         "jots_op_create": (_P, [_P, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int,
                                 C.c_double, C.c_double, C.c_int]),
         "jots_op_destroy": (None, [_P]),
@@ -205,6 +208,10 @@ class Mesh:
         _chk(load_library().jots_mesh_copy(self._h, _ptr(verts), _ptr(elems), _ptr(bdr), _ptr(battr)))
         return verts, elems, bdr, battr
 
+    def set_vertices(self, verts):
+        """New vertex coordinates [n_verts, dim] on the same topology (mfem::Mesh::SetVertices)."""
+        _chk(load_library().jots_mesh_set_vertices(self._h, _ptr(np.ascontiguousarray(verts, dtype=np.float64))))
+
     def __del__(self):
         if getattr(self, "_h", None) and _LIB is not None:
             _LIB.jots_mesh_destroy(self._h)
@@ -263,6 +270,25 @@ class Space:
         out = np.empty(n, dtype=np.int32)
         load_library().jots_space_essential_dofs(self._h, _ptr(a), a.size, _ptr(out))
         return out
+
+    def rowtiles(self, ess, tile_elems, min_fill=0.0):
+        """Row-structured tiles of the TMA element kernel: structured array (e0, nv, any_ess, base[D*D], ess[D*D]),
+        empty when the space has no row structure."""
+        ess = np.ascontiguousarray(ess, dtype=np.int32)
+        rec = C.c_int(0)
+        lib = load_library()
+        n = lib.jots_space_rowtiles(self._h, _ptr(ess), ess.size, tile_elems, min_fill, C.byref(rec), None)
+        if n < 0:
+            raise JotsError(_err())
+        dd = (self.order + 1) ** 2
+        dt = np.dtype([("e0", "<i4"), ("nv", "<i4"), ("any_ess", "<i4"), ("pad", "<i4"), ("base", "<i4", (dd + dd % 2,)),
+                       ("ess", "<u8", (dd,))])
+        if n == 0:
+            return np.empty(0, dtype=dt)
+        assert rec.value == dt.itemsize, (rec.value, dt.itemsize)
+        buf = np.empty(n * rec.value, dtype=np.uint8)
+        lib.jots_space_rowtiles(self._h, _ptr(ess), ess.size, tile_elems, min_fill, C.byref(rec), _ptr(buf))
+        return buf.view(dt)
 
     def __del__(self):
         if getattr(self, "_h", None) and _LIB is not None:
@@ -332,6 +358,7 @@ class Context:
                 "dots", "last_linear_iters", "last_linear_converged", "last_newton_iters", "last_newton_converged"]
         d = {k: int(v) for k, v in zip(keys, out)}
         d["last_linear_norm"], d["last_newton_norm"] = float(norms[0]), float(norms[1])
+        d["rowtile_applies"] = int(load_library().jots_ctx_rowtile_applies(self._h))
         return d
 
     def reset_stats(self):
