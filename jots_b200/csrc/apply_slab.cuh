@@ -629,10 +629,14 @@ template <int D, int Q, int NP> struct Elem3Stride {
     static constexpr int raw = NPA * PSET;
     static constexpr int value = raw + ((Slab3Layout<D, Q>::ESM - raw % 16) + 16) % 16;
 };
+// Staging buffers for the L-vector values: two (values of tile i+1 land while tile i is in phases 1-3), or one when the
+// tile is so large that a second buffer would cost a resident block (Q2, E = 16: 52 KB instead of 59 KB per block keeps
+// four blocks per SM); the single buffer is refilled right after phase 1 and has phases 2-3 to land.
+template <int Q, int E> struct Slab3Stages { static constexpr int value = (Q == 4 && E >= 16) ? 1 : 2; };
 template <int D, int Q, int NP, int E> struct Slab3Smem {
     static constexpr int ND = D * D * D;
     static constexpr size_t planes = (size_t)E * Elem3Stride<D, Q, NP>::value * sizeof(double);
-    static constexpr size_t stage = (size_t)2 * 2 * E * ND * sizeof(double);
+    static constexpr size_t stage = (size_t)Slab3Stages<Q, E>::value * 2 * E * ND * sizeof(double);
     static constexpr size_t idx = (size_t)3 * E * ND * sizeof(int);
     static constexpr size_t total = planes + stage + idx;
 };
@@ -915,8 +919,9 @@ __global__ void __launch_bounds__(T) form_apply_slab3_kernel(const FormArgs a, c
     constexpr bool NEED_Z = C::Z_GRAD || NF > 0;
     extern __shared__ __align__(16) double smem[];
     double* planes = smem;
-    double* stage = smem + (size_t)E * ES;                                  // [2][2][E*ND]
-    int* idxbuf = reinterpret_cast<int*>(stage + (size_t)2 * 2 * E * ND);   // [3][E*ND]
+    constexpr int NSTG = Slab3Stages<Q, E>::value;
+    double* stage = smem + (size_t)E * ES;                                  // [NSTG][2][E*ND]
+    int* idxbuf = reinterpret_cast<int*>(stage + (size_t)NSTG * 2 * E * ND);   // [3][E*ND]
     const int tid = threadIdx.x;
     const int ntiles = (a.nelem + E - 1) / E;
     const int nmine = blockIdx.x < ntiles ? (ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
@@ -938,7 +943,7 @@ __global__ void __launch_bounds__(T) form_apply_slab3_kernel(const FormArgs a, c
         if (i < nmine) {
             const int n = nvalid(tile_of(i)) * ND;
             const int* ix = idxbuf + (i % 3) * E * ND;
-            double* sx = stage + (size_t)(i % 2) * 2 * E * ND;
+            double* sx = stage + (size_t)(i % NSTG) * 2 * E * ND;
             double* sz = sx + E * ND;
 #pragma unroll 1
             for (int m = tid; m < n; m += T) {
@@ -972,9 +977,9 @@ __global__ void __launch_bounds__(T) form_apply_slab3_kernel(const FormArgs a, c
         issue_idx(it + 2);
         cp_async_wait<1>();          // values of tile it and gather rows of tile it+1 have landed
         __syncthreads();
-        issue_vals(it + 1);
+        if (NSTG == 2) issue_vals(it + 1);
         const int* ix = idxbuf + (it % 3) * E * ND;
-        const double* sx = stage + (size_t)(it % 2) * 2 * E * ND;
+        const double* sx = stage + (size_t)(it % NSTG) * 2 * E * ND;
         const double* sz = sx + E * ND;
 
         // ---------------- phase 1: z contraction from the staged values ---------------------------
@@ -1021,6 +1026,7 @@ __global__ void __launch_bounds__(T) form_apply_slab3_kernel(const FormArgs a, c
             }
         }
         __syncthreads();
+        if (NSTG == 1) issue_vals(it + 1);   // the staging buffer is free again; the copies land during phases 2-3
 
         // ---------------- phase 2: half a quadrature plane per thread ----------------------------
         const unsigned p2mask = __ballot_sync(0xffffffffu, tid < E * Q * 2);

@@ -17,6 +17,11 @@
 // of their arithmetic and of the FP64 atomics, makes both fit one pass of the block at E = 16 (99 of 128 threads,
 // so phase 2 can use all 128), and turns the scatter into contiguous runs: lane n adds to base[k*D + j] + n.  No
 // index ever travels through memory.
+//
+// A pencil thread owns its plane slots (element, ij) in both phases, so phase 3 of tile i and phase 1 of tile i+1
+// need no barrier between them: they are fused into one pass ("phase 3+1"), which leaves two block barriers per
+// tile and lets the latency-bound tails of one overlap the loads of the other.  Pencils and the issue of the bulk
+// copies are spread evenly over the warps (a bulk copy is a warp-serialised uniform-datapath instruction).
 #pragma once
 #include "apply_slab.cuh"
 
@@ -76,7 +81,10 @@ struct Slab4Smem {
 // Q2 with up to two property fields: cap at 128 registers so that four blocks stay resident per SM
 template <int Q, int CF> struct Slab4MinBlocks { static constexpr int value = Q != 4 ? 1 : CF == CF_FULL ? 2 : CF == CF_FULLC ? 3 : 4; };
 
-template <int D, int Q, int OP, int CF, int E, int T>
+// TMA_ROWS: the rows come by cp.async.bulk (one warp-serialised UBLKCP per row); otherwise by coalesced 8-byte cp.async
+// issued by all threads (no alignment window, completion through cp.async.mbarrier.arrive on the same mbarrier).  The
+// tile descriptor always comes by one bulk copy.
+template <int D, int Q, int OP, int CF, int E, int T, bool TMA_ROWS>
 __global__ void __launch_bounds__(T, Slab4MinBlocks<Q, CF>::value) form_apply_slab4_kernel(const FormArgs a, const Slab2Tables<D, Q> t) {
     typedef SlabCfg<OP, CF> C;
     constexpr int NF = C::NF, NFA = NF > 0 ? NF : 1, NP = C::NP;
@@ -88,7 +96,11 @@ __global__ void __launch_bounds__(T, Slab4MinBlocks<Q, CF>::value) form_apply_sl
     constexpr int NV = NEED_Z ? 2 : 1;
     typedef Slab4Smem<D, Q, NP, E, NV> S;
     constexpr int RS = S::RS, NROW = S::NROW, NNMAX = S::LMAX;
-    constexpr int ISSUE0 = T - 32;   // the last warp issues the copies (it has the fewest pencils in phases 1 / 3)
+    constexpr int NW = T / 32;
+    constexpr int NPEN = NNMAX * D;                        // unique pencils of a full tile
+    constexpr int PPW = (NPEN + NW - 1) / NW;              // pencils per warp when one pass suffices
+    constexpr bool ONE_PASS = PPW <= 32;
+    constexpr int RPW = (NROW + NW - 1) / NW;              // bulk copies issued per warp (by its last RPW lanes)
     extern __shared__ __align__(16) double smem[];
     double* planes = smem;
     double* rows = smem + (size_t)E * ES;                                        // [2][NROW][RS]
@@ -96,7 +108,7 @@ __global__ void __launch_bounds__(T, Slab4MinBlocks<Q, CF>::value) form_apply_sl
     unsigned long long* rowbar = reinterpret_cast<unsigned long long*>(desc + 3);     // [2]
     unsigned long long* descbar = rowbar + 2;                                    // [3]
     const RowTile<D>* gdesc = static_cast<const RowTile<D>*>(a.rowtiles);
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int ntiles = a.n_rowtiles;
     const int nmine = (int)blockIdx.x < ntiles ? (ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
     auto tile_of = [&](int i) { return (int)blockIdx.x + i * (int)gridDim.x; };
@@ -105,8 +117,8 @@ __global__ void __launch_bounds__(T, Slab4MinBlocks<Q, CF>::value) form_apply_sl
     const int zpar = NEED_Z ? (int)((reinterpret_cast<unsigned long long>(a.z) >> 3) & 1ull) : 0;
 
     if (tid == 0) {
-        mbar_init(&rowbar[0], NROW);
-        mbar_init(&rowbar[1], NROW);
+        mbar_init(&rowbar[0], TMA_ROWS ? NROW : T);
+        mbar_init(&rowbar[1], TMA_ROWS ? NROW : T);
         mbar_init(&descbar[0], 1);
         mbar_init(&descbar[1], 1);
         mbar_init(&descbar[2], 1);
@@ -116,15 +128,32 @@ __global__ void __launch_bounds__(T, Slab4MinBlocks<Q, CF>::value) form_apply_sl
 
     // descriptor of tile i -> desc[i % 3]
     auto issue_desc = [&](int i) {
-        if (tid == ISSUE0 && i < nmine) {
+        if (tid == 0 && i < nmine) {
             mbar_arrive_expect_tx(&descbar[i % 3], (unsigned)sizeof(RowTile<D>));
             bulk_g2s(&desc[i % 3], gdesc + tile_of(i), (unsigned)sizeof(RowTile<D>), &descbar[i % 3]);
         }
     };
-    // L-vector rows of tile i -> rows[i % 2]; lane r < NROW of the issuing warp owns row r (x rows first, then z rows)
+    // L-vector rows of tile i -> rows[i % 2]; row r (x rows first, then z rows) is issued by lane 32 - RPW + r % RPW of
+    // warp r / RPW
     auto issue_rows = [&](int i) {
-        const int r = tid - ISSUE0;
-        if (r >= 0 && r < NROW && i < nmine) {
+        if constexpr (!TMA_ROWS) {
+            if (i < nmine) {
+                mbar_wait(&descbar[i % 3], (unsigned)((i / 3) & 1));
+                const RowTile<D>& d = desc[i % 3];
+                const int L = P * d.nv + 1;
+                double* stage = rows + (size_t)(i % 2) * NROW * RS;
+#pragma unroll 1
+                for (int c = tid; c < NROW * NNMAX; c += T) {
+                    const int r = c / NNMAX, m = c - r * NNMAX;
+                    const int v = r / DD, rr = r - v * DD;
+                    if (m < L) cp_async8(stage + r * RS + m, (v ? a.z : a.x) + ((long long)d.base[rr] + m));
+                }
+                asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];\n" ::"r"(smem_u32(&rowbar[i % 2])) : "memory");
+            }
+            return;
+        }
+        const int r = warp * RPW + (lane - (32 - RPW));
+        if (lane >= 32 - RPW && r < NROW && i < nmine) {
             mbar_wait(&descbar[i % 3], (unsigned)((i / 3) & 1));
             const RowTile<D>& d = desc[i % 3];
             const int v = r / DD, rr = r - v * DD;
@@ -148,9 +177,139 @@ __global__ void __launch_bounds__(T, Slab4MinBlocks<Q, CF>::value) form_apply_sl
         }
     };
 
+    // phase 1 of tile i for pencil (node n, j): z contraction of x, z and the nodal property fields -> planes
+    auto phase1 = [&](int i, int n, int j) {
+        const RowTile<D>& d = desc[i % 3];
+        const int nv = d.nv;
+        if (n >= P * nv + 1) return;
+        const bool ess_tile = d.any_ess != 0;
+        const double* rx = rows + (size_t)(i % 2) * NROW * RS;
+        const double* rz = rx + DD * RS;
+        double xr[D], zr[D], fr[NFA][D];
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+            const int rr = k * D + j;
+            const int b = d.base[rr];
+            xr[k] = rx[rr * RS + (TMA_ROWS ? ((b + xpar) & 1) : 0) + n];
+            if (ess_tile && a.mask_in && ((d.ess[rr] >> n) & 1ull)) xr[k] = 0.0;
+            if (NEED_Z) {
+                zr[k] = rz[rr * RS + (TMA_ROWS ? ((b + zpar) & 1) : 0) + n];
+                if (NF > 0) {
+                    double f[NFA];
+                    nodal_fields<CF, OP>(a.mat, zr[k], f);
+#pragma unroll
+                    for (int m = 0; m < NF; ++m)
+                        fr[m][k] = CF == CF_K ? (a.ck * a.inv_rc) * f[m] : (CF == CF_LINFIELDS && m == 2) ? a.ck * f[m] : f[m];
+                }
+            }
+        }
+        // node n is local node ib of element ea (if that element exists) and, when it closes element ea - 1,
+        // local node P of that one
+        const int ea = n / P, ib = n - ea * P;
+        const bool has0 = ea < nv, has1 = (ib == 0 && ea >= 1);
+        double* d0 = planes + ea * ES + j * D + ib;
+        double* d1 = d0 - ES + P;
+#pragma unroll
+        for (int qz = 0; qz < Q; ++qz) {
+            double s = 0.0, sg = 0.0, zs = 0.0, zg = 0.0, fs[NFA];
+#pragma unroll
+            for (int k = 0; k < D; ++k) {
+                s += t.B[qz * D + k] * xr[k];
+                if (C::X_GRAD) sg += t.G[qz * D + k] * xr[k];
+                if (C::Z_GRAD) { zs += t.B[qz * D + k] * zr[k]; zg += t.G[qz * D + k] * zr[k]; }
+            }
+#pragma unroll
+            for (int m = 0; m < NF; ++m) {
+                fs[m] = 0.0;
+#pragma unroll
+                for (int k = 0; k < D; ++k) fs[m] += t.B[qz * D + k] * fr[m][k];
+            }
+            if (has0) {
+                d0[C::P_XB * PSET + qz * PS] = s;
+                if (C::X_GRAD) d0[C::P_XG * PSET + qz * PS] = sg;
+                if (C::Z_GRAD) { d0[C::P_ZB * PSET + qz * PS] = zs; d0[C::P_ZG * PSET + qz * PS] = zg; }
+#pragma unroll
+                for (int m = 0; m < NF; ++m) d0[(C::P_F0 + m) * PSET + qz * PS] = fs[m];
+            }
+            if (has1) {
+                d1[C::P_XB * PSET + qz * PS] = s;
+                if (C::X_GRAD) d1[C::P_XG * PSET + qz * PS] = sg;
+                if (C::Z_GRAD) { d1[C::P_ZB * PSET + qz * PS] = zs; d1[C::P_ZG * PSET + qz * PS] = zg; }
+#pragma unroll
+                for (int m = 0; m < NF; ++m) d1[(C::P_F0 + m) * PSET + qz * PS] = fs[m];
+            }
+        }
+    };
+    // phase 3 of tile i for pencil (node n, j): sum the result planes of the elements sharing the node, transposed z
+    // contraction, contiguous scatter (lane n -> base[k*D + j] + n)
+    auto phase3 = [&](int i, int n, int j) {
+        const RowTile<D>& d = desc[i % 3];
+        const int nv = d.nv;
+        if (n >= P * nv + 1) return;
+        const bool ess_tile = d.any_ess != 0;
+        const int ea = n / P, ib = n - ea * P;
+        const bool has0 = ea < nv, has1 = (ib == 0 && ea >= 1);
+        const double* s0 = planes + ea * ES + j * D + ib;
+        const double* s1 = s0 - ES + P;
+        double Aq[Q], Bq[Q];
+#pragma unroll
+        for (int qz = 0; qz < Q; ++qz) { Aq[qz] = 0.0; Bq[qz] = 0.0; }
+        if (has0) {
+#pragma unroll
+            for (int qz = 0; qz < Q; ++qz) {
+                Aq[qz] = s0[qz * PS] + s0[PSET + qz * PS];
+                Bq[qz] = s0[2 * PSET + qz * PS] + s0[3 * PSET + qz * PS];
+            }
+        }
+        if (has1) {
+#pragma unroll
+            for (int qz = 0; qz < Q; ++qz) {
+                Aq[qz] += s1[qz * PS] + s1[PSET + qz * PS];
+                Bq[qz] += s1[2 * PSET + qz * PS] + s1[3 * PSET + qz * PS];
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+            double sa = 0.0, sb = 0.0;   // two independent chains
+#pragma unroll
+            for (int qz = 0; qz < Q; ++qz) { sa += t.B[qz * D + k] * Aq[qz]; sb += t.G[qz * D + k] * Bq[qz]; }
+            const double s = sa + sb;
+            const int rr = k * D + j;
+            const long long g = (long long)d.base[rr] + n;
+            const bool is_ess = ess_tile && ((d.ess[rr] >> n) & 1ull);
+            if (!is_ess || !a.mask_out) atomicAdd(a.y + g, s);
+            else if (a.diag_one) a.y[g] = a.x[g];   // every writer stores the same value
+        }
+    };
+    // fused pass over the pencils: phase 3 of tile i3 (if >= 0), then phase 1 of tile i1 (if < nmine).  A pencil
+    // thread owns its plane slots, so the only ordering needed is program order within the thread.
+    auto pencil_pass = [&](int i3, int i1) {
+        const bool do1 = i1 < nmine;
+        if (do1) {
+            mbar_wait(&descbar[i1 % 3], (unsigned)((i1 / 3) & 1));
+            mbar_wait(&rowbar[i1 % 2], (unsigned)((i1 / 2) & 1));
+        }
+        if (ONE_PASS) {
+            const int u = warp * PPW + lane;
+            if (lane < PPW && u < NPEN) {
+                const int j = u / NNMAX, n = u - j * NNMAX;
+                if (i3 >= 0) phase3(i3, n, j);
+                if (do1) phase1(i1, n, j);
+            }
+        } else {
+#pragma unroll 1
+            for (int u = tid; u < NPEN; u += T) {
+                const int j = u / NNMAX, n = u - j * NNMAX;
+                if (i3 >= 0) phase3(i3, n, j);
+                if (do1) phase1(i1, n, j);
+            }
+        }
+    };
+
     issue_desc(0);
     issue_desc(1);
     issue_rows(0);
+    issue_rows(1);
 
     // geometry of a uniform mesh is loop invariant
     double gxx = 0, gyy = 0, gzz = 0, det = 0;
@@ -162,81 +321,12 @@ __global__ void __launch_bounds__(T, Slab4MinBlocks<Q, CF>::value) form_apply_sl
         det = gm[9];
     }
 
-    for (int it = 0; it < nmine; ++it) {
-        // slot (it+2) % 3 held tile it-1 (last used in its phase 3), stage (it+1) % 2 held tile it-1 (last read in its
-        // phase 1): both are behind the __syncthreads that closed the previous iteration
-        issue_desc(it + 2);
-        issue_rows(it + 1);
-        mbar_wait(&descbar[it % 3], (unsigned)((it / 3) & 1));
-        mbar_wait(&rowbar[it % 2], (unsigned)((it / 2) & 1));
-        const RowTile<D>& d = desc[it % 3];
-        const int e0 = d.e0, nv = d.nv;
-        const int NN = P * nv + 1;                 // nodes of a row of this tile
-        const bool ess_tile = d.any_ess != 0;
-        const double* rx = rows + (size_t)(it % 2) * NROW * RS;
-        const double* rz = rx + DD * RS;
+    pencil_pass(-1, 0);
+    __syncthreads();
 
-        // ---------------- phase 1: z contraction of the unique nodal pencils (node n, j) ----------
-#pragma unroll 1
-        for (int u = tid; u < NNMAX * D; u += T) {
-            const int j = u / NNMAX, n = u - j * NNMAX;
-            if (n >= NN) continue;
-            double xr[D], zr[D], fr[NFA][D];
-#pragma unroll
-            for (int k = 0; k < D; ++k) {
-                const int rr = k * D + j;
-                const int b = d.base[rr];
-                xr[k] = rx[rr * RS + ((b + xpar) & 1) + n];
-                if (ess_tile && a.mask_in && ((d.ess[rr] >> n) & 1ull)) xr[k] = 0.0;
-                if (NEED_Z) {
-                    zr[k] = rz[rr * RS + ((b + zpar) & 1) + n];
-                    if (NF > 0) {
-                        double f[NFA];
-                        nodal_fields<CF, OP>(a.mat, zr[k], f);
-#pragma unroll
-                        for (int m = 0; m < NF; ++m)
-                            fr[m][k] = CF == CF_K ? (a.ck * a.inv_rc) * f[m] : (CF == CF_LINFIELDS && m == 2) ? a.ck * f[m] : f[m];
-                    }
-                }
-            }
-            // node n is local node ib of element ea (if that element exists) and, when it closes element ea - 1,
-            // local node P of that one
-            const int ea = n / P, ib = n - ea * P;
-            const bool has0 = ea < nv, has1 = (ib == 0 && ea >= 1);
-            double* d0 = planes + ea * ES + j * D + ib;
-            double* d1 = d0 - ES + P;
-#pragma unroll
-            for (int qz = 0; qz < Q; ++qz) {
-                double s = 0.0, sg = 0.0, zs = 0.0, zg = 0.0, fs[NFA];
-#pragma unroll
-                for (int k = 0; k < D; ++k) {
-                    s += t.B[qz * D + k] * xr[k];
-                    if (C::X_GRAD) sg += t.G[qz * D + k] * xr[k];
-                    if (C::Z_GRAD) { zs += t.B[qz * D + k] * zr[k]; zg += t.G[qz * D + k] * zr[k]; }
-                }
-#pragma unroll
-                for (int m = 0; m < NF; ++m) {
-                    fs[m] = 0.0;
-#pragma unroll
-                    for (int k = 0; k < D; ++k) fs[m] += t.B[qz * D + k] * fr[m][k];
-                }
-                if (has0) {
-                    d0[C::P_XB * PSET + qz * PS] = s;
-                    if (C::X_GRAD) d0[C::P_XG * PSET + qz * PS] = sg;
-                    if (C::Z_GRAD) { d0[C::P_ZB * PSET + qz * PS] = zs; d0[C::P_ZG * PSET + qz * PS] = zg; }
-#pragma unroll
-                    for (int m = 0; m < NF; ++m) d0[(C::P_F0 + m) * PSET + qz * PS] = fs[m];
-                }
-                if (has1) {
-                    d1[C::P_XB * PSET + qz * PS] = s;
-                    if (C::X_GRAD) d1[C::P_XG * PSET + qz * PS] = sg;
-                    if (C::Z_GRAD) { d1[C::P_ZB * PSET + qz * PS] = zs; d1[C::P_ZG * PSET + qz * PS] = zg; }
-#pragma unroll
-                    for (int m = 0; m < NF; ++m) d1[(C::P_F0 + m) * PSET + qz * PS] = fs[m];
-                }
-            }
-        }
-        __syncthreads();
+    for (int it = 0; it < nmine; ++it) {
+        // slot (it+2) % 3 held the descriptor of tile it-1, dead since the pass that closed the previous iteration
+        issue_desc(it + 2);
 
         // ---------------- phase 2: half a quadrature plane per thread ----------------------------
         const unsigned p2mask = __ballot_sync(0xffffffffu, tid < E * Q * 2);
@@ -244,7 +334,7 @@ __global__ void __launch_bounds__(T, Slab4MinBlocks<Q, CF>::value) form_apply_sl
             const int el = tid / (2 * Q), r = tid - el * 2 * Q, qz = r >> 1;
             const bool h = r & 1;
             if (a.geom_stride != 0) {
-                int e = e0 + el;
+                int e = desc[it % 3].e0 + el;
                 if (e >= a.nelem) e = a.nelem - 1;
                 const double* gm = a.geom + (size_t)e * a.geom_stride;
                 gxx = gm[0] * gm[0] + gm[1] * gm[1] + gm[2] * gm[2];
@@ -258,44 +348,11 @@ __global__ void __launch_bounds__(T, Slab4MinBlocks<Q, CF>::value) form_apply_sl
         }
         __syncthreads();
 
-        // ---------------- phase 3: transposed z contraction per unique pencil + contiguous scatter ----
-#pragma unroll 1
-        for (int u = tid; u < NNMAX * D; u += T) {
-            const int j = u / NNMAX, n = u - j * NNMAX;
-            if (n >= NN) continue;
-            const int ea = n / P, ib = n - ea * P;
-            const bool has0 = ea < nv, has1 = (ib == 0 && ea >= 1);
-            const double* s0 = planes + ea * ES + j * D + ib;
-            const double* s1 = s0 - ES + P;
-            double Aq[Q], Bq[Q];
-#pragma unroll
-            for (int qz = 0; qz < Q; ++qz) { Aq[qz] = 0.0; Bq[qz] = 0.0; }
-            if (has0) {
-#pragma unroll
-                for (int qz = 0; qz < Q; ++qz) {
-                    Aq[qz] = s0[qz * PS] + s0[PSET + qz * PS];
-                    Bq[qz] = s0[2 * PSET + qz * PS] + s0[3 * PSET + qz * PS];
-                }
-            }
-            if (has1) {
-#pragma unroll
-                for (int qz = 0; qz < Q; ++qz) {
-                    Aq[qz] += s1[qz * PS] + s1[PSET + qz * PS];
-                    Bq[qz] += s1[2 * PSET + qz * PS] + s1[3 * PSET + qz * PS];
-                }
-            }
-#pragma unroll
-            for (int k = 0; k < D; ++k) {
-                double s = 0.0;
-#pragma unroll
-                for (int qz = 0; qz < Q; ++qz) s += t.B[qz * D + k] * Aq[qz] + t.G[qz * D + k] * Bq[qz];
-                const int rr = k * D + j;
-                const long long g = (long long)d.base[rr] + n;
-                const bool is_ess = ess_tile && ((d.ess[rr] >> n) & 1ull);
-                if (!is_ess || !a.mask_out) atomicAdd(a.y + g, s);
-                else if (a.diag_one) a.y[g] = a.x[g];   // every writer stores the same value
-            }
-        }
+        // ---------------- phase 3 of this tile + phase 1 of the next one ---------------------------
+        // stage it % 2 held the rows of tile it (read by the previous pass): free for tile it+2, which lands while
+        // tile it+1 is in phase 2
+        issue_rows(it + 2);
+        pencil_pass(it, it + 1);
         __syncthreads();
     }
 }

@@ -44,8 +44,8 @@ int slab4_tile_elems(int p) {
     return 0;
 }
 
-template <int D, int Q, int OP, int CF, int E>
-static int launch_slab4e(const FormArgs& a, const TablesRT& r, cudaStream_t st) {
+template <int D, int Q, int OP, int CF, int E, bool TMA_ROWS>
+static int launch_slab4s(const FormArgs& a, const TablesRT& r, cudaStream_t st) {
     constexpr int T = (E * 2 * Q + 31) / 32 * 32;
     typedef SlabCfg<OP, CF> C;
     constexpr bool NEED_Z = C::Z_GRAD || C::NF > 0;
@@ -60,12 +60,22 @@ static int launch_slab4e(const FormArgs& a, const TablesRT& r, cudaStream_t st) 
         }
     }
     const size_t smem = Slab4Smem<D, Q, C::NP, E, NEED_Z ? 2 : 1>::total;
-    auto kern = form_apply_slab4_kernel<D, Q, OP, CF, E, T>;
+    auto kern = form_apply_slab4_kernel<D, Q, OP, CF, E, T, TMA_ROWS>;
     static PerDevice4 pd;
     const int grid_max = pd.get(kern, T, smem);
     const int ntiles = a.n_rowtiles;
     kern<<<ntiles < grid_max ? ntiles : grid_max, T, smem, st>>>(a, t);
     return 0;
+}
+
+// JOTS_SLAB4_STAGE=cpasync: rows by 8-byte cp.async instead of TMA bulk copies (A/B; Q2 only)
+template <int D, int Q, int OP, int CF, int E>
+static int launch_slab4e(const FormArgs& a, const TablesRT& r, cudaStream_t st) {
+    if constexpr (Q == 4 && E == 16) {
+        static const bool cpasync = [] { const char* e = getenv("JOTS_SLAB4_STAGE"); return e && e[0] == 'c'; }();
+        if (cpasync) return launch_slab4s<D, Q, OP, CF, E, false>(a, r, st);
+    }
+    return launch_slab4s<D, Q, OP, CF, E, true>(a, r, st);
 }
 
 template <int D, int Q, int OP, int CF>

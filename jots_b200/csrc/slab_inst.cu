@@ -76,18 +76,27 @@ static int launch_slab3e(const FormArgs& a, const TablesRT& r, cudaStream_t st) 
     kern<<<ntiles < grid_max ? ntiles : grid_max, T, smem, st>>>(a, t);
     return 0;
 }
+static int slab_elems() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("JOTS_SLAB_ELEMS"); v = e ? atoi(e) : 16; }
+    return v;
+}
 template <int D, int Q, int OP, int CF>
 static int launch_slab3(const FormArgs& a, const TablesRT& r, cudaStream_t st) {
-    if constexpr (Q == 4) return launch_slab3e<D, Q, OP, CF, 14>(a, r, st);   // E = 12 / 16 measured 13 % / 17 % slower
+    if constexpr (Q == 4) {
+        // E = 12 / 16 with two staging buffers measured 13 % / 17 % slower than 14 (16: three blocks per SM); E = 16 with
+        // one staging buffer keeps four blocks and all 128 threads busy in phase 2: Jacobian apply 1.32 -> 1.29 ms,
+        // residual 1.19 -> 1.13 ms at 17 M DOFs (JOTS_SLAB_ELEMS=14 selects the old tile).  Fusing phase 3 of a tile with
+        // phase 1 of the next (two barriers per tile) measured 1.5 % slower and was dropped.
+        if constexpr (CF != CF_FULL && CF != CF_FULLC) {
+            if (slab_elems() == 16) return launch_slab3e<D, Q, OP, CF, 16>(a, r, st);
+        }
+        return launch_slab3e<D, Q, OP, CF, 14>(a, r, st);
+    }
     else if constexpr (Q == 5) return launch_slab3e<D, Q, OP, CF, 12>(a, r, st);
     else return launch_slab3e<D, Q, OP, CF, 32>(a, r, st);
 }
 
-static int slab_elems() {
-    static int v = -1;
-    if (v < 0) { const char* e = getenv("JOTS_SLAB_ELEMS"); v = e ? atoi(e) : 14; }
-    return v;
-}
 template <int D, int Q, int OP, int CF>
 static int launch_slab2(const FormArgs& a, const TablesRT& r, cudaStream_t st) {
     if constexpr (Q == 4) return slab_elems() == 28 ? launch_slab2e<D, Q, OP, CF, 28>(a, r, st) : launch_slab2e<D, Q, OP, CF, 14>(a, r, st);
