@@ -107,6 +107,10 @@ int64_t jots_ctx_essential_dofs(jots_ctx_t c, int32_t* out);        /* ess_tdof_
 int jots_ctx_update_bcs(jots_ctx_t c, double time);                 /* BoundaryCondition::UpdateCoeff */
 int jots_ctx_apply_dirichlet(jots_ctx_t c, double* u, int loc, int only_time_dependent); /* ProjectBdrCoefficient, src/jots_driver.cpp:684-707 */
 int jots_ctx_set_material_state(jots_ctx_t c, const double* u, int loc); /* UpdateAllCoeffs(u), src/jots_driver.cpp:664 */
+/* Output-side property fields (OutputManager::UpdateGridFunctions -> ProjectCoefficient of the registered
+   MaterialProperty coefficient, src/output_manager.cpp:63-73, src/jots_driver.cpp:343): nodal values of property
+   `which` (0 rho, 1 C, 2 k), or of its first / second derivative (order 1 / 2), at the material state last set. */
+int jots_ctx_material_field(jots_ctx_t c, int which, int order, double* out, int loc);
 /* counters: applies, diag assemblies, krylov iters, newton iters, residual evals, steps,
    kernel launches, dots, last linear iters, last linear converged, last newton iters, last newton converged */
 int jots_ctx_stats(jots_ctx_t c, int64_t out[12], double norms[2]);

@@ -139,8 +139,22 @@ template <int D, int Q, int NP> struct Elem2Stride {
     static constexpr int value = raw + (((D * D) % 16 - raw % 16) + 16) % 16;   // == D*D (mod 16)
 };
 
-template <int D, int QC>
-__device__ __forceinline__ void xpassC(const double (&in)[D * D], const double* tab, double (&out)[D * QC]) {
+// Mirror symmetry of the 1-D tables (Gauss / Gauss-Lobatto points are symmetric about 1/2): row Q-1-q is row q read
+// backwards, with a sign flip for derivatives.  SymTab serves the upper rows from the lower ones at compile time, so
+// that a table has Q*D/2 distinct values and the whole working set (B, G, W B, W G: 24 doubles at Q2) stays in
+// uniform registers instead of being re-fetched from the constant bank.  The host symmetrises the tables
+// (fill_slab2_tables), so the aliasing changes no bit.
+template <int D, int Q, int SIGN>
+struct SymTab {
+    const double* p;
+    __device__ __forceinline__ double operator[](int idx) const {
+        const int q = idx / D, i = idx - q * D;
+        return (2 * q < Q) ? p[idx] : SIGN * p[(Q - 1 - q) * D + (D - 1 - i)];
+    }
+};
+
+template <int D, int QC, class Tab>
+__device__ __forceinline__ void xpassC(const double (&in)[D * D], const Tab tab, double (&out)[D * QC]) {
 #pragma unroll
     for (int j = 0; j < D; ++j)
 #pragma unroll
@@ -151,8 +165,8 @@ __device__ __forceinline__ void xpassC(const double (&in)[D * D], const double* 
             out[j * QC + c] = s;
         }
 }
-template <int D, int Q, int QC>
-__device__ __forceinline__ void ypassC(const double (&in)[D * QC], const double* tab, double (&out)[Q * QC]) {
+template <int D, int Q, int QC, class Tab>
+__device__ __forceinline__ void ypassC(const double (&in)[D * QC], const Tab tab, double (&out)[Q * QC]) {
 #pragma unroll
     for (int qy = 0; qy < Q; ++qy)
 #pragma unroll
@@ -163,8 +177,8 @@ __device__ __forceinline__ void ypassC(const double (&in)[D * QC], const double*
             out[qy * QC + c] = s;
         }
 }
-template <int D, int Q, int QC>
-__device__ __forceinline__ void ypassTC(const double (&in)[Q * QC], const double* tab, double (&out)[D * QC]) {
+template <int D, int Q, int QC, class Tab>
+__device__ __forceinline__ void ypassTC(const double (&in)[Q * QC], const Tab tab, double (&out)[D * QC]) {
 #pragma unroll
     for (int j = 0; j < D; ++j)
 #pragma unroll
@@ -175,8 +189,8 @@ __device__ __forceinline__ void ypassTC(const double (&in)[Q * QC], const double
             out[j * QC + c] = s;
         }
 }
-template <int D, int QC>
-__device__ __forceinline__ void xpassTC_acc(const double (&in)[D * QC], const double* tab, double scale, double (&acc)[D * D]) {
+template <int D, int QC, class Tab>
+__device__ __forceinline__ void xpassTC_acc(const double (&in)[D * QC], const Tab tab, double scale, double (&acc)[D * D]) {
 #pragma unroll
     for (int j = 0; j < D; ++j)
 #pragma unroll
@@ -186,6 +200,16 @@ __device__ __forceinline__ void xpassTC_acc(const double (&in)[D * QC], const do
             for (int c = 1; c < QC; ++c) s += tab[c * D + i] * in[j * QC + c];
             acc[j * D + i] += scale * s;
         }
+}
+// acc[j][i] += sum_c tab[c][i] in[j][c]  (input already scaled: one DFMA per term, straight into the accumulator)
+template <int D, int QC, class Tab>
+__device__ __forceinline__ void xpassTC_add(const double (&in)[D * QC], const Tab tab, double (&acc)[D * D]) {
+#pragma unroll
+    for (int j = 0; j < D; ++j)
+#pragma unroll
+        for (int i = 0; i < D; ++i)
+#pragma unroll
+            for (int c = 0; c < QC; ++c) acc[j * D + i] += tab[c * D + i] * in[j * QC + c];
 }
 // reverse the i index of a D x D plane when flip is set (branch-free selects)
 template <int D>
@@ -652,6 +676,9 @@ __device__ __forceinline__ void slab_phase2(const FormArgs& a, const Slab2Tables
     typedef SlabCfg<OP, CF> C;
     constexpr int QC = (Q + 1) / 2;
     constexpr int DD = D * D;
+    // mirrored rows come from the lower half of each table; for even Q the half-weight tables are the full-weight ones
+    const SymTab<D, Q, 1> tB{t.B}, tBW{t.BW}, tBWh{Q % 2 == 0 ? t.BW : t.BWh};
+    const SymTab<D, Q, -1> tG{t.G}, tGW{t.GW}, tGWh{Q % 2 == 0 ? t.GW : t.GWh};
     int mo[D];   // mirrored column offsets of the h = 1 thread
 #pragma unroll
     for (int i = 0; i < D; ++i) mo[i] = (MIRROR && h) ? D - 1 - i : i;
@@ -680,8 +707,8 @@ __device__ __forceinline__ void slab_phase2(const FormArgs& a, const Slab2Tables
         constexpr int F_K = 0, F_DK = 1, F_R = 2, F_DR = 3, F_D2R = 4, F_C = RHO ? 5 : 2, F_DC = RHO ? 6 : 3, F_D2C = RHO ? 7 : 4;
         auto field = [&](int n, double (&out)[NQH]) {
             getp(C::P_F0 + n, p9);
-            xpassC<D, QC>(p9, t.B, t6);
-            ypassC<D, Q, QC>(t6, t.B, out);
+            xpassC<D, QC>(p9, tB, t6);
+            ypassC<D, Q, QC>(t6, tB, out);
         };
         double a1[NQH], a2[NQH], nb[NQH], ndb[NQH];
         {
@@ -730,9 +757,9 @@ __device__ __forceinline__ void slab_phase2(const FormArgs& a, const Slab2Tables
         }
         double xB6[D * QC], xG6[D * QC], zB6[D * QC], zG6[D * QC], S[NQH];
         getp(C::P_XB, p9);
-        xpassC<D, QC>(p9, t.B, xB6);
-        if (C::X_GRAD) xpassC<D, QC>(p9, t.G, xG6);
-        ypassC<D, Q, QC>(xB6, t.B, S);                                   // x at the quadrature points
+        xpassC<D, QC>(p9, tB, xB6);
+        if (C::X_GRAD) xpassC<D, QC>(p9, tG, xG6);
+        ypassC<D, Q, QC>(xB6, tB, S);                                   // x at the quadrature points
         if (OP == OP_JAC) {
 #pragma unroll
             for (int q = 0; q < NQH; ++q) { a2[q] *= S[q]; ndb[q] *= S[q]; }   // alpha' x, (-beta') x
@@ -740,27 +767,29 @@ __device__ __forceinline__ void slab_phase2(const FormArgs& a, const Slab2Tables
 #pragma unroll
         for (int q = 0; q < NQH; ++q) S[q] *= a.cm;
         getp(C::P_ZB, p9);
-        xpassC<D, QC>(p9, t.B, zB6);
-        xpassC<D, QC>(p9, t.G, zG6);
+        xpassC<D, QC>(p9, tB, zB6);
+        xpassC<D, QC>(p9, tG, zG6);
         // one direction at a time: F_d = a1 xd + (alpha' x) zd (Jacobian) | a1 zd (residual);
         // S += g_dd (2 nb zd xd + (-beta') x zd^2) | g_dd nb zd^2
-        auto direction = [&](int dir, const double* tabX, const double* tabY, const double* tabXT, const double* tabYT, double gdd,
-                             double (&acc)[DD]) {
+        auto direction = [&](int dir, double gdd, double (&acc)[DD]) {
             double F[NQH], zd[NQH];
             if (dir == 2) {
                 getp(C::P_ZG, p9);
-                xpassC<D, QC>(p9, t.B, t6);
-                ypassC<D, Q, QC>(t6, t.B, zd);
+                xpassC<D, QC>(p9, tB, t6);
+                ypassC<D, Q, QC>(t6, tB, zd);
                 if (OP == OP_JAC) {
                     getp(C::P_XG, p9);
-                    xpassC<D, QC>(p9, t.B, t6);
-                    ypassC<D, Q, QC>(t6, t.B, F);
+                    xpassC<D, QC>(p9, tB, t6);
+                    ypassC<D, Q, QC>(t6, tB, F);
                 }
             } else {
-                ypassC<D, Q, QC>(dir == 0 ? zG6 : zB6, tabY, zd);
-                if (OP == OP_JAC) ypassC<D, Q, QC>(dir == 0 ? xG6 : xB6, tabY, F);
+                if (dir == 0) ypassC<D, Q, QC>(zG6, tB, zd);
+                else ypassC<D, Q, QC>(zB6, tG, zd);
+                if (OP == OP_JAC) {
+                    if (dir == 0) ypassC<D, Q, QC>(xG6, tB, F);
+                    else ypassC<D, Q, QC>(xB6, tG, F);
+                }
             }
-            (void)tabX;
 #pragma unroll
             for (int q = 0; q < NQH; ++q) {
                 if (OP == OP_JAC) {
@@ -771,48 +800,50 @@ __device__ __forceinline__ void slab_phase2(const FormArgs& a, const Slab2Tables
                     F[q] = a1[q] * zd[q];
                 }
             }
-            ypassTC<D, Q, QC>(F, tabYT, t6);
-            xpassTC_acc<D, QC>(t6, tabXT, wz * gdd, acc);
+            if (dir == 1) ypassTC<D, Q, QC>(F, tGW, t6);
+            else ypassTC<D, Q, QC>(F, tBW, t6);
+            if (dir == 0) xpassTC_acc<D, QC>(t6, tGWh, wz * gdd, acc);
+            else xpassTC_acc<D, QC>(t6, tBWh, wz * gdd, acc);
         };
-        direction(0, t.G, t.B, t.GWh, t.BW, gxx, A);
-        direction(1, t.B, t.G, t.BWh, t.GW, gyy, A);
-        direction(2, t.B, t.B, t.BWh, t.BW, gzz, Bp);
-        ypassTC<D, Q, QC>(S, t.BW, t6);
-        xpassTC_acc<D, QC>(t6, t.BWh, wz, A);
+        direction(0, gxx, A);
+        direction(1, gyy, A);
+        direction(2, gzz, Bp);
+        ypassTC<D, Q, QC>(S, tBW, t6);
+        xpassTC_acc<D, QC>(t6, tBWh, wz, A);
     } else {
         double a1[Q * QC], a2x[Q * QC];
         double a1c = 0.0;
         if (CF == CF_CONST) a1c = a.ck * a.a0;
         else {
             getp(C::P_F0 + (CF == CF_LINFIELDS ? 2 : 0), p9);
-            xpassC<D, QC>(p9, t.B, t6);
-            ypassC<D, Q, QC>(t6, t.B, a1);
+            xpassC<D, QC>(p9, tB, t6);
+            ypassC<D, Q, QC>(t6, tB, a1);
             if (CF == CF_LINFIELDS) {
                 // mass coefficient rho_h * C_h at the quadrature points (ProductCoefficient of two
                 // interpolated fields, linear_conduction_operator.cpp:20,59) -> a2x
                 double cq[Q * QC];
                 getp(C::P_F0, p9);
-                xpassC<D, QC>(p9, t.B, t6);
-                ypassC<D, Q, QC>(t6, t.B, a2x);
+                xpassC<D, QC>(p9, tB, t6);
+                ypassC<D, Q, QC>(t6, tB, a2x);
                 getp(C::P_F0 + 1, p9);
-                xpassC<D, QC>(p9, t.B, t6);
-                ypassC<D, Q, QC>(t6, t.B, cq);
+                xpassC<D, QC>(p9, tB, t6);
+                ypassC<D, Q, QC>(t6, tB, cq);
     #pragma unroll
                 for (int q = 0; q < Q * QC; ++q) a2x[q] *= cq[q];
             }
             if (OP == OP_JAC) {
                 getp(C::P_F0 + 1, p9);
-                xpassC<D, QC>(p9, t.B, t6);
-                ypassC<D, Q, QC>(t6, t.B, a2x);
+                xpassC<D, QC>(p9, tB, t6);
+                ypassC<D, Q, QC>(t6, tB, a2x);
             }
         }
         double xB6[D * QC], xG6[D * QC], vy6[D * QC];
         getp(C::P_XB, p9);
-        xpassC<D, QC>(p9, t.B, xB6);
-        if (C::X_GRAD) xpassC<D, QC>(p9, t.G, xG6);
+        xpassC<D, QC>(p9, tB, xB6);
+        if (C::X_GRAD) xpassC<D, QC>(p9, tG, xG6);
         {
             double xv[Q * QC];
-            ypassC<D, Q, QC>(xB6, t.B, xv);
+            ypassC<D, Q, QC>(xB6, tB, xv);
             if (OP == OP_JAC && CF != CF_CONST) {
     #pragma unroll
                 for (int q = 0; q < Q * QC; ++q) a2x[q] *= xv[q];
@@ -821,19 +852,19 @@ __device__ __forceinline__ void slab_phase2(const FormArgs& a, const Slab2Tables
     #pragma unroll
                 for (int q = 0; q < Q * QC; ++q) xv[q] *= a2x[q];
             }
-            ypassTC<D, Q, QC>(xv, t.BW, vy6);
+            ypassTC<D, Q, QC>(xv, tBW, vy6);
         }
         const double c_m = a.cm * (CF == CF_CONST || CF == CF_K ? a.m0 : 1.0) * wz;
         double zB6[D * QC], zG6[D * QC];
         if (C::Z_GRAD) {
             getp(C::P_ZB, p9);
-            xpassC<D, QC>(p9, t.B, zB6);
-            xpassC<D, QC>(p9, t.G, zG6);
+            xpassC<D, QC>(p9, tB, zB6);
+            xpassC<D, QC>(p9, tG, zG6);
         }
         {   // x direction (both G's carry the mirror sign: it cancels)
             double F[Q * QC];
-            if (OP == OP_RES) ypassC<D, Q, QC>(zG6, t.B, F);
-            else ypassC<D, Q, QC>(xG6, t.B, F);
+            if (OP == OP_RES) ypassC<D, Q, QC>(zG6, tB, F);
+            else ypassC<D, Q, QC>(xG6, tB, F);
             if (CF == CF_CONST) {
     #pragma unroll
                 for (int q = 0; q < Q * QC; ++q) F[q] *= a1c;
@@ -842,18 +873,23 @@ __device__ __forceinline__ void slab_phase2(const FormArgs& a, const Slab2Tables
                 for (int q = 0; q < Q * QC; ++q) F[q] *= a1[q];
                 if (OP == OP_JAC) {
                     double zd[Q * QC];
-                    ypassC<D, Q, QC>(zG6, t.B, zd);
+                    ypassC<D, Q, QC>(zG6, tB, zd);
     #pragma unroll
                     for (int q = 0; q < Q * QC; ++q) F[q] += a2x[q] * zd[q];
                 }
             }
-            ypassTC<D, Q, QC>(F, t.BW, t6);
-            xpassTC_acc<D, QC>(t6, t.GWh, wz * gxx, A);
+            ypassTC<D, Q, QC>(F, tBW, t6);
+            {
+                const double cx = wz * gxx;
+#pragma unroll
+                for (int i = 0; i < D * QC; ++i) t6[i] *= cx;
+            }
+            xpassTC_add<D, QC>(t6, tGWh, A);
         }
         {   // y direction (+ mass)
             double F[Q * QC];
-            if (OP == OP_RES) ypassC<D, Q, QC>(zB6, t.G, F);
-            else ypassC<D, Q, QC>(xB6, t.G, F);
+            if (OP == OP_RES) ypassC<D, Q, QC>(zB6, tG, F);
+            else ypassC<D, Q, QC>(xB6, tG, F);
             if (CF == CF_CONST) {
     #pragma unroll
                 for (int q = 0; q < Q * QC; ++q) F[q] *= a1c;
@@ -862,22 +898,22 @@ __device__ __forceinline__ void slab_phase2(const FormArgs& a, const Slab2Tables
                 for (int q = 0; q < Q * QC; ++q) F[q] *= a1[q];
                 if (OP == OP_JAC) {
                     double zd[Q * QC];
-                    ypassC<D, Q, QC>(zB6, t.G, zd);
+                    ypassC<D, Q, QC>(zB6, tG, zd);
     #pragma unroll
                     for (int q = 0; q < Q * QC; ++q) F[q] += a2x[q] * zd[q];
                 }
             }
-            ypassTC<D, Q, QC>(F, t.GW, t6);
+            ypassTC<D, Q, QC>(F, tGW, t6);
             const double cy = wz * gyy;
     #pragma unroll
             for (int i = 0; i < D * QC; ++i) t6[i] = cy * t6[i] + c_m * vy6[i];
-            xpassTC_acc<D, QC>(t6, t.BWh, 1.0, A);
+            xpassTC_add<D, QC>(t6, tBWh, A);
         }
         {   // z direction
             double F[Q * QC];
             getp(OP == OP_RES ? C::P_ZG : C::P_XG, p9);
-            xpassC<D, QC>(p9, t.B, t6);
-            ypassC<D, Q, QC>(t6, t.B, F);
+            xpassC<D, QC>(p9, tB, t6);
+            ypassC<D, Q, QC>(t6, tB, F);
             if (CF == CF_CONST) {
     #pragma unroll
                 for (int q = 0; q < Q * QC; ++q) F[q] *= a1c;
@@ -887,14 +923,19 @@ __device__ __forceinline__ void slab_phase2(const FormArgs& a, const Slab2Tables
                 if (OP == OP_JAC) {
                     double zd[Q * QC];
                     getp(C::P_ZG, p9);
-                    xpassC<D, QC>(p9, t.B, t6);
-                    ypassC<D, Q, QC>(t6, t.B, zd);
+                    xpassC<D, QC>(p9, tB, t6);
+                    ypassC<D, Q, QC>(t6, tB, zd);
     #pragma unroll
                     for (int q = 0; q < Q * QC; ++q) F[q] += a2x[q] * zd[q];
                 }
             }
-            ypassTC<D, Q, QC>(F, t.BW, t6);
-            xpassTC_acc<D, QC>(t6, t.BWh, wz * gzz, Bp);
+            ypassTC<D, Q, QC>(F, tBW, t6);
+            {
+                const double cz = wz * gzz;
+#pragma unroll
+                for (int i = 0; i < D * QC; ++i) t6[i] *= cz;
+            }
+            xpassTC_add<D, QC>(t6, tBWh, Bp);
         }
     }
     flip_plane<D>(A, h);

@@ -286,6 +286,20 @@ int jots_ctx_apply_dirichlet(jots_ctx_t c, double* u, int loc, int only_td) {
 int jots_ctx_set_material_state(jots_ctx_t c, const double* u, int loc) {
     JOTS_TRY In i(c->c, u, loc); c->c->set_mat_state(i.p); c->c->sync(); return 0; JOTS_CATCH_INT
 }
+int jots_ctx_material_field(jots_ctx_t c, int which, int order, double* out, int loc) {
+    JOTS_TRY
+    Ctx* x = c->c;
+    if (which < 0 || which > 2 || order < 0 || order > 2) throw std::runtime_error("jots_ctx_material_field: which in {0,1,2} (rho, C, k), order in {0,1,2}");
+    const Poly& P = which == 0 ? x->mat.rho : which == 1 ? x->mat.C : x->mat.k;
+    if (P.n > 1 && x->mat_state.n != (size_t)x->n)
+        throw std::runtime_error("jots_ctx_material_field: temperature-dependent property but no material state set (jots_ctx_set_material_state)");
+    Out o(x, out, loc);
+    v_poly_field(x->stream, x->n, P, order, P.n > 1 ? x->mat_state.p : nullptr, o.p);
+    ++x->stats.kernel_launches;
+    o.finish();
+    return 0;
+    JOTS_CATCH_INT
+}
 int jots_ctx_stats(jots_ctx_t c, int64_t out[12], double norms[2]) {
     const Stats& s = c->c->stats;
     out[0] = s.applies; out[1] = s.diag_assemblies; out[2] = s.krylov_iters; out[3] = s.newton_iters;

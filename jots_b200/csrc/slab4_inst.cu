@@ -5,6 +5,7 @@
 
 #include "apply_slab4.cuh"
 #include "diag_face_host.hpp"
+#include "slab_tables.hpp"
 #include "launch.hpp"
 
 namespace jots {
@@ -50,15 +51,7 @@ static int launch_slab4s(const FormArgs& a, const TablesRT& r, cudaStream_t st) 
     typedef SlabCfg<OP, CF> C;
     constexpr bool NEED_Z = C::Z_GRAD || C::NF > 0;
     Slab2Tables<D, Q> t;
-    for (int q = 0; q < Q; ++q) {
-        t.W[q] = r.W[q];
-        const double half = (Q % 2 == 1 && q == Q / 2) ? 0.5 : 1.0;
-        for (int i = 0; i < D; ++i) {
-            t.B[q * D + i] = r.B[q * D + i]; t.G[q * D + i] = r.G[q * D + i];
-            t.BW[q * D + i] = r.W[q] * r.B[q * D + i]; t.GW[q * D + i] = r.W[q] * r.G[q * D + i];
-            t.BWh[q * D + i] = half * r.W[q] * r.B[q * D + i]; t.GWh[q * D + i] = half * r.W[q] * r.G[q * D + i];
-        }
-    }
+    fill_slab2_tables<D, Q>(r, t);
     const size_t smem = Slab4Smem<D, Q, C::NP, E, NEED_Z ? 2 : 1>::total;
     auto kern = form_apply_slab4_kernel<D, Q, OP, CF, E, T, TMA_ROWS>;
     static PerDevice4 pd;

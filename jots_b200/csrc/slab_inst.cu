@@ -4,6 +4,7 @@
 
 #include "apply_slab.cuh"
 #include "diag_face_host.hpp"
+#include "slab_tables.hpp"
 #include "launch.hpp"
 
 namespace jots {
@@ -35,15 +36,7 @@ static int launch_slab2e(const FormArgs& a, const TablesRT& r, cudaStream_t st) 
     constexpr int T = ((E * (2 * Q > D * D ? 2 * Q : D * D)) + 31) / 32 * 32;
     typedef SlabCfg<OP, CF> C;
     Slab2Tables<D, Q> t;
-    for (int q = 0; q < Q; ++q) {
-        t.W[q] = r.W[q];
-        const double half = (Q % 2 == 1 && q == Q / 2) ? 0.5 : 1.0;
-        for (int i = 0; i < D; ++i) {
-            t.B[q * D + i] = r.B[q * D + i]; t.G[q * D + i] = r.G[q * D + i];
-            t.BW[q * D + i] = r.W[q] * r.B[q * D + i]; t.GW[q * D + i] = r.W[q] * r.G[q * D + i];
-            t.BWh[q * D + i] = half * r.W[q] * r.B[q * D + i]; t.GWh[q * D + i] = half * r.W[q] * r.G[q * D + i];
-        }
-    }
+    fill_slab2_tables<D, Q>(r, t);
     const size_t smem = (size_t)E * Elem2Stride<D, Q, C::NP>::value * sizeof(double);
     auto kern = form_apply_slab2_kernel<D, Q, OP, CF, E, T>;
     static PerDevice pd;
@@ -59,15 +52,7 @@ static int launch_slab3e(const FormArgs& a, const TablesRT& r, cudaStream_t st) 
     constexpr int T = (E * 2 * Q + 31) / 32 * 32;
     typedef SlabCfg<OP, CF> C;
     Slab2Tables<D, Q> t;
-    for (int q = 0; q < Q; ++q) {
-        t.W[q] = r.W[q];
-        const double half = (Q % 2 == 1 && q == Q / 2) ? 0.5 : 1.0;
-        for (int i = 0; i < D; ++i) {
-            t.B[q * D + i] = r.B[q * D + i]; t.G[q * D + i] = r.G[q * D + i];
-            t.BW[q * D + i] = r.W[q] * r.B[q * D + i]; t.GW[q * D + i] = r.W[q] * r.G[q * D + i];
-            t.BWh[q * D + i] = half * r.W[q] * r.B[q * D + i]; t.GWh[q * D + i] = half * r.W[q] * r.G[q * D + i];
-        }
-    }
+    fill_slab2_tables<D, Q>(r, t);
     const size_t smem = Slab3Smem<D, Q, C::NP, E>::total;
     auto kern = form_apply_slab3_kernel<D, Q, OP, CF, E, T>;
     static PerDevice pd;

@@ -1,5 +1,6 @@
 #include "vec.cuh"
 #include "vec.hpp"
+#include "coef.cuh"
 
 namespace jots {
 
@@ -64,6 +65,17 @@ __global__ void k_set_idx(int n, const int* __restrict__ idx, double v, double* 
 __global__ void k_copy_idx(int n, const int* __restrict__ idx, const double* __restrict__ x, double* y) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) y[idx[i]] = x[idx[i]];
+}
+
+// nodal material-property field (order 0) or its first / second derivative with respect to T at the state u: what
+// OutputManager::UpdateGridFunctions projects for the registered property coefficients
+// (/root/reference/src/output_manager.cpp:63-73, src/jots_driver.cpp:343, src/material_property.cpp:36-81)
+__global__ void k_poly_field(int64_t n, Poly P, int order, const double* __restrict__ u, double* __restrict__ out) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        double val, d1, d2;
+        poly_eval(P, u ? u[i] : 0.0, val, d1, d2);
+        out[i] = order == 0 ? val : order == 1 ? d1 : d2;
+    }
 }
 
 // interface exchange helpers
@@ -212,6 +224,9 @@ void v_set_idx(cudaStream_t st, int n, const int* idx, double v, double* y) {
 }
 void v_copy_idx(cudaStream_t st, int n, const int* idx, const double* x, double* y) {
     if (n > 0) k_copy_idx<<<(n + 255) / 256, 256, 0, st>>>(n, idx, x, y);
+}
+void v_poly_field(cudaStream_t st, int64_t n, const Poly& P, int order, const double* u, double* out) {
+    if (n > 0) k_poly_field<<<grid_for(n, 8), VEC_THREADS, 0, st>>>(n, P, order, u, out);
 }
 void v_pack(cudaStream_t st, int n, const int* idx, const double* y, double* out) {
     if (n > 0) k_pack<<<(n + 255) / 256, 256, 0, st>>>(n, idx, y, out);

@@ -2,6 +2,8 @@
 #include <cuda_runtime.h>
 #include <cstdint>
 
+#include "forms.hpp"
+
 namespace jots {
 constexpr int VEC_THREADS = 256;
 constexpr int DOT_MAX_BLOCKS = 148 * 8;
@@ -18,6 +20,7 @@ void v_fill(cudaStream_t st, int64_t n, double a, double* y);
 void v_rsqrt(cudaStream_t st, int64_t n, const double* d, double* y);
 void v_recip(cudaStream_t st, int64_t n, const double* d, double* y);
 void v_hash_unit(cudaStream_t st, int64_t n, const int64_t* gidx, int64_t offset, double* y);
+void v_poly_field(cudaStream_t st, int64_t n, const Poly& P, int order, const double* u, double* out);   // property field / d/dT / d2/dT2
 void v_set_idx(cudaStream_t st, int n, const int* idx, double v, double* y);
 void v_copy_idx(cudaStream_t st, int n, const int* idx, const double* x, double* y);
 void v_pack(cudaStream_t st, int n, const int* idx, const double* y, double* out);

@@ -76,6 +76,7 @@ def load_library():
         "jots_ctx_update_bcs": (C.c_int, [_P, C.c_double]),
         "jots_ctx_apply_dirichlet": (C.c_int, [_P, _P, C.c_int, C.c_int]),
         "jots_ctx_set_material_state": (C.c_int, [_P, _P, C.c_int]),
+        "jots_ctx_material_field": (C.c_int, [_P, C.c_int, C.c_int, _P, C.c_int]),
         "jots_ctx_stats": (C.c_int, [_P, _P, _P]),
         "jots_ctx_reset_stats": (C.c_int, [_P]),
         "jots_ctx_rowtile_applies": (C.c_int64, [_P]),
@@ -349,6 +350,12 @@ class Context:
 
     def set_material_state(self, u):
         _chk(load_library().jots_ctx_set_material_state(self._h, _ptr(_f64(u)), _loc(u)))
+
+    def material_field(self, which, order=0, out=None):
+        """Nodal field of property `which` (0 rho, 1 C, 2 k) or its first / second T-derivative at the material state."""
+        out = np.empty(self.n) if out is None else out
+        _chk(load_library().jots_ctx_material_field(self._h, which, order, _ptr(out), _loc(out)))
+        return out
 
     def stats(self):
         out = np.zeros(12, dtype=np.int64)

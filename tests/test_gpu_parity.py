@@ -350,3 +350,19 @@ def test_general_multilinear_elements(J, tmp_path, dim, p, props):
     assert rel(dev.op.neumann_vector(), it.b_vec) < APPLY_TOL
     assert dev.run() == 2
     assert rel(dev.get_u(), orc.run()) < FIELD_TOL
+
+
+@pytest.mark.parametrize("props", ["full", "k", "const"])
+def test_material_property_output_fields(J, tmp_path, props):
+    """Property fields the reference's OutputManager projects for output (output_manager.cpp:63-73, jots_driver.cpp:343)
+    and their T-derivatives (material_property.cpp:36-81): device Horner evaluation vs the oracle's repeated products."""
+    dev, orc = build(J, tmp_path, "Nonlinear_Unsteady", 3, 2, props)
+    state = smooth_state(orc)
+    dev.ctx.set_material_state(state)
+    for which, short in enumerate(("rho", "C", "k")):
+        mp = orc.props[short]
+        mp.update(state)
+        for order, ref in enumerate((mp.coeff, mp.dcoeff, mp.d2coeff)):
+            f = dev.ctx.material_field(which, order)
+            ref = np.broadcast_to(np.asarray(ref, dtype=float), f.shape)
+            assert np.abs(f - ref).max() <= 1e-13 * max(np.abs(ref).max(), 1e-300), (short, order)
