@@ -337,9 +337,9 @@ def main():
             "gpu_launches": st["kernel_launches"],
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "algorithmic_bytes": alg_bytes,
-                         "kernel": "form_apply_slab3_kernel<OP_JAC,CF_K> (Jacobian-vector apply, 24 B/DOF algorithmic; incl. the "
+                         "kernel": "form_apply_slab3_kernel<3,4,OP_JAC,CF_KL|CF_K,16,128> (Jacobian-vector apply, 24 B/DOF algorithmic; incl. the "
                                    "memset of y and the essential-row fix-up launches)",
-                         "note": "this kernel is FP64-pipe bound (about 740 FP64 instructions per DOF against 24 B/DOF), not HBM "
+                         "note": "this kernel is FP64-pipe bound (about 640 FP64 instructions per DOF against 24 B/DOF), not HBM "
                                  "bound: see fp64_pipe_active_pct (ncu) and DESIGN.md 5.1",
                          "fp64_pipe_active_pct": fp64_pct,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6.65 TB/s",

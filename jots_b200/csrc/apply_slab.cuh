@@ -831,7 +831,7 @@ __device__ __forceinline__ void slab_phase2(const FormArgs& a, const Slab2Tables
     #pragma unroll
                 for (int q = 0; q < Q * QC; ++q) a2x[q] *= cq[q];
             }
-            if (OP == OP_JAC) {
+            if (OP == OP_JAC && CF != CF_KL) {
                 getp(C::P_F0 + 1, p9);
                 xpassC<D, QC>(p9, tB, t6);
                 ypassC<D, Q, QC>(t6, tB, a2x);
@@ -844,7 +844,12 @@ __device__ __forceinline__ void slab_phase2(const FormArgs& a, const Slab2Tables
         {
             double xv[Q * QC];
             ypassC<D, Q, QC>(xB6, tB, xv);
-            if (OP == OP_JAC && CF != CF_CONST) {
+            if (OP == OP_JAC && CF == CF_KL) {
+                // k linear in T: the interpolant of the nodal k' is the uniform leading coefficient
+                const double a2c = a.ck * a.inv_rc * a.mat.k.c[0];
+    #pragma unroll
+                for (int q = 0; q < Q * QC; ++q) a2x[q] = a2c * xv[q];
+            } else if (OP == OP_JAC && CF != CF_CONST) {
     #pragma unroll
                 for (int q = 0; q < Q * QC; ++q) a2x[q] *= xv[q];
             }
@@ -854,7 +859,7 @@ __device__ __forceinline__ void slab_phase2(const FormArgs& a, const Slab2Tables
             }
             ypassTC<D, Q, QC>(xv, tBW, vy6);
         }
-        const double c_m = a.cm * (CF == CF_CONST || CF == CF_K ? a.m0 : 1.0) * wz;
+        const double c_m = a.cm * (CF == CF_CONST || CF == CF_K || CF == CF_KL ? a.m0 : 1.0) * wz;
         double zB6[D * QC], zG6[D * QC];
         if (C::Z_GRAD) {
             getp(C::P_ZB, p9);
@@ -1040,7 +1045,7 @@ __global__ void __launch_bounds__(T) form_apply_slab3_kernel(const FormArgs a, c
                         nodal_fields<CF, OP>(a.mat, zr[k], f);
 #pragma unroll
                         for (int n = 0; n < NF; ++n)
-                            fr[n][k] = CF == CF_K ? (a.ck * a.inv_rc) * f[n] : (CF == CF_LINFIELDS && n == 2) ? a.ck * f[n] : f[n];
+                            fr[n][k] = (CF == CF_K || CF == CF_KL) ? (a.ck * a.inv_rc) * f[n] : (CF == CF_LINFIELDS && n == 2) ? a.ck * f[n] : f[n];
                     }
                 }
             }

@@ -42,6 +42,7 @@ template <int OP> struct CoefNF<CF_LINFIELDS, OP> { static constexpr int value =
 template <> struct CoefNF<CF_K, OP_LIN> { static constexpr int value = 1; };
 template <> struct CoefNF<CF_K, OP_RES> { static constexpr int value = 1; };
 template <> struct CoefNF<CF_K, OP_JAC> { static constexpr int value = 2; };
+template <int OP> struct CoefNF<CF_KL, OP> { static constexpr int value = 1; };
 template <int OP> struct CoefNF<CF_FULL, OP> { static constexpr int value = 8; };
 template <int OP> struct CoefNF<CF_FULLC, OP> { static constexpr int value = 5; };
 
@@ -51,6 +52,8 @@ __device__ __forceinline__ void nodal_fields(const MatSet& mat, double u, double
     double v, d1, d2;
     if (CF == CF_LINFIELDS) {
         f[0] = poly_val(mat.rho, u); f[1] = poly_val(mat.C, u); f[2] = poly_val(mat.k, u);
+    } else if (CF == CF_KL) {
+        f[0] = poly_val(mat.k, u);
     } else if (CF == CF_K) {
         if (OP == OP_JAC) { poly_eval(mat.k, u, v, d1, d2); f[0] = v; f[1] = d1; }
         else f[0] = poly_val(mat.k, u);

@@ -32,7 +32,9 @@ namespace jots {
 
 enum { OP_LIN = 0, OP_JAC = 1, OP_RES = 2 };
 enum { CF_CONST = 0, CF_LINFIELDS = 1, CF_K = 2, CF_FULL = 3,
-       CF_FULLC = 4 };   // CF_FULL with a uniform density (slab kernel only, chosen at launch): k, k', C, C', C''
+       CF_FULLC = 4,     // CF_FULL with a uniform density (slab kernel only, chosen at launch): k, k', C, C', C''
+       CF_KL = 5 };      // CF_K with k linear in T (two polynomial coefficients): k'_h is uniform, one interpolated field
+                         // instead of two in the Jacobian apply (slab kernel only, chosen at launch)
 
 constexpr int MAX_POLY = 8;
 

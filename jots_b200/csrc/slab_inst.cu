@@ -94,8 +94,18 @@ static int slab_variant() {
     return v;
 }
 
+static bool slab_klin() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("JOTS_SLAB_KLIN"); v = e ? atoi(e) : 1; }
+    return v != 0;
+}
+
 template <int D, int Q>
 static int dispatch(int op, int cf, const FormArgs& a, const TablesRT& t, cudaStream_t st) {
+    // k(T) linear (two coefficients, the reference's own cases): k'_h is uniform, one property field less in the
+    // Jacobian apply (JOTS_SLAB_KLIN=0 keeps the general kernel)
+    if (op == OP_JAC && cf == CF_K && a.mat.k.n == 2 && slab_klin() && !(slab_variant() == 2 || a.nonpersistent))
+        return launch_slab3<D, Q, OP_JAC, CF_KL>(a, t, st);
 #define CASE(OPV, CFV)                                                                              \
     if (op == OPV && cf == CFV) {                                                                   \
         if constexpr (Q < 5) {                                                                      \

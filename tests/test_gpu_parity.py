@@ -34,6 +34,7 @@ HF0 = "HeatFlux, 0"
 PROPS = {
     "const": [("Density_rho", "Uniform, 8000"), ("Specific_Heat_C", "Uniform, 500"), ("Thermal_Conductivity_k", "Uniform, 10")],
     "k": [("Density_rho", "Uniform, 8000"), ("Specific_Heat_C", "Uniform, 500"), ("Thermal_Conductivity_k", "Polynomial, 0.09, -17")],
+    "k2": [("Density_rho", "Uniform, 8000"), ("Specific_Heat_C", "Uniform, 500"), ("Thermal_Conductivity_k", "Polynomial, 1e-4, 0.09, -17")],
     "kc": [("Density_rho", "Uniform, 8000"), ("Specific_Heat_C", "Polynomial, 4.5, -850"),
            ("Thermal_Conductivity_k", "Polynomial, 1e-4, 0.09, -17")],
     "full": [("Density_rho", "Polynomial, 1e-3, -0.5, 8000"), ("Specific_Heat_C", "Polynomial, 4.5, -850"),
@@ -128,10 +129,11 @@ def test_nonlinear_forms(J, tmp_path, dim, p, props):
 
 
 @pytest.mark.parametrize("p", [1, 2, 3])
-@pytest.mark.parametrize("props", ["const", "k", "kc", "full"])
+@pytest.mark.parametrize("props", ["const", "k", "k2", "kc", "full"])
 @pytest.mark.parametrize("sim", ["Linearized_Unsteady", "Nonlinear_Unsteady"])
 def test_axis_aligned_fast_path(J, tmp_path, sim, props, p):
-    """Axis-aligned (graded) bricks take the register-slab kernel: same checks as above."""
+    """Axis-aligned (graded) bricks take the register-slab kernel: same checks as above.  "k" (k linear in T) runs the
+    Jacobian kernel with a uniform k' (CF_KL), "k2" (quadratic k) the general one."""
     dev, orc = build(J, tmp_path, sim, 3, p, props, grade=0.6, shear=0.0, n=(5, 3, 4))
     n = dev.n
     state = smooth_state(orc)
