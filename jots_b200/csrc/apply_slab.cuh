@@ -954,7 +954,11 @@ __device__ __forceinline__ void slab_phase2(const FormArgs& a, const Slab2Tables
     for (int m = 0; m < DD; ++m) { outp[m] = A[m]; outp[2 * PSET + m] = Bp[m]; }
 }
 
-template <int D, int Q, int OP, int CF, int E, int T>
+// SPLIT (tiles with more pencils than threads, Q2 E = 16: 144 pencils on 128 threads): the E*D*D - T left-over pencils of
+// phases 1 and 3 are not run as a second full pass on a few lanes (every other warp waits at the barrier for it: 20 % of
+// the warp time in the r1m profile) but cut into 2Q (phase 1: one quadrature plane of the x- or the z-planes each) and 2D
+// (phase 3: one output node and half of the quadrature planes each) pieces that fill the block once more with short work.
+template <int D, int Q, int OP, int CF, int E, int T, bool SPLIT = false>
 __global__ void __launch_bounds__(T) form_apply_slab3_kernel(const FormArgs a, const Slab2Tables<D, Q> t) {
     typedef SlabCfg<OP, CF> C;
     constexpr int NF = C::NF, NFA = NF > 0 ? NF : 1, NP = C::NP;
@@ -969,6 +973,13 @@ __global__ void __launch_bounds__(T) form_apply_slab3_kernel(const FormArgs a, c
     double* stage = smem + (size_t)E * ES;                                  // [NSTG][2][E*ND]
     int* idxbuf = reinterpret_cast<int*>(stage + (size_t)NSTG * 2 * E * ND);   // [3][E*ND]
     const int tid = threadIdx.x;
+    constexpr int LEFT = E * D * D - T;                     // pencils beyond one pass of the block
+    static_assert(!SPLIT || (LEFT > 0 && LEFT * 2 * Q <= T && Q % 2 == 0), "split pass: left-over pieces must fit one pass");
+    __shared__ double s_tab[SPLIT ? 2 * Q * D : 1];         // B then G: the split pass indexes them at run time
+    if (SPLIT && tid == 0) {
+#pragma unroll
+        for (int m = 0; m < Q * D; ++m) { s_tab[m] = t.B[m]; s_tab[Q * D + m] = t.G[m]; }
+    }
     const int ntiles = (a.nelem + E - 1) / E;
     const int nmine = blockIdx.x < ntiles ? (ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
     auto tile_of = [&](int i) { return (int)blockIdx.x + i * (int)gridDim.x; };
@@ -1030,7 +1041,7 @@ __global__ void __launch_bounds__(T) form_apply_slab3_kernel(const FormArgs a, c
 
         // ---------------- phase 1: z contraction from the staged values ---------------------------
 #pragma unroll 1
-        for (int item = tid; item < nv * DD; item += T) {
+        for (int item = tid; item < (SPLIT && nv * DD > T ? T : nv * DD); item += T) {
             const int el = item / DD, ij = item - el * DD;
             double xr[D], zr[D], fr[NFA][D];
 #pragma unroll
@@ -1071,6 +1082,48 @@ __global__ void __launch_bounds__(T) form_apply_slab3_kernel(const FormArgs a, c
                 }
             }
         }
+        if constexpr (SPLIT) {
+            // left-over pencils: piece = (pencil, quadrature plane qz, x-planes | z-planes and property fields)
+            const int item = T + tid / (2 * Q), part = tid - (tid / (2 * Q)) * (2 * Q), qz = part >> 1;
+            if (item < nv * DD) {
+                const int el = item / DD, ij = item - el * DD;
+                double* base = planes + el * ES + ij;
+                const double* tb = s_tab + qz * D;
+                const double* tg = s_tab + Q * D + qz * D;
+                if ((part & 1) == 0) {
+                    double sv = 0.0, sg = 0.0;
+#pragma unroll
+                    for (int k = 0; k < D; ++k) {
+                        const int m = el * ND + ij + DD * k;
+                        const double xv = (ix[m] < 0 && a.mask_in) ? 0.0 : sx[m];
+                        sv += tb[k] * xv;
+                        sg += tg[k] * xv;
+                    }
+                    base[C::P_XB * PSET + qz * PS] = sv;
+                    if (C::X_GRAD) base[C::P_XG * PSET + qz * PS] = sg;
+                } else if (NEED_Z) {
+                    double zs = 0.0, zg = 0.0, fs[NFA];
+#pragma unroll
+                    for (int n = 0; n < NFA; ++n) fs[n] = 0.0;
+#pragma unroll
+                    for (int k = 0; k < D; ++k) {
+                        const double zv = sz[el * ND + ij + DD * k];
+                        zs += tb[k] * zv;
+                        zg += tg[k] * zv;
+                        if (NF > 0) {
+                            double f[NFA];
+                            nodal_fields<CF, OP>(a.mat, zv, f);
+#pragma unroll
+                            for (int n = 0; n < NF; ++n)
+                                fs[n] += tb[k] * ((CF == CF_K || CF == CF_KL) ? (a.ck * a.inv_rc) * f[n] : (CF == CF_LINFIELDS && n == 2) ? a.ck * f[n] : f[n]);
+                        }
+                    }
+                    if (C::Z_GRAD) { base[C::P_ZB * PSET + qz * PS] = zs; base[C::P_ZG * PSET + qz * PS] = zg; }
+#pragma unroll
+                    for (int n = 0; n < NF; ++n) base[(C::P_F0 + n) * PSET + qz * PS] = fs[n];
+                }
+            }
+        }
         __syncthreads();
         if (NSTG == 1) issue_vals(it + 1);   // the staging buffer is free again; the copies land during phases 2-3
 
@@ -1096,7 +1149,7 @@ __global__ void __launch_bounds__(T) form_apply_slab3_kernel(const FormArgs a, c
 
         // ---------------- phase 3: transposed z contraction + scatter ----------------------------
 #pragma unroll 1
-        for (int item = tid; item < nv * DD; item += T) {
+        for (int item = tid; item < (SPLIT && nv * DD > T ? T : nv * DD); item += T) {
             const int el = item / DD, ij = item - el * DD;
             const double* base = planes + el * ES + ij;
             double Aq[Q], Bq[Q];
@@ -1110,6 +1163,26 @@ __global__ void __launch_bounds__(T) form_apply_slab3_kernel(const FormArgs a, c
                 double s = 0.0;
 #pragma unroll
                 for (int qz = 0; qz < Q; ++qz) s += t.B[qz * D + k] * Aq[qz] + t.G[qz * D + k] * Bq[qz];
+                const int g = ix[el * ND + ij + DD * k];
+                if (g >= 0) atomicAdd(a.y + g, s);
+                else if (!a.mask_out) atomicAdd(a.y + (~g), s);
+                else if (a.diag_one) a.y[~g] = a.x[~g];   // every writer stores the same value
+            }
+        }
+        if constexpr (SPLIT) {
+            // left-over pencils: piece = (pencil, output node k, lower | upper half of the quadrature planes); the two
+            // halves meet in the atomic
+            const int item = T + tid / (2 * D), r = tid - (tid / (2 * D)) * (2 * D), k = r >> 1, q0 = (r & 1) * (Q / 2);
+            if (tid < LEFT * 2 * D && item < nv * DD) {
+                const int el = item / DD, ij = item - el * DD;
+                const double* base = planes + el * ES + ij;
+                double s = 0.0;
+#pragma unroll
+                for (int dq = 0; dq < Q / 2; ++dq) {
+                    const int qz = q0 + dq;
+                    s += s_tab[qz * D + k] * (base[qz * PS] + base[PSET + qz * PS]) +
+                         s_tab[Q * D + qz * D + k] * (base[2 * PSET + qz * PS] + base[3 * PSET + qz * PS]);
+                }
                 const int g = ix[el * ND + ij + DD * k];
                 if (g >= 0) atomicAdd(a.y + g, s);
                 else if (!a.mask_out) atomicAdd(a.y + (~g), s);

@@ -46,7 +46,7 @@ static int launch_slab2e(const FormArgs& a, const TablesRT& r, cudaStream_t st) 
     return 0;
 }
 
-template <int D, int Q, int OP, int CF, int E>
+template <int D, int Q, int OP, int CF, int E, bool SPLIT = false>
 static int launch_slab3e(const FormArgs& a, const TablesRT& r, cudaStream_t st) {
     // thread count follows phase 2 (2Q threads per element); phases 1/3 read shared memory and loop
     constexpr int T = (E * 2 * Q + 31) / 32 * 32;
@@ -54,7 +54,7 @@ static int launch_slab3e(const FormArgs& a, const TablesRT& r, cudaStream_t st) 
     Slab2Tables<D, Q> t;
     fill_slab2_tables<D, Q>(r, t);
     const size_t smem = Slab3Smem<D, Q, C::NP, E>::total;
-    auto kern = form_apply_slab3_kernel<D, Q, OP, CF, E, T>;
+    auto kern = form_apply_slab3_kernel<D, Q, OP, CF, E, T, SPLIT>;
     static PerDevice pd;
     const int grid_max = pd.get(kern, T, smem);
     const int ntiles = (a.nelem + E - 1) / E;
@@ -74,7 +74,9 @@ static int launch_slab3(const FormArgs& a, const TablesRT& r, cudaStream_t st) {
         // residual 1.19 -> 1.13 ms at 17 M DOFs (JOTS_SLAB_ELEMS=14 selects the old tile).  Fusing phase 3 of a tile with
         // phase 1 of the next (two barriers per tile) measured 1.5 % slower and was dropped.
         if constexpr (CF != CF_FULL && CF != CF_FULLC) {
-            if (slab_elems() == 16) return launch_slab3e<D, Q, OP, CF, 16>(a, r, st);
+            // JOTS_SLAB_SPLIT=1: left-over pencils of phases 1 / 3 as one pass of short pieces (apply_slab.cuh, SPLIT)
+            static const bool split = [] { const char* e = getenv("JOTS_SLAB_SPLIT"); return e && e[0] == '1'; }();
+            if (slab_elems() == 16) return split ? launch_slab3e<D, Q, OP, CF, 16, true>(a, r, st) : launch_slab3e<D, Q, OP, CF, 16>(a, r, st);
         }
         return launch_slab3e<D, Q, OP, CF, 14>(a, r, st);
     }
