@@ -41,3 +41,25 @@ def test_committed_golden_fields_are_the_oracle_output(name, tmp_path):
     ini = make_case(name, tmp_path)
     u = OJ.JOTSDriver(OJ.Config(ini)).run()
     assert np.linalg.norm(u - gold[name]) <= 1e-12 * np.linalg.norm(gold[name])
+
+
+@pytest.mark.parametrize("p", [1, 2, 3, 4])
+def test_oracle_convergence_order_on_a_smooth_nonlinear_steady_problem(p, tmp_path):
+    """The reference's regressions pin the discretisation at Q2 only.  Here: steady conduction with
+    k(T) = 1 + T, T(0) = 0, T(1) = 1 on [0,1] x [0,.2] x [0,.1] -- Kirchhoff transform theta = T + T^2/2 = 1.5 x, so
+    T = -1 + sqrt(1 + 3x) is smooth -- must converge with order p+1 in the reference's error functional for every order
+    the space supports (basis, Gauss-Lobatto nodes, p+2-point quadrature and the Newton Jacobian all enter)."""
+    from oracle import mesh as OM
+    exact = lambda x, t: -1.0 + np.sqrt(1.0 + 3.0 * x[:, 0])
+    hf0 = "HeatFlux, 0"
+    errs = []
+    for nx in (2, 4, 8):
+        from cases import ini_text
+        ini = str(tmp_path / ("c%d.ini" % nx))
+        with open(ini, "w") as f:
+            f.write(ini_text("Steady", "unused", 0.5, [("Thermal_Conductivity_k", "Polynomial, 1, 1")],
+                             ["Isothermal, 0", hf0, hf0, "Isothermal, 1", hf0, hf0], time=False, newton=200, solver="CG", order=p))
+        drv = OJ.JOTSDriver(OJ.Config(ini), mesh=OM.make_brick(nx, 2, 1, 1.0, 0.2, 0.1))
+        errs.append(analytic.reference_error(drv.space, drv.run(), exact, 0.0))
+    orders = [np.log2(errs[i] / errs[i + 1]) for i in range(2)]
+    assert p + 0.5 <= orders[0] <= p + 1.7 and p + 0.7 <= orders[1] <= p + 1.7, (p, errs, orders)
