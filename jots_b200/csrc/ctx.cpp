@@ -190,7 +190,7 @@ void Ctx::set_bcs(const std::vector<BCSpec>& b) {
 void Ctx::build_rowtiles() {
     d_rowtiles.release();
     n_rowtiles = 0;
-    if (space.dim != 3 || !geom_diag || !use_slab || slab_variant < 4 || space.nelem == 0) return;
+    if (space.dim != 3 || !geom_diag || !use_slab || (slab_variant != 4 && slab_variant != 5) || space.nelem == 0) return;
     const int E = slab4_tile_elems(space.p);
     if (E <= 0) return;
     std::vector<unsigned char> tab;

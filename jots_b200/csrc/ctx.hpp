@@ -103,7 +103,7 @@ public:
     DArr<unsigned char> d_essmark;
     DArr<unsigned char> d_rowtiles;   // RowTile<D> table of the row-structured slab kernel (empty: not applicable)
     int n_rowtiles = 0, rowtile_elems = 0;
-    int slab_variant = 3;             // JOTS_SLAB_VARIANT: 2 non-persistent, 3 pipelined gather-table kernel, 4 row-structured (TMA)
+    int slab_variant = 3;             // JOTS_SLAB_VARIANT: 2 non-persistent, 3 pipelined gather-table kernel (default), 4 / 5 row-structured (TMA), 6 experimental warp-specialised
     void build_rowtiles();            // from space.gather + essential marks; all-or-nothing
     int geom_stride = 10;
     bool geom_diag = false;   // diagonal metric on every element

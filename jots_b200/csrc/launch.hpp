@@ -12,6 +12,7 @@ namespace jots {
 int launch_form_apply(int dim, int p, int op, int cf, const FormArgs& a, const TablesRT& t, cudaStream_t st);
 int launch_form_apply_slab(int p, int op, int cf, const FormArgs& a, const TablesRT& t, cudaStream_t st);
 int launch_form_apply_slab4(int p, int op, int cf, const FormArgs& a, const TablesRT& t, cudaStream_t st);
+int launch_form_apply_slab5(int p, int op, int cf, const FormArgs& a, const TablesRT& t, cudaStream_t st);   // experimental
 int slab4_tile_elems(int p);   // elements per RowTile for order p (0: none)
 int launch_form_diag_slab(int p, int op, int cf, const FormArgs& a, const TablesRT& t, cudaStream_t st);
 int launch_form_diag(int dim, int p, int op, int cf, const FormArgs& a, const TablesRT& t, cudaStream_t st);
