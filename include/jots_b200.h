@@ -156,6 +156,11 @@ jots_comm_t jots_comm_create(const char id[128], int rank, int nranks, int devic
 void jots_comm_destroy(jots_comm_t c);
 jots_ctx_t jots_ctx_create_part(jots_part_t p, int device, jots_comm_t comm);
 
+/* Config (src/config_file.cpp:7-172) parsed on the host, as "key=value" lines (scalars, then "mat:<name>=a|b|..." and
+   "bc:<attribute>=a|b|..."): lets the key set, defaults and parsing quirks be compared with the reference's without a
+   device.  Returns the length needed (including the terminating 0), -1 on error. */
+int64_t jots_config_dump(const char* ini_path, char* out, int64_t cap);
+
 /* ---- driver shim: Config + the hot-path part of JOTSDriver::Run (src/jots_driver.cpp:568-725) --- */
 jots_driver_t jots_driver_create(const char* ini_path, int device);
 jots_driver_t jots_driver_create_on_mesh(const char* ini_path, jots_mesh_t mesh, int device);

@@ -3,6 +3,7 @@
 
 #include <algorithm>
 #include <cstring>
+#include <sstream>
 #include <exception>
 #include <string>
 
@@ -213,6 +214,39 @@ int64_t jots_space_rowtiles(jots_space_t s, const int32_t* ess, int64_t n_ess, i
         if (record_bytes) *record_bytes = nt > 0 ? (int)(tab.size() / (size_t)nt) : 0;
         if (out && nt > 0) std::memcpy(out, tab.data(), tab.size());
         return nt;
+    } catch (const std::exception& ex) { fail(ex); return -1; }
+}
+
+// ---- config (host only) -----------------------------------------------------------------------
+int64_t jots_config_dump(const char* ini_path, char* out, int64_t cap) {
+    try {
+        Config cfg(ini_path);
+        std::ostringstream os;
+        os.precision(17);
+        os << "sim_type=" << cfg.sim_type << "\nmesh_file=" << cfg.mesh_file << "\nuse_restart=" << (int)cfg.use_restart
+           << "\nfe_order=" << cfg.fe_order << "\nserial_refine=" << cfg.serial_refine << "\nparallel_refine=" << cfg.parallel_refine
+           << "\ninitial_temp=" << cfg.initial_temp << "\nwith_precice=" << (int)cfg.with_precice
+           << "\nusing_time_integration=" << (int)cfg.using_time_integration << "\ntime_scheme=" << cfg.time_scheme << "\ndt=" << cfg.dt
+           << "\nmax_timesteps=" << cfg.max_timesteps << "\nsolver=" << cfg.solver << "\nprec=" << cfg.prec << "\nabs_tol=" << cfg.abs_tol
+           << "\nrel_tol=" << cfg.rel_tol << "\nmax_iter=" << cfg.max_iter << "\nusing_newton=" << (int)cfg.using_newton
+           << "\nnewton_max_iter=" << cfg.newton_max_iter << "\nnewton_abs_tol=" << cfg.newton_abs_tol << "\nnewton_rel_tol=" << cfg.newton_rel_tol << "\n";
+        for (auto& kv : cfg.mat_props) {
+            os << "mat:" << kv.first << "=";
+            for (size_t i = 0; i < kv.second.size(); ++i) os << (i ? "|" : "") << kv.second[i];
+            os << "\n";
+        }
+        for (auto& kv : cfg.bcs) {
+            os << "bc:" << kv.first << "=";
+            for (size_t i = 0; i < kv.second.size(); ++i) os << (i ? "|" : "") << kv.second[i];
+            os << "\n";
+        }
+        const std::string s = os.str();
+        if (out && cap > 0) {
+            const size_t nc = std::min<size_t>(s.size(), (size_t)cap - 1);
+            std::memcpy(out, s.data(), nc);
+            out[nc] = 0;
+        }
+        return (int64_t)s.size() + 1;
     } catch (const std::exception& ex) { fail(ex); return -1; }
 }
 

@@ -65,6 +65,7 @@ def load_library():
         "jots_space_copy_nodes": (C.c_int, [_P, _P]),
         "jots_space_essential_dofs": (C.c_int64, [_P, _P, C.c_int, _P]),
         "jots_space_rowtiles": (C.c_int64, [_P, _P, C.c_int64, C.c_int, C.c_double, _P, _P]),
+        "jots_config_dump": (C.c_int64, [C.c_char_p, _P, C.c_int64]),
         "jots_ctx_create": (_P, [_P, C.c_int]),
         "jots_ctx_destroy": (None, [_P]),
         "jots_ctx_size": (C.c_int64, [_P]),
@@ -172,6 +173,21 @@ def _f64(a):
         if a.dtype != np.float64 or not a.flags.c_contiguous:
             raise JotsError("host vectors must be contiguous float64 arrays")
     return a
+
+
+def config_dump(ini_path):
+    """The host-side Config of an .ini file as a dict (scalars as strings, 'mat:<name>' / 'bc:<attr>' as lists)."""
+    lib = load_library()
+    n = lib.jots_config_dump(os.fsencode(ini_path), None, 0)
+    if n < 0:
+        raise JotsError(_err())
+    buf = C.create_string_buffer(n)
+    lib.jots_config_dump(os.fsencode(ini_path), C.cast(buf, C.c_void_p), n)
+    out = {}
+    for line in buf.value.decode().splitlines():
+        k, v = line.split("=", 1)
+        out[k] = v.split("|") if k.startswith(("mat:", "bc:")) else v
+    return out
 
 
 class Mesh:

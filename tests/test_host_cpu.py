@@ -240,3 +240,56 @@ def test_rowtiles_absent_without_row_structure(tmp_path):
     s = J.Space(J.Mesh.brick(6, 3, 2, 0.01, 0.02, 0.03), 2)
     assert len(s.rowtiles(np.zeros(0, np.int32), 16, min_fill=0.75)) == 0
     assert len(s.rowtiles(np.zeros(0, np.int32), 16, min_fill=0.0)) == 6
+
+
+def _config_pairs(path):
+    """(library Config, oracle Config) of one .ini as comparable dicts."""
+    import jots_b200 as J
+    from oracle import jots as OJ
+    d = J.config_dump(path)
+    o = OJ.Config(path)
+    lib = {k: d[k] for k in ("sim_type", "mesh_file", "time_scheme", "solver", "prec")}
+    ora = {k: getattr(o, k) for k in lib}
+    for k in ("use_restart", "with_precice", "using_time_integration", "using_newton"):
+        lib[k], ora[k] = bool(int(d[k])), bool(getattr(o, k))
+    for k in ("fe_order", "serial_refine", "parallel_refine", "max_timesteps", "max_iter", "newton_max_iter"):
+        lib[k], ora[k] = int(d[k]), int(getattr(o, k))
+    for k in ("initial_temp", "dt", "abs_tol", "rel_tol", "newton_abs_tol", "newton_rel_tol"):
+        lib[k], ora[k] = float(d[k]), float(getattr(o, k))
+    lib["mat"] = {k[4:]: v for k, v in d.items() if k.startswith("mat:")}
+    ora["mat"] = {k: list(v) for k, v in o.mat_props.items()}
+    lib["bcs"] = {int(k[3:]): v for k, v in d.items() if k.startswith("bc:")}
+    ora["bcs"] = {int(k): list(v) for k, v in o.bcs.items()}
+    return lib, ora
+
+
+def test_config_defaults_and_quirks_match_the_oracle(tmp_path):
+    """Config (config_file.cpp:7-172): missing sections take the defaults, a commented-out [NewtonSolverSettings] means
+    zero Newton iterations (Heated_Plate as shipped), non-numeric values fall back to the default."""
+    from cases import ini_text
+    variants = {
+        "full": ini_text("Nonlinear_Unsteady", "m.mesh", 300, [("Density_rho", "Uniform, 8000"), ("Specific_Heat_C", "Polynomial, 4.5, -850"),
+                         ("Thermal_Conductivity_k", "Polynomial, 1e-4, 0.09, -17")], ["HeatFlux, 7.5e5", "Isothermal, 300", "Sinusoidal_Isothermal, 1, 2, 3, 4"],
+                         newton=50, solver="CG", prec="Jacobi", steps=7, dt="2.5e-3", order=3, scheme="RK4", refine=2),
+        "steady_no_newton": ini_text("Steady", "m.mesh", 0.5, [("Thermal_Conductivity_k", "Uniform, 1")], ["Isothermal, 0", "Isothermal, 1"], time=False),
+        "minimal": "[FiniteElementSetup]\nMesh_File=x.mesh\n\n[MaterialProperties]\nThermal_Conductivity_k=Uniform, 2\n\n[BoundaryConditions]\nBoundary_Attr_1=HeatFlux, 0\n",
+        "bad_numbers": "[FiniteElementSetup]\nFE_Order=two\nInitial_Temperature=hot\nMesh_File=x.mesh\n\n[MaterialProperties]\nDensity_rho=Uniform, 1\n\n"
+                       "[BoundaryConditions]\nBoundary_Attr_2=Isothermal, 5\n\n[TimeIntegration]\nDelta_Time=fast\nMax_Timesteps=3.7\n\n[LinearSolverSettings]\nMax_Iterations=lots\n",
+    }
+    for name, txt in variants.items():
+        p = str(tmp_path / (name + ".ini"))
+        with open(p, "w") as f:
+            f.write(txt)
+        lib, ora = _config_pairs(p)
+        assert lib == ora, (name, {k: (lib[k], ora[k]) for k in lib if lib[k] != ora[k]})
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree not present (GPU box)")
+def test_every_shipped_config_parses_like_the_oracle():
+    """All .ini files the reference ships (examples/ and tests/*.ini.in): same keys, values and defaults on both sides."""
+    import glob
+    paths = sorted(glob.glob(os.path.join(REF, "examples", "**", "*.ini"), recursive=True))
+    assert len(paths) >= 10
+    for p in paths:
+        lib, ora = _config_pairs(p)
+        assert lib == ora, (p, {k: (lib[k], ora[k]) for k in lib if lib[k] != ora[k]})
