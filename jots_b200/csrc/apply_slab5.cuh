@@ -35,7 +35,10 @@ template <int D, int Q, int NP, int E> struct Slab5Smem {
 
 __device__ __forceinline__ void pencil_group_barrier() { asm volatile("bar.sync 1, 128;\n" ::: "memory"); }
 
-template <int D, int Q, int OP, int CF, int E>
+// SPLIT: the E*D*D - 128 left-over pencils of phases 1 and 3 as one more pass of short pieces (as in apply_slab.cuh,
+// where the pieces are validated) instead of a second full pass on 16 lanes -- the pencil group is the latency-critical
+// side of the hand-over.
+template <int D, int Q, int OP, int CF, int E, bool SPLIT = false>
 __global__ void __launch_bounds__(256, 2) form_apply_slab5_kernel(const FormArgs a, const Slab2Tables<D, Q> t) {
     typedef SlabCfg<OP, CF> C;
     constexpr int NF = C::NF, NFA = NF > 0 ? NF : 1, NP = C::NP;
@@ -46,6 +49,13 @@ __global__ void __launch_bounds__(256, 2) form_apply_slab5_kernel(const FormArgs
     constexpr bool NEED_Z = C::Z_GRAD || NF > 0;
     constexpr int TP = 128;                                  // threads per warp group
     static_assert(E * 2 * Q == TP, "one plane thread per (element, quadrature plane, half)");
+    constexpr int LEFT = E * D * D - TP;
+    static_assert(!SPLIT || (LEFT > 0 && LEFT * 2 * Q <= TP && Q % 2 == 0), "split pass: left-over pieces must fit one pass");
+    __shared__ double s_tab[SPLIT ? 2 * Q * D : 1];         // B then G, indexed at run time by the split pass
+    if (SPLIT && threadIdx.x == 0) {
+#pragma unroll
+        for (int m = 0; m < Q * D; ++m) { s_tab[m] = t.B[m]; s_tab[Q * D + m] = t.G[m]; }
+    }
     extern __shared__ __align__(16) double smem[];
     double* planes = smem;                                                  // [2][E*ES]
     double* sx = smem + (size_t)2 * E * ES;                                 // [E*ND]
@@ -132,7 +142,7 @@ __global__ void __launch_bounds__(256, 2) form_apply_slab5_kernel(const FormArgs
             double* pb = planes + (size_t)(i & 1) * E * ES;
             const int nit = nvalid(i) * DD;
 #pragma unroll 1
-            for (int item = ptid; item < nit; item += TP) {
+            for (int item = ptid; item < (SPLIT && nit > TP ? TP : nit); item += TP) {
                 const int el = item / DD, ij = item - el * DD;
                 double xr[D], zr[D], fr[NFA][D];
 #pragma unroll
@@ -173,6 +183,48 @@ __global__ void __launch_bounds__(256, 2) form_apply_slab5_kernel(const FormArgs
                     }
                 }
             }
+            if constexpr (SPLIT) {
+                // left-over pencils: piece = (pencil, quadrature plane qz, x-planes | z-planes and property fields)
+                const int item = TP + ptid / (2 * Q), part = ptid - (ptid / (2 * Q)) * (2 * Q), qz = part >> 1;
+                if (item < nit) {
+                    const int el = item / DD, ij = item - el * DD;
+                    double* base = pb + el * ES + ij;
+                    const double* tb = s_tab + qz * D;
+                    const double* tg = s_tab + Q * D + qz * D;
+                    if ((part & 1) == 0) {
+                        double sv = 0.0, sg = 0.0;
+#pragma unroll
+                        for (int k = 0; k < D; ++k) {
+                            const int m = el * ND + ij + DD * k;
+                            const double xv = (ix[m] < 0 && a.mask_in) ? 0.0 : sx[m];
+                            sv += tb[k] * xv;
+                            sg += tg[k] * xv;
+                        }
+                        base[C::P_XB * PSET + qz * PS] = sv;
+                        if (C::X_GRAD) base[C::P_XG * PSET + qz * PS] = sg;
+                    } else if (NEED_Z) {
+                        double zs = 0.0, zg = 0.0, fs[NFA];
+#pragma unroll
+                        for (int n = 0; n < NFA; ++n) fs[n] = 0.0;
+#pragma unroll
+                        for (int k = 0; k < D; ++k) {
+                            const double zv = sz[el * ND + ij + DD * k];
+                            zs += tb[k] * zv;
+                            zg += tg[k] * zv;
+                            if (NF > 0) {
+                                double f[NFA];
+                                nodal_fields<CF, OP>(a.mat, zv, f);
+#pragma unroll
+                                for (int n = 0; n < NF; ++n)
+                                    fs[n] += tb[k] * ((CF == CF_K || CF == CF_KL) ? (a.ck * a.inv_rc) * f[n] : (CF == CF_LINFIELDS && n == 2) ? a.ck * f[n] : f[n]);
+                            }
+                        }
+                        if (C::Z_GRAD) { base[C::P_ZB * PSET + qz * PS] = zs; base[C::P_ZG * PSET + qz * PS] = zg; }
+#pragma unroll
+                        for (int n = 0; n < NF; ++n) base[(C::P_F0 + n) * PSET + qz * PS] = fs[n];
+                    }
+                }
+            }
         };
         // phase 3 of tile i: transposed z contraction of the result planes of buffer i % 2 + scatter
         auto phase3 = [&](int i) {
@@ -180,7 +232,7 @@ __global__ void __launch_bounds__(256, 2) form_apply_slab5_kernel(const FormArgs
             const double* pb = planes + (size_t)(i & 1) * E * ES;
             const int nit = nvalid(i) * DD;
 #pragma unroll 1
-            for (int item = ptid; item < nit; item += TP) {
+            for (int item = ptid; item < (SPLIT && nit > TP ? TP : nit); item += TP) {
                 const int el = item / DD, ij = item - el * DD;
                 const double* base = pb + el * ES + ij;
                 double Aq[Q], Bq[Q];
@@ -195,6 +247,25 @@ __global__ void __launch_bounds__(256, 2) form_apply_slab5_kernel(const FormArgs
 #pragma unroll
                     for (int qz = 0; qz < Q; ++qz) { sa += t.B[qz * D + k] * Aq[qz]; sb += t.G[qz * D + k] * Bq[qz]; }
                     const double s = sa + sb;
+                    const int g = ix[el * ND + ij + DD * k];
+                    if (g >= 0) atomicAdd(a.y + g, s);
+                    else if (!a.mask_out) atomicAdd(a.y + (~g), s);
+                    else if (a.diag_one) a.y[~g] = a.x[~g];   // every writer stores the same value
+                }
+            }
+            if constexpr (SPLIT) {
+                // left-over pencils: piece = (pencil, output node k, lower | upper half of the quadrature planes)
+                const int item = TP + ptid / (2 * D), r = ptid - (ptid / (2 * D)) * (2 * D), k = r >> 1, q0 = (r & 1) * (Q / 2);
+                if (ptid < LEFT * 2 * D && item < nit) {
+                    const int el = item / DD, ij = item - el * DD;
+                    const double* base = pb + el * ES + ij;
+                    double s = 0.0;
+#pragma unroll
+                    for (int dq = 0; dq < Q / 2; ++dq) {
+                        const int qz = q0 + dq;
+                        s += s_tab[qz * D + k] * (base[qz * PS] + base[PSET + qz * PS]) +
+                             s_tab[Q * D + qz * D + k] * (base[2 * PSET + qz * PS] + base[3 * PSET + qz * PS]);
+                    }
                     const int g = ix[el * ND + ij + DD * k];
                     if (g >= 0) atomicAdd(a.y + g, s);
                     else if (!a.mask_out) atomicAdd(a.y + (~g), s);

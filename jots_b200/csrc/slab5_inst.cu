@@ -30,19 +30,26 @@ struct PerDevice5 {
 };
 }  // namespace
 
-template <int OP, int CF>
-static int launch_slab5(const FormArgs& a, const TablesRT& r, cudaStream_t st) {
+template <int OP, int CF, bool SPLIT>
+static int launch_slab5s(const FormArgs& a, const TablesRT& r, cudaStream_t st) {
     constexpr int D = 3, Q = 4, E = 16;
     typedef SlabCfg<OP, CF> C;
     Slab2Tables<D, Q> t;
     fill_slab2_tables<D, Q>(r, t);
     const size_t smem = Slab5Smem<D, Q, C::NP, E>::total;
-    auto kern = form_apply_slab5_kernel<D, Q, OP, CF, E>;
+    auto kern = form_apply_slab5_kernel<D, Q, OP, CF, E, SPLIT>;
     static PerDevice5 pd;
     const int grid_max = pd.get(kern, 256, smem);
     const int ntiles = (a.nelem + E - 1) / E;
     kern<<<ntiles < grid_max ? ntiles : grid_max, 256, smem, st>>>(a, t);
     return 0;
+}
+
+// JOTS_SLAB5_SPLIT=1: left-over pencils as short pieces
+template <int OP, int CF>
+static int launch_slab5(const FormArgs& a, const TablesRT& r, cudaStream_t st) {
+    static const bool split = [] { const char* e = getenv("JOTS_SLAB5_SPLIT"); return e && e[0] == '1'; }();
+    return split ? launch_slab5s<OP, CF, true>(a, r, st) : launch_slab5s<OP, CF, false>(a, r, st);
 }
 
 // Q2 hexes with a diagonal metric; returns non-zero when (op, cf) has no instantiation
