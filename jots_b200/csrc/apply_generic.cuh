@@ -138,7 +138,7 @@ __global__ void __launch_bounds__(Q* Q* NE) form_apply_kernel(const FormArgs a, 
             if (NEED_Z || NF > 0) zr[k] = a.z[idx];
             if (NF > 0) {
                 double f[NFA];
-                nodal_fields<CF, OP>(a.mat, zr[k], f);
+                nodal_fields<CF, OP>(a.mat, a.zc ? a.zc[idx] : zr[k], f);
 #pragma unroll
                 for (int n = 0; n < NF; ++n) fr[n][k] = f[n];
             }

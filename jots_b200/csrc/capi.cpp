@@ -263,8 +263,7 @@ void jots_ctx_destroy(jots_ctx_t c) { delete c; }
 int64_t jots_ctx_size(jots_ctx_t c) { return c->c->n; }
 int jots_ctx_set_stream(jots_ctx_t c, void* s) {
     JOTS_TRY
-    c->c->sync();
-    c->c->stream = (cudaStream_t)s;
+    c->c->set_stream((cudaStream_t)s);
     return 0;
     JOTS_CATCH_INT
 }

@@ -157,6 +157,14 @@ Ctx::~Ctx() {
     halo_destroy(halo);
 }
 
+void Ctx::set_stream(cudaStream_t s) {
+    JOTS_CUDA(cudaSetDevice(device));
+    sync();
+    if (own_stream && stream) cudaStreamDestroy(stream);
+    own_stream = false;
+    stream = s;
+}
+
 void Ctx::set_materials(const Poly& rho, const Poly& C, const Poly& k) {
     mat.rho = rho; mat.C = C; mat.k = k;
 }
@@ -222,6 +230,7 @@ FormArgs Ctx::make_args(const FormSpec& f, const double* x, double* y, bool for_
     a.geom_diag = (geom_diag && use_slab) ? 1 : 0;
     a.geomq = d_geomq.p;
     a.x = x; a.z = f.state; a.y = y;
+    a.zc = (f.coef_state && f.coef_state != f.state) ? f.coef_state : nullptr;
     a.nelem = (int)space.nelem;
     a.mask_in = f.mask_in; a.mask_out = f.mask_out;
     a.diag_one = (f.diag_one && f.mask_out && !halo && !for_diag) ? 1 : 0;   // multi-GPU: after the interface sum

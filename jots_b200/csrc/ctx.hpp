@@ -63,6 +63,7 @@ struct FormSpec {
     bool mask_in = false, mask_out = false;
     bool diag_one = false;          // y[ess] = x[ess] (EliminateRowsCols / DIAG_ONE)
     const double* state = nullptr;  // frozen state z
+    const double* coef_state = nullptr;  // properties evaluated on this vector instead of z (null: on z)
     double bdr_mass_scale = 0.0;    // + scale * int_bdr (g/(rho C))' phi_i phi_j  (0 = absent)
 };
 
@@ -142,6 +143,9 @@ public:
     void copy(const double* x, double* y) { JOTS_CUDA(cudaMemcpyAsync(y, x, n * sizeof(double), cudaMemcpyDeviceToDevice, stream)); }
     void zero_ess(double* y) { v_set_idx(stream, (int)ess.size(), d_ess.p, 0.0, y); stats.kernel_launches += !ess.empty(); }
     void sync() { JOTS_CUDA(cudaStreamSynchronize(stream)); }
+    // run on the caller's stream from now on: the context's own stream is drained and destroyed, the caller keeps
+    // ownership of s (it is never destroyed here)
+    void set_stream(cudaStream_t s);
 
     FormArgs make_args(const FormSpec& f, const double* x, double* y, bool for_diag) const;
 private:

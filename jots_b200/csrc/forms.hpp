@@ -56,6 +56,8 @@ struct FormArgs {
     const double* geomq;  // non-affine (general multilinear) meshes: [nelem][NQ][10] per quadrature point, else null
     const double* x;      // input vector
     const double* z;      // frozen state (coefficients + grad z); may be null for CF_CONST/OP_LIN
+    const double* zc;     // state the nodal property polynomials are evaluated on when it differs from z (explicit
+                          // stages: properties frozen at the last UpdateMatProps), else null; generic kernel only
     double* y;            // output, accumulated with atomics (caller zeroes it)
     int nelem;
     int mask_in;          // treat x as zero on essential DOFs (eliminated columns)

@@ -8,7 +8,7 @@ namespace jots {
 
 int launch_form_apply(int dim, int p, int op, int cf, const FormArgs& a, const TablesRT& t, cudaStream_t st) {
     if (a.nelem <= 0) return 0;
-    if (dim == 3 && a.geom_diag) {
+    if (dim == 3 && a.geom_diag && !a.zc) {
         // fast path: register-slab kernel (axis-aligned hexes, CF_CONST / CF_K, Q1-Q2)
         // JOTS_SLAB_VARIANT=6: experimental warp-specialised kernel (apply_slab5.cuh)
         static const bool slab5 = [] { const char* e = getenv("JOTS_SLAB_VARIANT"); return e && atoi(e) == 6; }();

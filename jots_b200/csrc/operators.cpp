@@ -204,13 +204,17 @@ void NonlinearConductionOperator::A_mult(const double* zz, double* y) {
     f.op = OP_RES; f.cm = 0.0; f.ck = -1.0; f.cb = 1.0; f.m0 = 1.0;
     f.mask_in = true; f.mask_out = !all_const;
     f.state = z.p;
+    // explicit Mult never refreshes the property GridFunctions (nl_conduction_operator.cpp:281-297): the polynomials stay
+    // evaluated on the vector of the last UpdateMatProps / ProcessNewState, only the gradient follows the stage vector
+    const double* cstate = c->mat_state.p ? c->mat_state.p : z.p;
+    f.coef_state = cstate;
     if (all_const) { f.cf = CF_CONST; f.a0 = m.k.c[0] * inv_rc; }
     else if (!has_BN) { f.cf = CF_K; f.inv_rc = inv_rc; }
     else f.cf = CF_FULL;
     c->apply_form(f, tmp.p, y);
     if (has_BN) {
         if (c->any_flux()) {
-            c->neumann_vector(1.0, z.p, tmp2.p, true, 1.0, true);
+            c->neumann_vector(1.0, cstate, tmp2.p, true, 1.0, true);
             v_axpy(c->stream, c->n, 1.0, tmp2.p, y);
             ++c->stats.kernel_launches;
         }

@@ -92,10 +92,22 @@ void ChebyshevPrec::set_operator(LinOp* op) {
     lanczos_extreme_eigs(alphas, betas, lmax, lmin);
     const double ub = 1.1 * lmax, lb = lmin + fraction * (ub - lmin);
     const double theta = 0.5 * (ub + lb), delta = 0.5 * (ub - lb);
-    const double den = 2 * delta * theta * theta - delta * delta * theta - delta * delta * delta + 2 * theta * theta * theta;
-    coef[0] = (4 * delta * theta - delta * delta + 6 * theta * theta) / den;
-    coef[1] = -(2 * delta + 6 * theta) / den;
-    coef[2] = 2.0 / den;
+    // hypre_ParCSRRelax_Cheby_Setup: cheby_order = order - 1 ("we are using the order of p(A)"); MFEM's default
+    // poly_order = 2 is therefore the degree-1 polynomial, one operator application per smoother call
+    order = poly_order - 1;
+    coef[0] = coef[1] = coef[2] = 0.0;
+    if (order <= 0) { order = 0; coef[0] = 1.0 / theta; }
+    else if (order == 1) {
+        const double den = theta * theta + delta * theta;
+        coef[0] = (delta + 2 * theta) / den;
+        coef[1] = -1.0 / den;
+    } else {
+        order = 2;
+        const double den = 2 * delta * theta * theta - delta * delta * theta - delta * delta * delta + 2 * theta * theta * theta;
+        coef[0] = (4 * delta * theta - delta * delta + 6 * theta * theta) / den;
+        coef[1] = -(2 * delta + 6 * theta) / den;
+        coef[2] = 2.0 / den;
+    }
 }
 
 void ChebyshevPrec::mult(const double* r, double* z) {

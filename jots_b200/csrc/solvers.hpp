@@ -44,15 +44,15 @@ struct JacobiPrec : Precond {
     const double* jacobi_dinv() const override { return dinv.p; }
 };
 
-// HypreSmoother::Chebyshev (type 16): order 2, fraction 0.3, 10 CG iterations for the eigenvalue
-// estimate of D^-1/2 A D^-1/2 from a deterministic pseudo-random vector
+// HypreSmoother::Chebyshev (type 16): poly_order 2 (= degree-1 polynomial in hypre: cheby_order = order - 1),
+// fraction 0.3, 10 CG iterations for the eigenvalue estimate of D^-1/2 A D^-1/2 from a deterministic pseudo-random vector
 struct ChebyshevPrec : Precond {
     Ctx* c;
     LinOp* A = nullptr;
     DArr<double> ds, t0, t1, t2, t3;
     double coef[3] = {0, 0, 0};
     double lmax = 0, lmin = 0;
-    int order = 2, eig_iters = 10;
+    int poly_order = 2, order = 1, eig_iters = 10;   // order = degree of p = poly_order - 1
     double fraction = 0.3;
     explicit ChebyshevPrec(Ctx* ctx) : c(ctx) {}
     void set_operator(LinOp* A) override;

@@ -51,11 +51,13 @@ class JacobiSmoother:
 
 
 class ChebyshevSmoother:
-    """HypreSmoother::Chebyshev (type 16), order 2, poly_fraction 0.3, 10 CG iterations for the
-    eigenvalue estimate of D^-1/2 A D^-1/2 (App. A.5)."""
+    """HypreSmoother::Chebyshev (type 16), poly_order 2, poly_fraction 0.3, 10 CG iterations for the
+    eigenvalue estimate of D^-1/2 A D^-1/2 (App. A.5).  hypre_ParCSRRelax_Cheby_Setup/Solve use
+    ``cheby_order = order - 1`` ("we are using the order of p(A)"), so MFEM's poly_order = 2 is the
+    degree-1 polynomial c0 + c1 A^: ONE operator application per smoother call."""
 
-    def __init__(self, order=2, fraction=0.3, eig_iters=10):
-        self.order = order
+    def __init__(self, poly_order=2, fraction=0.3, eig_iters=10):
+        self.order = poly_order - 1          # degree of p
         self.fraction = fraction
         self.eig_iters = eig_iters
 
@@ -68,10 +70,18 @@ class ChebyshevSmoother:
         lb = lmin + self.fraction * (ub - lmin)
         theta = 0.5 * (ub + lb)
         delta = 0.5 * (ub - lb)
-        den = 2 * delta * theta ** 2 - delta ** 2 * theta - delta ** 3 + 2 * theta ** 3
-        self.c = np.array([(4 * delta * theta - delta ** 2 + 6 * theta ** 2) / den,
-                           -(2 * delta + 6 * theta) / den,
-                           2.0 / den])
+        if self.order == 0:
+            self.c = np.array([1.0 / theta])
+        elif self.order == 1:
+            den = theta * theta + delta * theta
+            self.c = np.array([(delta + 2 * theta) / den, -1.0 / den])
+        elif self.order == 2:
+            den = 2 * delta * theta ** 2 - delta ** 2 * theta - delta ** 3 + 2 * theta ** 3
+            self.c = np.array([(4 * delta * theta - delta ** 2 + 6 * theta ** 2) / den,
+                               -(2 * delta + 6 * theta) / den,
+                               2.0 / den])
+        else:
+            raise ValueError("poly_order > 3 is not used by JOTS (HypreSmoother default is 2)")
 
     def _ahat(self, v):
         return self.ds * (self.A @ (self.ds * v))

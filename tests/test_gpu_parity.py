@@ -161,6 +161,29 @@ def test_axis_aligned_fast_path(J, tmp_path, sim, props, p):
         assert rel(d, Jm.diagonal()) < APPLY_TOL, rel(d, Jm.diagonal())
 
 
+@pytest.mark.parametrize("p,n,props", [(2, (24, 24, 20), "k"), (2, (24, 24, 20), "full"), (3, (16, 16, 15), "k"), (1, (40, 40, 32), "k2")])
+def test_fast_path_persistent_loop_against_the_oracle(J, tmp_path, p, n, props):
+    """More tiles than resident blocks (Q2: 11 520 elements = 720 16-element tiles on at most 592 blocks): every block of
+    the persistent kernel takes the `it >= 1` path -- refill of the single staging buffer, rotation of the index buffers --
+    and the result is compared with the ORACLE's assembled sparse Jacobian / residual / diagonal, not with another kernel."""
+    dev, orc = build(J, tmp_path, "Nonlinear_Unsteady", 3, p, props, grade=0.6, shear=0.0, n=n, steps=1)
+    nd = dev.n
+    state = smooth_state(orc)
+    x = rnd(nd, 31)
+    k = 50.0 * rnd(nd, 32)
+    it = orc.it
+    it.u_n = state
+    it.new_state(k)
+    r = dev.op.form_apply(J.FORM_RESIDUAL, k, np.empty(nd), state=state)
+    assert rel(r, it.mult(k)) < APPLY_TOL
+    Jm = it.gradient(k)
+    z = state + it.dt * k
+    y = dev.op.form_apply(J.FORM_SYSTEM, x, np.empty(nd), state=z)
+    assert rel(y, Jm @ x) < APPLY_TOL, rel(y, Jm @ x)
+    d = dev.op.form_diagonal(J.FORM_SYSTEM, np.empty(nd), state=z)
+    assert rel(d, Jm.diagonal()) < APPLY_TOL, rel(d, Jm.diagonal())
+
+
 @pytest.mark.parametrize("dim,p,shear", [(3, 2, 0.2), (3, 2, 0.0), (3, 1, 0.0), (3, 3, 0.2), (2, 2, 0.2), (2, 1, 0.2)])
 def test_steady_forms(J, tmp_path, dim, p, shear):
     dev, orc = build(J, tmp_path, "Steady", dim, p, "k", grade=0.4, shear=shear, solver="CG")
@@ -195,8 +218,8 @@ def test_linearized_steps_all_solvers(J, tmp_path, solver, prec):
 @pytest.mark.parametrize("solver,prec", [("FGMRES", "Chebyshev"), ("GMRES", "Jacobi"), ("CG", "Jacobi")])
 @pytest.mark.parametrize("props", ["const", "k", "full"])
 def test_nonlinear_steps(J, tmp_path, solver, prec, props):
-    if solver == "CG" and props != "const":
-        pytest.skip("the Jacobian is non-symmetric when k depends on T (SURVEY.md finding 5)")
+    # CG on the non-symmetric Jacobian of the k(T) / C(T) cases is what BASELINE configs[3] ("Newton-CG") and bench.py
+    # run: MFEM's CG control flow is followed on both sides, so fields and Newton counts must still agree
     dev, orc = build(J, tmp_path, "Nonlinear_Unsteady", 3, 2, props, solver=solver, prec=prec, n=(6, 3, 2), steps=3)
     assert dev.run() == 3
     u_ref = orc.run()
@@ -212,6 +235,20 @@ def test_explicit_paths(J, tmp_path, sim, scheme):
     dev, orc = build(J, tmp_path, sim, 2, 2, "const", scheme=scheme, dt="1e-5", steps=4, n=(4, 3, 1))
     assert dev.run() == 4
     assert rel(dev.get_u(), orc.run()) < FIELD_TOL
+
+
+@pytest.mark.parametrize("scheme", ["Euler_Explicit", "RK4"])
+@pytest.mark.parametrize("dim,props", [(3, "k"), (3, "kc"), (2, "full")])
+def test_explicit_stages_keep_the_properties_of_the_last_update(J, tmp_path, scheme, dim, props):
+    """NonlinearConductionOperator::Mult (nl_conduction_operator.cpp:281-297) never refreshes the property
+    GridFunctions: RK4 stages 2-4 take the gradient of the stage vector with k, rho, C frozen at the vector of the last
+    UpdateMatProps (jots_driver.cpp:656-671).  Polynomial properties, so a kernel that re-evaluated them on the stage
+    vector differs from the oracle by 1e-4, far above the tolerance."""
+    dev, orc = build(J, tmp_path, "Nonlinear_Unsteady", dim, 2, props, scheme=scheme, dt="1e-2", steps=6, n=(4, 3, 2), shear=0.0,
+                     bcs=["HeatFlux, 7.5e5", "Isothermal, 350"] + [HF0] * (1 if dim == 2 else 3) + ["HeatFlux, -2e5"])
+    assert dev.run() == 6
+    u_ref = orc.run()   # refreshing the properties on every stage would move this field by 7e-5 .. 3e-4 (relative l2)
+    assert rel(dev.get_u(), u_ref) < FIELD_TOL
 
 
 @pytest.mark.parametrize("name", sorted(CASES))
