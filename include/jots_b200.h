@@ -92,6 +92,20 @@ int64_t jots_space_essential_dofs(jots_space_t s, const int32_t* attrs, int n_at
 int64_t jots_space_rowtiles(jots_space_t s, const int32_t* ess, int64_t n_ess, int tile_elems, double min_fill,
                             int* record_bytes, unsigned char* out);
 
+/* Element patches of the unique-pencil element kernel (apply_patch.cuh), exposed so that the index contract can be
+   checked bit-exactly on the host: px x py x 1 lattice-adjacent hexes with aligned local axes whose nodes are listed
+   once.  Record (int32): ((p)px+1)((p)py+1)(p+1) nodes in [k][J][I] order (essential DOFs as ~index, 0x80000000 where no
+   element of the patch touches the slot), then px*py element ids (-1: hole), padded to a multiple of 4.  The lattice is
+   recovered from the gather table, whatever the DOF numbering (replaces the per-element gather of
+   ParNonlinearForm::Mult / GetGradient, src/nl_conduction_operator.cpp:27-67).  Returns the number of patches (0: not a
+   conforming lattice or order < 2), -1 on error; *fill = elements / (patches*px*py); fills out[] when non-NULL. */
+int64_t jots_space_patches(jots_space_t s, const int32_t* ess, int64_t n_ess, int px, int py, int* record_ints,
+                           double* fill, int32_t* out);
+
+/* Patch size the kernel uses for an order (0 x 0: no patch kernel) and, when items != NULL (room for 128), its phase-3 work
+   items: pencil | n_visits << 8 | (element << 5 | local ij) << 10 | (element << 5 | local ij) << 20.  Returns the item count. */
+int jots_patch_shape(int order, int* px, int* py, uint32_t* items);
+
 /* ---- device context ----------------------------------------------------------------------------- */
 jots_ctx_t jots_ctx_create(jots_space_t s, int device);
 void jots_ctx_destroy(jots_ctx_t c);
@@ -115,6 +129,9 @@ int jots_ctx_material_field(jots_ctx_t c, int which, int order, double* out, int
    kernel launches, dots, last linear iters, last linear converged, last newton iters, last newton converged */
 int jots_ctx_stats(jots_ctx_t c, int64_t out[12], double norms[2]);
 int64_t jots_ctx_rowtile_applies(jots_ctx_t c);   /* operator applies that ran the row-structured (TMA) element kernel */
+/* element patches of the unique-pencil kernel this context runs (0 patches: the gather-table kernels are in use):
+   number of patches, fill = elements / (patches x elements per patch), operator applies that ran the patch kernel */
+int jots_ctx_patch_info(jots_ctx_t c, int64_t* n_patches, double* fill, int64_t* applies);
 int jots_ctx_reset_stats(jots_ctx_t c);
 
 /* ---- operators (JOTSIterator + TimeDependentOperator) ------------------------------------------- */

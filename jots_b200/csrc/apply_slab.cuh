@@ -669,10 +669,12 @@ template <int D, int Q, int NP, int E> struct Slab3Smem {
 // in-plane contraction and the quadrature-point physics in registers.  pl points at plane (id 0, qz) of the
 // element; plane id sits at pl + id*PSET.  The two result planes alias input planes 0..3 of the same (element,
 // qz): only this thread pair (adjacent lanes) ever touches them, __syncwarp orders last read before first write.
-template <int D, int Q, int OP, int CF, int PSET, bool MIRROR>
+// RS is the row stride of a plane (D in the per-element layout; the node-row length of a patch in apply_patch.cuh).
+// ALIAS = false: the results go to outA / outB (D*D contiguous doubles each) instead of the aliased input planes.
+template <int D, int Q, int OP, int CF, int PSET, bool MIRROR, int RS = D, bool ALIAS = true>
 __device__ __forceinline__ void slab_phase2(const FormArgs& a, const Slab2Tables<D, Q>& t, double* pl, const bool h,
                                             const double wz, const double gxx, const double gyy, const double gzz,
-                                            const unsigned p2mask) {
+                                            const unsigned p2mask, double* outA = nullptr, double* outB = nullptr) {
     typedef SlabCfg<OP, CF> C;
     constexpr int QC = (Q + 1) / 2;
     constexpr int DD = D * D;
@@ -688,10 +690,10 @@ __device__ __forceinline__ void slab_phase2(const FormArgs& a, const Slab2Tables
 #pragma unroll
             for (int jj = 0; jj < D; ++jj)
 #pragma unroll
-                for (int i = 0; i < D; ++i) out[jj * D + i] = p[jj * D + mo[i]];
+                for (int i = 0; i < D; ++i) out[jj * D + i] = p[jj * RS + mo[i]];
         } else {
 #pragma unroll
-            for (int m = 0; m < DD; ++m) out[m] = p[m];
+            for (int m = 0; m < DD; ++m) out[m] = p[(m / D) * RS + (m % D)];
             flip_plane<D>(out, h);
         }
     };
@@ -947,11 +949,16 @@ __device__ __forceinline__ void slab_phase2(const FormArgs& a, const Slab2Tables
     flip_plane<D>(Bp, h);
     // result planes alias input planes [0..3][qz] of this (element, qz): only this thread pair
     // (adjacent lanes) ever touches them
-    __syncwarp(p2mask);
-    // A -> plane h, Bp -> plane 2 + h (layout chosen so that the pair's stores do not collide)
-    double* outp = pl + (h ? 1 : 0) * PSET;
+    if constexpr (ALIAS) {
+        __syncwarp(p2mask);
+        // A -> plane h, Bp -> plane 2 + h (layout chosen so that the pair's stores do not collide)
+        double* outp = pl + (h ? 1 : 0) * PSET;
 #pragma unroll
-    for (int m = 0; m < DD; ++m) { outp[m] = A[m]; outp[2 * PSET + m] = Bp[m]; }
+        for (int m = 0; m < DD; ++m) { outp[m] = A[m]; outp[2 * PSET + m] = Bp[m]; }
+    } else {
+#pragma unroll
+        for (int m = 0; m < DD; ++m) { outA[m] = A[m]; outB[m] = Bp[m]; }
+    }
 }
 
 // SPLIT (tiles with more pencils than threads, Q2 E = 16: 144 pencils on 128 threads): the E*D*D - T left-over pencils of

@@ -217,6 +217,25 @@ int64_t jots_space_rowtiles(jots_space_t s, const int32_t* ess, int64_t n_ess, i
     } catch (const std::exception& ex) { fail(ex); return -1; }
 }
 
+int64_t jots_space_patches(jots_space_t s, const int32_t* ess, int64_t n_ess, int px, int py, int* record_ints, double* fill, int32_t* out) {
+    try {
+        std::vector<int> e(ess, ess + n_ess);
+        std::vector<int> tab;
+        const int64_t np = make_patches(s->s, e, px, py, tab, fill);
+        if (record_ints) *record_ints = np > 0 ? (int)(tab.size() / (size_t)np) : 0;
+        if (out && np > 0) std::memcpy(out, tab.data(), tab.size() * sizeof(int));
+        return np;
+    } catch (const std::exception& ex) { fail(ex); return -1; }
+}
+
+int jots_patch_shape(int order, int* px, int* py, uint32_t* items) {
+    int x = 0, y = 0;
+    patch_shape(order, x, y);
+    if (px) *px = x;
+    if (py) *py = y;
+    return (items && x > 0) ? patch_items(order, items) : 0;
+}
+
 // ---- config (host only) -----------------------------------------------------------------------
 int64_t jots_config_dump(const char* ini_path, char* out, int64_t cap) {
     try {
@@ -342,6 +361,12 @@ int jots_ctx_stats(jots_ctx_t c, int64_t out[12], double norms[2]) {
     return 0;
 }
 int64_t jots_ctx_rowtile_applies(jots_ctx_t c) { return c->c->stats.rowtile_applies; }
+int jots_ctx_patch_info(jots_ctx_t c, int64_t* n_patches, double* fill, int64_t* applies) {
+    if (n_patches) *n_patches = c->c->n_patches;
+    if (fill) *fill = c->c->patch_fill;
+    if (applies) *applies = c->c->stats.patch_applies;
+    return 0;
+}
 int jots_ctx_reset_stats(jots_ctx_t c) { c->c->stats = Stats(); return 0; }
 
 // ---- operators --------------------------------------------------------------------------------

@@ -192,6 +192,26 @@ void Ctx::set_bcs(const std::vector<BCSpec>& b) {
     d_gather_ess.upload(ge);
     d_gattr.alloc(std::max<size_t>(bcs.size(), 1));
     build_rowtiles();
+    build_patches();
+}
+
+// Element patches of apply_patch.cuh (make_patches, patches.cpp): rebuilt with the essential set
+void Ctx::build_patches() {
+    d_patches.release();
+    n_patches = 0; patch_fill = 0.0;
+    if (space.dim != 3 || !geom_diag || !use_slab || slab_variant != 7 || space.nelem == 0) return;
+    int px = 0, py = 0;
+    patch_shape(space.p, px, py);
+    if (px <= 0) return;
+    std::vector<int> tab;
+    double fill = 0.0;
+    const int64_t np = make_patches(space, ess, px, py, tab, &fill);
+    double min_fill = 0.6;
+    if (const char* ev = std::getenv("JOTS_PATCH_MIN_FILL")) min_fill = std::atof(ev);
+    if (np <= 0 || np > 0x7fffffffLL || fill < min_fill) return;
+    d_patches.upload(tab);
+    n_patches = (int)np;
+    patch_fill = fill;
 }
 
 // Row-structured tiles of apply_slab4.cuh (make_rowtiles, mesh.cpp): all-or-nothing, rebuilt with the essential set
@@ -240,6 +260,8 @@ FormArgs Ctx::make_args(const FormSpec& f, const double* x, double* y, bool for_
     a.n_rowtiles = n_rowtiles;
     a.rowtile_elems = rowtile_elems;
     a.nvec = n;
+    a.patches = (n_patches > 0 && !for_diag) ? d_patches.p : nullptr;
+    a.n_patches = n_patches;
     return a;
 }
 
@@ -275,6 +297,7 @@ void Ctx::apply_form(const FormSpec& f, const double* x, double* y) {
     if (n_if > 0 && n_if < space.nelem) {
         // interface elements first, their exchange overlaps the interior elements
         a.rowtiles = nullptr; a.n_rowtiles = 0;   // element sub-ranges: gather-table kernels only
+        a.patches = nullptr; a.n_patches = 0;
         FormArgs ai = a;
         ai.nelem = (int)n_if;
         rc = launch_form_apply(space.dim, space.p, f.op, f.cf, ai, tabs, stream);
@@ -295,7 +318,11 @@ void Ctx::apply_form(const FormSpec& f, const double* x, double* y) {
         // bricks: row-structured TMA kernel (no gather table); otherwise / when not instantiated the gather-table kernels
         rc = (a.rowtiles && a.geom_diag && space.dim == 3) ? launch_form_apply_slab4(space.p, f.op, f.cf, a, tabs, stream) : 1;
         if (!rc) ++stats.rowtile_applies;
-        else rc = launch_form_apply(space.dim, space.p, f.op, f.cf, a, tabs, stream);
+        if (rc && a.patches && a.geom_diag && space.dim == 3 && !a.zc) {
+            rc = launch_form_apply_patch(space.p, f.op, f.cf, a, tabs, stream);
+            if (!rc) ++stats.patch_applies;
+        }
+        if (rc) rc = launch_form_apply(space.dim, space.p, f.op, f.cf, a, tabs, stream);
     }
     if (rc) throw std::runtime_error("form (op=" + std::to_string(f.op) + ", cf=" + std::to_string(f.cf) + ") is not instantiated, rc=" + std::to_string(rc));
     stats.kernel_launches += 2;

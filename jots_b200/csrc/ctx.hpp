@@ -69,7 +69,7 @@ struct FormSpec {
 
 struct Stats {
     long long applies = 0, diag_assemblies = 0, krylov_iters = 0, newton_iters = 0, residual_evals = 0, steps = 0,
-              kernel_launches = 0, dots = 0, halo_exchanges = 0, rowtile_applies = 0;
+              kernel_launches = 0, dots = 0, halo_exchanges = 0, rowtile_applies = 0, patch_applies = 0;
     double last_linear_norm = 0, last_newton_norm = 0;
     int last_linear_converged = 1, last_newton_converged = 1, last_linear_iters = 0, last_newton_iters = 0;
 };
@@ -104,8 +104,13 @@ public:
     DArr<unsigned char> d_essmark;
     DArr<unsigned char> d_rowtiles;   // RowTile<D> table of the row-structured slab kernel (empty: not applicable)
     int n_rowtiles = 0, rowtile_elems = 0;
-    int slab_variant = 3;             // JOTS_SLAB_VARIANT: 2 non-persistent, 3 pipelined gather-table kernel (default), 4 / 5 row-structured (TMA), 6 experimental warp-specialised
+    int slab_variant = 7;             // JOTS_SLAB_VARIANT: 7 unique-pencil patch kernel where the mesh is a lattice (default), 3 pipelined gather-table kernel,
+                                      // 2 non-persistent, 4 / 5 row-structured (TMA), 6 experimental warp-specialised
     void build_rowtiles();            // from space.gather + essential marks; all-or-nothing
+    DArr<int> d_patches;              // element patches of the unique-pencil kernel (patches.cpp); empty: not applicable
+    int n_patches = 0;
+    double patch_fill = 0.0;          // nelem / (patches * elements per patch)
+    void build_patches();             // rebuilt with the essential set; used when the fill is at least JOTS_PATCH_MIN_FILL (0.6)
     int geom_stride = 10;
     bool geom_diag = false;   // diagonal metric on every element
     bool use_slab = true;     // JOTS_DISABLE_SLAB=1 forces the generic kernel

@@ -73,6 +73,9 @@ struct FormArgs {
     int n_rowtiles;
     int rowtile_elems;    // tile length E the table was built for
     long long nvec;       // length of x / z / y
+    // element patches of the unique-pencil kernel (apply_patch.cuh, patches.cpp): null when the mesh is not (mostly) a lattice
+    const int* patches;
+    int n_patches;
 };
 
 // Row-structured tile of the slab4 kernel: nv <= E consecutive elements (in element order) forming a row along the

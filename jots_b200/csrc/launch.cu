@@ -10,9 +10,6 @@ int launch_form_apply(int dim, int p, int op, int cf, const FormArgs& a, const T
     if (a.nelem <= 0) return 0;
     if (dim == 3 && a.geom_diag && !a.zc) {
         // fast path: register-slab kernel (axis-aligned hexes, CF_CONST / CF_K, Q1-Q2)
-        // JOTS_SLAB_VARIANT=6: experimental warp-specialised kernel (apply_slab5.cuh)
-        static const bool slab5 = [] { const char* e = getenv("JOTS_SLAB_VARIANT"); return e && atoi(e) == 6; }();
-        if (slab5 && !a.nonpersistent && launch_form_apply_slab5(p, op, cf, a, t, st) == 0) return 0;
         if (launch_form_apply_slab(p, op, cf, a, t, st) == 0) return 0;
     }
     if (dim == 3) {

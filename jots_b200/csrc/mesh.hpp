@@ -76,4 +76,11 @@ Space make_space(const Mesh& m, int p);
 // tiles are on average less than min_fill full.  ess: sorted essential DOFs (one bit per row node in the record).
 int64_t make_rowtiles(const Space& s, const std::vector<int>& ess, int E, double min_fill, std::vector<unsigned char>& tab);
 
+// Element patches of the unique-pencil slab kernel (apply_patch.cuh): PX x PY x 1 lattice-adjacent hexes with aligned local
+// axes, their (D-1)PX+1 x (D-1)PY+1 x D nodes listed once.  Record (ints): nodes [k][J][I] (essential DOFs as ~index,
+// 0x80000000 where no element of the patch touches the slot), then PX*PY element ids (-1: hole), padded to a multiple of 4.
+// The lattice is recovered from the gather table (any L-vector numbering).  Returns the number of patches, 0 when the mesh
+// is not a conforming lattice; *fill = nelem / (patches * PX * PY).
+int64_t make_patches(const Space& s, const std::vector<int>& ess, int PX, int PY, std::vector<int>& tab, double* fill);
+
 }  // namespace jots

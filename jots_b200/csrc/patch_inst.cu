@@ -1,0 +1,88 @@
+// Instantiations of the unique-pencil patch kernel (apply_patch.cuh): Q2 hexes, 4 x 4 x 1 patches, 128 threads.
+#include <cstdlib>
+#include <mutex>
+
+#include "apply_patch.cuh"
+#include "diag_face_host.hpp"
+#include "launch.hpp"
+#include "slab_tables.hpp"
+
+namespace jots {
+
+namespace {
+struct PerDevicePatch {
+    std::mutex m;
+    int grid_max[64] = {0};
+    template <class K>
+    int get(K kern, int threads, size_t smem) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        std::lock_guard<std::mutex> lock(m);
+        if (!grid_max[dev]) {
+            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            int sms = 148, per_sm = 1;
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem);
+            grid_max[dev] = sms * (per_sm > 0 ? per_sm : 1);
+        }
+        return grid_max[dev];
+    }
+};
+
+template <int D, int Q, int OP, int CF, int PX, int PY>
+int launch_patch(const FormArgs& a, const TablesRT& r, cudaStream_t st) {
+    constexpr int T = (PX * PY * 2 * Q + 31) / 32 * 32;
+    typedef SlabCfg<OP, CF> C;
+    Slab2Tables<D, Q> t;
+    fill_slab2_tables<D, Q>(r, t);
+    static const PatchItems items = build_patch_items<D, PX, PY>();
+    const size_t smem = PatchSmem<D, Q, C::NP, PX, PY>::total;
+    auto kern = form_apply_patch_kernel<D, Q, OP, CF, PX, PY, T>;
+    static PerDevicePatch pd;
+    const int grid_max = pd.get(kern, T, smem);
+    kern<<<a.n_patches < grid_max ? a.n_patches : grid_max, T, smem, st>>>(a, t, items);
+    return 0;
+}
+
+bool klin_enabled() {
+    static const bool v = [] { const char* e = getenv("JOTS_SLAB_KLIN"); return !e || atoi(e) != 0; }();
+    return v;
+}
+
+template <int D, int Q, int PX, int PY>
+int dispatch_patch(int op, int cf, const FormArgs& a, const TablesRT& t, cudaStream_t st) {
+    if (op == OP_JAC && cf == CF_K && a.mat.k.n == 2 && klin_enabled()) return launch_patch<D, Q, OP_JAC, CF_KL, PX, PY>(a, t, st);
+#define CASE(OPV, CFV) if (op == OPV && cf == CFV) return launch_patch<D, Q, OPV, CFV, PX, PY>(a, t, st);
+    CASE(OP_LIN, CF_CONST) CASE(OP_LIN, CF_K) CASE(OP_JAC, CF_K) CASE(OP_RES, CF_CONST) CASE(OP_RES, CF_K)
+    CASE(OP_LIN, CF_LINFIELDS)
+#undef CASE
+    const bool rho_uniform = a.mat.rho.n == 1;   // five property fields instead of eight
+    if (op == OP_JAC && cf == CF_FULL)
+        return rho_uniform ? launch_patch<D, Q, OP_JAC, CF_FULLC, PX, PY>(a, t, st) : launch_patch<D, Q, OP_JAC, CF_FULL, PX, PY>(a, t, st);
+    if (op == OP_RES && cf == CF_FULL)
+        return rho_uniform ? launch_patch<D, Q, OP_RES, CF_FULLC, PX, PY>(a, t, st) : launch_patch<D, Q, OP_RES, CF_FULL, PX, PY>(a, t, st);
+    return 1;
+}
+}  // namespace
+
+void patch_shape(int p, int& px, int& py) {
+    if (p == 2) { px = 4; py = 4; }
+    else { px = 0; py = 0; }
+}
+
+// phase-3 work items of the kernel for order p (host copy, for the index-contract test); returns their number
+int patch_items(int p, unsigned* out) {
+    if (p != 2) return 0;
+    const PatchItems it = build_patch_items<3, 4, 4>();
+    for (int i = 0; i < it.n; ++i) out[i] = it.item[i];
+    return it.n;
+}
+
+// returns 0 when launched, non-zero when this (order, op, cf) has no patch instantiation
+int launch_form_apply_patch(int p, int op, int cf, const FormArgs& a, const TablesRT& t, cudaStream_t st) {
+    if (!a.patches || a.n_patches <= 0) return 1;
+    if (p == 2) return dispatch_patch<3, 4, 4, 4>(op, cf, a, t, st);
+    return 1;
+}
+
+}  // namespace jots

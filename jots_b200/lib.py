@@ -65,6 +65,8 @@ def load_library():
         "jots_space_copy_nodes": (C.c_int, [_P, _P]),
         "jots_space_essential_dofs": (C.c_int64, [_P, _P, C.c_int, _P]),
         "jots_space_rowtiles": (C.c_int64, [_P, _P, C.c_int64, C.c_int, C.c_double, _P, _P]),
+        "jots_space_patches": (C.c_int64, [_P, _P, C.c_int64, C.c_int, C.c_int, _P, _P, _P]),
+        "jots_patch_shape": (C.c_int, [C.c_int, _P, _P, _P]),
         "jots_config_dump": (C.c_int64, [C.c_char_p, _P, C.c_int64]),
         "jots_ctx_create": (_P, [_P, C.c_int]),
         "jots_ctx_destroy": (None, [_P]),
@@ -79,6 +81,7 @@ def load_library():
         "jots_ctx_set_material_state": (C.c_int, [_P, _P, C.c_int]),
         "jots_ctx_material_field": (C.c_int, [_P, C.c_int, C.c_int, _P, C.c_int]),
         "jots_ctx_stats": (C.c_int, [_P, _P, _P]),
+        "jots_ctx_patch_info": (C.c_int, [_P, _P, _P, _P]),
         "jots_ctx_reset_stats": (C.c_int, [_P]),
         "jots_ctx_rowtile_applies": (C.c_int64, [_P]),
         "jots_op_create": (_P, [_P, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int,
@@ -173,6 +176,14 @@ def _f64(a):
         if a.dtype != np.float64 or not a.flags.c_contiguous:
             raise JotsError("host vectors must be contiguous float64 arrays")
     return a
+
+
+def patch_shape(order):
+    """(px, py, items) of the unique-pencil patch kernel for an FE order; px == 0: none."""
+    px, py = C.c_int(0), C.c_int(0)
+    items = np.zeros(128, dtype=np.uint32)
+    n = load_library().jots_patch_shape(order, C.byref(px), C.byref(py), _ptr(items))
+    return px.value, py.value, items[:n]
 
 
 def config_dump(ini_path):
@@ -307,6 +318,21 @@ class Space:
         lib.jots_space_rowtiles(self._h, _ptr(ess), ess.size, tile_elems, min_fill, C.byref(rec), _ptr(buf))
         return buf.view(dt)
 
+    def patches(self, ess, px=4, py=4):
+        """Element patches of the unique-pencil kernel: (records [n_patches, record_ints] int32, fill); record = nodes
+        [k][J][I] (essential as ~index, 0x80000000 unused), then px*py element ids (-1: hole).  Empty when not a lattice."""
+        ess = np.ascontiguousarray(ess, dtype=np.int32)
+        rec, fill = C.c_int(0), C.c_double(0.0)
+        lib = load_library()
+        n = lib.jots_space_patches(self._h, _ptr(ess), ess.size, px, py, C.byref(rec), C.byref(fill), None)
+        if n < 0:
+            raise JotsError(_err())
+        if n == 0:
+            return np.empty((0, 0), dtype=np.int32), 0.0
+        buf = np.empty((n, rec.value), dtype=np.int32)
+        lib.jots_space_patches(self._h, _ptr(ess), ess.size, px, py, C.byref(rec), C.byref(fill), _ptr(buf))
+        return buf, float(fill.value)
+
     def __del__(self):
         if getattr(self, "_h", None) and _LIB is not None:
             _LIB.jots_space_destroy(self._h)
@@ -382,6 +408,9 @@ class Context:
         d = {k: int(v) for k, v in zip(keys, out)}
         d["last_linear_norm"], d["last_newton_norm"] = float(norms[0]), float(norms[1])
         d["rowtile_applies"] = int(load_library().jots_ctx_rowtile_applies(self._h))
+        npch, fill, app = C.c_int64(0), C.c_double(0.0), C.c_int64(0)
+        load_library().jots_ctx_patch_info(self._h, C.byref(npch), C.byref(fill), C.byref(app))
+        d["n_patches"], d["patch_fill"], d["patch_applies"] = int(npch.value), float(fill.value), int(app.value)
         return d
 
     def reset_stats(self):

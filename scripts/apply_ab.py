@@ -14,8 +14,7 @@ CONFIGS = {
     "slab3_gather_E14": {"JOTS_SLAB_VARIANT": "3", "JOTS_SLAB_ELEMS": "14"},
     "slab3_gather_E16": {"JOTS_SLAB_VARIANT": "3", "JOTS_SLAB_ELEMS": "16"},
     "slab3_split_E16": {"JOTS_SLAB_VARIANT": "3", "JOTS_SLAB_ELEMS": "16", "JOTS_SLAB_SPLIT": "1"},
-    "slab5_warp_specialised": {"JOTS_SLAB_VARIANT": "6"},
-    "slab5_warp_specialised_split": {"JOTS_SLAB_VARIANT": "6", "JOTS_SLAB5_SPLIT": "1"},
+    "patch_4x4": {"JOTS_SLAB_VARIANT": "7"},
     "slab4_rows_E16": {"JOTS_SLAB_VARIANT": "4", "JOTS_SLAB4_ELEMS": "16"},
     "slab4_rows_E14": {"JOTS_SLAB_VARIANT": "4", "JOTS_SLAB4_ELEMS": "14"},
     "slab4_cpasync_E16": {"JOTS_SLAB_VARIANT": "4", "JOTS_SLAB4_ELEMS": "16", "JOTS_SLAB4_STAGE": "cpasync"},

@@ -1,0 +1,111 @@
+"""GPU parity of the unique-pencil patch kernel (jots_b200/csrc/apply_patch.cuh, the default element kernel for Q2 hexes on
+lattice meshes) against the CPU oracle, through the C ABI: full and ragged patches, holes, graded geometry (one Jacobian
+record per element), essential faces, every form the kernel is instantiated for, and whole time steps.  The build helper
+writes a mesh FILE, so the lattice is recovered from a first-appearance DOF numbering; the brick / partitioned paths are
+covered by test_gpu_parity.py::test_fast_path_persistent_loop_against_the_oracle, smoke() and test_gpu_dist.py."""
+import os
+
+import numpy as np
+import pytest
+
+from test_gpu_parity import APPLY_TOL, FIELD_TOL, HF0, build, rel, rnd, smooth_state
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def J():
+    import jots_b200
+    if jots_b200.load_library().jots_device_count() < 1:
+        pytest.fail("no CUDA device")
+    return jots_b200
+
+
+@pytest.fixture(autouse=True)
+def _force_patches():
+    """ragged patches too: the default keeps the gather-table kernel below a fill of 0.6"""
+    old = {k: os.environ.get(k) for k in ("JOTS_PATCH_MIN_FILL", "JOTS_SLAB_VARIANT")}
+    os.environ["JOTS_PATCH_MIN_FILL"] = "0"
+    os.environ.pop("JOTS_SLAB_VARIANT", None)
+    yield
+    for k, v in old.items():
+        if v is None:
+            os.environ.pop(k, None)
+        else:
+            os.environ[k] = v
+
+
+@pytest.mark.parametrize("props", ["const", "k", "k2", "kc", "full"])
+@pytest.mark.parametrize("sim", ["Linearized_Unsteady", "Nonlinear_Unsteady"])
+@pytest.mark.parametrize("n", [(5, 3, 4), (8, 8, 3), (1, 1, 1), (13, 9, 2)])
+def test_patch_kernel_forms(J, tmp_path, sim, props, n):
+    dev, orc = build(J, tmp_path, sim, 3, 2, props, grade=0.6, shear=0.0, n=n)
+    st0 = dev.ctx.stats()
+    assert st0["n_patches"] == -(-n[0] // 4) * -(-n[1] // 4) * n[2]
+    nd = dev.n
+    state = smooth_state(orc)
+    x = rnd(nd, 11)
+    it = orc.it
+    if sim == "Linearized_Unsteady":
+        orc.u = state.copy()
+        orc.update_mat_props(True)
+        for form, mat in ((J.FORM_MASS, it.M_mat), (J.FORM_STIFFNESS, it.K_mat), (J.FORM_SYSTEM, it.A_mat)):
+            y = dev.op.form_apply(form, x, np.empty(nd), state=state)
+            assert rel(y, mat @ x) < APPLY_TOL, (form, rel(y, mat @ x))
+        assert dev.ctx.stats()["patch_applies"] - st0["patch_applies"] == 3
+    else:
+        k = 50.0 * rnd(nd, 12)
+        it.u_n = state
+        it.new_state(k)
+        r = dev.op.form_apply(J.FORM_RESIDUAL, k, np.empty(nd), state=state)
+        assert rel(r, it.mult(k)) < APPLY_TOL, rel(r, it.mult(k))
+        Jm = it.gradient(k)
+        y = dev.op.form_apply(J.FORM_SYSTEM, x, np.empty(nd), state=state + it.dt * k)
+        assert rel(y, Jm @ x) < APPLY_TOL, rel(y, Jm @ x)
+        assert dev.ctx.stats()["patch_applies"] - st0["patch_applies"] == 2
+
+
+@pytest.mark.parametrize("sim,props,solver,prec", [("Nonlinear_Unsteady", "k", "CG", "Jacobi"), ("Nonlinear_Unsteady", "full", "FGMRES", "Chebyshev"),
+                                                   ("Linearized_Unsteady", "full", "GMRES", "Jacobi"), ("Steady", "k", "CG", "Chebyshev")])
+def test_patch_kernel_time_steps(J, tmp_path, sim, props, solver, prec):
+    """Whole steps: temperature field against the oracle, and identical Krylov / Newton counts to the gather-table kernel."""
+    dev, orc = build(J, tmp_path, sim, 3, 2, props, solver=solver, prec=prec, n=(9, 6, 3), steps=3,
+                     bcs=["HeatFlux, 7.5e5", "Isothermal, 350", HF0, "Sinusoidal_Isothermal, 50, 40, 0.3, 400", HF0, HF0])
+    dev.run()
+    st = dev.ctx.stats()
+    assert st["patch_applies"] > 0
+    u_ref = orc.run()
+    assert rel(dev.get_u(), u_ref) < FIELD_TOL
+    os.environ["JOTS_SLAB_VARIANT"] = "3"
+    dev3, _ = build(J, tmp_path, sim, 3, 2, props, solver=solver, prec=prec, n=(9, 6, 3), steps=3,
+                    bcs=["HeatFlux, 7.5e5", "Isothermal, 350", HF0, "Sinusoidal_Isothermal, 50, 40, 0.3, 400", HF0, HF0])
+    dev3.run()
+    st3 = dev3.ctx.stats()
+    assert st3["patch_applies"] == 0 and st3["n_patches"] == 0
+    assert st3["newton_iters"] == st["newton_iters"] and abs(st3["krylov_iters"] - st["krylov_iters"]) <= 2
+    assert rel(dev3.get_u(), dev.get_u()) < 1e-10
+
+
+def test_patch_kernel_on_a_brick_with_vectors_on_odd_offsets(J, tmp_path):
+    """Device pointers that are only 8-byte aligned (cp.async 8-byte gathers have no stronger requirement)."""
+    import torch
+    from cases import ini_text
+    from test_gpu_parity import PROPS
+    ini = str(tmp_path / "c.ini")
+    with open(ini, "w") as f:
+        f.write(ini_text("Nonlinear_Unsteady", "unused", 300, PROPS["k"], ["HeatFlux, 7.5e5", HF0, HF0, "Isothermal, 300", HF0, HF0],
+                         newton=50, steps=1, order=2))
+    dev = J.Driver(ini, 0, mesh=J.Mesh.brick(12, 8, 5, 0.01, 0.01, 0.01))
+    n = dev.n
+    assert dev.ctx.stats()["n_patches"] == 3 * 2 * 5
+    g = torch.Generator(device="cuda").manual_seed(5)
+    buf = torch.empty(3 * (n + 1), dtype=torch.float64, device="cuda").uniform_(-1.0, 1.0, generator=g)
+    x, z = buf[1:n + 1], buf[n + 2:2 * n + 2]
+    z.mul_(100.0).add_(500.0)
+    y0 = torch.empty(n, dtype=torch.float64, device="cuda")
+    y1 = buf[2 * n + 3:3 * n + 3]
+    torch.cuda.synchronize()
+    dev.op.form_apply(J.FORM_SYSTEM, x.clone(), y0, state=z.clone())
+    dev.op.form_apply(J.FORM_SYSTEM, x, y1, state=z)
+    torch.cuda.synchronize()
+    assert float((y0 - y1).abs().max()) <= 1e-12 * float(y0.abs().max())

@@ -293,3 +293,83 @@ def test_every_shipped_config_parses_like_the_oracle():
     for p in paths:
         lib, ora = _config_pairs(p)
         assert lib == ora, (p, {k: (lib[k], ora[k]) for k in lib if lib[k] != ora[k]})
+
+
+@pytest.mark.parametrize("source", ["brick", "ragged_brick", "file_mesh", "subdomain"])
+def test_patches_reproduce_the_gather_table_bit_exact(tmp_path, source):
+    """Element patches of the unique-pencil kernel (apply_patch.cuh, patches.cpp): every element sits in exactly one patch
+    slot, its 27 nodes are found at [k][2 ly + j][2 lx + i] with the essential complement, slots that no element touches
+    are marked unused, and the kernel's phase-3 items visit every (element slot, local ij) exactly once.  The lattice is
+    recovered from the gather table alone: lexicographic bricks, first-appearance numbering of a mesh file and the
+    owned-first numbering of a partitioned subdomain all give full patches."""
+    import jots_b200 as J
+    from cases import write_brick_mesh
+    p, D = 2, 3
+    px, py, items = J.patch_shape(p)
+    assert (px, py) == (4, 4) and len(items) == 90
+    if source == "brick":
+        s = J.Space(J.Mesh.brick(8, 12, 3, 0.01, 0.02, 0.03), p)
+    elif source == "ragged_brick":
+        s = J.Space(J.Mesh.brick(6, 5, 2, 0.01, 0.02, 0.03), p)
+    elif source == "file_mesh":
+        path = str(tmp_path / "m.mesh")
+        write_brick_mesh(path, 8, 4, 3, 0.01, 0.02, 0.015, grade=0.4)
+        s = J.Space(J.Mesh.read(path), p)
+    else:
+        mesh = J.Mesh.brick(16, 8, 4, 0.01, 0.02, 0.03)
+        part = J.Partition(mesh, J.Space(mesh, p), 2, 1)
+        s = part.space()
+    g = s.gather()
+    ne = g.shape[0]
+    ess = s.essential_dofs([1, 5]) if source != "subdomain" else np.unique(g[: ne // 3, :9].ravel()).astype(np.int32)
+    em = np.zeros(s.n_dof, bool)
+    em[ess] = True
+    tab, fill = s.patches(ess, px, py)
+    nxn, nyn = 2 * px + 1, 2 * py + 1
+    npen, nn = nxn * nyn, nxn * nyn * D
+    assert tab.shape[1] == (nn + px * py + 3) // 4 * 4
+    assert abs(fill - ne / (tab.shape[0] * px * py)) < 1e-15
+    if source != "ragged_brick":
+        assert fill == 1.0
+    INVALID = -2 ** 31
+    seen = np.zeros(ne, int)
+    for rec in tab:
+        nodes = rec[:nn].reshape(D, nyn, nxn)
+        elems = rec[nn:nn + px * py]
+        touched = np.zeros((D, nyn, nxn), bool)
+        for slot, e in enumerate(elems):
+            if e < 0:
+                continue
+            seen[e] += 1
+            ly, lx = divmod(slot, px)
+            ge = g[e].reshape(D, D, D)                       # [k][j][i]
+            want = np.where(em[ge], ~ge, ge)
+            assert (nodes[:, 2 * ly:2 * ly + 3, 2 * lx:2 * lx + 3] == want).all()
+            touched[:, 2 * ly:2 * ly + 3, 2 * lx:2 * lx + 3] = True
+        assert (nodes[~touched] == INVALID).all() and (nodes[touched] != INVALID).all()
+    assert (seen == 1).all()
+    # phase-3 items: every (element slot, local ij) of a full patch exactly once, on the right pencil
+    visits = np.zeros((px * py, D * D), int)
+    for it in items:
+        pencil, nv = int(it) & 0xff, (int(it) >> 8) & 3
+        J_, I_ = divmod(pencil, nxn)
+        assert 1 <= nv <= 2
+        for v in range(nv):
+            ev = (int(it) >> (10 + 10 * v)) & 0x3ff
+            el, ij = ev >> 5, ev & 31
+            ly, lx = divmod(el, px)
+            j, i = divmod(ij, D)
+            assert (2 * ly + j, 2 * lx + i) == (J_, I_)
+            visits[el, ij] += 1
+    assert (visits == 1).all()
+
+
+def test_patches_absent_when_the_mesh_is_not_a_lattice(tmp_path):
+    """Q1 has no face-interior node to recover the lattice from (and no patch instantiation); a 99 x 1 x 1 row keeps the
+    gather-table kernel through the fill threshold of the context (fill 0.25 here)."""
+    import jots_b200 as J
+    s1 = J.Space(J.Mesh.brick(4, 4, 4, 1.0, 1.0, 1.0), 1)
+    assert s1.patches(np.zeros(0, np.int32))[0].shape[0] == 0
+    s = J.Space(J.Mesh.brick(99, 1, 1, 0.01, 0.01, 0.01), 2)
+    tab, fill = s.patches(np.zeros(0, np.int32))
+    assert tab.shape[0] == 25 and abs(fill - 99 / 400) < 1e-12
