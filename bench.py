@@ -85,20 +85,32 @@ class ClockSampler:
 CPU_BIN = os.path.join(ROOT, "oracle", "_build", "jots_cpu_port")
 
 
-def cpu_port_run(order, n, steps, threads=0):
+def host_threads():
+    """Threads the CPU arm may use: every core this process is allowed on (torchrun exports OMP_NUM_THREADS=1 to its
+    workers, which is why the thread count is passed explicitly and the variable overridden)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
+def cpu_port_run(order, n, steps, threads=None):
     """The C/OpenMP restatement of the reference's algorithm (oracle/c/jots_cpu_port.c: dense element
     Jacobians -> CSR at every Newton iteration, SpMV-based Jacobi-PCG) on a bounded sample of the same
     workload (same physics, n^3 elements), on all host cores."""
+    threads = host_threads() if not threads else threads
     if not os.path.exists(CPU_BIN):
         subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle", "c")], stdout=subprocess.DEVNULL)
     cmd = [CPU_BIN, str(n), str(n), str(n), "0.01", "0.01", "0.01", str(order), "1e-2", str(steps), "8000", "500", "300",
            "7.5e5", "300", "1e-10", "1e-16", "100", "1e-10", "100", str(threads), "2", "0.09", "-17"]
+    env = dict(os.environ, OMP_NUM_THREADS=str(threads))
+    env.pop("OMP_PROC_BIND", None)
     try:
-        out = subprocess.check_output(cmd)
+        out = subprocess.check_output(cmd, env=env)
     except (subprocess.CalledProcessError, OSError):
         # binary built on another CPU generation: rebuild on this host and retry once
         subprocess.check_call(["make", "-B", "-C", os.path.join(ROOT, "oracle", "c")], stdout=subprocess.DEVNULL)
-        out = subprocess.check_output(cmd)
+        out = subprocess.check_output(cmd, env=env)
     r = json.loads(out.decode())
     r["gdofs"] = r["ndof"] * r["krylov_iters"] / r["time"] / 1e9
     r["steps_per_s"] = r["steps"] / r["time"]
@@ -134,23 +146,40 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    n = args.cpu_n
+    n = cpu_sample_n(args)
     use_c = (args.solver == "CG" and args.prec == "Jacobi")
     if use_c:
         if args.warmup:
             cpu_port_run(args.order, max(4, n // 4), 1)
         r = cpu_port_run(args.order, n, args.steps)
     else:
-        r = cpu_oracle_run(args.order, args.solver, args.prec, min(n, 12), args.steps)
+        n = min(n, 12)
+        r = cpu_oracle_run(args.order, args.solver, args.prec, n, args.steps)
         r["threads"] = 1
+    # the config names the workload of the GPU arm AND the bounded sample of it that was actually timed here
+    cfg = workload_config(args, max(1, args.gpus))
+    cfg["workload"] += "; TIMED HERE: a bounded sample of it, %dx%dx%d Q%d hexes = %d DOFs per step (same physics, solver and tolerances)" % (
+        n, n, n, args.order, r["ndof"])
+    cfg["sample_n_elem"] = [n, n, n]
+    cfg["sample_n_dof"] = r["ndof"]
     line = {"impl": "reference", "metric": METRIC, "value": r["gdofs"], "unit": "GDOF/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * r["time"] / max(r["steps"], 1), "higher_is_better": True, "scaling": args.scaling,
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload_config(args, max(1, args.gpus)),
+            "config": cfg,
             "steps_per_s": r["steps_per_s"],
-            "cpu_baseline": cpu_baseline_entry(r, n if use_c else min(n, 12), args.order),
+            "cpu_baseline": cpu_baseline_entry(r, n, args.order),
             "e2e": {"value": r["gdofs"], "unit": "GDOF/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
+
+
+def cpu_sample_n(args):
+    """Elements per direction of the CPU sample.  The port's cost per step grows like n^4 (DOFs x Krylov iterations), so the
+    sample is as large as a run of steps + warm-up steps allows within a few minutes: small samples spend a larger share in
+    the per-Newton CSR assembly and understate the CPU's GDOF/s."""
+    if args.cpu_n > 0:
+        return args.cpu_n
+    total = args.steps + (1 if args.warmup else 0)
+    return 64 if total <= 4 else 56 if total <= 8 else 48 if total <= 24 else 40
 
 
 def box_dims(world):
@@ -184,6 +213,72 @@ def workload_config(args, world):
             "l2_policy": "vectors (136 MB each at 128^3 elements per GPU) exceed the 126 MB L2; no explicit flush"}
 
 
+def partition_parity_check(args, J, dist, comm, rank, world, local):
+    """N > 1: the same small problem (24^3 Q-order hexes, this bench's physics and solver, 2 steps) solved by the partitioned
+    ranks and by rank 0 alone on one GPU: relative l2 difference of the temperature fields (north_star bound 1e-8) and
+    equality of the Newton / Krylov iteration counts.  Evidence in the SCALE record that the multi-GPU numbers are numbers of
+    a correct solve."""
+    import numpy as np
+    n = 24
+    tmp = tempfile.mkdtemp()
+    ini = os.path.join(tmp, "parity.ini")
+    write_ini(ini, args.order, args.solver, args.prec, 2)
+    drv = J.Driver(ini, local, mesh=J.Mesh.brick(n, n, n, 0.01, 0.01, 0.01), comm=comm)
+    drv.run()
+    gid, n_owned = drv.global_ids()
+    st = drv.ctx.stats()
+    mine = (np.asarray(gid[:n_owned]), drv.get_u()[:n_owned], st["krylov_iters"], st["newton_iters"])
+    parts = [None] * world if rank == 0 else None
+    dist.gather_object(mine, parts, dst=0)
+    del drv
+    if rank != 0:
+        return None
+    ref = J.Driver(ini, local, mesh=J.Mesh.brick(n, n, n, 0.01, 0.01, 0.01))
+    ref.run()
+    u_ref = ref.get_u()
+    st1 = ref.ctx.stats()
+    u = np.full(u_ref.shape, np.nan)
+    for g, v, _, _ in parts:
+        u[g] = v
+    rel = float(np.linalg.norm(u - u_ref) / np.linalg.norm(u_ref))
+    return {"n_elem": [n, n, n], "order": args.order, "steps": 2, "rel_l2_vs_single_gpu": rel, "tolerance": 1e-8, "ok": bool(rel <= 1e-8),
+            "krylov_iters": {"partitioned": parts[0][2], "single_gpu": st1["krylov_iters"]},
+            "newton_iters": {"partitioned": parts[0][3], "single_gpu": st1["newton_iters"]},
+            "all_dofs_covered": bool(np.isfinite(u).all())}
+
+
+def strong_scaling_leg(args, J, torch, dist, comm, rank, world, local, barrier):
+    """A FIXED global brick (default 256^3 Q2 hexes = 135 005 697 DOFs, domain 0.01^3 for every N) box-partitioned over the
+    N GPUs: 1 warm-up + 2 timed steps, device timed, max over ranks.  north_star's strong-scaling number."""
+    ne = args.strong_elems
+    tmp = tempfile.mkdtemp()
+    ini = os.path.join(tmp, "strong.ini")
+    write_ini(ini, args.order, args.solver, args.prec, 10 ** 9)
+    t0 = time.perf_counter()
+    drv = J.Driver(ini, local, mesh=J.Mesh.brick(ne, ne, ne, 0.01, 0.01, 0.01), comm=comm)
+    setup_s = time.perf_counter() - t0
+    stream = torch.cuda.current_stream()
+    drv.ctx.set_stream(stream.cuda_stream)
+    drv.run(1)
+    barrier()
+    drv.ctx.reset_stats()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    drv.run(2)
+    e1.record(stream)
+    barrier()
+    st = drv.ctx.stats()
+    t = torch.tensor([e0.elapsed_time(e1), float(st["krylov_iters"]), setup_s], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    del drv
+    nd = (ne * args.order + 1) ** 3
+    ms = float(t[0])
+    return {"n_elem": [ne, ne, ne], "domain": [0.01, 0.01, 0.01], "n_dof": nd, "steps": 2, "warmup": 1, "ms_per_step": ms / 2,
+            "value": nd * int(t[1]) / (ms * 1e-3) / 1e9, "unit": "GDOF/s", "krylov_iters": int(t[1]), "newton_iters": st["newton_iters"],
+            "host_setup_s": float(t[2]), "scaling": "strong"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -194,10 +289,14 @@ def main():
     ap.add_argument("--order", type=int, default=2)
     ap.add_argument("--solver", default="CG")
     ap.add_argument("--prec", default="Jacobi")
-    ap.add_argument("--cpu-n", type=int, default=40, help="elements per direction of the CPU-baseline sample")
+    ap.add_argument("--cpu-n", type=int, default=0, help="elements per direction of the CPU sample (0: by the number of steps, 40..64)")
     ap.add_argument("--apply-reps", type=int, default=100, help="timed operator applies (after 20 warm-up applies)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--variant", default="A", choices=["A", "B"], help="B: C(T) = 4.5 T - 850 as well (FGMRES recommended)")
+    ap.add_argument("--strong-elems", type=int, default=256,
+                    help="N > 1: elements per direction of the FIXED global brick of the extra strong-scaling leg (256 -> 135 M DOFs at Q2; 0: off)")
+    ap.add_argument("--strong-at-1", action="store_true", help="run the strong-scaling leg at N = 1 too (about a minute of host set-up)")
+    ap.add_argument("--no-multi-checks", action="store_true", help="N > 1: skip the partitioned-vs-single-GPU parity check")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="N>1: weak = --n elements per direction per GPU, strong = --n for the global brick")
     args = ap.parse_args()
@@ -302,6 +401,7 @@ def main():
     torch.cuda.synchronize()
     drv.op.form_time(J.FORM_SYSTEM, x, y, state_dev=z, reps=min(20, max(2, args.apply_reps)))   # warm-up applies
     apply_ms = drv.op.form_time(J.FORM_SYSTEM, x, y, state_dev=z, reps=args.apply_reps)
+    kernel_label = drv.ctx.last_kernel()          # the element kernel these applies actually launched
     res_ms = drv.op.form_time(J.FORM_RESIDUAL, x, y, state_dev=z, reps=max(2, args.apply_reps // 4))
     peaks = {}
     pk_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -310,13 +410,24 @@ def main():
     peak = float(peaks.get("hbm_gbs", 6650.0))
     alg_bytes = 24.0 * ndof
     achieved = alg_bytes / (apply_ms * 1e-3) / 1e9
-    # dram__bytes_read + dram__bytes_write of the same kernel from the committed ncu --set full capture
-    traffic, fp64_pct = None, None
-    tr_path = os.path.join(ROOT, "profiles", "traffic_jac_q2_n128.json")
-    if os.path.exists(tr_path) and args.order == 2 and args.n == 128:
-        tr = json.load(open(tr_path))
-        if tr.get("n_dof") == ndof:
-            traffic, fp64_pct = tr["dram_bytes_per_launch"], tr.get("fp64_pipe_active_pct")
+    # ncu --set full figures of the SAME kernel (label and vector length must match, else they are left out):
+    # dram__bytes_read + dram__bytes_write, FP64 pipe utilisation, FP64 thread instructions per launch
+    traffic, fp64_pct, fp64_instr, stats_src = None, None, None, None
+    ks_path = os.path.join(ROOT, "profiles", "kernel_stats.json")
+    if os.path.exists(ks_path):
+        for e in json.load(open(ks_path)):
+            if e.get("kernel") == kernel_label and e.get("n_dof") == ndof:
+                traffic, fp64_pct = e["dram_bytes_per_launch"], e.get("fp64_pipe_active_pct")
+                fp64_instr, stats_src = e.get("fp64_thread_instr_per_launch"), e.get("source")
+
+    # ---- N > 1: correctness of the partitioned solve + a strong-scaling leg, both in the driver's view ----------------
+    extra = {}
+    if world > 1 and not args.no_multi_checks:
+        extra["parity_check"] = partition_parity_check(args, J, dist, comm, rank, world, local)
+        trace("parity check done")
+    if args.strong_elems > 0 and (world > 1 or args.strong_at_1):
+        extra["strong"] = strong_scaling_leg(args, J, torch, dist if world > 1 else None, comm, rank, world, local, barrier)
+        trace("strong-scaling leg done")
 
     def finish():
         if world > 1:
@@ -337,20 +448,33 @@ def main():
             "gpu_launches": st["kernel_launches"],
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "algorithmic_bytes": alg_bytes,
-                         "kernel": "form_apply_slab3_kernel<3,4,OP_JAC,CF_KL|CF_K,16,128> (Jacobian-vector apply, 24 B/DOF algorithmic; incl. the "
-                                   "memset of y and the essential-row fix-up launches)",
-                         "note": "this kernel is FP64-pipe bound (about 640 FP64 instructions per DOF against 24 B/DOF), not HBM "
-                                 "bound: see fp64_pipe_active_pct (ncu) and DESIGN.md 5.1",
+                         "kernel": kernel_label,
+                         "timed": "Jacobian-vector apply, 24 B/DOF algorithmic (x, z in, y out); CUDA events on the launching stream around "
+                                  "%d applies, each = memset of y + this kernel + the essential-row fix-up" % args.apply_reps,
+                         "note": "this kernel is FP64-pipe bound (fp64.instr_per_dof FP64 instructions against 24 B/DOF), not HBM "
+                                 "bound: fp64.frac_of_peak is the fraction that matters (DESIGN.md 5)",
                          "fp64_pipe_active_pct": fp64_pct,
+                         "kernel_stats_source": stats_src,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6.65 TB/s",
                          "frac_of_8TBs_spec": achieved / 8000.0}}
+    clk_mhz = (line["clocks"].get("sm_mhz") or line["clocks"].get("sm_max_mhz") or 1965.0)
+    if fp64_instr:
+        # FP64 peak of this GPU: SMs x 64 FP64 lanes per clock x SM clock under load (instructions, not flops)
+        sms = torch.cuda.get_device_properties(local).multi_processor_count
+        fp64_peak = sms * 64 * clk_mhz * 1e6
+        line["roofline"]["fp64"] = {"instr_per_launch": fp64_instr, "instr_per_dof": fp64_instr / ndof,
+                                    "achieved_ginstr_s": fp64_instr / (apply_ms * 1e-3) / 1e9, "peak_ginstr_s": fp64_peak / 1e9,
+                                    "frac_of_peak": fp64_instr / (apply_ms * 1e-3) / fp64_peak,
+                                    "peak_definition": "%d SMs x 64 FP64 lanes/clk x %.0f MHz (median SM clock in the timed region)" % (sms, clk_mhz)}
     if not args.no_cpu and world == 1 and args.variant == "A":
         if args.solver == "CG" and args.prec == "Jacobi":
-            line["cpu_baseline"] = cpu_baseline_entry(cpu_port_run(args.order, args.cpu_n, 2), args.cpu_n, args.order)
+            n_cpu = args.cpu_n if args.cpu_n > 0 else 48
+            line["cpu_baseline"] = cpu_baseline_entry(cpu_port_run(args.order, n_cpu, 2), n_cpu, args.order)
         else:
             r = cpu_oracle_run(args.order, args.solver, args.prec, 12, 2)
             r["threads"] = 1
             line["cpu_baseline"] = cpu_baseline_entry(r, 12, args.order)
+    line.update(extra)
     print(json.dumps(line), flush=True)
     del drv, comm
     finish()

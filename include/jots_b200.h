@@ -132,6 +132,8 @@ int64_t jots_ctx_rowtile_applies(jots_ctx_t c);   /* operator applies that ran t
 /* element patches of the unique-pencil kernel this context runs (0 patches: the gather-table kernels are in use):
    number of patches, fill = elements / (patches x elements per patch), operator applies that ran the patch kernel */
 int jots_ctx_patch_info(jots_ctx_t c, int64_t* n_patches, double* fill, int64_t* applies);
+/* label of the element kernel the last operator apply launched, e.g. "form_apply_patch_kernel<3,4,OP_JAC,CF_KL,4,4,128>" */
+const char* jots_ctx_last_kernel(jots_ctx_t c);
 int jots_ctx_reset_stats(jots_ctx_t c);
 
 /* ---- operators (JOTSIterator + TimeDependentOperator) ------------------------------------------- */

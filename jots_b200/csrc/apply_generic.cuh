@@ -96,6 +96,7 @@ __device__ __forceinline__ void grad_field(const double (&u)[QZ], double (&g0)[Q
 
 template <int D, int Q, int DZ, int QZ, int OP, int CF, int NE>
 __global__ void __launch_bounds__(Q* Q* NE) form_apply_kernel(const FormArgs a, const Tables<D, Q, DZ, QZ> t) {
+    if (a.skip && *a.skip != 0.0) return;   // enqueued ahead of a Krylov solve that has already stopped
     constexpr int NF = CoefNF<CF, OP>::value;
     constexpr int NFA = NF > 0 ? NF : 1;
     constexpr int ND = D * D * DZ;

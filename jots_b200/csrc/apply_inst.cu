@@ -29,6 +29,8 @@ static int launch_one(const FormArgs& a, const TablesRT& r, cudaStream_t st) {
     const int grid = (a.nelem + NE - 1) / NE;
     const size_t smem = (size_t)NE * 2 * QZ * Q * Q * sizeof(double);
     form_apply_kernel<D, Q, DZ, QZ, OP, CF, NE><<<grid, block, smem, st>>>(a, t);
+    static const std::string label = kernel_label("form_apply_kernel", D, Q, OP, CF, ("," + std::to_string(DZ) + "," + std::to_string(QZ) + "," + std::to_string(NE)).c_str());
+    last_element_kernel() = label.c_str();
     return 0;
 }
 

@@ -90,6 +90,7 @@ struct PatchSmem {
 
 template <int D, int Q, int OP, int CF, int PX, int PY, int T>
 __global__ void __launch_bounds__(T) form_apply_patch_kernel(const FormArgs a, const Slab2Tables<D, Q> t, const PatchItems items) {
+    if (a.skip && *a.skip != 0.0) return;   // enqueued ahead of a Krylov solve that has already stopped
     typedef SlabCfg<OP, CF> C;
     typedef PatchDims<D, PX, PY> PD;
     typedef PatchSmem<D, Q, C::NP, PX, PY> SM;

@@ -1,0 +1,316 @@
+// Two-phase unique-pencil patch kernel for the forms whose coefficients need no interpolated property field: uniform
+// properties (CF_CONST) and k(T) LINEAR in T with uniform rho, C (the reference's own k(T) cases and BASELINE configs[3]).
+//
+// For a linear k(T) = c0 T + c1 the interpolant of the nodal k values IS c0 z_h + c1 (interpolation is linear and the basis
+// is a partition of unity), so the quadrature-point conductivity comes from the interpolated state that the Jacobian /
+// residual need anyway, and no nodal polynomial is evaluated at all.  What is left of phase 1 of apply_patch.cuh -- the
+// contraction of x and z along the pencil direction -- is done by the phase-2 threads themselves, straight from the staged
+// nodal values (27 + 27 shared-memory loads and FP64 FMAs per plane, all lanes of a quadrature column reading the same
+// word: broadcast, conflict free).  That costs 7 % more FP64 instructions and removes a whole latency-bound phase with its
+// barrier (27 % of a block's time in the three-phase patch kernel, profiles/r2b):
+//
+//   per tile:   [ all warps: quadrature planes -> result planes ]  barrier  [ worker warps: z-transpose + atomics ]
+//
+// with ONE block barrier per tile: the result planes are double buffered (the mirrored thread pair first adds its two half
+// results with one shuffle exchange, so a buffer is 11 KB), hence phase 3 of tile t overlaps phase 2 of tile t+1 of the warps
+// that are done.  The last warp is the block's copy engine (descriptors two tiles ahead, nodal values one tile ahead,
+// cp.async; it zero-fills eliminated columns and unused slots) and joins phase 2.
+#pragma once
+#include "apply_patch.cuh"
+
+namespace jots {
+
+// result planes: word (r, el, j, i) at r*QS + el*ES + j*JS + i, r = 2 qz + (0: in-plane sum A, 1: z-derivative part B);
+// (ES, JS, QS) found by exhaustive search: phase-2 stores conflict free, phase-3 loads 1.67 wavefronts on average
+template <int D, int PX, int PY> struct Patch2Out { static constexpr int ES = D * D + 2, JS = D, QS = PX * PY * (D * D + 2) + 2; };
+
+template <int D, int PX, int PY>
+inline PatchItems build_patch2_items() {
+    typedef Patch2Out<D, PX, PY> O;
+    PatchItems it = build_patch_items<D, PX, PY>();
+    for (int n = 0; n < it.n; ++n) {
+        unsigned v = it.item[n], out = v & 0x3ffu;
+        for (int s = 0; s < 2; ++s) {
+            const unsigned ev = (v >> (10 + 10 * s)) & 0x3ffu, el = ev >> 5, ij = ev & 31;
+            out |= (el * O::ES + (ij / D) * O::JS + ij % D) << (10 + 10 * s);
+        }
+        it.item[n] = out;     // pencil | nv << 8 | offset0 << 10 | offset1 << 20, element = offset / ES
+    }
+    return it;
+}
+
+template <int D, int Q, int PX, int PY>
+struct Patch2Smem {
+    typedef PatchDims<D, PX, PY> PD;
+    typedef Patch2Out<D, PX, PY> O;
+    static constexpr int stage = 2 * 2 * PD::NN + (2 * 2 * PD::NN) % 2;   // [buffer][x | z][node]
+    static constexpr int out = 2 * 2 * Q * O::QS;                          // [buffer][r][QS]
+    static constexpr int tab = 2 * Q * D + (2 * Q * D) % 2;                // B rows then G rows
+    static constexpr size_t total = (size_t)(stage + out + tab) * sizeof(double) + (size_t)4 * PD::REC * sizeof(int);
+};
+
+// KLIN: k(T) = c0 T + c1 (else uniform properties).  OP as in forms.hpp.
+// Measured dead ends (profiles/README.md r2d, r2e), so that they are not tried again: issuing phase 3 of tile t-1 branch-free
+// inside phase 2 of tile t (registers: 3 % slower); moving the copy-engine role to another warp with every tile to even out
+// the four scheduler partitions (5 % slower).
+template <int D, int Q, int OP, bool KLIN, int PX, int PY, int T>
+__global__ void __launch_bounds__(T, 4) form_apply_patch2_kernel(const FormArgs a, const Slab2Tables<D, Q> t, const PatchItems items) {
+    if (a.skip && *a.skip != 0.0) return;   // enqueued ahead of a Krylov solve that has already stopped
+    typedef PatchDims<D, PX, PY> PD;
+    typedef Patch2Out<D, PX, PY> O;
+    typedef Patch2Smem<D, Q, PX, PY> SM;
+    constexpr int NPEN = PD::NPEN, NN = PD::NN, E = PD::E, REC = PD::REC, RS = PD::NXN;
+    constexpr int DD = D * D, QC = (Q + 1) / 2, NQH = Q * QC;
+    constexpr bool X_GRAD = (OP != OP_RES), Z_GRAD = (OP != OP_LIN), NEED_Z = Z_GRAD || KLIN;
+    constexpr int NWORK = T - 32;
+    static_assert(T == E * 2 * Q, "one thread per (element, quadrature plane, half)");
+    static_assert(Q % 2 == 0, "even quadrature rules only (no shared middle column)");
+    extern __shared__ __align__(16) double smem[];
+    double* stage = smem;
+    double* outbuf = smem + SM::stage;
+    double* s_tab = outbuf + SM::out;
+    int* ring = reinterpret_cast<int*>(s_tab + SM::tab);                // [4][REC]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int NWARP = T / 32;
+    const bool copier = warp == NWARP - 1;              // the block's copy engine
+    const unsigned my_item = tid < items.n ? items.item[tid] : 0u;
+    const int ntiles = a.n_patches;
+    const int nmine = (int)blockIdx.x < ntiles ? (ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+    if (tid < Q * D) { s_tab[tid] = t.B[tid]; s_tab[Q * D + tid] = t.G[tid]; }
+
+    auto issue_desc = [&](int i) {
+        if (i < nmine) {
+            const int* src = a.patches + (size_t)((int)blockIdx.x + i * (int)gridDim.x) * REC;
+            int* dst = ring + (i & 3) * REC;
+#pragma unroll
+            for (int m = 0; m < (REC / 4 + 31) / 32; ++m) {
+                const int c = lane + 32 * m;
+                if (c < REC / 4) cp_async16(dst + 4 * c, src + 4 * c);
+            }
+        }
+    };
+    auto issue_vals = [&](int i) {
+        if (i < nmine) {
+            const int* dsc = ring + (i & 3) * REC;
+            double* sx = stage + (size_t)(i & 1) * 2 * NN;
+            double* sz = sx + NN;
+            int g[(NN + 31) / 32];
+#pragma unroll
+            for (int m = 0; m < (NN + 31) / 32; ++m) { const int n = lane + 32 * m; g[m] = n < NN ? dsc[n] : PATCH_INVALID; }
+#pragma unroll
+            for (int m = 0; m < (NN + 31) / 32; ++m) {
+                const int n = lane + 32 * m;
+                if (n < NN) {
+                    if (g[m] == PATCH_INVALID) { sx[n] = 0.0; if (NEED_Z) sz[n] = 0.0; }
+                    else {
+                        const int idx = g[m] < 0 ? ~g[m] : g[m];
+                        if (g[m] < 0 && a.mask_in) sx[n] = 0.0;     // eliminated column
+                        else cp_async8(sx + n, a.x + idx);
+                        if (NEED_Z) cp_async8(sz + n, a.z + idx);
+                    }
+                }
+            }
+        }
+    };
+
+    if (copier) { issue_desc(0); issue_desc(1); cp_async_commit(); cp_async_wait<0>(); }
+    __syncthreads();
+    if (copier) { issue_vals(0); cp_async_commit(); cp_async_wait<0>(); }
+    __syncthreads();
+
+    // thread constants of phase 2
+    const int el = tid / (2 * Q), r = tid - el * 2 * Q, qz = r >> 1;
+    const bool h = r & 1;
+    const int ex = el % PX, ey = el / PX;
+    const int node0 = (D - 1) * ey * RS + (D - 1) * ex;
+    int mo[D];
+#pragma unroll
+    for (int i = 0; i < D; ++i) mo[i] = h ? D - 1 - i : i;
+    double gxx = 0, gyy = 0, gzz = 0, det = 0;
+    if (a.geom_stride == 0) {
+        const double* gm = a.geom;
+        gxx = gm[0] * gm[0] + gm[1] * gm[1] + gm[2] * gm[2];
+        gyy = gm[3] * gm[3] + gm[4] * gm[4] + gm[5] * gm[5];
+        gzz = gm[6] * gm[6] + gm[7] * gm[7] + gm[8] * gm[8];
+        det = gm[9];
+    }
+    const SymTab<D, Q, 1> tB{t.B}, tBW{t.BW};
+    const SymTab<D, Q, -1> tG{t.G}, tGW{t.GW};
+    // linear conductivity: a1 = ck inv_rc (c0 z + c1), a2 = ck inv_rc c0;  uniform: a1 = ck a0
+    const double s0 = KLIN ? a.ck * a.inv_rc * a.mat.k.c[0] : 0.0;
+    const double s1 = KLIN ? a.ck * a.inv_rc * a.mat.k.c[1] : a.ck * a.a0;
+    const double cmass = a.cm * a.m0;
+
+    // phase 3 of tile i: transposed z contraction + scatter of this thread's item.  Branch free up to the atomics: the
+    // loads are unconditional (every address is valid), contributions of holes are deselected.
+    auto phase3 = [&](int i, unsigned my_item) {
+        const int p3_pencil = my_item & 0xff, p3_nv = (my_item >> 8) & 3;
+        const int p3_off0 = (my_item >> 10) & 0x3ff, p3_off1 = (my_item >> 20) & 0x3ff;
+        const int* dsc = ring + (i & 3) * REC;
+        const double* ob = outbuf + (size_t)(i & 1) * 2 * Q * O::QS;
+        const bool v0 = dsc[NN + p3_off0 / O::ES] >= 0, v1 = p3_nv > 1 && dsc[NN + p3_off1 / O::ES] >= 0;
+        int g[D];
+#pragma unroll
+        for (int k = 0; k < D; ++k) g[k] = dsc[k * NPEN + p3_pencil];
+        double Aq[Q], Bq[Q];
+#pragma unroll
+        for (int q = 0; q < Q; ++q) {
+            const double a0 = ob[(2 * q) * O::QS + p3_off0], a1v = ob[(2 * q) * O::QS + p3_off1];
+            const double b0 = ob[(2 * q + 1) * O::QS + p3_off0], b1 = ob[(2 * q + 1) * O::QS + p3_off1];
+            Aq[q] = (v0 ? a0 : 0.0) + (v1 ? a1v : 0.0);
+            Bq[q] = (v0 ? b0 : 0.0) + (v1 ? b1 : 0.0);
+        }
+        const bool any = v0 || v1;
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+            // two short chains instead of one of length 2Q
+            double sa = t.B[k] * Aq[0], sb = t.G[k] * Bq[0];
+#pragma unroll
+            for (int q = 1; q < Q; ++q) { sa += t.B[q * D + k] * Aq[q]; sb += t.G[q * D + k] * Bq[q]; }
+            const double sum = sa + sb;
+            if (any) {
+                if (g[k] >= 0) atomicAdd(a.y + g[k], sum);
+                else if (g[k] != PATCH_INVALID) {
+                    if (!a.mask_out) atomicAdd(a.y + (~g[k]), sum);
+                    else if (a.diag_one) a.y[~g[k]] = a.x[~g[k]];   // every writer stores the same value
+                }
+            }
+        }
+    };
+
+    for (int it = 0; it < nmine; ++it) {
+        const int* dsc = ring + (it & 3) * REC;
+        if (copier) {
+            issue_desc(it + 2);
+            issue_vals(it + 1);
+            cp_async_commit();
+        }
+        // ---------------- phase 2: quadrature planes from the staged nodal values, half a plane per thread ---------------
+        {
+            const double* sx = stage + (size_t)(it & 1) * 2 * NN + node0;
+            const double* sz = sx + NN;
+            const int eid = dsc[NN + el];
+            if (a.geom_stride != 0) {
+                const double* gm = a.geom + (size_t)(eid < 0 ? 0 : eid) * a.geom_stride;
+                gxx = gm[0] * gm[0] + gm[1] * gm[1] + gm[2] * gm[2];
+                gyy = gm[3] * gm[3] + gm[4] * gm[4] + gm[5] * gm[5];
+                gzz = gm[6] * gm[6] + gm[7] * gm[7] + gm[8] * gm[8];
+                det = gm[9];
+            }
+            const double wz = t.W[qz] * det;
+            double tb[D], tg[D];
+#pragma unroll
+            for (int k = 0; k < D; ++k) { tb[k] = s_tab[qz * D + k]; tg[k] = s_tab[Q * D + qz * D + k]; }
+            // plane of this quadrature layer: out[jj][i] = sum_k c[k] src[k][jj][mirrored i]
+            auto zplane = [&](const double* src, const double (&c)[D], double (&out)[DD]) {
+#pragma unroll
+                for (int jj = 0; jj < D; ++jj)
+#pragma unroll
+                    for (int i = 0; i < D; ++i) {
+                        double s = c[0] * src[jj * RS + mo[i]];
+#pragma unroll
+                        for (int k = 1; k < D; ++k) s += c[k] * src[k * NPEN + jj * RS + mo[i]];
+                        out[jj * D + i] = s;
+                    }
+            };
+            double p9[DD], t6[D * QC], A[DD], Bp[DD];
+#pragma unroll
+            for (int i = 0; i < DD; ++i) { A[i] = 0.0; Bp[i] = 0.0; }
+            double xB6[D * QC], xG6[D * QC], vy6[D * QC], zB6[D * QC], zG6[D * QC], a1[NQH], a2x[NQH];
+            zplane(sx, tb, p9);
+            xpassC<D, QC>(p9, tB, xB6);
+            if (X_GRAD) xpassC<D, QC>(p9, tG, xG6);
+            if (NEED_Z) {
+                zplane(sz, tb, p9);
+                xpassC<D, QC>(p9, tB, zB6);
+                if (Z_GRAD) xpassC<D, QC>(p9, tG, zG6);
+            }
+            {
+                double xv[NQH];
+                ypassC<D, Q, QC>(xB6, tB, xv);                       // x at the quadrature points
+                if (KLIN) {
+                    ypassC<D, Q, QC>(zB6, tB, a1);                   // z at the quadrature points
+#pragma unroll
+                    for (int q = 0; q < NQH; ++q) a1[q] = s0 * a1[q] + s1;
+                    if (OP == OP_JAC) {
+#pragma unroll
+                        for (int q = 0; q < NQH; ++q) a2x[q] = s0 * xv[q];
+                    }
+                }
+                ypassTC<D, Q, QC>(xv, tBW, vy6);
+            }
+            const double c_m = cmass * wz;
+            auto scaleF = [&](double (&F)[NQH], const double (&zd6)[D * QC], const SymTab<D, Q, 1>* tb_, const SymTab<D, Q, -1>* tg_) {
+                if (KLIN) {
+#pragma unroll
+                    for (int q = 0; q < NQH; ++q) F[q] *= a1[q];
+                    if (OP == OP_JAC) {
+                        double zd[NQH];
+                        if (tb_) ypassC<D, Q, QC>(zd6, *tb_, zd); else ypassC<D, Q, QC>(zd6, *tg_, zd);
+#pragma unroll
+                        for (int q = 0; q < NQH; ++q) F[q] += a2x[q] * zd[q];
+                    }
+                } else {
+#pragma unroll
+                    for (int q = 0; q < NQH; ++q) F[q] *= s1;
+                }
+            };
+            {   // x direction (both G's carry the mirror sign: it cancels)
+                double F[NQH];
+                if (OP == OP_RES) ypassC<D, Q, QC>(zG6, tB, F);
+                else ypassC<D, Q, QC>(xG6, tB, F);
+                scaleF(F, zG6, &tB, nullptr);
+                ypassTC<D, Q, QC>(F, tBW, t6);
+                const double cx = wz * gxx;
+#pragma unroll
+                for (int i = 0; i < D * QC; ++i) t6[i] *= cx;
+                xpassTC_add<D, QC>(t6, tGW, A);
+            }
+            {   // y direction (+ mass)
+                double F[NQH];
+                if (OP == OP_RES) ypassC<D, Q, QC>(zB6, tG, F);
+                else ypassC<D, Q, QC>(xB6, tG, F);
+                scaleF(F, zB6, nullptr, &tG);
+                ypassTC<D, Q, QC>(F, tGW, t6);
+                const double cy = wz * gyy;
+#pragma unroll
+                for (int i = 0; i < D * QC; ++i) t6[i] = cy * t6[i] + c_m * vy6[i];
+                xpassTC_add<D, QC>(t6, tBW, A);
+            }
+            {   // z direction: the G-contracted planes are formed here, not kept
+                double F[NQH];
+                zplane(OP == OP_RES ? sz : sx, tg, p9);
+                xpassC<D, QC>(p9, tB, t6);
+                ypassC<D, Q, QC>(t6, tB, F);
+                if (KLIN && OP == OP_JAC) {
+                    double zd6[D * QC];
+                    zplane(sz, tg, p9);
+                    xpassC<D, QC>(p9, tB, zd6);
+                    scaleF(F, zd6, &tB, nullptr);
+                } else scaleF(F, t6, &tB, nullptr);
+                ypassTC<D, Q, QC>(F, tBW, t6);
+                const double cz = wz * gzz;
+#pragma unroll
+                for (int i = 0; i < D * QC; ++i) t6[i] *= cz;
+                xpassTC_add<D, QC>(t6, tBW, Bp);
+            }
+            flip_plane<D>(A, h);
+            flip_plane<D>(Bp, h);
+            // the pair (adjacent lanes) adds its two halves: h = 0 ends up with the in-plane sum, h = 1 with the z part
+            double* op = outbuf + (size_t)(it & 1) * 2 * Q * O::QS + (size_t)r * O::QS + el * O::ES;
+#pragma unroll
+            for (int m = 0; m < DD; ++m) {
+                const double mine = h ? Bp[m] : A[m];
+                const double other = __shfl_xor_sync(0xffffffffu, h ? A[m] : Bp[m], 1);
+                op[(m / D) * O::JS + m % D] = mine + other;
+            }
+        }
+        if (copier) cp_async_wait<0>();      // nodal values of tile it+1 and the descriptor of tile it+2 have landed
+        __syncthreads();
+
+        // ---------------- phase 3: transposed z contraction + scatter (worker warps; the others run ahead) ---------------
+        if (tid < items.n) phase3(it, my_item);
+    }
+}
+
+}  // namespace jots

@@ -226,6 +226,7 @@ __device__ __forceinline__ void flip_plane(double (&p)[D * D], bool flip) {
 
 template <int D, int Q, int OP, int CF, int E, int T>
 __global__ void __launch_bounds__(T) form_apply_slab2_kernel(const FormArgs a, const Slab2Tables<D, Q> t) {
+    if (a.skip && *a.skip != 0.0) return;   // enqueued ahead of a Krylov solve that has already stopped
     typedef SlabCfg<OP, CF> C;
     constexpr int NF = C::NF, NFA = NF > 0 ? NF : 1, NP = C::NP;
     constexpr int QC = (Q + 1) / 2;
@@ -967,6 +968,7 @@ __device__ __forceinline__ void slab_phase2(const FormArgs& a, const Slab2Tables
 // (phase 3: one output node and half of the quadrature planes each) pieces that fill the block once more with short work.
 template <int D, int Q, int OP, int CF, int E, int T, bool SPLIT = false>
 __global__ void __launch_bounds__(T) form_apply_slab3_kernel(const FormArgs a, const Slab2Tables<D, Q> t) {
+    if (a.skip && *a.skip != 0.0) return;   // enqueued ahead of a Krylov solve that has already stopped
     typedef SlabCfg<OP, CF> C;
     constexpr int NF = C::NF, NFA = NF > 0 ? NF : 1, NP = C::NP;
     constexpr int PS = Elem3Stride<D, Q, NP>::PS, PSET = Elem3Stride<D, Q, NP>::PSET;

@@ -86,6 +86,7 @@ template <int Q, int CF> struct Slab4MinBlocks { static constexpr int value = Q 
 // tile descriptor always comes by one bulk copy.
 template <int D, int Q, int OP, int CF, int E, int T, bool TMA_ROWS>
 __global__ void __launch_bounds__(T, Slab4MinBlocks<Q, CF>::value) form_apply_slab4_kernel(const FormArgs a, const Slab2Tables<D, Q> t) {
+    if (a.skip && *a.skip != 0.0) return;   // enqueued ahead of a Krylov solve that has already stopped
     typedef SlabCfg<OP, CF> C;
     constexpr int NF = C::NF, NFA = NF > 0 ? NF : 1, NP = C::NP;
     constexpr int PS = Elem3Stride<D, Q, NP>::PS, PSET = Elem3Stride<D, Q, NP>::PSET;

@@ -367,6 +367,7 @@ int jots_ctx_patch_info(jots_ctx_t c, int64_t* n_patches, double* fill, int64_t*
     if (applies) *applies = c->c->stats.patch_applies;
     return 0;
 }
+const char* jots_ctx_last_kernel(jots_ctx_t c) { return c->c->last_kernel; }
 int jots_ctx_reset_stats(jots_ctx_t c) { c->c->stats = Stats(); return 0; }
 
 // ---- operators --------------------------------------------------------------------------------

@@ -262,6 +262,7 @@ FormArgs Ctx::make_args(const FormSpec& f, const double* x, double* y, bool for_
     a.nvec = n;
     a.patches = (n_patches > 0 && !for_diag) ? d_patches.p : nullptr;
     a.n_patches = n_patches;
+    a.skip = for_diag ? nullptr : apply_skip;
     return a;
 }
 
@@ -326,6 +327,7 @@ void Ctx::apply_form(const FormSpec& f, const double* x, double* y) {
     }
     if (rc) throw std::runtime_error("form (op=" + std::to_string(f.op) + ", cf=" + std::to_string(f.cf) + ") is not instantiated, rc=" + std::to_string(rc));
     stats.kernel_launches += 2;
+    last_kernel = last_element_kernel();
     if (f.bdr_mass_scale != 0.0 && any_flux()) {
         FaceArgs fa = base_face_args(*this, bdr_mass_quad_points(space.p));
         fa.z = f.state; fa.x = x; fa.y = y; fa.mask_in = f.mask_in; fa.mask_out = f.mask_out; fa.scale = f.bdr_mass_scale;

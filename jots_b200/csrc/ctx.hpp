@@ -95,6 +95,8 @@ public:
     std::vector<int> ess;                // sorted essential DOFs (GetEssentialTrueDofs)
     std::vector<std::vector<int>> bc_dofs;  // per BC: DOFs of its boundary elements
     Stats stats;
+    const double* apply_skip = nullptr;   // device flag forwarded to the element kernels (FormArgs::skip)
+    const char* last_kernel = "";     // element kernel of the last apply_form (launch.hpp: last_element_kernel)
     Halo* halo = nullptr;
 
     // --- device tables

@@ -76,6 +76,8 @@ struct FormArgs {
     // element patches of the unique-pencil kernel (apply_patch.cuh, patches.cpp): null when the mesh is not (mostly) a lattice
     const int* patches;
     int n_patches;
+    // device flag: the kernel returns at once when *skip != 0 (iterations enqueued ahead of a converged Krylov solve)
+    const double* skip;
 };
 
 // Row-structured tile of the slab4 kernel: nv <= E consecutive elements (in element order) forming a row along the

@@ -6,6 +6,16 @@
 
 namespace jots {
 
+const char*& last_element_kernel() {
+    static thread_local const char* name = "";
+    return name;
+}
+std::string kernel_label(const char* base, int D, int Q, int op, int cf, const char* tail) {
+    static const char* ops[] = {"OP_LIN", "OP_JAC", "OP_RES"};
+    static const char* cfs[] = {"CF_CONST", "CF_LINFIELDS", "CF_K", "CF_FULL", "CF_FULLC", "CF_KL"};
+    return std::string(base) + "<" + std::to_string(D) + "," + std::to_string(Q) + "," + ops[op] + "," + cfs[cf] + tail + ">";
+}
+
 int launch_form_apply(int dim, int p, int op, int cf, const FormArgs& a, const TablesRT& t, cudaStream_t st) {
     if (a.nelem <= 0) return 0;
     if (dim == 3 && a.geom_diag && !a.zc) {

@@ -2,11 +2,17 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <string>
+
 #include "diag_face_host.hpp"
 #include "forms.hpp"
 
 namespace jots {
 
+// label of the element kernel the calling thread launched last ("form_apply_patch_kernel<3,4,OP_JAC,CF_KL,4,4,128>"), so
+// that measurements name the kernel that actually ran (bench.py: roofline.kernel)
+const char*& last_element_kernel();
+std::string kernel_label(const char* base, int D, int Q, int op, int cf, const char* tail);
 
 // returns 0 on success, non-zero when the (shape, op, cf) combination is not instantiated
 int launch_form_apply(int dim, int p, int op, int cf, const FormArgs& a, const TablesRT& t, cudaStream_t st);

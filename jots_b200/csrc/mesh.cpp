@@ -312,10 +312,15 @@ void locate_boundary_faces(const Mesh& m, std::vector<int64_t>& be, std::vector<
     // oracle order: f outer loop, e inner loop, first hit wins
     std::vector<std::vector<int>> lvs(nf);
     for (int f = 0; f < nf; ++f) face_vertices_local(dim, f, lvs[f]);
+    // cheap filter before the hash: a face can only be a boundary face if every vertex of it lies on some boundary face
+    std::vector<unsigned char> on_bdr((size_t)m.n_verts(), 0);
+    for (size_t i = 0; i < m.bdr.size(); ++i) on_bdr[(size_t)m.bdr[i]] = 1;
     for (int f = 0; f < nf; ++f)
         for (int64_t e = 0; e < m.n_elem(); ++e) {
             FK k{{-1, -1, -1, -1}};
-            for (int v = 0; v < nfv; ++v) k[v] = m.elems[e * nv + lvs[f][v]];
+            bool all = true;
+            for (int v = 0; v < nfv; ++v) { k[v] = m.elems[e * nv + lvs[f][v]]; all = all && on_bdr[(size_t)k[v]]; }
+            if (!all) continue;
             std::sort(k.begin(), k.begin() + nfv);
             if (wanted.find(k) == wanted.end()) continue;
             found.emplace(k, std::make_pair(e, f));

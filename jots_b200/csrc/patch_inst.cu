@@ -2,7 +2,7 @@
 #include <cstdlib>
 #include <mutex>
 
-#include "apply_patch.cuh"
+#include "apply_patch2.cuh"
 #include "diag_face_host.hpp"
 #include "launch.hpp"
 #include "slab_tables.hpp"
@@ -41,7 +41,33 @@ int launch_patch(const FormArgs& a, const TablesRT& r, cudaStream_t st) {
     static PerDevicePatch pd;
     const int grid_max = pd.get(kern, T, smem);
     kern<<<a.n_patches < grid_max ? a.n_patches : grid_max, T, smem, st>>>(a, t, items);
+    static const std::string label = kernel_label("form_apply_patch_kernel", D, Q, OP, CF, ("," + std::to_string(PX) + "," + std::to_string(PY) + "," + std::to_string(T)).c_str());
+    last_element_kernel() = label.c_str();
     return 0;
+}
+
+template <int D, int Q, int OP, bool KLIN, int PX, int PY>
+int launch_patch2(const FormArgs& a, const TablesRT& r, cudaStream_t st) {
+    constexpr int T = PX * PY * 2 * Q;
+    Slab2Tables<D, Q> t;
+    fill_slab2_tables<D, Q>(r, t);
+    static const PatchItems items = build_patch2_items<D, PX, PY>();
+    const size_t smem = Patch2Smem<D, Q, PX, PY>::total;
+    auto kern = form_apply_patch2_kernel<D, Q, OP, KLIN, PX, PY, T>;
+    static PerDevicePatch pd;
+    const int grid_max = pd.get(kern, T, smem);
+    if (items.n > T - 32) return 1;      // phase 3 must be one pass of the worker warps
+    kern<<<a.n_patches < grid_max ? a.n_patches : grid_max, T, smem, st>>>(a, t, items);
+    static const std::string label = kernel_label("form_apply_patch2_kernel", D, Q, OP, KLIN ? CF_KL : CF_CONST,
+                                                  ("," + std::to_string(PX) + "," + std::to_string(PY) + "," + std::to_string(T)).c_str());
+    last_element_kernel() = label.c_str();
+    return 0;
+}
+
+// JOTS_PATCH2=0 keeps the three-phase patch kernel for the forms the two-phase kernel covers (A/B runs)
+bool patch2_enabled() {
+    static const bool v = [] { const char* e = getenv("JOTS_PATCH2"); return !e || atoi(e) != 0; }();
+    return v;
 }
 
 bool klin_enabled() {
@@ -51,6 +77,15 @@ bool klin_enabled() {
 
 template <int D, int Q, int PX, int PY>
 int dispatch_patch(int op, int cf, const FormArgs& a, const TablesRT& t, cudaStream_t st) {
+    if (patch2_enabled() && klin_enabled()) {
+        // uniform properties, or k(T) linear with uniform rho, C: no interpolated property field is needed
+        const bool klin = cf == CF_K && a.mat.k.n == 2;
+        if (cf == CF_CONST || klin) {
+            if (op == OP_LIN) return klin ? launch_patch2<D, Q, OP_LIN, true, PX, PY>(a, t, st) : launch_patch2<D, Q, OP_LIN, false, PX, PY>(a, t, st);
+            if (op == OP_JAC && klin) return launch_patch2<D, Q, OP_JAC, true, PX, PY>(a, t, st);
+            if (op == OP_RES) return klin ? launch_patch2<D, Q, OP_RES, true, PX, PY>(a, t, st) : launch_patch2<D, Q, OP_RES, false, PX, PY>(a, t, st);
+        }
+    }
     if (op == OP_JAC && cf == CF_K && a.mat.k.n == 2 && klin_enabled()) return launch_patch<D, Q, OP_JAC, CF_KL, PX, PY>(a, t, st);
 #define CASE(OPV, CFV) if (op == OPV && cf == CFV) return launch_patch<D, Q, OPV, CFV, PX, PY>(a, t, st);
     CASE(OP_LIN, CF_CONST) CASE(OP_LIN, CF_K) CASE(OP_JAC, CF_K) CASE(OP_RES, CF_CONST) CASE(OP_RES, CF_K)
@@ -73,7 +108,7 @@ void patch_shape(int p, int& px, int& py) {
 // phase-3 work items of the kernel for order p (host copy, for the index-contract test); returns their number
 int patch_items(int p, unsigned* out) {
     if (p != 2) return 0;
-    const PatchItems it = build_patch_items<3, 4, 4>();
+    const PatchItems it = build_patch_items<3, 4, 4>();   // the two-phase kernel re-encodes the same visits as offsets
     for (int i = 0; i < it.n; ++i) out[i] = it.item[i];
     return it.n;
 }

@@ -58,6 +58,7 @@ static int launch_slab4s(const FormArgs& a, const TablesRT& r, cudaStream_t st) 
     const int grid_max = pd.get(kern, T, smem);
     const int ntiles = a.n_rowtiles;
     kern<<<ntiles < grid_max ? ntiles : grid_max, T, smem, st>>>(a, t);
+    last_element_kernel() = "form_apply_slab4_kernel";
     return 0;
 }
 

@@ -43,6 +43,8 @@ static int launch_slab2e(const FormArgs& a, const TablesRT& r, cudaStream_t st) 
     pd.get(kern, T, smem);
     const int grid = (a.nelem + E - 1) / E;
     kern<<<grid, T, smem, st>>>(a, t);
+    static const std::string label = kernel_label("form_apply_slab2_kernel", D, Q, OP, CF, ("," + std::to_string(E) + "," + std::to_string(T)).c_str());
+    last_element_kernel() = label.c_str();
     return 0;
 }
 
@@ -59,6 +61,8 @@ static int launch_slab3e(const FormArgs& a, const TablesRT& r, cudaStream_t st) 
     const int grid_max = pd.get(kern, T, smem);
     const int ntiles = (a.nelem + E - 1) / E;
     kern<<<ntiles < grid_max ? ntiles : grid_max, T, smem, st>>>(a, t);
+    static const std::string label = kernel_label("form_apply_slab3_kernel", D, Q, OP, CF, ("," + std::to_string(E) + "," + std::to_string(T) + (SPLIT ? ",split" : "")).c_str());
+    last_element_kernel() = label.c_str();
     return 0;
 }
 static int slab_elems() {

@@ -2,6 +2,7 @@
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 
 #include "halo.hpp"
 
@@ -133,6 +134,12 @@ void ChebyshevPrec::mult(const double* r, double* z) {
 Krylov::Krylov(Ctx* ctx, int kind_, int prec_kind) : c(ctx), kind(kind_) {
     if (prec_kind == PREC_JACOBI) prec.reset(new JacobiPrec(ctx));
     else if (prec_kind == PREC_CHEBYSHEV) prec.reset(new ChebyshevPrec(ctx));
+    if (const char* e = std::getenv("JOTS_CG_HOST_SCALARS")) device_scalars = !(e[0] == '1');
+}
+
+Krylov::~Krylov() {
+    if (cgd.h) cudaFreeHost(cgd.h);
+    for (auto& e : cgd.ev) if (e) cudaEventDestroy(e);
 }
 
 double* Krylov::w(int i) {
@@ -172,6 +179,7 @@ void Krylov::cg(const double* b, double* x) {
     if (den == 0.0) { info.final_norm = std::sqrt(nom); return; }
     info.iterations = max_iter;
     double betanom = nom;
+    if ((!prec || dinv) && device_scalars) { cg_device_loop(x, r, z, d, dinv, nom, den, r0); return; }
     int i = 1;
     while (true) {
         const double alpha = nom / den;
@@ -198,6 +206,61 @@ void Krylov::cg(const double* b, double* x) {
         if (den == 0.0) { info.iterations = i; break; }
         nom = betanom;
     }
+    info.final_norm = std::sqrt(std::fabs(betanom));
+}
+
+// The iteration loop of cg() with every scalar in device memory (vec.cu: k_cgd_*): alpha = nom / den, the convergence test
+// and beta = betanom / nom are evaluated by the kernels themselves, so the host only enqueues iterations -- in chunks, at most
+// two chunks ahead of the last stop flag it has seen -- and never waits for a scalar.  Kernels enqueued past the stopping
+// iteration return at once (the element kernel through FormArgs::skip), so x, the iteration count and the final norm are
+// exactly those of the host-sequenced loop.
+void Krylov::cg_device_loop(double* x, double* r, double* z, double* d, const double* dinv, double nom, double den, double r0) {
+    const int64_t n = c->n;
+    cudaStream_t st = c->stream;
+    constexpr int CHUNK = 8, NSLOT = 4;
+    if (!cgd.S.p) {
+        cgd.S.alloc(8);
+        JOTS_CUDA(cudaMallocHost((void**)&cgd.h, sizeof(double) * 8 * (NSLOT + 1)));
+        for (int k = 0; k < NSLOT; ++k) JOTS_CUDA(cudaEventCreateWithFlags(&cgd.ev[k], cudaEventDisableTiming));
+    }
+    double* S = cgd.S.p;
+    double* init = cgd.h + 8 * NSLOT;
+    init[0] = nom; init[1] = 0.0; init[2] = den; init[3] = r0; init[4] = 0.0; init[5] = 0.0; init[6] = nom; init[7] = 0.0;
+    JOTS_CUDA(cudaMemcpyAsync(S, init, 8 * sizeof(double), cudaMemcpyHostToDevice, st));
+    c->apply_skip = S + 4;
+    int launched = 0, chunk = 0;
+    bool stopped = false;
+    while (launched < max_iter && !stopped) {
+        if (chunk >= 2) {
+            // the stop flag as it was after chunk - 2
+            JOTS_CUDA(cudaEventSynchronize(cgd.ev[(chunk - 2) % NSLOT]));
+            if (cgd.h[8 * ((chunk - 2) % NSLOT) + 4] != 0.0) { stopped = true; break; }
+        }
+        for (int k = 0; k < CHUNK && launched < max_iter; ++k) {
+            const int i = ++launched;
+            v_cgd_update(st, n, c->n_owned, S, i, d, z, x, r, dinv, z, c->dot_scratch());
+            c->allreduce_scalars(S + (i & 1), 1);
+            const bool last = (i == max_iter);
+            v_cgd_direction(st, n, S, i, dinv ? z : r, d, !last);
+            c->stats.kernel_launches += 2;
+            if (last) break;
+            apply(d, z);
+            v_cgd_dot(st, c->n_owned, S, d, z, c->dot_scratch());
+            c->allreduce_scalars(S + 2, 1);
+            ++c->stats.kernel_launches; ++c->stats.dots;
+        }
+        JOTS_CUDA(cudaMemcpyAsync(cgd.h + 8 * (chunk % NSLOT), S, 8 * sizeof(double), cudaMemcpyDeviceToHost, st));
+        JOTS_CUDA(cudaEventRecord(cgd.ev[chunk % NSLOT], st));
+        ++chunk;
+    }
+    c->apply_skip = nullptr;
+    JOTS_CUDA(cudaMemcpyAsync(cgd.h, S, 8 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    JOTS_CUDA(cudaStreamSynchronize(st));
+    const double* h = cgd.h;
+    const int code = (int)h[4];
+    double betanom;
+    if (code != 0) { info.iterations = (int)h[5]; betanom = h[6]; info.converged = (code == 1); }
+    else { info.iterations = max_iter; betanom = h[6]; }
     info.final_norm = std::sqrt(std::fabs(betanom));
 }
 

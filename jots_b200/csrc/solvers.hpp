@@ -82,7 +82,17 @@ struct Krylov {
     Krylov(Ctx* ctx, int kind_, int prec_kind);
     void set_operator(LinOp* op) { A = op; if (prec) prec->set_operator(op); }
     void mult(const double* b, double* x);   // iterative_mode = false: x0 = 0
+    // CG with Jacobi / no preconditioner keeps its scalars on the device (no host round trip per iteration);
+    // JOTS_CG_HOST_SCALARS=1 selects the host-sequenced loop (same results; kept for A/B timing)
+    bool device_scalars = true;
+    ~Krylov();
 private:
+    struct CgDevice {
+        DArr<double> S;              // vec.cu: k_cgd_* scalar block
+        double* h = nullptr;         // pinned: NSLOT polling slots + the initial values
+        cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    } cgd;
+    void cg_device_loop(double* x, double* r, double* z, double* d, const double* dinv, double nom, double den, double r0);
     double* w(int i);
     void cg(const double* b, double* x);
     void gmres(const double* b, double* x, bool flexible);

@@ -129,6 +129,66 @@ __global__ void __launch_bounds__(VEC_THREADS) k_cg_update(int64_t n, int64_t n_
     grid_reduce<1>(v, s, result);
 }
 
+// ---- device-resident CG: the scalars of mfem::CGSolver::Mult live in device memory, so an iteration needs no host round trip.
+// S[0], S[1] = (B r, r) ping-pong: iteration i reads nom = S[(i+1)&1] and writes betanom = S[i&1];  S[2] = den = (d, A d);
+// S[3] = r0 (stopping threshold);  S[4] = stop code (0 running, 1 converged, 2 negative (B r, r), 3 den == 0);
+// S[5] = iteration at which it stopped;  S[6] = last (B r, r).  Every decision is a function of fully reduced scalars that
+// were final before the kernel started, so all blocks of a kernel take the same branch (grid_reduce needs that).
+__global__ void __launch_bounds__(VEC_THREADS) k_cgd_update(int64_t n, int64_t n_owned, double* S, int i, const double* __restrict__ d,
+                                                             const double* Ad, double* x, double* r, const double* __restrict__ dinv,
+                                                             double* z, DotScratch s) {
+    if (S[4] != 0.0) return;
+    const double den = S[2], nom = S[(i + 1) & 1];
+    if (den == 0.0) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) { S[5] = (double)i; S[6] = nom; __threadfence(); S[4] = 3.0; }
+        return;
+    }
+    const double alpha = nom / den;
+    double v[1] = {0.0};
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += stride) {
+        x[k] += alpha * d[k];
+        const double ri = r[k] - alpha * Ad[k];
+        r[k] = ri;
+        double zi = ri;
+        if (dinv) { zi = dinv[k] * ri; z[k] = zi; }
+        if (k < n_owned) v[0] += ri * zi;
+    }
+    grid_reduce<1>(v, s, &S[i & 1]);
+}
+// convergence test of iteration i, then d = zz + beta d (update == 0: test only, the last iteration)
+__global__ void __launch_bounds__(VEC_THREADS) k_cgd_direction(int64_t n, double* S, int i, const double* __restrict__ zz, double* d, int update) {
+    if (S[4] != 0.0) return;
+    const double betanom = S[i & 1], nom = S[(i + 1) & 1];
+    const bool first = blockIdx.x == 0 && threadIdx.x == 0;
+    if (betanom < 0.0 || betanom <= S[3]) {
+        if (first) { S[5] = (double)i; S[6] = betanom; __threadfence(); S[4] = betanom < 0.0 ? 2.0 : 1.0; }
+        return;
+    }
+    if (first) S[6] = betanom;
+    if (!update) return;
+    const double beta = betanom / nom;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += stride) d[k] = zz[k] + beta * d[k];
+}
+__global__ void __launch_bounds__(VEC_THREADS) k_cgd_dot(int64_t n, double* S, const double* __restrict__ a, const double* __restrict__ b, DotScratch s) {
+    if (S[4] != 0.0) return;
+    double v[1] = {0.0};
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += stride) v[0] += a[k] * b[k];
+    grid_reduce<1>(v, s, &S[2]);
+}
+void v_cgd_update(cudaStream_t st, int64_t n, int64_t n_owned, double* S, int i, const double* d, const double* Ad, double* x, double* r,
+                  const double* dinv, double* z, DotScratch s) {
+    k_cgd_update<<<grid_for(n, 8), VEC_THREADS, 0, st>>>(n, n_owned, S, i, d, Ad, x, r, dinv, z, s);
+}
+void v_cgd_direction(cudaStream_t st, int64_t n, double* S, int i, const double* zz, double* d, bool update) {
+    k_cgd_direction<<<update ? grid_for(n) : 1, VEC_THREADS, 0, st>>>(n, S, i, zz, d, update ? 1 : 0);
+}
+void v_cgd_dot(cudaStream_t st, int64_t n_owned, double* S, const double* a, const double* b, DotScratch s) {
+    k_cgd_dot<<<grid_for(n_owned, 8), VEC_THREADS, 0, st>>>(n_owned, S, a, b, s);
+}
+
 // max over a vector (JOTSDriver::PostprocessIteration blow-up check, jots_driver.cpp:739): per-block
 // maxima, final maximum by the last block to finish
 __global__ void __launch_bounds__(VEC_THREADS) k_max(int64_t n, const double* __restrict__ x, DotScratch s, double* result) {

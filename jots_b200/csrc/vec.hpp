@@ -33,4 +33,9 @@ void v_mul2(cudaStream_t st, int64_t n, const double* d, const double* x, double
 void v_dots(cudaStream_t st, int64_t n, int nv, const double* const* a, const double* const* b, DotScratch s, double* result);
 void v_cg_update(cudaStream_t st, int64_t n, int64_t n_owned, double alpha, const double* d, const double* Ad, double* x, double* r,
                  const double* dinv, double* z, DotScratch s, double* result);
+// device-resident CG scalars (vec.cu: S layout)
+void v_cgd_update(cudaStream_t st, int64_t n, int64_t n_owned, double* S, int i, const double* d, const double* Ad, double* x, double* r,
+                  const double* dinv, double* z, DotScratch s);
+void v_cgd_direction(cudaStream_t st, int64_t n, double* S, int i, const double* zz, double* d, bool update);
+void v_cgd_dot(cudaStream_t st, int64_t n_owned, double* S, const double* a, const double* b, DotScratch s);
 }  // namespace jots

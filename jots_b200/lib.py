@@ -82,6 +82,7 @@ def load_library():
         "jots_ctx_material_field": (C.c_int, [_P, C.c_int, C.c_int, _P, C.c_int]),
         "jots_ctx_stats": (C.c_int, [_P, _P, _P]),
         "jots_ctx_patch_info": (C.c_int, [_P, _P, _P, _P]),
+        "jots_ctx_last_kernel": (C.c_char_p, [_P]),
         "jots_ctx_reset_stats": (C.c_int, [_P]),
         "jots_ctx_rowtile_applies": (C.c_int64, [_P]),
         "jots_op_create": (_P, [_P, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int,
@@ -412,6 +413,10 @@ class Context:
         load_library().jots_ctx_patch_info(self._h, C.byref(npch), C.byref(fill), C.byref(app))
         d["n_patches"], d["patch_fill"], d["patch_applies"] = int(npch.value), float(fill.value), int(app.value)
         return d
+
+    def last_kernel(self):
+        """Label of the element kernel the last operator apply launched."""
+        return (load_library().jots_ctx_last_kernel(self._h) or b"").decode()
 
     def reset_stats(self):
         _chk(load_library().jots_ctx_reset_stats(self._h))

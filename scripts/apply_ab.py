@@ -14,7 +14,8 @@ CONFIGS = {
     "slab3_gather_E14": {"JOTS_SLAB_VARIANT": "3", "JOTS_SLAB_ELEMS": "14"},
     "slab3_gather_E16": {"JOTS_SLAB_VARIANT": "3", "JOTS_SLAB_ELEMS": "16"},
     "slab3_split_E16": {"JOTS_SLAB_VARIANT": "3", "JOTS_SLAB_ELEMS": "16", "JOTS_SLAB_SPLIT": "1"},
-    "patch_4x4": {"JOTS_SLAB_VARIANT": "7"},
+    "patch3_4x4": {"JOTS_SLAB_VARIANT": "7", "JOTS_PATCH2": "0"},     # three-phase unique-pencil patch kernel
+    "patch2_4x4": {"JOTS_SLAB_VARIANT": "7"},                         # two-phase patch kernel (default)
     "slab4_rows_E16": {"JOTS_SLAB_VARIANT": "4", "JOTS_SLAB4_ELEMS": "16"},
     "slab4_rows_E14": {"JOTS_SLAB_VARIANT": "4", "JOTS_SLAB4_ELEMS": "14"},
     "slab4_cpasync_E16": {"JOTS_SLAB_VARIANT": "4", "JOTS_SLAB4_ELEMS": "16", "JOTS_SLAB4_STAGE": "cpasync"},
@@ -47,9 +48,11 @@ def child(name, n, order, reps, variant):
         drv.op.form_apply(form, x, y, state=z)
         torch.cuda.synchronize()
         out[key + "_norm"] = float(torch.linalg.vector_norm(y))
-        np.save(os.path.join(os.environ["AB_DIR"], "%s_%s.npy" % (name, key)), y[::97].cpu().numpy())
+        if os.environ.get("AB_DIR"):      # absent when the child is run on its own (ncu captures)
+            np.save(os.path.join(os.environ["AB_DIR"], "%s_%s.npy" % (name, key)), y[::97].cpu().numpy())
     out["jac_gdofs"] = ndof / out["jac_ms"] / 1e6
-    out["rowtile_applies"] = drv.ctx.stats()["rowtile_applies"]
+    out["kernel"] = drv.ctx.last_kernel()
+    out["patch_applies"] = drv.ctx.stats()["patch_applies"]
     print(json.dumps(out), flush=True)
 
 

@@ -405,3 +405,32 @@ def test_material_property_output_fields(J, tmp_path, props):
             f = dev.ctx.material_field(which, order)
             ref = np.broadcast_to(np.asarray(ref, dtype=float), f.shape)
             assert np.abs(f - ref).max() <= 1e-13 * max(np.abs(ref).max(), 1e-300), (short, order)
+
+
+@pytest.mark.parametrize("sim,props,n,max_it", [("Nonlinear_Unsteady", "k", (6, 3, 2), 100), ("Linearized_Unsteady", "const", (9, 5, 3), 100),
+                                                ("Nonlinear_Unsteady", "k", (8, 8, 4), 7), ("Steady", "k", (6, 3, 2), 100)])
+def test_cg_with_device_resident_scalars_matches_the_host_sequenced_loop(J, tmp_path, monkeypatch, sim, props, n, max_it):
+    """CG + Jacobi keeps alpha, beta and the stopping test on the device and enqueues iterations ahead of the stop flag
+    (solvers.cpp: cg_device_loop); kernels past the stopping iteration must be no-ops: same Krylov / Newton counts and the same
+    field as the loop that reads the scalars back every iteration (mfem::CGSolver::Mult control flow), whether the solve
+    converges early, stops at an iteration that is not a multiple of the chunk, or runs into Max_Iterations."""
+    out = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("JOTS_CG_HOST_SCALARS", mode)
+        dev, orc = build(J, tmp_path, sim, 3, 2, props, solver="CG", prec="Jacobi", n=n, steps=2)
+        if max_it != 100:
+            # fewer Krylov iterations than a chunk: Newton may not converge, the comparison is between the two loops only
+            txt = open(str(tmp_path / "c.ini")).read().replace("Max_Iterations=100\nAbsolute_Tolerance=1e-16\nRelative_Tolerance=1e-10\n\n[NewtonSolverSettings]\nMax_Iterations=50",
+                                                                 "Max_Iterations=%d\nAbsolute_Tolerance=1e-16\nRelative_Tolerance=1e-10\n\n[NewtonSolverSettings]\nMax_Iterations=50" % max_it)
+            open(str(tmp_path / "c.ini"), "w").write(txt)
+            dev = J.Driver(str(tmp_path / "c.ini"))
+        try:
+            dev.run()
+        except J.JotsError:
+            pass      # Newton non-convergence with a 7-iteration Krylov budget is fatal, as in the reference
+        st = dev.ctx.stats()
+        out[mode] = (st["krylov_iters"], st["newton_iters"], st["last_linear_iters"], st["last_linear_converged"], dev.get_u())
+    assert out["0"][:4] == out["1"][:4], (out["0"][:4], out["1"][:4])
+    assert rel(out["0"][4], out["1"][4]) < 1e-12
+    if max_it == 100:
+        assert rel(out["0"][4], orc.run()) < FIELD_TOL
