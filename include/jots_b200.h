@@ -163,6 +163,23 @@ int jots_op_form_time(jots_op_t op, int form, const double* x_dev, const double*
 /* deterministic partition built redundantly on every rank; dims = {px,py,pz} or NULL (automatic box
    partition of bricks, recursive coordinate bisection otherwise) */
 jots_part_t jots_partition_create(jots_mesh_t mesh, jots_space_t global_space, int nranks, int rank, const int32_t* dims);
+/* The CALLER's decomposition: what ParMesh(comm, mesh) and ParFiniteElementSpace hold on this rank
+   (src/jots_driver.cpp:178,196), so that the binding runs under the reference's own `mpirun -np N` partition.
+     gather / bdr_gather      element and boundary-face DOF tables in the caller's L-vector numbering (local lexicographic node
+                              order, like jots_space_create_from_tables), bdr_* = the rank's own boundary elements;
+     ldof_global_id[n_ldof]   global true-DOF number of every L-vector DOF (ParFiniteElementSpace::GetGlobalTDofNumber);
+     ldof_of_true[n_true]     L-vector index of each OWNED true DOF, in the caller's true-DOF order;
+     nbr_rank / nbr_ptr / nbr_ldofs   for every rank sharing DOFs with this one: the shared L-vector DOFs (any order, the
+                              library sorts both sides by global id).
+   The subdomain is numbered owned DOFs first IN THE CALLER'S TRUE-DOF ORDER (a true-DOF vector is the leading part of a local
+   vector: jots_ctx_expand_true), ghosts behind them; jots_partition_copy returns the global ids in that order.  Boundary DOF
+   sets (ess_tdof_list, Dirichlet projection) are completed across ranks by a marker exchange in jots_ctx_set_bcs, as
+   GetEssentialTrueDofs does. */
+jots_part_t jots_partition_create_from_tables(int dim, int order, int64_t n_ldof, int64_t n_elem, const int32_t* gather, const double* elem_corners,
+                                              int64_t n_bdr, const int32_t* bdr_gather, const double* bdr_corners, const int32_t* bdr_attr,
+                                              const int64_t* ldof_global_id, int64_t n_true, const int32_t* ldof_of_true,
+                                              int n_nbr, const int32_t* nbr_rank, const int64_t* nbr_ptr, const int32_t* nbr_ldofs,
+                                              int rank, int nranks);
 void jots_partition_destroy(jots_part_t p);
 int jots_partition_info(jots_part_t p, int64_t* n_local, int64_t* n_owned, int64_t* n_global, int64_t* n_elem,
                         int* n_neighbors, int64_t* n_shared);
@@ -174,6 +191,10 @@ int jots_comm_unique_id(char out[128]);                               /* rank 0,
 jots_comm_t jots_comm_create(const char id[128], int rank, int nranks, int device);
 void jots_comm_destroy(jots_comm_t c);
 jots_ctx_t jots_ctx_create_part(jots_part_t p, int device, jots_comm_t comm);
+/* true-DOF vector (the n_owned leading entries, what mfem::Vector u holds on this rank) -> consistent local vector of
+   jots_ctx_size entries: the ghost entries are fetched from their owners (P of ParFiniteElementSpace).  Collective.
+   tvec and lvec may be the same buffer (of full local length). */
+int jots_ctx_expand_true(jots_ctx_t c, const double* tvec, double* lvec, int loc);
 
 /* Config (src/config_file.cpp:7-172) parsed on the host, as "key=value" lines (scalars, then "mat:<name>=a|b|..." and
    "bc:<attribute>=a|b|..."): lets the key set, defaults and parsing quirks be compared with the reference's without a

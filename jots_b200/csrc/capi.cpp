@@ -286,6 +286,18 @@ int jots_ctx_set_stream(jots_ctx_t c, void* s) {
     return 0;
     JOTS_CATCH_INT
 }
+int jots_ctx_expand_true(jots_ctx_t c, const double* tvec, double* lvec, int loc) {
+    JOTS_TRY
+    Ctx* x = c->c;
+    Out o(x, lvec, loc);
+    const cudaMemcpyKind kind = loc == JOTS_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    if (!(loc == JOTS_DEVICE && tvec == lvec))
+        JOTS_CUDA(cudaMemcpyAsync(o.p, tvec, (size_t)x->n_owned * sizeof(double), kind, x->stream));
+    x->expand_owned(o.p);
+    o.finish();
+    return 0;
+    JOTS_CATCH_INT
+}
 int jots_ctx_sync(jots_ctx_t c) { JOTS_TRY c->c->sync(); return 0; JOTS_CATCH_INT }
 int jots_ctx_set_material(jots_ctx_t c, int which, int model, const double* coeffs, int n) {
     JOTS_TRY
@@ -518,6 +530,19 @@ jots_part_t jots_partition_create(jots_mesh_t mesh, jots_space_t global, int nra
     partition_elements(mesh->m, nranks, dims ? d : nullptr, er);
     auto* h = new jots_part_s;
     h->p = make_partition(global->s, er, nranks, rank);
+    return h;
+    JOTS_CATCH_PTR
+}
+jots_part_t jots_partition_create_from_tables(int dim, int order, int64_t n_ldof, int64_t n_elem, const int32_t* gather, const double* elem_corners,
+                                              int64_t n_bdr, const int32_t* bdr_gather, const double* bdr_corners, const int32_t* bdr_attr,
+                                              const int64_t* ldof_global_id, int64_t n_true, const int32_t* ldof_of_true,
+                                              int n_nbr, const int32_t* nbr_rank, const int64_t* nbr_ptr, const int32_t* nbr_ldofs,
+                                              int rank, int nranks) {
+    JOTS_TRY
+    if (!gather || !elem_corners || !ldof_global_id || !ldof_of_true) throw std::runtime_error("jots_partition_create_from_tables: null table");
+    auto* h = new jots_part_s;
+    h->p = make_partition_from_tables(dim, order, n_ldof, n_elem, gather, elem_corners, n_bdr, bdr_gather, bdr_corners, bdr_attr,
+                                      ldof_global_id, n_true, ldof_of_true, n_nbr, nbr_rank, nbr_ptr, nbr_ldofs, rank, nranks);
     return h;
     JOTS_CATCH_PTR
 }

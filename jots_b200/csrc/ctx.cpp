@@ -165,6 +165,12 @@ void Ctx::set_stream(cudaStream_t s) {
     stream = s;
 }
 
+void Ctx::expand_owned(double* v) {
+    if (!halo || n_owned >= n) return;
+    JOTS_CUDA(cudaMemsetAsync(v + n_owned, 0, (size_t)(n - n_owned) * sizeof(double), stream));
+    halo_sum_exchange(*this, v);
+}
+
 void Ctx::set_materials(const Poly& rho, const Poly& C, const Poly& k) {
     mat.rho = rho; mat.C = C; mat.k = k;
 }
@@ -179,10 +185,28 @@ void Ctx::set_bcs(const std::vector<BCSpec>& b) {
     for (size_t i = 0; i < bcs.size(); ++i) {
         std::vector<int> one{(int)i + 1};
         space.essential_dofs(one, bc_dofs[i]);
+        if (space.sync_bdr_markers && halo) {
+            // caller-supplied subdomain: a shared DOF may lie on a boundary face that only a neighbour's element has; sum the
+            // 0/1 markers over the interface like ParFiniteElementSpace::GetEssentialTrueDofs synchronises its marker
+            std::vector<double> mk((size_t)n, 0.0);
+            for (int d : bc_dofs[i]) mk[d] = 1.0;
+            DArr<double> dm;
+            dm.upload(mk);
+            halo_sum_exchange(*this, dm.p);
+            JOTS_CUDA(cudaMemcpyAsync(mk.data(), dm.p, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, stream));
+            sync();
+            bc_dofs[i].clear();
+            for (int64_t d = 0; d < n; ++d) if (mk[d] != 0.0) bc_dofs[i].push_back((int)d);
+        }
         d_bc_dofs[i].upload(bc_dofs[i]);
         if (bcs[i].essential()) attrs.push_back((int)i + 1);
     }
-    space.essential_dofs(attrs, ess);
+    if (space.sync_bdr_markers && halo) {
+        ess.clear();
+        for (int a : attrs) ess.insert(ess.end(), bc_dofs[a - 1].begin(), bc_dofs[a - 1].end());
+        std::sort(ess.begin(), ess.end());
+        ess.erase(std::unique(ess.begin(), ess.end()), ess.end());
+    } else space.essential_dofs(attrs, ess);
     d_ess.upload(ess);
     std::vector<unsigned char> em((size_t)n, 0);
     for (int d : ess) em[d] = 1;

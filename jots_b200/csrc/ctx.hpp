@@ -150,6 +150,9 @@ public:
     void copy(const double* x, double* y) { JOTS_CUDA(cudaMemcpyAsync(y, x, n * sizeof(double), cudaMemcpyDeviceToDevice, stream)); }
     void zero_ess(double* y) { v_set_idx(stream, (int)ess.size(), d_ess.p, 0.0, y); stats.kernel_launches += !ess.empty(); }
     void sync() { JOTS_CUDA(cudaStreamSynchronize(stream)); }
+    // owner -> ghost broadcast of a local vector whose owned (leading n_owned) entries are valid: P of the reference's
+    // ParFiniteElementSpace, done as zero-the-ghosts + interface sum-exchange.  No-op on one GPU.
+    void expand_owned(double* v);
     // run on the caller's stream from now on: the context's own stream is drained and destroyed, the caller keeps
     // ownership of s (it is never destroyed here)
     void set_stream(cudaStream_t s);

@@ -61,6 +61,7 @@ struct Space {
     double bl[3] = {0, 0, 0};
     // subdomain spaces: DOFs of the GLOBAL boundary elements of attribute attributes[i] (local ids)
     bool has_attr_dofs = false;
+    bool sync_bdr_markers = false;   // caller-supplied subdomain: complete the boundary DOF sets by a marker exchange (Ctx::set_bcs)
     std::vector<std::vector<int>> attr_dofs;
 
     void node_coordinates(std::vector<double>& out) const;  // [ndof*dim]

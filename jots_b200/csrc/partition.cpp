@@ -1,5 +1,7 @@
 #include "partition.hpp"
 
+#include "basis.hpp"
+
 #include <algorithm>
 #include <numeric>
 #include <stdexcept>
@@ -63,6 +65,30 @@ void partition_elements(const Mesh& m, int nranks, const int* dims_in, std::vect
     std::vector<int64_t> ids(ne);
     std::iota(ids.begin(), ids.end(), 0);
     rcb(cen, dim, ids, 0, ne, 0, nranks, elem_rank);
+}
+
+// send / receive offsets and the canonical-order reduction lists from nbr_rank / nbr_dofs
+static void finish_exchange_lists(Partition& P) {
+    const int rank = P.rank;
+    P.nbr_offset.assign(P.nbr_rank.size() + 1, 0);
+    for (size_t k = 0; k < P.nbr_rank.size(); ++k) {
+        P.nbr_offset[k + 1] = P.nbr_offset[k] + (int)P.nbr_dofs[k].size();
+        P.send_idx.insert(P.send_idx.end(), P.nbr_dofs[k].begin(), P.nbr_dofs[k].end());
+    }
+    // canonical-order reduction lists
+    std::vector<std::vector<std::pair<int, int>>> contrib(P.n_local);  // (rank, recv index)
+    for (size_t k = 0; k < P.nbr_rank.size(); ++k)
+        for (size_t j = 0; j < P.nbr_dofs[k].size(); ++j)
+            contrib[P.nbr_dofs[k][j]].emplace_back(P.nbr_rank[k], P.nbr_offset[k] + (int)j);
+    P.red_ptr.push_back(0);
+    for (int64_t i = 0; i < P.n_local; ++i) {
+        if (contrib[i].empty()) continue;
+        contrib[i].emplace_back(rank, -1);
+        std::sort(contrib[i].begin(), contrib[i].end());
+        P.red_dof.push_back((int)i);
+        for (auto& c : contrib[i]) P.red_src.push_back(c.second);
+        P.red_ptr.push_back((int)P.red_src.size());
+    }
 }
 
 Partition make_partition(const Space& G, const std::vector<int>& elem_rank, int nranks, int rank) {
@@ -146,25 +172,79 @@ Partition make_partition(const Space& G, const std::vector<int>& elem_rank, int 
         P.nbr_rank.push_back(s);
         P.nbr_dofs.push_back(by_rank[s]);
     }
-    P.nbr_offset.assign(P.nbr_rank.size() + 1, 0);
-    for (size_t k = 0; k < P.nbr_rank.size(); ++k) {
-        P.nbr_offset[k + 1] = P.nbr_offset[k] + (int)P.nbr_dofs[k].size();
-        P.send_idx.insert(P.send_idx.end(), P.nbr_dofs[k].begin(), P.nbr_dofs[k].end());
+    finish_exchange_lists(P);
+    return P;
+}
+
+// A subdomain from the CALLER's decomposition (what ParMesh(comm, mesh) + ParFiniteElementSpace hold on one rank,
+// /root/reference/src/jots_driver.cpp:178,196): local tables in the caller's L-vector numbering, the owned true DOFs in the
+// caller's true-DOF order, and per neighbour the shared L-vector DOFs.  The subdomain is renumbered like make_partition
+// numbers it -- owned DOFs first, in the caller's true-DOF order, so a true-DOF vector IS the leading part of a local
+// vector; ghosts after them in ascending global id -- and shared lists are sorted by global id, so both sides of an
+// interface agree whatever order the caller listed them in.
+Partition make_partition_from_tables(int dim, int p, int64_t n_ldof, int64_t n_elem, const int* gather, const double* elem_corner,
+                                     int64_t n_bdr, const int* bdr_gather, const double* bdr_corner, const int* bdr_attr,
+                                     const int64_t* ldof_global_id, int64_t n_true, const int* ldof_of_true,
+                                     int n_nbr, const int* nbr_rank, const int64_t* nbr_ptr, const int* nbr_ldofs, int rank, int nranks) {
+    if (nranks > 64) throw std::runtime_error("at most 64 subdomains are supported");
+    if (p < 1 || p > 4 || (dim != 2 && dim != 3)) throw std::runtime_error("partition tables: dim must be 2 or 3, order 1..4");
+    Partition P;
+    P.rank = rank; P.nranks = nranks;
+    P.n_local = n_ldof; P.n_owned = n_true;
+    // caller L index -> local index
+    std::vector<int> perm((size_t)n_ldof, -1);
+    for (int64_t t = 0; t < n_true; ++t) {
+        const int l = ldof_of_true[t];
+        if (l < 0 || l >= n_ldof || perm[l] >= 0) throw std::runtime_error("partition tables: ldof_of_true is not an injective map into the L-vector");
+        perm[l] = (int)t;
     }
-    // canonical-order reduction lists
-    std::vector<std::vector<std::pair<int, int>>> contrib(P.n_local);  // (rank, recv index)
-    for (size_t k = 0; k < P.nbr_rank.size(); ++k)
-        for (size_t j = 0; j < P.nbr_dofs[k].size(); ++j)
-            contrib[P.nbr_dofs[k][j]].emplace_back(P.nbr_rank[k], P.nbr_offset[k] + (int)j);
-    P.red_ptr.push_back(0);
-    for (int64_t i = 0; i < P.n_local; ++i) {
-        if (contrib[i].empty()) continue;
-        contrib[i].emplace_back(rank, -1);
-        std::sort(contrib[i].begin(), contrib[i].end());
-        P.red_dof.push_back((int)i);
-        for (auto& c : contrib[i]) P.red_src.push_back(c.second);
-        P.red_ptr.push_back((int)P.red_src.size());
+    std::vector<int> ghosts;
+    for (int64_t l = 0; l < n_ldof; ++l) if (perm[l] < 0) ghosts.push_back((int)l);
+    std::sort(ghosts.begin(), ghosts.end(), [&](int a, int b) { return ldof_global_id[a] < ldof_global_id[b]; });
+    for (size_t g = 0; g < ghosts.size(); ++g) perm[ghosts[g]] = (int)(n_true + (int64_t)g);
+    P.global_id.assign((size_t)n_ldof, 0);
+    int64_t gmax = -1;
+    for (int64_t l = 0; l < n_ldof; ++l) { P.global_id[perm[l]] = ldof_global_id[l]; gmax = std::max(gmax, ldof_global_id[l]); }
+    P.n_global = gmax + 1;          // a lower bound: only used for reporting
+    Space& L = P.local;
+    L.dim = dim; L.p = p; L.D = p + 1; L.Q = domain_quad_points(dim, p);
+    L.nloc = 1; for (int a = 0; a < dim; ++a) L.nloc *= L.D;
+    L.nfl = L.nloc / L.D;
+    L.nodes = gauss_lobatto_01(L.D);
+    L.ndof = n_ldof; L.nelem = n_elem; L.nbdr = n_bdr;
+    L.gather.resize((size_t)n_elem * L.nloc);
+    for (size_t i = 0; i < L.gather.size(); ++i) {
+        if (gather[i] < 0 || gather[i] >= n_ldof) throw std::runtime_error("partition tables: gather entry out of range");
+        L.gather[i] = perm[gather[i]];
     }
+    const int nv = 1 << dim, nfv = 1 << (dim - 1);
+    L.elem_corner.assign(elem_corner, elem_corner + (size_t)n_elem * nv * dim);
+    L.bdr_gather.resize((size_t)n_bdr * L.nfl);
+    for (size_t i = 0; i < L.bdr_gather.size(); ++i) L.bdr_gather[i] = perm[bdr_gather[i]];
+    L.bdr_corner.assign(bdr_corner, bdr_corner + (size_t)n_bdr * nfv * dim);
+    L.bdr_attr.assign(bdr_attr, bdr_attr + n_bdr);
+    L.bdr_elem.assign((size_t)n_bdr, -1);
+    L.bdr_face.assign((size_t)n_bdr, -1);
+    L.attributes = L.bdr_attr;
+    std::sort(L.attributes.begin(), L.attributes.end());
+    L.attributes.erase(std::unique(L.attributes.begin(), L.attributes.end()), L.attributes.end());
+    // a shared DOF may lie on a boundary face of a neighbour's element only: the boundary DOF sets are completed by a
+    // marker exchange when the boundary conditions are set (MFEM: GetEssentialTrueDofs synchronises the marker)
+    L.sync_bdr_markers = true;
+    P.local_elems.resize((size_t)n_elem);
+    std::iota(P.local_elems.begin(), P.local_elems.end(), 0);
+    std::vector<std::pair<int, std::vector<int>>> nb;
+    for (int k = 0; k < n_nbr; ++k) {
+        if (nbr_rank[k] < 0 || nbr_rank[k] >= nranks || nbr_rank[k] == rank) throw std::runtime_error("partition tables: bad neighbour rank");
+        std::vector<int> d;
+        for (int64_t j = nbr_ptr[k]; j < nbr_ptr[k + 1]; ++j) d.push_back(perm[nbr_ldofs[j]]);
+        std::sort(d.begin(), d.end(), [&](int a, int b) { return P.global_id[a] < P.global_id[b]; });
+        d.erase(std::unique(d.begin(), d.end()), d.end());
+        nb.emplace_back(nbr_rank[k], std::move(d));
+    }
+    std::sort(nb.begin(), nb.end(), [](const std::pair<int, std::vector<int>>& a, const std::pair<int, std::vector<int>>& b) { return a.first < b.first; });
+    for (auto& kv : nb) { P.nbr_rank.push_back(kv.first); P.nbr_dofs.push_back(std::move(kv.second)); }
+    finish_exchange_lists(P);
     return P;
 }
 

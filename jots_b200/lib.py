@@ -81,6 +81,8 @@ def load_library():
         "jots_ctx_set_material_state": (C.c_int, [_P, _P, C.c_int]),
         "jots_ctx_material_field": (C.c_int, [_P, C.c_int, C.c_int, _P, C.c_int]),
         "jots_ctx_stats": (C.c_int, [_P, _P, _P]),
+        "jots_ctx_expand_true": (C.c_int, [_P, _P, _P, C.c_int]),
+        "jots_partition_create_from_tables": (_P, [C.c_int, C.c_int, C.c_int64, C.c_int64, _P, _P, C.c_int64, _P, _P, _P, _P, C.c_int64, _P, C.c_int, _P, _P, _P, C.c_int, C.c_int]),
         "jots_ctx_patch_info": (C.c_int, [_P, _P, _P, _P]),
         "jots_ctx_last_kernel": (C.c_char_p, [_P]),
         "jots_ctx_reset_stats": (C.c_int, [_P]),
@@ -353,6 +355,24 @@ class Context:
         self._h = _handle(handle if handle is not None else load_library().jots_ctx_create(space._h, device))
         self.n = load_library().jots_ctx_size(self._h)
 
+    @classmethod
+    def from_partition(cls, part, device, comm):
+        """Context of one subdomain (jots_ctx_create_part); comm may be None (no exchange: single-rank testing)."""
+        h = load_library().jots_ctx_create_part(part._h, device, comm._h if comm is not None else None)
+        obj = cls(handle=_handle(h), owner=(part, comm))
+        obj._borrowed = False
+        obj.n_owned = part.n_owned
+        return obj
+
+    def expand_true(self, tvec, out=None):
+        """True-DOF vector (n_owned entries, the caller's true-DOF order) -> consistent local vector (collective)."""
+        out = np.empty(self.n) if out is None else out
+        t = np.ascontiguousarray(tvec, dtype=np.float64)
+        buf = np.zeros(self.n)
+        buf[:t.size] = t
+        _chk(load_library().jots_ctx_expand_true(self._h, _ptr(buf), _ptr(out), _loc(out)))
+        return out
+
     def set_stream(self, stream):
         _chk(load_library().jots_ctx_set_stream(self._h, C.c_void_p(int(stream))))
 
@@ -486,15 +506,39 @@ class Operator:
 class Partition:
     """One subdomain of a partitioned space (host-side index sets only)."""
 
-    def __init__(self, mesh, space, nranks, rank, dims=None):
-        d = None if dims is None else np.asarray(dims, dtype=np.int32)
-        self._h = _handle(load_library().jots_partition_create(mesh._h, space._h, nranks, rank, _ptr(d)))
+    def __init__(self, mesh, space, nranks, rank, dims=None, handle=None):
+        if handle is None:
+            d = None if dims is None else np.asarray(dims, dtype=np.int32)
+            handle = load_library().jots_partition_create(mesh._h, space._h, nranks, rank, _ptr(d))
+        self._h = _handle(handle)
         nl, no, ng, ne, ns = C.c_int64(), C.c_int64(), C.c_int64(), C.c_int64(), C.c_int64()
         nn = C.c_int()
         _chk(load_library().jots_partition_info(self._h, nl, no, ng, ne, nn, ns))
         self.n_local, self.n_owned, self.n_global, self.n_elem = nl.value, no.value, ng.value, ne.value
         self.n_neighbors, self.n_shared = nn.value, ns.value
         self.rank, self.nranks = rank, nranks
+
+    @classmethod
+    def from_tables(cls, dim, order, gather, elem_corners, bdr_gather, bdr_corners, bdr_attr, ldof_global_id, ldof_of_true,
+                    neighbors, rank, nranks):
+        """The caller's decomposition (ParMesh + ParFiniteElementSpace tables of one rank): neighbors = [(rank, L-vector
+        DOFs shared with it), ...]."""
+        g = np.ascontiguousarray(gather, dtype=np.int32)
+        ec = np.ascontiguousarray(elem_corners, dtype=np.float64)
+        bg = np.ascontiguousarray(bdr_gather, dtype=np.int32)
+        bc = np.ascontiguousarray(bdr_corners, dtype=np.float64)
+        ba = np.ascontiguousarray(bdr_attr, dtype=np.int32)
+        gid = np.ascontiguousarray(ldof_global_id, dtype=np.int64)
+        lt = np.ascontiguousarray(ldof_of_true, dtype=np.int32)
+        nr = np.ascontiguousarray([r for r, _ in neighbors], dtype=np.int32)
+        ptr = np.zeros(len(neighbors) + 1, dtype=np.int64)
+        for i, (_, d) in enumerate(neighbors):
+            ptr[i + 1] = ptr[i] + len(d)
+        nd = np.ascontiguousarray(np.concatenate([np.asarray(d, dtype=np.int32) for _, d in neighbors]) if neighbors else np.zeros(0, np.int32))
+        h = _handle(load_library().jots_partition_create_from_tables(dim, order, gid.size, g.shape[0], _ptr(g), _ptr(ec), ba.size, _ptr(bg),
+                                                                     _ptr(bc), _ptr(ba), _ptr(gid), lt.size, _ptr(lt), len(neighbors), _ptr(nr),
+                                                                     _ptr(ptr), _ptr(nd), rank, nranks))
+        return cls(None, None, nranks, rank, handle=h)
 
     def space(self):
         return Space(handle=load_library().jots_partition_space(self._h))

@@ -107,3 +107,72 @@ def test_partitioned_solve_on_a_mesh_file_rcb(tmp_path):
         u[g[:n_owned]] = ul[:n_owned]
     assert not np.isnan(u).any()
     assert np.linalg.norm(u - u_ref) / np.linalg.norm(u_ref) < 1e-8
+
+
+def _worker_tables(rank, world, shape, uid, q):
+    """One rank of the binding a JOTS maintainer would write: the subdomain comes from the CALLER's decomposition tables
+    (scrambled L-vector numbering, true-DOF vectors), the step loop is JOTSDriver::Run's order of calls on the C ABI."""
+    import jots_b200 as J
+    from test_host_cpu import _caller_tables
+    comm = J.Comm(uid, rank, world, rank)
+    mesh = J.Mesh.brick(*shape)
+    ref = J.Partition(mesh, J.Space(mesh, 2), world, rank)
+    part = J.Partition.from_tables(rank=rank, nranks=world, **_caller_tables(ref, 7 + rank))
+    ctx = J.Context.from_partition(part, rank, comm)
+    ctx.set_material(0, ("Uniform", 8000))
+    ctx.set_material(1, ("Polynomial", 4.5, -850))
+    ctx.set_material(2, ("Polynomial", 0.09, -17))
+    ctx.set_bcs([("HeatFlux", 7.5e5), ("Isothermal", 350), ("HeatFlux", 0), ("Sinusoidal_Isothermal", 50, 40, 0.3, 400), ("HeatFlux", 0), ("HeatFlux", -1e5)])
+    u = ctx.expand_true(np.full(part.n_owned, 300.0))           # true-DOF vector -> local vector
+    ctx.update_bcs(0.0)
+    ctx.apply_dirichlet(u)
+    ctx.set_material_state(u)
+    op = J.Operator(ctx, J.NONLINEAR_UNSTEADY, dt=1e-2, solver=J.FGMRES, prec=J.CHEBYSHEV, newton_max_iter=50)
+    t = 0.0
+    for step in range(3):
+        ctx.update_bcs(t)
+        ctx.apply_dirichlet(u, only_time_dependent=(step > 0))
+        ctx.set_material_state(u)
+        for which in (1, 2):
+            op.process_mat_prop_update(which)
+        t = op.iterate(u, t)
+    g, _ = part.global_ids()
+    q.put((rank, g[:part.n_owned], u[:part.n_owned], ctx.essential_dofs().size, ctx.stats()))
+    del op, ctx, comm
+
+
+def test_partitioned_solve_from_caller_supplied_tables(tmp_path):
+    """jots_partition_create_from_tables + jots_ctx_create_part + the operator entry points, one rank per GPU: the field
+    equals the single-domain oracle's; boundary DOF sets are completed by the marker exchange (an x1 / y0 edge DOF whose
+    boundary faces belong to another rank's elements must still be essential)."""
+    world = min(_ngpu(), 4)
+    if world < 2:
+        pytest.skip("needs at least 2 GPUs")
+    import torch.multiprocessing as mp
+    import jots_b200 as J
+    from oracle import jots as OJ, mesh as OM
+    from cases import ini_text
+    from test_gpu_parity import PROPS, HF0
+    shape = (6, 4, 4, 0.012, 0.01, 0.008)
+    bcs = ["HeatFlux, 7.5e5", "Isothermal, 350", HF0, "Sinusoidal_Isothermal, 50, 40, 0.3, 400", HF0, "HeatFlux, -1e5"]
+    props = [("Density_rho", "Uniform, 8000"), ("Specific_Heat_C", "Polynomial, 4.5, -850"), ("Thermal_Conductivity_k", "Polynomial, 0.09, -17")]
+    ini = str(tmp_path / "c.ini")
+    with open(ini, "w") as f:
+        f.write(ini_text("Nonlinear_Unsteady", "unused", 300, props, bcs, newton=50, solver="FGMRES", prec="Chebyshev", steps=3, order=2))
+    uid = J.Comm.unique_id()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker_tables, args=(r, world, shape, uid, q)) for r in range(world)]
+    for pr in procs:
+        pr.start()
+    res = [q.get(timeout=300) for _ in range(world)]
+    for pr in procs:
+        pr.join(timeout=60)
+    orc = OJ.JOTSDriver(OJ.Config(ini), mesh=OM.make_brick(*shape))
+    u_ref = orc.run()
+    u = np.full(u_ref.size, np.nan)
+    for rank, g, ul, ness, st in res:
+        u[g] = ul
+    assert not np.isnan(u).any()
+    assert np.linalg.norm(u - u_ref) / np.linalg.norm(u_ref) < 1e-8
+    assert sum(st["newton_iters"] for _, _, _, _, st in res) == world * orc.it.stats["newton_iters"]

@@ -373,3 +373,59 @@ def test_patches_absent_when_the_mesh_is_not_a_lattice(tmp_path):
     s = J.Space(J.Mesh.brick(99, 1, 1, 0.01, 0.01, 0.01), 2)
     tab, fill = s.patches(np.zeros(0, np.int32))
     assert tab.shape[0] == 25 and abs(fill - 99 / 400) < 1e-12
+
+
+def _caller_tables(part, seed):
+    """Emulate what ParMesh + ParFiniteElementSpace hold on one rank: the subdomain of `part` with its L-vector DOFs in a
+    scrambled (caller) numbering, true DOFs in ascending global id, shared lists per neighbour in scrambled order."""
+    rng = np.random.default_rng(seed)
+    s = part.space()
+    gid, _ = part.global_ids()
+    n = part.n_local
+    sigma = rng.permutation(n)                 # caller index j <-> library local index sigma[j]
+    inv = np.empty(n, dtype=np.int64)
+    inv[sigma] = np.arange(n)
+    g = inv[s.gather()]
+    bg, ba, _, _ = s.boundary()
+    ec, bc = s.corners()
+    nbrs = [(r, rng.permutation(inv[idx])) for r, idx in part.neighbors()]
+    rng.shuffle(nbrs)
+    return dict(dim=s.dim, order=s.order, gather=g, elem_corners=ec, bdr_gather=inv[bg], bdr_corners=bc, bdr_attr=ba,
+                ldof_global_id=gid[sigma], ldof_of_true=inv[:part.n_owned], neighbors=nbrs)
+
+
+@pytest.mark.parametrize("shape,p,nranks", [((6, 4, 4), 2, 4), ((5, 3, 2), 3, 2), ((4, 4, 4), 1, 8)])
+def test_partition_from_caller_tables_matches_the_library_partition_bit_exact(shape, p, nranks):
+    """jots_partition_create_from_tables (the caller's ParMesh / ParFiniteElementSpace decomposition with an arbitrary L-vector
+    numbering) must give, index for index, the subdomain jots_partition_create builds: local numbering (owned first in true-DOF
+    order, ghosts by global id), gather and boundary tables, neighbours with their shared lists, canonical reduction lists."""
+    import jots_b200 as J
+    mesh = J.Mesh.brick(*shape, 0.01, 0.02, 0.03)
+    space = J.Space(mesh, p)
+    for rank in range(nranks):
+        ref = J.Partition(mesh, space, nranks, rank)
+        t = _caller_tables(ref, 100 + rank)
+        new = J.Partition.from_tables(rank=rank, nranks=nranks, **t)
+        assert (new.n_local, new.n_owned, new.n_elem, new.n_neighbors, new.n_shared) == (ref.n_local, ref.n_owned, ref.n_elem, ref.n_neighbors, ref.n_shared)
+        assert (new.global_ids()[0] == ref.global_ids()[0]).all()
+        sn, sr = new.space(), ref.space()
+        assert (sn.gather() == sr.gather()).all()
+        assert (sn.boundary()[0] == sr.boundary()[0]).all() and (sn.boundary()[1] == sr.boundary()[1]).all()
+        assert np.array_equal(sn.corners()[0], sr.corners()[0]) and np.array_equal(sn.corners()[1], sr.corners()[1])
+        for (ra, ia), (rb, ib) in zip(new.neighbors(), ref.neighbors()):
+            assert ra == rb and (ia == ib).all()
+        for a, b in zip(new.reduction(), ref.reduction()):
+            assert (a == b).all()
+
+
+def test_partition_from_caller_tables_rejects_bad_input():
+    import jots_b200 as J
+    mesh = J.Mesh.brick(4, 2, 2, 1.0, 1.0, 1.0)
+    ref = J.Partition(mesh, J.Space(mesh, 2), 2, 0)
+    t = _caller_tables(ref, 3)
+    bad = dict(t, ldof_of_true=np.concatenate([t["ldof_of_true"][:-1], t["ldof_of_true"][:1]]))   # a true DOF listed twice
+    with pytest.raises(J.JotsError, match="injective"):
+        J.Partition.from_tables(rank=0, nranks=2, **bad)
+    bad = dict(t, neighbors=[(0, t["neighbors"][0][1])])                                            # itself as a neighbour
+    with pytest.raises(J.JotsError, match="neighbour"):
+        J.Partition.from_tables(rank=0, nranks=2, **bad)
