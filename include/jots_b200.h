@@ -106,6 +106,16 @@ int64_t jots_space_patches(jots_space_t s, const int32_t* ess, int64_t n_ess, in
    items: pencil | n_visits << 8 | (element << 5 | local ij) << 10 | (element << 5 | local ij) << 20.  Returns the item count. */
 int jots_patch_shape(int order, int* px, int* py, uint32_t* items);
 
+/* MFEM-native -> lexicographic local DOF order (H1_FECollection(order, dim), src/jots_driver.cpp:194-196).
+   jots_h1_dof_map: map[l] = position of lexicographic node l = i + (p+1)(j + (p+1)k) in the native order (vertices, edge
+   interiors, face interiors, interior) = H1_HexahedronElement / H1_QuadrilateralElement::GetDofMap().  Restated from the MFEM
+   4.7 sources, which are not part of the reference tree: a binding should assert it once against GetDofMap().
+   jots_gather_from_native: an element-DOF table as FiniteElementSpace::GetElementDofs returns it ([n_elem][(p+1)^dim], native
+   order, -1-d for d where MFEM flags a sign) -> the lexicographic table jots_space_create_from_tables and
+   jots_partition_create_from_tables expect. */
+int jots_h1_dof_map(int dim, int order, int32_t* map);
+int jots_gather_from_native(int dim, int order, int64_t n_elem, const int32_t* native, int32_t* lexicographic);
+
 /* ---- device context ----------------------------------------------------------------------------- */
 jots_ctx_t jots_ctx_create(jots_space_t s, int device);
 void jots_ctx_destroy(jots_ctx_t c);
@@ -145,6 +155,12 @@ jots_op_t jots_op_create(jots_ctx_t c, int sim_type, double dt, int time_scheme,
                          int solver, int prec, double rel_tol, double abs_tol, int max_iter,
                          double newton_rel_tol, double newton_abs_tol, int newton_max_iter);
 void jots_op_destroy(jots_op_t op);
+/* Factory::CreatePrintLevel (src/jots_common.inl:57-91; keys LinearSolverSettings.Print_Level / NewtonSolverSettings.Print_Level,
+   src/config_file.cpp:140-141,161-162): "Errors, Warnings, Iterations" -> mask (errors 1, warnings 2, iterations 4, summary 8,
+   first-and-last 16; "None" clears, "All" sets all; -1 for an unknown label).  The driver shim applies the config's lists
+   itself; operators created with jots_op_create print nothing until a mask is set. */
+int jots_print_level_mask(const char* comma_separated_labels);
+int jots_op_set_print_level(jots_op_t op, int linear_solver_mask, int newton_mask);
 int jots_op_iterate(jots_op_t op, double* u, int loc, double* time_inout);     /* JOTSIterator::Iterate */
 int jots_op_implicit_solve(jots_op_t op, double dt, const double* u, double* k, int loc); /* ImplicitSolve */
 int jots_op_mult(jots_op_t op, const double* u, double* k, int loc);           /* explicit Mult */

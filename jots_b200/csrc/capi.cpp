@@ -236,6 +236,28 @@ int jots_patch_shape(int order, int* px, int* py, uint32_t* items) {
     return (items && x > 0) ? patch_items(order, items) : 0;
 }
 
+int jots_h1_dof_map(int dim, int order, int32_t* map) {
+    JOTS_TRY
+    std::vector<int> m;
+    h1_dof_map(dim, order, m);
+    for (size_t i = 0; i < m.size(); ++i) map[i] = m[i];
+    return 0;
+    JOTS_CATCH_INT
+}
+int jots_gather_from_native(int dim, int order, int64_t n_elem, const int32_t* native, int32_t* lexicographic) {
+    JOTS_TRY
+    std::vector<int> m;
+    h1_dof_map(dim, order, m);
+    const size_t nl = m.size();
+    for (int64_t e = 0; e < n_elem; ++e)
+        for (size_t l = 0; l < nl; ++l) {
+            const int32_t d = native[(size_t)e * nl + m[l]];
+            lexicographic[(size_t)e * nl + l] = d < 0 ? -1 - d : d;      // H1 DOFs carry no sign: -1-d encodes d
+        }
+    return 0;
+    JOTS_CATCH_INT
+}
+
 // ---- config (host only) -----------------------------------------------------------------------
 int64_t jots_config_dump(const char* ini_path, char* out, int64_t cap) {
     try {
@@ -402,6 +424,21 @@ jots_op_t jots_op_create(jots_ctx_t c, int sim_type, double dt, int scheme, int 
     JOTS_CATCH_PTR
 }
 void jots_op_destroy(jots_op_t op) { delete op; }
+int jots_op_set_print_level(jots_op_t op, int linear_mask, int newton_mask) {
+    JOTS_TRY op->it->set_print_level(linear_mask, newton_mask); return 0; JOTS_CATCH_INT
+}
+int jots_print_level_mask(const char* labels) {
+    try {
+        std::vector<std::string> v;
+        std::stringstream ss(labels ? labels : "");
+        std::string t;
+        while (std::getline(ss, t, ',')) {
+            const size_t a = t.find_first_not_of(" \t"), b = t.find_last_not_of(" \t");
+            if (a != std::string::npos) v.push_back(t.substr(a, b - a + 1));
+        }
+        return create_print_level(v);
+    } catch (const std::exception& ex) { fail(ex); return -1; }
+}
 int jots_op_iterate(jots_op_t op, double* u, int loc, double* time) {
     JOTS_TRY
     Out o(op->c, u, loc, true);

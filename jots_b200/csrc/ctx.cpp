@@ -437,4 +437,15 @@ double Ctx::max_local(const double* a) {
     return h_scal[0];
 }
 
+double Ctx::max_global(const double* a) {
+    v_max(stream, n, a, dot_scratch(), d_scal.p);
+    ++stats.kernel_launches;
+    if (halo) halo_allreduce_max(*this, d_scal.p, 1);
+    JOTS_CUDA(cudaMemcpyAsync(h_scal, d_scal.p, sizeof(double), cudaMemcpyDeviceToHost, stream));
+    JOTS_CUDA(cudaStreamSynchronize(stream));
+    return h_scal[0];
+}
+
+int Ctx::rank() const { return halo ? halo_rank(*this) : 0; }
+
 }  // namespace jots

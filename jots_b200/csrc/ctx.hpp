@@ -146,6 +146,8 @@ public:
     void copy_scalars(int nv, double* out);            // d_scal[0..nv) -> host, one synchronisation
     double norm(const double* a) ;
     double max_local(const double* a);   // rank-local maximum, as Vector::Max() in the reference
+    double max_global(const double* a);  // maximum over all ranks (ncclMax): collective
+    int rank() const;                    // 0 on one GPU
     void zero(double* y) { JOTS_CUDA(cudaMemsetAsync(y, 0, n * sizeof(double), stream)); }
     void copy(const double* x, double* y) { JOTS_CUDA(cudaMemcpyAsync(y, x, n * sizeof(double), cudaMemcpyDeviceToDevice, stream)); }
     void zero_ess(double* y) { v_set_idx(stream, (int)ess.size(), d_ess.p, 0.0, y); stats.kernel_launches += !ess.empty(); }

@@ -9,6 +9,12 @@
 
 namespace jots {
 
+// JOTS_QUIET=1 silences the driver's and the solvers' console output (the config keys Print_Level / Print_Freq still parse)
+bool quiet() {
+    static const bool q = [] { const char* e = std::getenv("JOTS_QUIET"); return e && e[0] == '1'; }();
+    return q;
+}
+
 static std::string trim(const std::string& s) {
     size_t a = s.find_first_not_of(" \t\r\n");
     if (a == std::string::npos) return "";
@@ -91,6 +97,7 @@ Config::Config(const std::string& p) : path(p) {
         time_scheme = get_str(ini, "TimeIntegration", "Time_Scheme", "Euler_Implicit");
         dt = get_dbl(ini, "TimeIntegration", "Delta_Time", 0.1);
         max_timesteps = get_int(ini, "TimeIntegration", "Max_Timesteps", 100);
+        time_print_freq = get_int(ini, "TimeIntegration", "Print_Freq", 1);
     }
     const char* LS = "LinearSolverSettings";
     solver = get_str(ini, LS, "Solver", "FGMRES");
@@ -98,13 +105,31 @@ Config::Config(const std::string& p) : path(p) {
     abs_tol = get_dbl(ini, LS, "Absolute_Tolerance", 1e-16);
     rel_tol = get_dbl(ini, LS, "Relative_Tolerance", 1e-10);
     max_iter = get_int(ini, LS, "Max_Iterations", 100);
+    ls_print_level = split_list(get_str(ini, LS, "Print_Level", "Errors, Warnings"));
     using_newton = ini.count("NewtonSolverSettings") > 0;
     if (using_newton) {
         const char* NS = "NewtonSolverSettings";
         newton_max_iter = get_int(ini, NS, "Max_Iterations", 100);
         newton_abs_tol = get_dbl(ini, NS, "Absolute_Tolerance", 1e-16);
         newton_rel_tol = get_dbl(ini, NS, "Relative_Tolerance", 1e-10);
+        newton_print_level = split_list(get_str(ini, NS, "Print_Level", "Errors, Warnings, Iterations"));
     }
+}
+
+int create_print_level(const std::vector<std::string>& labels) {
+    // IterativeSolver::PrintLevel: every label switches its flag on, "None" clears, "All" sets everything
+    int m = 0;
+    for (const std::string& l : labels) {
+        if (l == "None") m = 0;
+        else if (l == "Warnings") m |= PRINT_WARNINGS;
+        else if (l == "Errors") m |= PRINT_ERRORS;
+        else if (l == "Iterations") m |= PRINT_ITERATIONS;
+        else if (l == "FirstAndLast") m |= PRINT_FIRST_AND_LAST;
+        else if (l == "Summary") m |= PRINT_SUMMARY;
+        else if (l == "All") m = PRINT_ERRORS | PRINT_WARNINGS | PRINT_ITERATIONS | PRINT_SUMMARY | PRINT_FIRST_AND_LAST;
+        else throw std::runtime_error("Unknown print level: '" + l + "'");     // Print_Level_Map.at() throws in the reference
+    }
+    return m;
 }
 
 Poly parse_property(const std::vector<std::string>& info) {
@@ -193,8 +218,10 @@ JOTSDriver::JOTSDriver(const Config& cfg_, int device, const Mesh* mesh_in, Comm
     ls.solver = map_label(cfg.solver, {{"CG", SOLVER_CG}, {"GMRES", SOLVER_GMRES}, {"FGMRES", SOLVER_FGMRES}}, "solver");
     ls.prec = map_label(cfg.prec, {{"Jacobi", PREC_JACOBI}, {"Chebyshev", PREC_CHEBYSHEV}}, "preconditioner");
     ls.rel_tol = cfg.rel_tol; ls.abs_tol = cfg.abs_tol; ls.max_iter = cfg.max_iter;
+    ls.print = create_print_level(cfg.ls_print_level);
     NewtonSpec nw;
     nw.rel_tol = cfg.newton_rel_tol; nw.abs_tol = cfg.newton_abs_tol; nw.max_iter = cfg.newton_max_iter;
+    nw.print = create_print_level(cfg.newton_print_level);
     const int scheme = map_label(cfg.time_scheme, {{"Euler_Implicit", TS_EULER_IMPLICIT}, {"Euler_Explicit", TS_EULER_EXPLICIT}, {"RK4", TS_RK4}}, "time scheme");
     if (cfg.sim_type == "Linearized_Unsteady") {
         if (!(has_prop[0] && has_prop[1] && has_prop[2])) throw std::runtime_error("Linearized_Unsteady needs Density_rho, Specific_Heat_C and Thermal_Conductivity_k");
@@ -248,8 +275,12 @@ void JOTSDriver::Step() {
     UpdateAndApplyBCs();
     UpdateMatProps(true);
     Iteration();
-    // PostprocessIteration: blow-up check on the rank-local maximum (jots_driver.cpp:739-743)
-    if (check_blowup && ctx->max_local(u.p) > 1e10) throw std::runtime_error("JOTS has blown up");
+    // PostprocessIteration (jots_driver.cpp:727-743): step line every Print_Freq steps on rank 0, then the blow-up check.  The
+    // reference tests the rank-local maximum and MFEM_ABORT takes every rank down through MPI_Abort; here the maximum is
+    // all-reduced so that every rank throws together instead of leaving the others in the next collective.
+    if (cfg.using_time_integration && cfg.time_print_freq > 0 && it_num % cfg.time_print_freq == 0 && ctx->rank() == 0 && !quiet())
+        std::printf("Step #%10i || Time: %1.6e out of %-1.6e || dt: %1.6e \n", it_num, time, dt * max_timesteps, dt);
+    if (check_blowup && ctx->max_global(u.p) > 1e10) throw std::runtime_error("JOTS has blown up");
 }
 
 int JOTSDriver::Run(int max_steps) {

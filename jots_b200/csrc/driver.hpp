@@ -20,11 +20,16 @@ struct Config {
     bool use_restart = false, with_precice = false, using_time_integration = false, using_newton = false;
     int fe_order = 1, serial_refine = 0, parallel_refine = 0, max_timesteps = 100, max_iter = 100, newton_max_iter = 0;
     double initial_temp = 100.0, dt = 0.1, abs_tol = 1e-16, rel_tol = 1e-10, newton_abs_tol = 1e-16, newton_rel_tol = 1e-10;
+    // Print_Level lists (config_file.cpp:140-141,153,161-162) and TimeIntegration.Print_Freq (:128)
+    std::vector<std::string> ls_print_level{"Errors", "Warnings"}, newton_print_level{"Errors", "Warnings", "Iterations"};
+    int time_print_freq = 1;
     std::map<std::string, std::vector<std::string>> mat_props;
     std::map<int, std::vector<std::string>> bcs;
 };
 
 Poly parse_property(const std::vector<std::string>& info);
+// Factory::CreatePrintLevel (jots_common.inl:57-91): label list -> PRINT_* mask of solvers.hpp; an unknown label is an error
+int create_print_level(const std::vector<std::string>& labels);
 BCSpec parse_bc(const std::vector<std::string>& info);
 
 class JOTSDriver {

@@ -135,6 +135,13 @@ void halo_allreduce(Ctx& c, double* d_vals, int nv) {
     nccl_check(ncclAllReduce(d_vals, d_vals, nv, ncclDouble, ncclSum, h->comm->comm, c.stream), "ncclAllReduce");
 }
 
+void halo_allreduce_max(Ctx& c, double* d_vals, int nv) {
+    Halo* h = c.halo;
+    if (!h || h->comm->nranks == 1) return;
+    nccl_check(ncclAllReduce(d_vals, d_vals, nv, ncclDouble, ncclMax, h->comm->comm, c.stream), "ncclAllReduce(max)");
+}
+int halo_rank(const Ctx& c) { return c.halo ? c.halo->comm->rank : 0; }
+
 const int64_t* halo_global_index(Ctx& c) { return c.halo ? c.halo->d_gid.p : nullptr; }
 
 }  // namespace jots

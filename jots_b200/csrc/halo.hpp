@@ -23,5 +23,7 @@ void halo_exchange_begin(Ctx& c, double* y);
 void halo_exchange_end(Ctx& c);
 int64_t halo_interface_elems(const Ctx& c);
 void halo_allreduce(Ctx& c, double* d_vals, int nv);
+void halo_allreduce_max(Ctx& c, double* d_vals, int nv);
+int halo_rank(const Ctx& c);
 const int64_t* halo_global_index(Ctx& c);  // device array: local DOF -> global DOF
 }  // namespace jots

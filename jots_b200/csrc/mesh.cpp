@@ -492,6 +492,48 @@ void Space::essential_dofs(const std::vector<int>& attrs, std::vector<int>& out)
     out.erase(std::unique(out.begin(), out.end()), out.end());
 }
 
+void h1_dof_map(int dim, int p, std::vector<int>& map) {
+    if ((dim != 2 && dim != 3) || p < 1) throw std::runtime_error("h1_dof_map: dim 2 or 3, order >= 1");
+    const int p1 = p + 1;
+    int o = 0;
+    if (dim == 2) {
+        map.assign((size_t)p1 * p1, -1);
+        auto at = [&](int i, int j) -> int& { return map[(size_t)i + (size_t)j * p1]; };
+        at(0, 0) = o++; at(p, 0) = o++; at(p, p) = o++; at(0, p) = o++;
+        for (int i = 1; i < p; ++i) at(i, 0) = o++;            // edge (0,1)
+        for (int i = 1; i < p; ++i) at(p, i) = o++;            // edge (1,2)
+        for (int i = 1; i < p; ++i) at(p - i, p) = o++;        // edge (2,3)
+        for (int i = 1; i < p; ++i) at(0, p - i) = o++;        // edge (3,0)
+        for (int j = 1; j < p; ++j) for (int i = 1; i < p; ++i) at(i, j) = o++;
+        return;
+    }
+    map.assign((size_t)p1 * p1 * p1, -1);
+    auto at = [&](int i, int j, int k) -> int& { return map[(size_t)i + ((size_t)j + (size_t)k * p1) * p1]; };
+    at(0, 0, 0) = o++; at(p, 0, 0) = o++; at(p, p, 0) = o++; at(0, p, 0) = o++;
+    at(0, 0, p) = o++; at(p, 0, p) = o++; at(p, p, p) = o++; at(0, p, p) = o++;
+    // edges, in the order of Hexahedron::edges: (0,1) (1,2) (3,2) (0,3) (4,5) (5,6) (7,6) (4,7) (0,4) (1,5) (2,6) (3,7)
+    for (int i = 1; i < p; ++i) at(i, 0, 0) = o++;
+    for (int i = 1; i < p; ++i) at(p, i, 0) = o++;
+    for (int i = 1; i < p; ++i) at(i, p, 0) = o++;
+    for (int i = 1; i < p; ++i) at(0, i, 0) = o++;
+    for (int i = 1; i < p; ++i) at(i, 0, p) = o++;
+    for (int i = 1; i < p; ++i) at(p, i, p) = o++;
+    for (int i = 1; i < p; ++i) at(i, p, p) = o++;
+    for (int i = 1; i < p; ++i) at(0, i, p) = o++;
+    for (int i = 1; i < p; ++i) at(0, 0, i) = o++;
+    for (int i = 1; i < p; ++i) at(p, 0, i) = o++;
+    for (int i = 1; i < p; ++i) at(p, p, i) = o++;
+    for (int i = 1; i < p; ++i) at(0, p, i) = o++;
+    // faces, in the order of Mesh::GenerateFaces: (3,2,1,0) (0,1,5,4) (1,2,6,5) (2,3,7,6) (3,0,4,7) (4,5,6,7)
+    for (int j = 1; j < p; ++j) for (int i = 1; i < p; ++i) at(i, p - j, 0) = o++;
+    for (int j = 1; j < p; ++j) for (int i = 1; i < p; ++i) at(i, 0, j) = o++;
+    for (int j = 1; j < p; ++j) for (int i = 1; i < p; ++i) at(p, i, j) = o++;
+    for (int j = 1; j < p; ++j) for (int i = 1; i < p; ++i) at(p - i, p, j) = o++;
+    for (int j = 1; j < p; ++j) for (int i = 1; i < p; ++i) at(0, p - i, j) = o++;
+    for (int j = 1; j < p; ++j) for (int i = 1; i < p; ++i) at(i, j, p) = o++;
+    for (int k = 1; k < p; ++k) for (int j = 1; j < p; ++j) for (int i = 1; i < p; ++i) at(i, j, k) = o++;
+}
+
 int64_t make_rowtiles(const Space& s, const std::vector<int>& ess, int E, double min_fill, std::vector<unsigned char>& tab) {
     tab.clear();
     const int p = s.p, D = s.D, DD = D * D, ND = DD * D;

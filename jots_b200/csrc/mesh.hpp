@@ -70,6 +70,14 @@ struct Space {
 
 Space make_space(const Mesh& m, int p);
 
+// MFEM's native local DOF order of the H1 tensor elements (H1_QuadrilateralElement / H1_HexahedronElement::GetDofMap,
+// fem/fe/fe_h1.cpp of MFEM 4.7): vertices, then edge interiors (edge by edge, each in the direction of
+// increasing coordinate on hexes; quads run edges 2 and 3 backwards), then face interiors, then the element interior.
+// map[lexicographic index] = native index, i.e. what ParFiniteElementSpace::GetElementDofs returns at position map[l] is the
+// DOF of lexicographic node l = i + (p+1) (j + (p+1) k).  Restated from the MFEM sources (not in /root/reference): a binding
+// should assert it against GetDofMap() of the element it actually uses.
+void h1_dof_map(int dim, int p, std::vector<int>& map);
+
 // Row-structured tiles (RowTile<D> records of forms.hpp, apply_slab4.cuh): greedy segmentation of the element order
 // into runs of at most E elements in which DOF (i, j, k) of the m-th element is base[k*D + j] + p*m + i (contiguous
 // rows along the fastest lattice axis).  Returns the number of tiles, or 0 when some element is not even a run of

@@ -37,6 +37,7 @@ public:
     // material state: the vector the nodal polynomials were last evaluated on
     // (PolynomialProperty::UpdateAllCoeffs called from JOTSDriver::UpdateMatProps)
     virtual void SetMatState(const double* u) { c->set_mat_state(u); }
+    virtual void set_print_level(int linear_mask, int newton_mask) { ls.print = linear_mask; }
     Ctx* c;
     SolverSpec ls;
     DArr<double> b_vec;     // Neumann linear form
@@ -60,6 +61,7 @@ public:
     void ImplicitSolve(double dt_, const double* u, double* k) override;
     void CalculateRHS(const double* u, double* rhs);
     FormSpec M_spec(), K_spec(), A_spec();
+    void set_print_level(int linear_mask, int) override { ls.print = linear_mask; expl_solver->print = linear_mask; impl_solver->print = linear_mask; }
 private:
     void ReassembleM();
     void ReassembleK();
@@ -84,6 +86,7 @@ public:
     void A_mult(const double* z, double* y);          // ReducedSystemOperatorA::Mult
     FormSpec jacobian_spec(const double* z);          // R.GetGradient at state z
     void set_un(const double* un) { u_n = un; }       // JOTS_k_Operator::SetParameters
+    void set_print_level(int linear_mask, int newton_mask) override { ls.print = linear_mask; lin_solver->print = linear_mask; newton.print = newton_mask; }
     bool all_const = false, has_BN = false;
 private:
     NewtonSpec nw;
@@ -102,6 +105,7 @@ public:
     void new_state(const double* u) override {}
     void mult(const double* u, double* y) override;
     LinOp* gradient(const double* u) override;
+    void set_print_level(int linear_mask, int newton_mask) override { ls.print = linear_mask; lin_solver->print = linear_mask; newton.print = newton_mask; }
     bool zero_rhs_on_essential = false;  // reference quirk B.3: b_vec is NOT zeroed by default
 private:
     NewtonSpec nw;

@@ -157,7 +157,15 @@ void Krylov::mult(const double* b, double* x) {
     c->stats.last_linear_iters = info.iterations;
     c->stats.last_linear_norm = info.final_norm;
     c->stats.last_linear_converged = info.converged;
-    if (print > 0 && !info.converged) std::fprintf(stderr, "Krylov solver: no convergence in %d iterations (final norm %.3e)\n", info.iterations, info.final_norm);
+    // mfem::IterativeSolver print options (CGSolver / GMRESSolver / FGMRESSolver::Mult epilogue), rank 0 only
+    if (print != 0 && c->rank() == 0 && !quiet()) {
+        const char* name = kind == SOLVER_CG ? "PCG" : kind == SOLVER_GMRES ? "GMRES" : "FGMRES";
+        if ((print & PRINT_FIRST_AND_LAST) && !(print & PRINT_ITERATIONS))
+            std::printf("   Iteration : %3d  final norm = %g\n", info.iterations, info.final_norm);
+        if ((print & PRINT_SUMMARY) || ((print & PRINT_ITERATIONS) && !info.converged))
+            std::printf("%s: Number of iterations: %d\n", name, info.iterations);
+        if ((print & PRINT_WARNINGS) && !info.converged) std::printf("%s: No convergence!\n", name);
+    }
 }
 
 // mfem::CGSolver::Mult, preconditioned: monitors (B r, r)
@@ -179,7 +187,10 @@ void Krylov::cg(const double* b, double* x) {
     if (den == 0.0) { info.final_norm = std::sqrt(nom); return; }
     info.iterations = max_iter;
     double betanom = nom;
-    if ((!prec || dinv) && device_scalars) { cg_device_loop(x, r, z, d, dinv, nom, den, r0); return; }
+    const bool it_print = (print & PRINT_ITERATIONS) && c->rank() == 0 && !quiet();
+    if (it_print || ((print & PRINT_FIRST_AND_LAST) && c->rank() == 0 && !quiet())) std::printf("   Iteration : %3d  (B r, r) = %g\n", 0, nom);
+    // per-iteration output needs every (B r, r) on the host: the host-sequenced loop
+    if ((!prec || dinv) && device_scalars && !(print & PRINT_ITERATIONS)) { cg_device_loop(x, r, z, d, dinv, nom, den, r0); return; }
     int i = 1;
     while (true) {
         const double alpha = nom / den;
@@ -195,6 +206,7 @@ void Krylov::cg(const double* b, double* x) {
             prec->mult(r, z);
             betanom = c->dot(r, z);
         }
+        if (it_print) std::printf("   Iteration : %3d  (B r, r) = %g\n", i, betanom);
         if (betanom < 0) { info.iterations = i; break; }
         if (betanom <= r0) { info.converged = true; info.iterations = i; break; }
         if (++i > max_iter) break;
@@ -330,6 +342,8 @@ void Krylov::gmres(const double* b, double* x, bool flexible) {
             app_rot(Hh(i, i), Hh(i + 1, i), cs[i], sn[i]);
             app_rot(s[i], s[i + 1], cs[i], sn[i]);
             const double resid = std::fabs(s[i + 1]);
+            if ((print & PRINT_ITERATIONS) && c->rank() == 0 && !quiet())
+                std::printf("   Pass : %2d   Iteration : %3d  || %sr || = %g\n", (j - 1) / m + 1, j, flexible ? "" : "B ", resid);
             if (resid <= final_norm) {
                 update(i);
                 info.converged = true; info.final_norm = resid; info.iterations = j;
@@ -359,10 +373,15 @@ void Newton::mult(NewtonOp& op, Krylov& lin, const double* b, double* x) {
     ++c->stats.residual_evals;
     if (b) { v_axpy(c->stream, n, -1.0, b, r.p); ++c->stats.kernel_launches; }
     double norm = c->norm(r.p);
+    const double norm0 = norm;
     const double goal = std::max(rel_tol * norm, abs_tol);
     int it = 0;
     while (true) {
-        if (print > 0) std::fprintf(stderr, "Newton iteration %2d : ||r|| = %.6e\n", it, norm);
+        if ((print & PRINT_ITERATIONS) && c->rank() == 0 && !quiet()) {
+            std::printf("Newton iteration %2d : ||r|| = %g", it, norm);
+            if (it > 0) std::printf(", ||r||/||r_0|| = %g", norm0 > 0 ? norm / norm0 : 0.0);
+            std::printf("\n");
+        }
         if (!(norm == norm)) { converged = false; break; }
         if (norm <= goal) { converged = true; break; }
         if (it >= max_iter) { converged = false; break; }
@@ -380,6 +399,11 @@ void Newton::mult(NewtonOp& op, Krylov& lin, const double* b, double* x) {
     }
     iterations = it;
     final_norm = norm;
+    if (print != 0 && c->rank() == 0 && !quiet()) {
+        if ((print & PRINT_SUMMARY) || (!converged && (print & (PRINT_WARNINGS | PRINT_ITERATIONS))))
+            std::printf("Newton: Number of iterations: %d\n   ||r|| = %g\n", it, norm);
+        if (!converged && (print & (PRINT_SUMMARY | PRINT_WARNINGS))) std::printf("Newton: No convergence!\n");
+    }
     c->stats.newton_iters += it;
     c->stats.last_newton_iters = it;
     c->stats.last_newton_norm = norm;

@@ -12,6 +12,9 @@ namespace jots {
 
 enum { SOLVER_CG = 0, SOLVER_GMRES = 1, SOLVER_FGMRES = 2 };
 enum { PREC_JACOBI = 0, PREC_CHEBYSHEV = 1, PREC_NONE = -1 };
+// mfem::IterativeSolver::PrintLevel flags (Factory::CreatePrintLevel, jots_common.inl:57-91)
+enum { PRINT_ERRORS = 1, PRINT_WARNINGS = 2, PRINT_ITERATIONS = 4, PRINT_SUMMARY = 8, PRINT_FIRST_AND_LAST = 16 };
+bool quiet();   // JOTS_QUIET=1 (driver.cpp)
 
 struct LinOp {
     virtual ~LinOp() {}

@@ -67,6 +67,8 @@ def load_library():
         "jots_space_rowtiles": (C.c_int64, [_P, _P, C.c_int64, C.c_int, C.c_double, _P, _P]),
         "jots_space_patches": (C.c_int64, [_P, _P, C.c_int64, C.c_int, C.c_int, _P, _P, _P]),
         "jots_patch_shape": (C.c_int, [C.c_int, _P, _P, _P]),
+        "jots_h1_dof_map": (C.c_int, [C.c_int, C.c_int, _P]),
+        "jots_gather_from_native": (C.c_int, [C.c_int, C.c_int, C.c_int64, _P, _P]),
         "jots_config_dump": (C.c_int64, [C.c_char_p, _P, C.c_int64]),
         "jots_ctx_create": (_P, [_P, C.c_int]),
         "jots_ctx_destroy": (None, [_P]),
@@ -90,6 +92,8 @@ def load_library():
         "jots_op_create": (_P, [_P, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int,
                                 C.c_double, C.c_double, C.c_int]),
         "jots_op_destroy": (None, [_P]),
+        "jots_op_set_print_level": (C.c_int, [_P, C.c_int, C.c_int]),
+        "jots_print_level_mask": (C.c_int, [C.c_char_p]),
         "jots_op_iterate": (C.c_int, [_P, _P, C.c_int, _D]),
         "jots_op_implicit_solve": (C.c_int, [_P, C.c_double, _P, _P, C.c_int]),
         "jots_op_mult": (C.c_int, [_P, _P, _P, C.c_int]),
@@ -187,6 +191,21 @@ def patch_shape(order):
     items = np.zeros(128, dtype=np.uint32)
     n = load_library().jots_patch_shape(order, C.byref(px), C.byref(py), _ptr(items))
     return px.value, py.value, items[:n]
+
+
+def h1_dof_map(dim, order):
+    """map[lexicographic l] = MFEM-native local DOF index (GetDofMap of the H1 quad / hex element)."""
+    m = np.empty((order + 1) ** dim, dtype=np.int32)
+    _chk(load_library().jots_h1_dof_map(dim, order, _ptr(m)))
+    return m
+
+
+def gather_from_native(dim, order, native):
+    """Element-DOF table in MFEM's native local order -> lexicographic local order."""
+    nat = np.ascontiguousarray(native, dtype=np.int32)
+    out = np.empty_like(nat)
+    _chk(load_library().jots_gather_from_native(dim, order, nat.shape[0], _ptr(nat), _ptr(out)))
+    return out
 
 
 def config_dump(ini_path):

@@ -18,7 +18,9 @@ Visualization_Freq=0
 
 
 def ini_text(sim, mesh, t0, props, bcs, time=True, newton=None, solver="FGMRES", prec="Chebyshev",
-         steps=200, dt="1e-2", order=2, scheme="Euler_Implicit", refine=0):
+         steps=200, dt="1e-2", order=2, scheme="Euler_Implicit", refine=0, ls_print="Errors", newton_print="Errors", print_freq=1000000):
+    """ls_print / newton_print / print_freq: the reference's defaults ("Errors, Warnings", "Errors, Warnings, Iterations", 1)
+    would print a line per Newton iteration and per step; the test inputs keep the logs short."""
     s = "[FiniteElementSetup]\nSimulation_Type=%s\nFE_Order=%d\nUse_Restart=No\nMesh_File=%s\n" % (sim, order, mesh)
     s += "Serial_Refine=%d\nParallel_Refine=0\nInitial_Temperature=%s\n\n[MaterialProperties]\n" % (refine, t0)
     for k, v in props:
@@ -27,11 +29,11 @@ def ini_text(sim, mesh, t0, props, bcs, time=True, newton=None, solver="FGMRES",
     for i, v in enumerate(bcs):
         s += "Boundary_Attr_%d=%s\n" % (i + 1, v)
     if time:
-        s += "\n[TimeIntegration]\nTime_Scheme=%s\nDelta_Time=%s\nMax_Timesteps=%d\n" % (scheme, dt, steps)
+        s += "\n[TimeIntegration]\nTime_Scheme=%s\nDelta_Time=%s\nMax_Timesteps=%d\nPrint_Freq=%d\n" % (scheme, dt, steps, print_freq)
     s += "\n[LinearSolverSettings]\nSolver=%s\nPreconditioner=%s\nMax_Iterations=100\n" % (solver, prec)
-    s += "Absolute_Tolerance=1e-16\nRelative_Tolerance=1e-10\n"
+    s += "Absolute_Tolerance=1e-16\nRelative_Tolerance=1e-10\nPrint_Level=%s\n" % ls_print
     if newton is not None:
-        s += "\n[NewtonSolverSettings]\nMax_Iterations=%d\nAbsolute_Tolerance=1e-16\nRelative_Tolerance=1e-10\n" % newton
+        s += "\n[NewtonSolverSettings]\nMax_Iterations=%d\nAbsolute_Tolerance=1e-16\nRelative_Tolerance=1e-10\nPrint_Level=%s\n" % (newton, newton_print)
     return s + _COMMON_TAIL
 
 

@@ -420,8 +420,7 @@ def test_cg_with_device_resident_scalars_matches_the_host_sequenced_loop(J, tmp_
         dev, orc = build(J, tmp_path, sim, 3, 2, props, solver="CG", prec="Jacobi", n=n, steps=2)
         if max_it != 100:
             # fewer Krylov iterations than a chunk: Newton may not converge, the comparison is between the two loops only
-            txt = open(str(tmp_path / "c.ini")).read().replace("Max_Iterations=100\nAbsolute_Tolerance=1e-16\nRelative_Tolerance=1e-10\n\n[NewtonSolverSettings]\nMax_Iterations=50",
-                                                                 "Max_Iterations=%d\nAbsolute_Tolerance=1e-16\nRelative_Tolerance=1e-10\n\n[NewtonSolverSettings]\nMax_Iterations=50" % max_it)
+            txt = open(str(tmp_path / "c.ini")).read().replace("Max_Iterations=100\n", "Max_Iterations=%d\n" % max_it, 1)   # [LinearSolverSettings]
             open(str(tmp_path / "c.ini"), "w").write(txt)
             dev = J.Driver(str(tmp_path / "c.ini"))
         try:
@@ -434,3 +433,33 @@ def test_cg_with_device_resident_scalars_matches_the_host_sequenced_loop(J, tmp_
     assert rel(out["0"][4], out["1"][4]) < 1e-12
     if max_it == 100:
         assert rel(out["0"][4], orc.run()) < FIELD_TOL
+
+
+def test_print_levels_and_step_lines(J, tmp_path, capfd):
+    """Print_Level lists (Factory::CreatePrintLevel, jots_common.inl:57-91; config_file.cpp:140-141,161-162) and Print_Freq
+    (jots_driver.cpp:731-736): 'All' prints Newton / Krylov iteration lines and a step line per step, 'None' prints nothing,
+    an unknown label is an error (Print_Level_Map.at throws in the reference).  Results do not depend on the print level
+    (CG falls back to the host-sequenced loop when it has to print every iteration)."""
+    from cases import ini_text
+    fields = {}
+    for name, lsp, nwp, freq in (("all", "All", "Errors, Warnings, Iterations", 1), ("none", "None", "None", 1000000)):
+        mesh = J.Mesh.brick(6, 3, 2, 0.01, 0.01, 0.01)
+        ini = str(tmp_path / (name + ".ini"))
+        with open(ini, "w") as f:
+            f.write(ini_text("Nonlinear_Unsteady", "unused", 300, PROPS["k"], ["HeatFlux, 7.5e5", HF0, HF0, "Isothermal, 300", HF0, HF0],
+                             newton=50, solver="CG", prec="Jacobi", steps=2, order=2, ls_print=lsp, newton_print=nwp, print_freq=freq))
+        capfd.readouterr()
+        dev = J.Driver(ini, 0, mesh=mesh)
+        dev.run()
+        out = capfd.readouterr().out
+        fields[name] = dev.get_u()
+        if name == "all":
+            assert out.count("Step #") == 2 and "Newton iteration  0 : ||r|| = " in out and "(B r, r) = " in out and "PCG: Number of iterations:" in out
+        else:
+            assert out.strip() == ""
+    assert rel(fields["all"], fields["none"]) < 1e-12
+    bad = str(tmp_path / "bad.ini")
+    with open(bad, "w") as f:
+        f.write(ini_text("Nonlinear_Unsteady", "unused", 300, PROPS["k"], [HF0] * 6, newton=5, steps=1, ls_print="Errors, Chatty"))
+    with pytest.raises(J.JotsError, match="print level"):
+        J.Driver(bad, 0, mesh=J.Mesh.brick(2, 2, 2, 1.0, 1.0, 1.0))

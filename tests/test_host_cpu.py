@@ -429,3 +429,51 @@ def test_partition_from_caller_tables_rejects_bad_input():
     bad = dict(t, neighbors=[(0, t["neighbors"][0][1])])                                            # itself as a neighbour
     with pytest.raises(J.JotsError, match="neighbour"):
         J.Partition.from_tables(rank=0, nranks=2, **bad)
+
+
+def test_print_level_masks():
+    """Factory::CreatePrintLevel (jots_common.inl:57-91): flags accumulate, None clears, All sets all, unknown labels fail."""
+    import jots_b200 as J
+    m = J.load_library().jots_print_level_mask
+    assert m(b"Errors, Warnings") == 3 and m(b"Errors, Warnings, Iterations") == 7
+    assert m(b"Summary") == 8 and m(b"FirstAndLast") == 16 and m(b"All") == 31
+    assert m(b"All, None") == 0 and m(b"None, Warnings") == 2 and m(b"") == 0
+    assert m(b"Verbose") == -1
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+@pytest.mark.parametrize("p", [1, 2, 3, 4])
+def test_h1_native_dof_map(dim, p):
+    """MFEM-native local order: a bijection with the vertices first, then edge interiors (p-1 per edge,
+    collinear, hex edges in increasing coordinate), face interiors ((p-1)^2 per face, coplanar on a boundary face), interior;
+    and jots_gather_from_native brings a natively ordered element table back to the lexicographic one bit-exactly."""
+    import jots_b200 as J
+    D = p + 1
+    m = J.h1_dof_map(dim, p)
+    assert sorted(m) == list(range(D ** dim))
+    coords = np.array([[l % D, (l // D) % D, l // (D * D)][:dim] for l in range(D ** dim)])
+    nat2coord = np.empty_like(coords)
+    nat2coord[m] = coords
+    nv, ne = 2 ** dim, (4 if dim == 2 else 12) * (p - 1)
+    assert all(set(c) <= {0, p} for c in nat2coord[:nv])                        # vertices first
+    expected_v = [(0, 0), (p, 0), (p, p), (0, p)] if dim == 2 else [(0, 0, 0), (p, 0, 0), (p, p, 0), (0, p, 0), (0, 0, p), (p, 0, p), (p, p, p), (0, p, p)]
+    assert [tuple(c) for c in nat2coord[:nv]] == expected_v
+    edges = nat2coord[nv:nv + ne].reshape(-1, max(p - 1, 1), dim) if p > 1 else np.zeros((0, 1, dim), int)
+    for e in edges:                                                             # one free coordinate, the others on the boundary
+        free = [a for a in range(dim) if len(set(e[:, a])) > 1 or e[0, a] not in (0, p)]
+        assert len(free) == 1 and all(e[0, a] in (0, p) and len(set(e[:, a])) == 1 for a in range(dim) if a != free[0])
+        step = np.diff(e[:, free[0]])
+        assert (step == 1).all() or (dim == 2 and (step == -1).all())
+    if dim == 3 and p > 1:
+        nf = 6 * (p - 1) ** 2
+        faces = nat2coord[nv + ne:nv + ne + nf].reshape(6, (p - 1) ** 2, 3)
+        for f in faces:
+            fixed = [a for a in range(3) if len(set(f[:, a])) == 1 and f[0, a] in (0, p)]
+            assert len(fixed) == 1
+        assert (np.all((nat2coord[nv + ne + nf:] > 0) & (nat2coord[nv + ne + nf:] < p)))
+    s = J.Space(J.Mesh.brick(3, 2, 2, 1.0, 1.0, 1.0) if dim == 3 else J.Mesh.rect(3, 2, 1.0, 1.0), p)
+    g = s.gather()
+    native = np.empty_like(g)
+    native[:, m] = g                                                           # native[e][map[l]] = lexicographic[e][l]
+    assert (J.gather_from_native(dim, p, native) == g).all()
+    assert (J.gather_from_native(dim, p, -1 - native) == g).all()              # MFEM's sign encoding is undone
