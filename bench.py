@@ -294,8 +294,9 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--variant", default="A", choices=["A", "B"], help="B: C(T) = 4.5 T - 850 as well (FGMRES recommended)")
     ap.add_argument("--strong-elems", type=int, default=256,
-                    help="N > 1: elements per direction of the FIXED global brick of the extra strong-scaling leg (256 -> 135 M DOFs at Q2; 0: off)")
-    ap.add_argument("--strong-at-1", action="store_true", help="run the strong-scaling leg at N = 1 too (about a minute of host set-up)")
+                    help="elements per direction of the FIXED global brick of the extra strong-scaling leg, run at every N so that the N = 1, 2, 4, 8 "
+                         "lines give north_star's strong-scaling curve (256 -> 135 M DOFs at Q2; 0: off)")
+    ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling leg (it costs about half a minute of host set-up at every N)")
     ap.add_argument("--no-multi-checks", action="store_true", help="N > 1: skip the partitioned-vs-single-GPU parity check")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="N>1: weak = --n elements per direction per GPU, strong = --n for the global brick")
@@ -425,7 +426,7 @@ def main():
     if world > 1 and not args.no_multi_checks:
         extra["parity_check"] = partition_parity_check(args, J, dist, comm, rank, world, local)
         trace("parity check done")
-    if args.strong_elems > 0 and (world > 1 or args.strong_at_1):
+    if args.strong_elems > 0 and not args.no_strong:
         extra["strong"] = strong_scaling_leg(args, J, torch, dist if world > 1 else None, comm, rank, world, local, barrier)
         trace("strong-scaling leg done")
 

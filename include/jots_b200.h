@@ -186,7 +186,8 @@ jots_part_t jots_partition_create(jots_mesh_t mesh, jots_space_t global_space, i
      ldof_global_id[n_ldof]   global true-DOF number of every L-vector DOF (ParFiniteElementSpace::GetGlobalTDofNumber);
      ldof_of_true[n_true]     L-vector index of each OWNED true DOF, in the caller's true-DOF order;
      nbr_rank / nbr_ptr / nbr_ldofs   for every rank sharing DOFs with this one: the shared L-vector DOFs (any order, the
-                              library sorts both sides by global id).
+                              library sorts both sides by global id);
+     bdr_attributes           the GLOBAL boundary attributes (ParMesh::bdr_attributes): a rank need not own a face of each.
    The subdomain is numbered owned DOFs first IN THE CALLER'S TRUE-DOF ORDER (a true-DOF vector is the leading part of a local
    vector: jots_ctx_expand_true), ghosts behind them; jots_partition_copy returns the global ids in that order.  Boundary DOF
    sets (ess_tdof_list, Dirichlet projection) are completed across ranks by a marker exchange in jots_ctx_set_bcs, as
@@ -195,7 +196,7 @@ jots_part_t jots_partition_create_from_tables(int dim, int order, int64_t n_ldof
                                               int64_t n_bdr, const int32_t* bdr_gather, const double* bdr_corners, const int32_t* bdr_attr,
                                               const int64_t* ldof_global_id, int64_t n_true, const int32_t* ldof_of_true,
                                               int n_nbr, const int32_t* nbr_rank, const int64_t* nbr_ptr, const int32_t* nbr_ldofs,
-                                              int rank, int nranks);
+                                              int n_bdr_attributes, const int32_t* bdr_attributes, int rank, int nranks);
 void jots_partition_destroy(jots_part_t p);
 int jots_partition_info(jots_part_t p, int64_t* n_local, int64_t* n_owned, int64_t* n_global, int64_t* n_elem,
                         int* n_neighbors, int64_t* n_shared);
@@ -211,6 +212,17 @@ jots_ctx_t jots_ctx_create_part(jots_part_t p, int device, jots_comm_t comm);
    jots_ctx_size entries: the ghost entries are fetched from their owners (P of ParFiniteElementSpace).  Collective.
    tvec and lvec may be the same buffer (of full local length). */
 int jots_ctx_expand_true(jots_ctx_t c, const double* tvec, double* lvec, int loc);
+
+/* ---- restart files: the VisItDataCollection of OutputManager::WriteRestartOutput (src/output_manager.cpp:15-21,89-95) and
+   the load path of JOTSDriver (src/jots_driver.cpp:214-257).  <prefix>_<cycle:06d>.mfem_root (JSON), <prefix>_<cycle:06d>/
+   mesh.000000 (MFEM mesh v1.0) and Temperature.000000 (H1 GridFunction, precision 16, values in MFEM's DOF numbering:
+   vertices, edges, faces, interiors -- restated from MFEM 4.7, see restart.cpp).  Single-domain form: on several GPUs rank 0
+   writes the whole field.  The driver shim honours Use_Restart / Restart_Prefix / Restart_Cycle / Restart_Freq.
+   jots_mfem_dof_numbering: out[node of the space] = MFEM DOF number; jots_restart_read returns the mesh (caller destroys) and
+   the values in MFEM numbering (call once with mfem_values == NULL for the count). */
+int jots_mfem_dof_numbering(jots_mesh_t m, jots_space_t s, int64_t* out);
+int jots_restart_write(const char* prefix, int cycle, double time, jots_mesh_t m, jots_space_t s, const double* u_nodes);
+jots_mesh_t jots_restart_read(const char* prefix, int cycle, int* order, int* cycle_out, double* time, int64_t* n_values, double* mfem_values);
 
 /* Config (src/config_file.cpp:7-172) parsed on the host, as "key=value" lines (scalars, then "mat:<name>=a|b|..." and
    "bc:<attribute>=a|b|..."): lets the key set, defaults and parsing quirks be compared with the reference's without a

@@ -10,6 +10,7 @@
 #include "driver.hpp"
 #include "halo.hpp"
 #include "launch.hpp"
+#include "restart.hpp"
 
 using namespace jots;
 
@@ -256,6 +257,32 @@ int jots_gather_from_native(int dim, int order, int64_t n_elem, const int32_t* n
         }
     return 0;
     JOTS_CATCH_INT
+}
+
+// ---- restart files (host only) ----------------------------------------------------------------------
+int jots_mfem_dof_numbering(jots_mesh_t m, jots_space_t s, int64_t* out) {
+    JOTS_TRY
+    std::vector<int64_t> num;
+    mfem_dof_numbering(m->m, s->s.p, s->s.gather, s->s.ndof, num);
+    std::memcpy(out, num.data(), num.size() * sizeof(int64_t));
+    return 0;
+    JOTS_CATCH_INT
+}
+int jots_restart_write(const char* prefix, int cycle, double time, jots_mesh_t m, jots_space_t s, const double* u_nodes) {
+    JOTS_TRY write_restart(prefix, cycle, time, m->m, s->s, u_nodes); return 0; JOTS_CATCH_INT
+}
+jots_mesh_t jots_restart_read(const char* prefix, int cycle, int* order, int* cycle_out, double* time, int64_t* n_values, double* mfem_values) {
+    JOTS_TRY
+    RestartData d = read_restart(prefix, cycle);
+    if (order) *order = d.order;
+    if (cycle_out) *cycle_out = d.cycle;
+    if (time) *time = d.time;
+    if (n_values) *n_values = (int64_t)d.mfem_values.size();
+    if (mfem_values) std::memcpy(mfem_values, d.mfem_values.data(), d.mfem_values.size() * sizeof(double));
+    auto* h = new jots_mesh_s;
+    h->m = std::move(d.mesh);
+    return h;
+    JOTS_CATCH_PTR
 }
 
 // ---- config (host only) -----------------------------------------------------------------------
@@ -574,12 +601,12 @@ jots_part_t jots_partition_create_from_tables(int dim, int order, int64_t n_ldof
                                               int64_t n_bdr, const int32_t* bdr_gather, const double* bdr_corners, const int32_t* bdr_attr,
                                               const int64_t* ldof_global_id, int64_t n_true, const int32_t* ldof_of_true,
                                               int n_nbr, const int32_t* nbr_rank, const int64_t* nbr_ptr, const int32_t* nbr_ldofs,
-                                              int rank, int nranks) {
+                                              int n_bdr_attributes, const int32_t* bdr_attributes, int rank, int nranks) {
     JOTS_TRY
     if (!gather || !elem_corners || !ldof_global_id || !ldof_of_true) throw std::runtime_error("jots_partition_create_from_tables: null table");
     auto* h = new jots_part_s;
     h->p = make_partition_from_tables(dim, order, n_ldof, n_elem, gather, elem_corners, n_bdr, bdr_gather, bdr_corners, bdr_attr,
-                                      ldof_global_id, n_true, ldof_of_true, n_nbr, nbr_rank, nbr_ptr, nbr_ldofs, rank, nranks);
+                                      ldof_global_id, n_true, ldof_of_true, n_nbr, nbr_rank, nbr_ptr, nbr_ldofs, n_bdr_attributes, bdr_attributes, rank, nranks);
     return h;
     JOTS_CATCH_PTR
 }

@@ -5,7 +5,10 @@
 #include <fstream>
 #include <sstream>
 
+#include <cstdio>
+
 #include "halo.hpp"
+#include "restart.hpp"
 
 namespace jots {
 
@@ -84,6 +87,8 @@ Config::Config(const std::string& p) : path(p) {
     serial_refine = get_int(ini, FE, "Serial_Refine", 0);
     parallel_refine = get_int(ini, FE, "Parallel_Refine", 0);
     initial_temp = get_dbl(ini, FE, "Initial_Temperature", 100.0);
+    restart_prefix = get_str(ini, FE, "Restart_Prefix", "restart");
+    restart_cycle = get_int(ini, FE, "Restart_Cycle", 0);
     if (!ini.count("MaterialProperties")) throw std::runtime_error("config file has no [MaterialProperties] section");
     for (auto& kv : ini["MaterialProperties"]) mat_props[kv.first] = split_list(kv.second);
     with_precice = ini.count("preCICE") > 0;
@@ -105,6 +110,8 @@ Config::Config(const std::string& p) : path(p) {
     abs_tol = get_dbl(ini, LS, "Absolute_Tolerance", 1e-16);
     rel_tol = get_dbl(ini, LS, "Relative_Tolerance", 1e-10);
     max_iter = get_int(ini, LS, "Max_Iterations", 100);
+    restart_freq = get_int(ini, "Output", "Restart_Freq", 10);
+    vis_freq = get_int(ini, "Output", "Visualization_Freq", 10);
     ls_print_level = split_list(get_str(ini, LS, "Print_Level", "Errors, Warnings"));
     using_newton = ini.count("NewtonSolverSettings") > 0;
     if (using_newton) {
@@ -172,15 +179,28 @@ static int map_label(const std::string& s, const std::vector<std::pair<std::stri
 }
 
 JOTSDriver::JOTSDriver(const Config& cfg_, int device, const Mesh* mesh_in, Comm* comm) : cfg(cfg_) {
-    if (cfg.with_precice || cfg.use_restart)
-        throw std::runtime_error("preCICE / restart configurations are handled by the reference's own driver (out of scope)");
+    if (cfg.with_precice)
+        throw std::runtime_error("preCICE configurations are handled by the reference's own driver (out of scope)");
     Mesh mesh;
-    if (mesh_in) mesh = *mesh_in;
+    RestartData restart;
+    int order = cfg.fe_order;
+    if (cfg.use_restart) {
+        // jots_driver.cpp:214-257: mesh, FE space and Temperature come from the VisIt data collection <prefix>_<cycle>,
+        // not from Mesh_File / FE_Order / Initial_Temperature
+        restart = read_restart(cfg.restart_prefix, cfg.restart_cycle);
+        mesh = restart.mesh;
+        order = restart.order;
+    } else if (mesh_in) mesh = *mesh_in;
     else {
         mesh = read_mfem_mesh(cfg.mesh_file);
         for (int i = 0; i < cfg.serial_refine + cfg.parallel_refine; ++i) mesh = uniform_refine(mesh);
     }
-    Space space = make_space(mesh, cfg.fe_order);
+    Space space = make_space(mesh, order);
+    if (cfg.restart_freq != 0) {
+        // WriteRestartOutput needs the mesh and the (global) space on the host: kept only when restarts are written
+        out_mesh.reset(new Mesh(mesh));
+        out_space.reset(new Space(space));
+    }
     if (comm && comm_size(comm) > 1) {
         // ParMesh(comm, mesh): one subdomain per rank (jots_driver.cpp:178)
         std::vector<int> elem_rank;
@@ -209,10 +229,17 @@ JOTSDriver::JOTSDriver(const Config& cfg_, int device, const Mesh* mesh_in, Comm
     if (cfg.using_time_integration) { it_num = 0; max_timesteps = cfg.max_timesteps; dt = cfg.dt; }
     else { it_num = -2; max_timesteps = -1; dt = 0.0; }
     time = 0.0;
+    if (cfg.use_restart) { it_num = restart.cycle; time = restart.time; }     // jots_driver.cpp:246-247
     for (auto& b : bcs) b.update(time);
     ctx->set_bcs(bcs);
     u.alloc(ctx->n);
-    v_fill(ctx->stream, ctx->n, cfg.initial_temp, u.p);
+    if (cfg.use_restart) {
+        std::vector<double> nodes, local((size_t)ctx->n);
+        restart_values_to_nodes(restart, space, nodes);
+        for (int64_t i = 0; i < ctx->n; ++i) local[i] = nodes[part ? part->global_id[i] : i];
+        JOTS_CUDA(cudaMemcpyAsync(u.p, local.data(), (size_t)ctx->n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        ctx->sync();
+    } else v_fill(ctx->stream, ctx->n, cfg.initial_temp, u.p);
     UpdateMatProps(false);
     SolverSpec ls;
     ls.solver = map_label(cfg.solver, {{"CG", SOLVER_CG}, {"GMRES", SOLVER_GMRES}, {"FGMRES", SOLVER_FGMRES}}, "solver");
@@ -281,6 +308,8 @@ void JOTSDriver::Step() {
     if (cfg.using_time_integration && cfg.time_print_freq > 0 && it_num % cfg.time_print_freq == 0 && ctx->rank() == 0 && !quiet())
         std::printf("Step #%10i || Time: %1.6e out of %-1.6e || dt: %1.6e \n", it_num, time, dt * max_timesteps, dt);
     if (check_blowup && ctx->max_global(u.p) > 1e10) throw std::runtime_error("JOTS has blown up");
+    // restart output at the input frequency (jots_driver.cpp:774-797; ParaView output stays with the reference's OutputManager)
+    if (cfg.using_time_integration && cfg.restart_freq != 0 && it_num % cfg.restart_freq == 0) WriteRestartOutput();
 }
 
 int JOTSDriver::Run(int max_steps) {
@@ -290,8 +319,30 @@ int JOTSDriver::Run(int max_steps) {
         ++done;
         if (max_steps >= 0 && done >= max_steps) break;
     }
+    // steady run: one restart file at the end when Restart_Freq != 0 (jots_driver.cpp:750-772)
+    if (!cfg.using_time_integration && cfg.restart_freq != 0 && done > 0) WriteRestartOutput();
     ctx->sync();
     return done;
+}
+
+void JOTSDriver::WriteRestartOutput() {
+    if (!out_mesh) throw std::runtime_error("restart output was not set up (Restart_Freq was 0 when the driver was built)");
+    std::vector<double> nodes;
+    if (part) {
+        // rank 0 collects the owned values of every rank (single-domain restart file)
+        std::vector<int64_t> gid;
+        std::vector<double> val;
+        halo_gather_owned(*ctx, u.p, gid, val);
+        if (ctx->rank() != 0) return;
+        nodes.assign((size_t)out_space->ndof, 0.0);
+        for (size_t i = 0; i < gid.size(); ++i) nodes[(size_t)gid[i]] = val[i];
+    } else {
+        nodes.resize((size_t)ctx->n);
+        JOTS_CUDA(cudaMemcpyAsync(nodes.data(), u.p, (size_t)ctx->n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        ctx->sync();
+    }
+    if (!quiet()) std::printf("Saving Restart File...\n");
+    write_restart(cfg.restart_prefix, it_num, time, *out_mesh, *out_space, nodes.data());
 }
 
 }  // namespace jots

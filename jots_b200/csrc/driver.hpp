@@ -12,6 +12,8 @@
 #include "partition.hpp"
 
 namespace jots {
+struct Mesh;
+struct Space;
 
 struct Config {
     explicit Config(const std::string& path);
@@ -23,6 +25,9 @@ struct Config {
     // Print_Level lists (config_file.cpp:140-141,153,161-162) and TimeIntegration.Print_Freq (:128)
     std::vector<std::string> ls_print_level{"Errors", "Warnings"}, newton_print_level{"Errors", "Warnings", "Iterations"};
     int time_print_freq = 1;
+    // restart files (config_file.cpp:45-46,166-170): VisIt data collection <Restart_Prefix>_<cycle>
+    std::string restart_prefix = "restart";
+    int restart_cycle = 0, restart_freq = 10, vis_freq = 10;
     std::map<std::string, std::vector<std::string>> mat_props;
     std::map<int, std::vector<std::string>> bcs;
 };
@@ -42,6 +47,9 @@ public:
     void Iteration();
     void Step();               // one pass of the Run() loop body
     int Run(int max_steps);    // max_steps < 0: run to max_timesteps; returns the number of steps done
+    void WriteRestartOutput(); // OutputManager::WriteRestartOutput (output_manager.cpp:89-95), restart.cpp
+    std::unique_ptr<Mesh> out_mesh;      // host copies for restart output (only when Restart_Freq != 0)
+    std::unique_ptr<Space> out_space;
     Config cfg;
     std::unique_ptr<Ctx> ctx;
     std::unique_ptr<JOTSIterator> it;

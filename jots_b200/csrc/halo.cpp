@@ -140,6 +140,49 @@ void halo_allreduce_max(Ctx& c, double* d_vals, int nv) {
     if (!h || h->comm->nranks == 1) return;
     nccl_check(ncclAllReduce(d_vals, d_vals, nv, ncclDouble, ncclMax, h->comm->comm, c.stream), "ncclAllReduce(max)");
 }
+void halo_gather_owned(Ctx& c, const double* v, std::vector<int64_t>& gid, std::vector<double>& val) {
+    Halo* h = c.halo;
+    gid.clear(); val.clear();
+    if (!h) return;
+    const int nr = h->comm->nranks, me = h->comm->rank;
+    // owned counts of every rank
+    DArr<long long> d_cnt;
+    d_cnt.alloc(nr);
+    const long long mine = c.n_owned;
+    JOTS_CUDA(cudaMemcpyAsync(d_cnt.p + me, &mine, sizeof(long long), cudaMemcpyHostToDevice, c.stream));
+    nccl_check(ncclAllGather(d_cnt.p + me, d_cnt.p, 1, ncclInt64, h->comm->comm, c.stream), "ncclAllGather");
+    std::vector<long long> cnt(nr);
+    JOTS_CUDA(cudaMemcpyAsync(cnt.data(), d_cnt.p, nr * sizeof(long long), cudaMemcpyDeviceToHost, c.stream));
+    JOTS_CUDA(cudaStreamSynchronize(c.stream));
+    if (me == 0) {
+        long long total = 0;
+        for (long long k : cnt) total += k;
+        DArr<long long> d_gid;
+        DArr<double> d_val;
+        d_gid.alloc(total); d_val.alloc(total);
+        JOTS_CUDA(cudaMemcpyAsync(d_gid.p, h->d_gid.p, (size_t)cnt[0] * sizeof(long long), cudaMemcpyDeviceToDevice, c.stream));
+        JOTS_CUDA(cudaMemcpyAsync(d_val.p, v, (size_t)cnt[0] * sizeof(double), cudaMemcpyDeviceToDevice, c.stream));
+        nccl_check(ncclGroupStart(), "ncclGroupStart");
+        long long off = cnt[0];
+        for (int r = 1; r < nr; ++r) {
+            nccl_check(ncclRecv(d_gid.p + off, cnt[r], ncclInt64, r, h->comm->comm, c.stream), "ncclRecv");
+            nccl_check(ncclRecv(d_val.p + off, cnt[r], ncclDouble, r, h->comm->comm, c.stream), "ncclRecv");
+            off += cnt[r];
+        }
+        nccl_check(ncclGroupEnd(), "ncclGroupEnd");
+        gid.resize((size_t)total); val.resize((size_t)total);
+        static_assert(sizeof(long long) == sizeof(int64_t), "64-bit ids");
+        JOTS_CUDA(cudaMemcpyAsync(gid.data(), d_gid.p, (size_t)total * sizeof(long long), cudaMemcpyDeviceToHost, c.stream));
+        JOTS_CUDA(cudaMemcpyAsync(val.data(), d_val.p, (size_t)total * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+        JOTS_CUDA(cudaStreamSynchronize(c.stream));
+    } else {
+        nccl_check(ncclGroupStart(), "ncclGroupStart");
+        nccl_check(ncclSend(h->d_gid.p, mine, ncclInt64, 0, h->comm->comm, c.stream), "ncclSend");
+        nccl_check(ncclSend(v, mine, ncclDouble, 0, h->comm->comm, c.stream), "ncclSend");
+        nccl_check(ncclGroupEnd(), "ncclGroupEnd");
+        JOTS_CUDA(cudaStreamSynchronize(c.stream));
+    }
+}
 int halo_rank(const Ctx& c) { return c.halo ? c.halo->comm->rank : 0; }
 
 const int64_t* halo_global_index(Ctx& c) { return c.halo ? c.halo->d_gid.p : nullptr; }

@@ -3,6 +3,7 @@
 // matvec.  Single-GPU contexts have halo == nullptr.
 #pragma once
 #include <cstdint>
+#include <vector>
 
 namespace jots {
 class Ctx;
@@ -25,5 +26,7 @@ int64_t halo_interface_elems(const Ctx& c);
 void halo_allreduce(Ctx& c, double* d_vals, int nv);
 void halo_allreduce_max(Ctx& c, double* d_vals, int nv);
 int halo_rank(const Ctx& c);
+// collective: rank 0 receives (global id, value) of the owned entries of every rank, in rank order (restart output)
+void halo_gather_owned(Ctx& c, const double* v, std::vector<int64_t>& gid, std::vector<double>& val);
 const int64_t* halo_global_index(Ctx& c);  // device array: local DOF -> global DOF
 }  // namespace jots

@@ -185,7 +185,8 @@ Partition make_partition(const Space& G, const std::vector<int>& elem_rank, int 
 Partition make_partition_from_tables(int dim, int p, int64_t n_ldof, int64_t n_elem, const int* gather, const double* elem_corner,
                                      int64_t n_bdr, const int* bdr_gather, const double* bdr_corner, const int* bdr_attr,
                                      const int64_t* ldof_global_id, int64_t n_true, const int* ldof_of_true,
-                                     int n_nbr, const int* nbr_rank, const int64_t* nbr_ptr, const int* nbr_ldofs, int rank, int nranks) {
+                                     int n_nbr, const int* nbr_rank, const int64_t* nbr_ptr, const int* nbr_ldofs,
+                                     int n_attributes, const int* attributes, int rank, int nranks) {
     if (nranks > 64) throw std::runtime_error("at most 64 subdomains are supported");
     if (p < 1 || p > 4 || (dim != 2 && dim != 3)) throw std::runtime_error("partition tables: dim must be 2 or 3, order 1..4");
     Partition P;
@@ -225,7 +226,9 @@ Partition make_partition_from_tables(int dim, int p, int64_t n_ldof, int64_t n_e
     L.bdr_attr.assign(bdr_attr, bdr_attr + n_bdr);
     L.bdr_elem.assign((size_t)n_bdr, -1);
     L.bdr_face.assign((size_t)n_bdr, -1);
-    L.attributes = L.bdr_attr;
+    // the GLOBAL attribute list (ParMesh::bdr_attributes): a rank need not own a face of every attribute
+    if (n_attributes > 0 && attributes) L.attributes.assign(attributes, attributes + n_attributes);
+    else L.attributes = L.bdr_attr;
     std::sort(L.attributes.begin(), L.attributes.end());
     L.attributes.erase(std::unique(L.attributes.begin(), L.attributes.end()), L.attributes.end());
     // a shared DOF may lie on a boundary face of a neighbour's element only: the boundary DOF sets are completed by a

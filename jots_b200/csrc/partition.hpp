@@ -39,6 +39,7 @@ Partition make_partition(const Space& global, const std::vector<int>& elem_rank,
 Partition make_partition_from_tables(int dim, int p, int64_t n_ldof, int64_t n_elem, const int* gather, const double* elem_corner,
                                      int64_t n_bdr, const int* bdr_gather, const double* bdr_corner, const int* bdr_attr,
                                      const int64_t* ldof_global_id, int64_t n_true, const int* ldof_of_true,
-                                     int n_nbr, const int* nbr_rank, const int64_t* nbr_ptr, const int* nbr_ldofs, int rank, int nranks);
+                                     int n_nbr, const int* nbr_rank, const int64_t* nbr_ptr, const int* nbr_ldofs,
+                                     int n_attributes, const int* attributes, int rank, int nranks);
 
 }  // namespace jots

@@ -69,6 +69,9 @@ def load_library():
         "jots_patch_shape": (C.c_int, [C.c_int, _P, _P, _P]),
         "jots_h1_dof_map": (C.c_int, [C.c_int, C.c_int, _P]),
         "jots_gather_from_native": (C.c_int, [C.c_int, C.c_int, C.c_int64, _P, _P]),
+        "jots_mfem_dof_numbering": (C.c_int, [_P, _P, _P]),
+        "jots_restart_write": (C.c_int, [C.c_char_p, C.c_int, C.c_double, _P, _P, _P]),
+        "jots_restart_read": (_P, [C.c_char_p, C.c_int, _P, _P, _P, _P, _P]),
         "jots_config_dump": (C.c_int64, [C.c_char_p, _P, C.c_int64]),
         "jots_ctx_create": (_P, [_P, C.c_int]),
         "jots_ctx_destroy": (None, [_P]),
@@ -84,7 +87,7 @@ def load_library():
         "jots_ctx_material_field": (C.c_int, [_P, C.c_int, C.c_int, _P, C.c_int]),
         "jots_ctx_stats": (C.c_int, [_P, _P, _P]),
         "jots_ctx_expand_true": (C.c_int, [_P, _P, _P, C.c_int]),
-        "jots_partition_create_from_tables": (_P, [C.c_int, C.c_int, C.c_int64, C.c_int64, _P, _P, C.c_int64, _P, _P, _P, _P, C.c_int64, _P, C.c_int, _P, _P, _P, C.c_int, C.c_int]),
+        "jots_partition_create_from_tables": (_P, [C.c_int, C.c_int, C.c_int64, C.c_int64, _P, _P, C.c_int64, _P, _P, _P, _P, C.c_int64, _P, C.c_int, _P, _P, _P, C.c_int, _P, C.c_int, C.c_int]),
         "jots_ctx_patch_info": (C.c_int, [_P, _P, _P, _P]),
         "jots_ctx_last_kernel": (C.c_char_p, [_P]),
         "jots_ctx_reset_stats": (C.c_int, [_P]),
@@ -206,6 +209,30 @@ def gather_from_native(dim, order, native):
     out = np.empty_like(nat)
     _chk(load_library().jots_gather_from_native(dim, order, nat.shape[0], _ptr(nat), _ptr(out)))
     return out
+
+
+def mfem_dof_numbering(mesh, space):
+    """out[node of `space`] = MFEM's DOF number of that node in the H1 space on `mesh` (restart files)."""
+    out = np.empty(space.n_dof, dtype=np.int64)
+    _chk(load_library().jots_mfem_dof_numbering(mesh._h, space._h, _ptr(out)))
+    return out
+
+
+def restart_write(prefix, cycle, time, mesh, space, u_nodes):
+    u = np.ascontiguousarray(u_nodes, dtype=np.float64)
+    _chk(load_library().jots_restart_write(str(prefix).encode(), int(cycle), float(time), mesh._h, space._h, _ptr(u)))
+
+
+def restart_read(prefix, cycle):
+    """(mesh, order, cycle, time, values in MFEM numbering) of the data collection <prefix>_<cycle>."""
+    lib = load_library()
+    order, cyc, n = C.c_int(), C.c_int(), C.c_int64()
+    t = C.c_double()
+    h = _handle(lib.jots_restart_read(str(prefix).encode(), int(cycle), C.byref(order), C.byref(cyc), C.byref(t), C.byref(n), None))
+    lib.jots_mesh_destroy(h)
+    vals = np.empty(n.value)
+    h = _handle(lib.jots_restart_read(str(prefix).encode(), int(cycle), None, None, None, None, _ptr(vals)))
+    return Mesh(h), order.value, cyc.value, t.value, vals
 
 
 def config_dump(ini_path):
@@ -539,7 +566,7 @@ class Partition:
 
     @classmethod
     def from_tables(cls, dim, order, gather, elem_corners, bdr_gather, bdr_corners, bdr_attr, ldof_global_id, ldof_of_true,
-                    neighbors, rank, nranks):
+                    neighbors, rank, nranks, attributes=None):
         """The caller's decomposition (ParMesh + ParFiniteElementSpace tables of one rank): neighbors = [(rank, L-vector
         DOFs shared with it), ...]."""
         g = np.ascontiguousarray(gather, dtype=np.int32)
@@ -556,7 +583,9 @@ class Partition:
         nd = np.ascontiguousarray(np.concatenate([np.asarray(d, dtype=np.int32) for _, d in neighbors]) if neighbors else np.zeros(0, np.int32))
         h = _handle(load_library().jots_partition_create_from_tables(dim, order, gid.size, g.shape[0], _ptr(g), _ptr(ec), ba.size, _ptr(bg),
                                                                      _ptr(bc), _ptr(ba), _ptr(gid), lt.size, _ptr(lt), len(neighbors), _ptr(nr),
-                                                                     _ptr(ptr), _ptr(nd), rank, nranks))
+                                                                     _ptr(ptr), _ptr(nd), 0 if attributes is None else len(attributes),
+                                                                     _ptr(None if attributes is None else np.ascontiguousarray(attributes, dtype=np.int32)),
+                                                                     rank, nranks))
         return cls(None, None, nranks, rank, handle=h)
 
     def space(self):

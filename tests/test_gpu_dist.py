@@ -13,7 +13,32 @@ def _ngpu():
     return jots_b200.load_library().jots_device_count()
 
 
-def _worker(rank, world, ini, shape, uid, q):
+def _guard(fn):
+    """A worker that dies must not leave the parent waiting for the queue time-out (GPU minutes): report the error."""
+    import functools
+
+    @functools.wraps(fn)
+    def run(*args):
+        q = args[-1]
+        try:
+            fn(*args)
+        except BaseException as e:      # noqa: BLE001
+            import traceback
+            q.put(("error", traceback.format_exc() + repr(e)))
+    return run
+
+
+def _collect(q, world):
+    res = []
+    for _ in range(world):
+        r = q.get(timeout=300)
+        if r[0] == "error":
+            pytest.fail("worker failed:\n" + r[1])
+        res.append(r)
+    return res
+
+
+def _worker_impl(rank, world, ini, shape, uid, q):
     import jots_b200 as J
     comm = J.Comm(uid, rank, world, rank)
     mesh = J.Mesh.brick(*shape) if shape is not None else None   # None: every rank reads Mesh_File
@@ -22,6 +47,10 @@ def _worker(rank, world, ini, shape, uid, q):
     g, n_owned = drv.global_ids()
     q.put((rank, steps, g, n_owned, drv.get_u(), drv.ctx.stats()))
     del drv, comm
+
+
+def _worker(*args):
+    _guard(_worker_impl)(*args)
 
 
 CASES = [
@@ -57,7 +86,7 @@ def test_partitioned_solve_matches_oracle(tmp_path, sim, props, solver, prec, p)
     procs = [ctx.Process(target=_worker, args=(r, world, ini, shape, uid, q)) for r in range(world)]
     for pr in procs:
         pr.start()
-    res = [q.get(timeout=300) for _ in range(world)]
+    res = _collect(q, world)
     for pr in procs:
         pr.join(timeout=60)
     orc = OJ.JOTSDriver(OJ.Config(ini), mesh=OM.make_brick(*shape))
@@ -98,7 +127,7 @@ def test_partitioned_solve_on_a_mesh_file_rcb(tmp_path):
     procs = [ctx.Process(target=_worker, args=(r, world, ini, None, uid, q)) for r in range(world)]
     for pr in procs:
         pr.start()
-    res = [q.get(timeout=300) for _ in range(world)]
+    res = _collect(q, world)
     for pr in procs:
         pr.join(timeout=60)
     u_ref = OJ.JOTSDriver(OJ.Config(ini)).run()
@@ -109,7 +138,11 @@ def test_partitioned_solve_on_a_mesh_file_rcb(tmp_path):
     assert np.linalg.norm(u - u_ref) / np.linalg.norm(u_ref) < 1e-8
 
 
-def _worker_tables(rank, world, shape, uid, q):
+def _worker_tables(*args):
+    _guard(_worker_tables_impl)(*args)
+
+
+def _worker_tables_impl(rank, world, shape, uid, q):
     """One rank of the binding a JOTS maintainer would write: the subdomain comes from the CALLER's decomposition tables
     (scrambled L-vector numbering, true-DOF vectors), the step loop is JOTSDriver::Run's order of calls on the C ABI."""
     import jots_b200 as J
@@ -117,7 +150,7 @@ def _worker_tables(rank, world, shape, uid, q):
     comm = J.Comm(uid, rank, world, rank)
     mesh = J.Mesh.brick(*shape)
     ref = J.Partition(mesh, J.Space(mesh, 2), world, rank)
-    part = J.Partition.from_tables(rank=rank, nranks=world, **_caller_tables(ref, 7 + rank))
+    part = J.Partition.from_tables(rank=rank, nranks=world, attributes=[1, 2, 3, 4, 5, 6], **_caller_tables(ref, 7 + rank))
     ctx = J.Context.from_partition(part, rank, comm)
     ctx.set_material(0, ("Uniform", 8000))
     ctx.set_material(1, ("Polynomial", 4.5, -850))
@@ -165,7 +198,7 @@ def test_partitioned_solve_from_caller_supplied_tables(tmp_path):
     procs = [ctx.Process(target=_worker_tables, args=(r, world, shape, uid, q)) for r in range(world)]
     for pr in procs:
         pr.start()
-    res = [q.get(timeout=300) for _ in range(world)]
+    res = _collect(q, world)
     for pr in procs:
         pr.join(timeout=60)
     orc = OJ.JOTSDriver(OJ.Config(ini), mesh=OM.make_brick(*shape))

@@ -116,3 +116,46 @@ def test_zero_time_steps(J, tmp_path):
     dev, orc = build(J, tmp_path, "Linearized_Unsteady", 3, 1, "const", steps=0)
     assert dev.run() == 0
     assert np.all(dev.get_u() == 300.0)
+
+
+@pytest.mark.parametrize("dim,order", [(2, 1), (3, 2)])
+def test_restart_files_round_trip_and_continuation(J, tmp_path, dim, order):
+    """The reference's Restart_Files regression (tests/linearized_unsteady_heat/Restart_Files.cpp:9-80: 2-D bar, Q1,
+    Sinusoidal_Isothermal, restart written at the last cycle, re-loaded field within 1e-12) plus a 3-D Q2 case, and the
+    stronger statement that N steps + restart + N steps equal 2N uninterrupted steps."""
+    from cases import ini_text, write_quad_mesh, write_brick_mesh
+    from test_gpu_parity import rel
+    mesh = str(tmp_path / "m.mesh")
+    if dim == 2:
+        write_quad_mesh(mesh, 20, 3, 1.0, 0.1, attrs=(1, 3, 1, 2))
+        props = [("Density_rho", "Uniform, 0.1"), ("Specific_Heat_C", "Uniform, 1000"), ("Thermal_Conductivity_k", "Uniform, 100")]
+        bcs = ["HeatFlux, 0", "Isothermal, 300", "Sinusoidal_Isothermal, 5, 6.283185307, 0, 300"]
+        dt = "0.001"
+    else:
+        write_brick_mesh(mesh, 5, 3, 2, 0.01, 0.02, 0.015, grade=0.3)
+        props = [("Density_rho", "Uniform, 8000"), ("Specific_Heat_C", "Polynomial, 4.5, -850"), ("Thermal_Conductivity_k", "Polynomial, 0.09, -17")]
+        bcs = ["HeatFlux, 7.5e5", "Isothermal, 350", "HeatFlux, 0", "Sinusoidal_Isothermal, 50, 40, 0.3, 400", "HeatFlux, 0", "HeatFlux, 0"]
+        dt = "1e-2"
+    n = 6
+    prefix = str(tmp_path / "restart")
+
+    def write(name, steps, restart_from=None, freq=0):
+        txt = ini_text("Linearized_Unsteady", mesh, 300, props, bcs, steps=steps, dt=dt, order=order)
+        txt = txt.replace("Restart_Freq=0", "Restart_Freq=%d" % freq)
+        txt = txt.replace("Use_Restart=No", "Use_Restart=%s\nRestart_Prefix=%s\nRestart_Cycle=%d" % ("Yes" if restart_from is not None else "No", prefix, restart_from or 0))
+        path = str(tmp_path / name)
+        open(path, "w").write(txt)
+        return path
+
+    d0 = J.Driver(write("first.ini", n, freq=n))
+    assert d0.run() == n
+    u_n = d0.get_u()
+    dr = J.Driver(write("restarted.ini", 2 * n, restart_from=n))
+    assert abs(dr.time() - d0.time()) < 1e-15 and dr.n == d0.n
+    assert np.abs(dr.get_u() - u_n).max() <= 1e-12 * np.abs(u_n).max()       # Restart_Files.cpp: EPSILON = 1e-12
+    assert dr.run() == n                                                       # cycles n+1 .. 2n
+    d2 = J.Driver(write("straight.ini", 2 * n))
+    assert d2.run() == 2 * n
+    assert rel(dr.get_u(), d2.get_u()) < 1e-10
+    with pytest.raises(J.JotsError, match="restart"):
+        J.Driver(write("missing.ini", n, restart_from=999))

@@ -477,3 +477,47 @@ def test_h1_native_dof_map(dim, p):
     native[:, m] = g                                                           # native[e][map[l]] = lexicographic[e][l]
     assert (J.gather_from_native(dim, p, native) == g).all()
     assert (J.gather_from_native(dim, p, -1 - native) == g).all()              # MFEM's sign encoding is undone
+
+
+@pytest.mark.parametrize("dim,p", [(3, 1), (3, 2), (3, 3), (2, 2), (2, 4)])
+def test_restart_files_round_trip_and_mfem_numbering(tmp_path, dim, p):
+    """Restart data collection (output_manager.cpp:15-21,89-95; jots_driver.cpp:214-257): root JSON + mesh + H1 grid function
+    in MFEM's DOF numbering.  The numbering is a bijection with the vertex DOFs first (= vertex ids), then p-1 DOFs per edge
+    running from the lower to the higher vertex id, then face and element interiors; write -> read gives back mesh, order,
+    cycle, time and the field to the 16 printed digits (the reference's restart test allows 1e-12)."""
+    import jots_b200 as J
+    mesh = J.Mesh.brick(3, 2, 2, 0.3, 0.2, 0.1) if dim == 3 else J.Mesh.rect(4, 3, 1.0, 0.5)
+    s = J.Space(mesh, p)
+    num = J.mfem_dof_numbering(mesh, s)
+    assert sorted(num) == list(range(s.n_dof))
+    verts, elems, _, _ = mesh.arrays()
+    nv = verts.shape[0]
+    X = s.node_coordinates()
+    # vertex DOFs: MFEM number = vertex id, at the vertex coordinates
+    for n in np.nonzero(num < nv)[0]:
+        assert np.allclose(X[n], verts[num[n]], atol=1e-14)
+    if p > 1:
+        # the p-1 DOFs of the first edge (element 0, local vertices 0 -> 1) lie on it, ordered from the lower vertex id
+        v0, v1 = elems[0][0], elems[0][1]
+        lo, hi = (v0, v1) if v0 < v1 else (v1, v0)
+        pos = {int(num[n]): X[n] for n in range(s.n_dof) if nv <= num[n] < nv + (p - 1)}
+        ts = [np.dot(pos[nv + j] - verts[lo], verts[hi] - verts[lo]) / np.dot(verts[hi] - verts[lo], verts[hi] - verts[lo]) for j in range(p - 1)]
+        assert all(0 < t < 1 for t in ts) and ts == sorted(ts)
+    rng = np.random.default_rng(3)
+    u = 300.0 + 50.0 * rng.standard_normal(s.n_dof)
+    prefix = str(tmp_path / "restart")
+    J.restart_write(prefix, 1000, 0.7251, mesh, s, u)
+    import json, os
+    root = json.load(open(prefix + "_001000.mfem_root"))["dsets"]["main"]
+    assert root["cycle"] == 1000 and root["domains"] == 1 and root["fields"]["Temperature"]["path"] == "restart_001000/Temperature.%06d"
+    assert open(prefix + "_001000/Temperature.000000").read().startswith("FiniteElementSpace\nFiniteElementCollection: H1_%dD_P%d\nVDim: 1\nOrdering: 0\n" % (dim, p))
+    m2, order, cyc, t, vals = J.restart_read(prefix, 1000)
+    assert (order, cyc) == (p, 1000) and abs(t - 0.7251) < 1e-15
+    v2, e2, b2, a2 = m2.arrays()
+    assert np.allclose(v2, verts, rtol=1e-15, atol=0) and (e2 == elems).all()
+    s2 = J.Space(m2, order)
+    back = vals[J.mfem_dof_numbering(m2, s2)]
+    # the re-read mesh is a FILE mesh (first-appearance node numbering): compare at the nodes' coordinates
+    X2 = s2.node_coordinates()
+    key = lambda A: np.lexsort(np.round(A / 1e-9).T[::-1])
+    assert np.abs(back[key(X2)] - u[key(X)]).max() <= 1e-13 * np.abs(u).max()
