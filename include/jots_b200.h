@@ -84,14 +84,6 @@ int jots_space_copy_bdr(jots_space_t s, int32_t* bdr_gather, int32_t* bdr_attr, 
 int jots_space_copy_nodes(jots_space_t s, double* xyz);             /* [n_dof*dim] */
 /* GetEssentialTrueDofs (src/jots_iterator.cpp:30): returns the count, fills out[] when non-NULL */
 int64_t jots_space_essential_dofs(jots_space_t s, const int32_t* attrs, int n_attrs, int32_t* out);
-/* Row-structured tiles of the TMA element kernel (apply_slab4.cuh), exposed so that the index contract can be
-   checked bit-exactly on the host: runs of at most tile_elems elements with contiguous DOF rows; one record per
-   tile = {int32 e0, nv, any_ess, pad; int32 base[D*D (+1 if odd)]; uint64 ess_bits[D*D]}.  Returns the number of
-   tiles (0: the space has no row structure, the gather-table kernel is used), -1 on error; *record_bytes = size
-   of one record; fills out[] (n_tiles*record_bytes) when non-NULL. */
-int64_t jots_space_rowtiles(jots_space_t s, const int32_t* ess, int64_t n_ess, int tile_elems, double min_fill,
-                            int* record_bytes, unsigned char* out);
-
 /* Element patches of the unique-pencil element kernel (apply_patch.cuh), exposed so that the index contract can be
    checked bit-exactly on the host: px x py x 1 lattice-adjacent hexes with aligned local axes whose nodes are listed
    once.  Record (int32): ((p)px+1)((p)py+1)(p+1) nodes in [k][J][I] order (essential DOFs as ~index, 0x80000000 where no
@@ -138,7 +130,6 @@ int jots_ctx_material_field(jots_ctx_t c, int which, int order, double* out, int
 /* counters: applies, diag assemblies, krylov iters, newton iters, residual evals, steps,
    kernel launches, dots, last linear iters, last linear converged, last newton iters, last newton converged */
 int jots_ctx_stats(jots_ctx_t c, int64_t out[12], double norms[2]);
-int64_t jots_ctx_rowtile_applies(jots_ctx_t c);   /* operator applies that ran the row-structured (TMA) element kernel */
 /* element patches of the unique-pencil kernel this context runs (0 patches: the gather-table kernels are in use):
    number of patches, fill = elements / (patches x elements per patch), operator applies that ran the patch kernel */
 int jots_ctx_patch_info(jots_ctx_t c, int64_t* n_patches, double* fill, int64_t* applies);

@@ -62,7 +62,6 @@ __global__ void __launch_bounds__(T, 4) form_apply_patch2_kernel(const FormArgs 
     constexpr int NPEN = PD::NPEN, NN = PD::NN, E = PD::E, REC = PD::REC, RS = PD::NXN;
     constexpr int DD = D * D, QC = (Q + 1) / 2, NQH = Q * QC;
     constexpr bool X_GRAD = (OP != OP_RES), Z_GRAD = (OP != OP_LIN), NEED_Z = Z_GRAD || KLIN;
-    constexpr int NWORK = T - 32;
     static_assert(T == E * 2 * Q, "one thread per (element, quadrature plane, half)");
     static_assert(Q % 2 == 0, "even quadrature rules only (no shared middle column)");
     extern __shared__ __align__(16) double smem[];

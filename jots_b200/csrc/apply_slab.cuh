@@ -224,225 +224,6 @@ __device__ __forceinline__ void flip_plane(double (&p)[D * D], bool flip) {
         }
 }
 
-template <int D, int Q, int OP, int CF, int E, int T>
-__global__ void __launch_bounds__(T) form_apply_slab2_kernel(const FormArgs a, const Slab2Tables<D, Q> t) {
-    if (a.skip && *a.skip != 0.0) return;   // enqueued ahead of a Krylov solve that has already stopped
-    typedef SlabCfg<OP, CF> C;
-    constexpr int NF = C::NF, NFA = NF > 0 ? NF : 1, NP = C::NP;
-    constexpr int QC = (Q + 1) / 2;
-    constexpr int PS = Plane2Stride<D>::value;
-    constexpr int ES = Elem2Stride<D, Q, NP>::value;
-    constexpr int ND = D * D * D, DD = D * D;
-    extern __shared__ __align__(16) double smem[];
-    const int tid = threadIdx.x;
-    const int e0 = blockIdx.x * E;
-
-    // ---------------- phase 1: gather + z contraction --------------------------------------------
-    for (int item = tid; item < E * DD; item += T) {
-        const int el = item / DD, ij = item - el * DD;
-        const int e = e0 + el;
-        if (e >= a.nelem) continue;
-        double xr[D], zr[D], fr[NFA][D];
-#pragma unroll
-        for (int k = 0; k < D; ++k) {
-            const int g = a.gather[(size_t)e * ND + ij + DD * k];
-            const int idx = g < 0 ? ~g : g;
-            xr[k] = (g < 0 && a.mask_in) ? 0.0 : a.x[idx];
-            if (C::Z_GRAD || NF > 0) {
-                zr[k] = a.z[idx];
-                if (NF > 0) {
-                    double f[NFA];
-                    nodal_fields<CF, OP>(a.mat, zr[k], f);
-#pragma unroll
-                    for (int n = 0; n < NF; ++n) fr[n][k] = f[n];
-                }
-            }
-        }
-        double* base = smem + el * ES + ij;
-#pragma unroll
-        for (int qz = 0; qz < Q; ++qz) {
-            double s = 0.0, sg = 0.0, zs = 0.0, zg = 0.0;
-#pragma unroll
-            for (int k = 0; k < D; ++k) {
-                s += t.B[qz * D + k] * xr[k];
-                if (C::X_GRAD) sg += t.G[qz * D + k] * xr[k];
-                if (C::Z_GRAD) { zs += t.B[qz * D + k] * zr[k]; zg += t.G[qz * D + k] * zr[k]; }
-            }
-            base[(C::P_XB * Q + qz) * PS] = s;
-            if (C::X_GRAD) base[(C::P_XG * Q + qz) * PS] = sg;
-            if (C::Z_GRAD) { base[(C::P_ZB * Q + qz) * PS] = zs; base[(C::P_ZG * Q + qz) * PS] = zg; }
-#pragma unroll
-            for (int n = 0; n < NF; ++n) {
-                double fs = 0.0;
-#pragma unroll
-                for (int k = 0; k < D; ++k) fs += t.B[qz * D + k] * fr[n][k];
-                base[((C::P_F0 + n) * Q + qz) * PS] = fs;
-            }
-        }
-    }
-    __syncthreads();
-
-    // ---------------- phase 2: half a quadrature plane per thread --------------------------------
-    if (tid < E * Q * 2) {
-        const int el = tid / (2 * Q), r = tid - el * 2 * Q, qz = r >> 1;
-        const bool h = r & 1;
-        int e = e0 + el;
-        if (e >= a.nelem) e = a.nelem - 1;
-        const double* gm = a.geom + (size_t)e * a.geom_stride;
-        const double gxx = gm[0] * gm[0] + gm[1] * gm[1] + gm[2] * gm[2];
-        const double gyy = gm[3] * gm[3] + gm[4] * gm[4] + gm[5] * gm[5];
-        const double gzz = gm[6] * gm[6] + gm[7] * gm[7] + gm[8] * gm[8];
-        const double wz = t.W[qz] * gm[9];
-        const double* pl = smem + el * ES + qz * PS;
-        auto getp = [&](int id, double (&out)[DD]) {
-            const double* p = pl + id * Q * PS;
-#pragma unroll
-            for (int m = 0; m < DD; ++m) out[m] = p[m];
-            flip_plane<D>(out, h);
-        };
-
-        double p9[DD], t6[D * QC], A[DD], Bp[DD];
-#pragma unroll
-        for (int i = 0; i < DD; ++i) { A[i] = 0.0; Bp[i] = 0.0; }
-        double a1[Q * QC], a2x[Q * QC];
-        double a1c = 0.0;
-        if (CF == CF_CONST) a1c = a.ck * a.a0;
-        else {
-            getp(C::P_F0, p9);
-            xpassC<D, QC>(p9, t.B, t6);
-            ypassC<D, Q, QC>(t6, t.B, a1);
-            const double sc = a.ck * a.inv_rc;
-#pragma unroll
-            for (int q = 0; q < Q * QC; ++q) a1[q] *= sc;
-            if (OP == OP_JAC) {
-                getp(C::P_F0 + 1, p9);
-                xpassC<D, QC>(p9, t.B, t6);
-                ypassC<D, Q, QC>(t6, t.B, a2x);
-            }
-        }
-        double xB6[D * QC], xG6[D * QC], vy6[D * QC];
-        getp(C::P_XB, p9);
-        xpassC<D, QC>(p9, t.B, xB6);
-        if (C::X_GRAD) xpassC<D, QC>(p9, t.G, xG6);
-        {
-            double xv[Q * QC];
-            ypassC<D, Q, QC>(xB6, t.B, xv);
-            if (OP == OP_JAC && CF != CF_CONST) {
-                const double sc = a.ck * a.inv_rc;
-#pragma unroll
-                for (int q = 0; q < Q * QC; ++q) a2x[q] *= sc * xv[q];
-            }
-            ypassTC<D, Q, QC>(xv, t.BW, vy6);
-        }
-        const double c_m = a.cm * (CF == CF_CONST || CF == CF_K ? a.m0 : 1.0) * wz;
-        double zB6[D * QC], zG6[D * QC];
-        if (C::Z_GRAD) {
-            getp(C::P_ZB, p9);
-            xpassC<D, QC>(p9, t.B, zB6);
-            xpassC<D, QC>(p9, t.G, zG6);
-        }
-        // ---- x direction (both G's carry the mirror sign: it cancels)
-        {
-            double F[Q * QC];
-            if (OP == OP_RES) ypassC<D, Q, QC>(zG6, t.B, F);
-            else ypassC<D, Q, QC>(xG6, t.B, F);
-            if (CF == CF_CONST) {
-#pragma unroll
-                for (int q = 0; q < Q * QC; ++q) F[q] *= a1c;
-            } else {
-#pragma unroll
-                for (int q = 0; q < Q * QC; ++q) F[q] *= a1[q];
-                if (OP == OP_JAC) {
-                    double zd[Q * QC];
-                    ypassC<D, Q, QC>(zG6, t.B, zd);
-#pragma unroll
-                    for (int q = 0; q < Q * QC; ++q) F[q] += a2x[q] * zd[q];
-                }
-            }
-            ypassTC<D, Q, QC>(F, t.BW, t6);
-            xpassTC_acc<D, QC>(t6, t.GWh, wz * gxx, A);
-        }
-        // ---- y direction (+ mass)
-        {
-            double F[Q * QC];
-            if (OP == OP_RES) ypassC<D, Q, QC>(zB6, t.G, F);
-            else ypassC<D, Q, QC>(xB6, t.G, F);
-            if (CF == CF_CONST) {
-#pragma unroll
-                for (int q = 0; q < Q * QC; ++q) F[q] *= a1c;
-            } else {
-#pragma unroll
-                for (int q = 0; q < Q * QC; ++q) F[q] *= a1[q];
-                if (OP == OP_JAC) {
-                    double zd[Q * QC];
-                    ypassC<D, Q, QC>(zB6, t.G, zd);
-#pragma unroll
-                    for (int q = 0; q < Q * QC; ++q) F[q] += a2x[q] * zd[q];
-                }
-            }
-            ypassTC<D, Q, QC>(F, t.GW, t6);
-            const double cy = wz * gyy;
-#pragma unroll
-            for (int i = 0; i < D * QC; ++i) t6[i] = cy * t6[i] + c_m * vy6[i];
-            xpassTC_acc<D, QC>(t6, t.BWh, 1.0, A);
-        }
-        // ---- z direction
-        {
-            double F[Q * QC];
-            getp(OP == OP_RES ? C::P_ZG : C::P_XG, p9);
-            xpassC<D, QC>(p9, t.B, t6);
-            ypassC<D, Q, QC>(t6, t.B, F);
-            if (CF == CF_CONST) {
-#pragma unroll
-                for (int q = 0; q < Q * QC; ++q) F[q] *= a1c;
-            } else {
-#pragma unroll
-                for (int q = 0; q < Q * QC; ++q) F[q] *= a1[q];
-                if (OP == OP_JAC) {
-                    double zd[Q * QC];
-                    getp(C::P_ZG, p9);
-                    xpassC<D, QC>(p9, t.B, t6);
-                    ypassC<D, Q, QC>(t6, t.B, zd);
-#pragma unroll
-                    for (int q = 0; q < Q * QC; ++q) F[q] += a2x[q] * zd[q];
-                }
-            }
-            ypassTC<D, Q, QC>(F, t.BW, t6);
-            xpassTC_acc<D, QC>(t6, t.BWh, wz * gzz, Bp);
-        }
-        flip_plane<D>(A, h);
-        flip_plane<D>(Bp, h);
-        double* outp = smem + el * ES + ((NP + (h ? 2 : 0)) * Q + qz) * PS;
-#pragma unroll
-        for (int m = 0; m < DD; ++m) { outp[m] = A[m]; outp[Q * PS + m] = Bp[m]; }
-    }
-    __syncthreads();
-
-    // ---------------- phase 3: transposed z contraction + scatter --------------------------------
-    for (int item = tid; item < E * DD; item += T) {
-        const int el = item / DD, ij = item - el * DD;
-        const int e = e0 + el;
-        if (e >= a.nelem) continue;
-        const double* base = smem + el * ES + NP * Q * PS + ij;
-        double Aq[Q], Bq[Q];
-#pragma unroll
-        for (int qz = 0; qz < Q; ++qz) {
-            Aq[qz] = base[qz * PS] + base[(2 * Q + qz) * PS];
-            Bq[qz] = base[(Q + qz) * PS] + base[(3 * Q + qz) * PS];
-        }
-#pragma unroll
-        for (int k = 0; k < D; ++k) {
-            double s = 0.0;
-#pragma unroll
-            for (int qz = 0; qz < Q; ++qz) s += t.B[qz * D + k] * Aq[qz] + t.G[qz * D + k] * Bq[qz];
-            const int g = a.gather[(size_t)e * ND + ij + DD * k];
-            if (g >= 0) atomicAdd(a.y + g, s);
-            else if (!a.mask_out) atomicAdd(a.y + (~g), s);
-                else if (a.diag_one) a.y[~g] = a.x[~g];   // every writer stores the same value
-        }
-    }
-}
-
 
 // =================================================================================================
 // Diagonal of an OP_LIN / OP_JAC form with the same three-phase structure: the diagonal of a
@@ -962,11 +743,7 @@ __device__ __forceinline__ void slab_phase2(const FormArgs& a, const Slab2Tables
     }
 }
 
-// SPLIT (tiles with more pencils than threads, Q2 E = 16: 144 pencils on 128 threads): the E*D*D - T left-over pencils of
-// phases 1 and 3 are not run as a second full pass on a few lanes (every other warp waits at the barrier for it: 20 % of
-// the warp time in the r1m profile) but cut into 2Q (phase 1: one quadrature plane of the x- or the z-planes each) and 2D
-// (phase 3: one output node and half of the quadrature planes each) pieces that fill the block once more with short work.
-template <int D, int Q, int OP, int CF, int E, int T, bool SPLIT = false>
+template <int D, int Q, int OP, int CF, int E, int T>
 __global__ void __launch_bounds__(T) form_apply_slab3_kernel(const FormArgs a, const Slab2Tables<D, Q> t) {
     if (a.skip && *a.skip != 0.0) return;   // enqueued ahead of a Krylov solve that has already stopped
     typedef SlabCfg<OP, CF> C;
@@ -982,13 +759,6 @@ __global__ void __launch_bounds__(T) form_apply_slab3_kernel(const FormArgs a, c
     double* stage = smem + (size_t)E * ES;                                  // [NSTG][2][E*ND]
     int* idxbuf = reinterpret_cast<int*>(stage + (size_t)NSTG * 2 * E * ND);   // [3][E*ND]
     const int tid = threadIdx.x;
-    constexpr int LEFT = E * D * D - T;                     // pencils beyond one pass of the block
-    static_assert(!SPLIT || (LEFT > 0 && LEFT * 2 * Q <= T && Q % 2 == 0), "split pass: left-over pieces must fit one pass");
-    __shared__ double s_tab[SPLIT ? 2 * Q * D : 1];         // B then G: the split pass indexes them at run time
-    if (SPLIT && tid == 0) {
-#pragma unroll
-        for (int m = 0; m < Q * D; ++m) { s_tab[m] = t.B[m]; s_tab[Q * D + m] = t.G[m]; }
-    }
     const int ntiles = (a.nelem + E - 1) / E;
     const int nmine = blockIdx.x < ntiles ? (ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
     auto tile_of = [&](int i) { return (int)blockIdx.x + i * (int)gridDim.x; };
@@ -1050,7 +820,7 @@ __global__ void __launch_bounds__(T) form_apply_slab3_kernel(const FormArgs a, c
 
         // ---------------- phase 1: z contraction from the staged values ---------------------------
 #pragma unroll 1
-        for (int item = tid; item < (SPLIT && nv * DD > T ? T : nv * DD); item += T) {
+        for (int item = tid; item < nv * DD; item += T) {
             const int el = item / DD, ij = item - el * DD;
             double xr[D], zr[D], fr[NFA][D];
 #pragma unroll
@@ -1091,48 +861,6 @@ __global__ void __launch_bounds__(T) form_apply_slab3_kernel(const FormArgs a, c
                 }
             }
         }
-        if constexpr (SPLIT) {
-            // left-over pencils: piece = (pencil, quadrature plane qz, x-planes | z-planes and property fields)
-            const int item = T + tid / (2 * Q), part = tid - (tid / (2 * Q)) * (2 * Q), qz = part >> 1;
-            if (item < nv * DD) {
-                const int el = item / DD, ij = item - el * DD;
-                double* base = planes + el * ES + ij;
-                const double* tb = s_tab + qz * D;
-                const double* tg = s_tab + Q * D + qz * D;
-                if ((part & 1) == 0) {
-                    double sv = 0.0, sg = 0.0;
-#pragma unroll
-                    for (int k = 0; k < D; ++k) {
-                        const int m = el * ND + ij + DD * k;
-                        const double xv = (ix[m] < 0 && a.mask_in) ? 0.0 : sx[m];
-                        sv += tb[k] * xv;
-                        sg += tg[k] * xv;
-                    }
-                    base[C::P_XB * PSET + qz * PS] = sv;
-                    if (C::X_GRAD) base[C::P_XG * PSET + qz * PS] = sg;
-                } else if (NEED_Z) {
-                    double zs = 0.0, zg = 0.0, fs[NFA];
-#pragma unroll
-                    for (int n = 0; n < NFA; ++n) fs[n] = 0.0;
-#pragma unroll
-                    for (int k = 0; k < D; ++k) {
-                        const double zv = sz[el * ND + ij + DD * k];
-                        zs += tb[k] * zv;
-                        zg += tg[k] * zv;
-                        if (NF > 0) {
-                            double f[NFA];
-                            nodal_fields<CF, OP>(a.mat, zv, f);
-#pragma unroll
-                            for (int n = 0; n < NF; ++n)
-                                fs[n] += tb[k] * ((CF == CF_K || CF == CF_KL) ? (a.ck * a.inv_rc) * f[n] : (CF == CF_LINFIELDS && n == 2) ? a.ck * f[n] : f[n]);
-                        }
-                    }
-                    if (C::Z_GRAD) { base[C::P_ZB * PSET + qz * PS] = zs; base[C::P_ZG * PSET + qz * PS] = zg; }
-#pragma unroll
-                    for (int n = 0; n < NF; ++n) base[(C::P_F0 + n) * PSET + qz * PS] = fs[n];
-                }
-            }
-        }
         __syncthreads();
         if (NSTG == 1) issue_vals(it + 1);   // the staging buffer is free again; the copies land during phases 2-3
 
@@ -1158,7 +886,7 @@ __global__ void __launch_bounds__(T) form_apply_slab3_kernel(const FormArgs a, c
 
         // ---------------- phase 3: transposed z contraction + scatter ----------------------------
 #pragma unroll 1
-        for (int item = tid; item < (SPLIT && nv * DD > T ? T : nv * DD); item += T) {
+        for (int item = tid; item < nv * DD; item += T) {
             const int el = item / DD, ij = item - el * DD;
             const double* base = planes + el * ES + ij;
             double Aq[Q], Bq[Q];
@@ -1172,26 +900,6 @@ __global__ void __launch_bounds__(T) form_apply_slab3_kernel(const FormArgs a, c
                 double s = 0.0;
 #pragma unroll
                 for (int qz = 0; qz < Q; ++qz) s += t.B[qz * D + k] * Aq[qz] + t.G[qz * D + k] * Bq[qz];
-                const int g = ix[el * ND + ij + DD * k];
-                if (g >= 0) atomicAdd(a.y + g, s);
-                else if (!a.mask_out) atomicAdd(a.y + (~g), s);
-                else if (a.diag_one) a.y[~g] = a.x[~g];   // every writer stores the same value
-            }
-        }
-        if constexpr (SPLIT) {
-            // left-over pencils: piece = (pencil, output node k, lower | upper half of the quadrature planes); the two
-            // halves meet in the atomic
-            const int item = T + tid / (2 * D), r = tid - (tid / (2 * D)) * (2 * D), k = r >> 1, q0 = (r & 1) * (Q / 2);
-            if (tid < LEFT * 2 * D && item < nv * DD) {
-                const int el = item / DD, ij = item - el * DD;
-                const double* base = planes + el * ES + ij;
-                double s = 0.0;
-#pragma unroll
-                for (int dq = 0; dq < Q / 2; ++dq) {
-                    const int qz = q0 + dq;
-                    s += s_tab[qz * D + k] * (base[qz * PS] + base[PSET + qz * PS]) +
-                         s_tab[Q * D + qz * D + k] * (base[2 * PSET + qz * PS] + base[3 * PSET + qz * PS]);
-                }
                 const int g = ix[el * ND + ij + DD * k];
                 if (g >= 0) atomicAdd(a.y + g, s);
                 else if (!a.mask_out) atomicAdd(a.y + (~g), s);

@@ -206,18 +206,6 @@ int64_t jots_space_essential_dofs(jots_space_t s, const int32_t* attrs, int n_at
     } catch (const std::exception& ex) { fail(ex); return -1; }
 }
 
-int64_t jots_space_rowtiles(jots_space_t s, const int32_t* ess, int64_t n_ess, int tile_elems, double min_fill,
-                            int* record_bytes, unsigned char* out) {
-    try {
-        std::vector<int> e(ess, ess + n_ess);
-        std::vector<unsigned char> tab;
-        const int64_t nt = make_rowtiles(s->s, e, tile_elems, min_fill, tab);
-        if (record_bytes) *record_bytes = nt > 0 ? (int)(tab.size() / (size_t)nt) : 0;
-        if (out && nt > 0) std::memcpy(out, tab.data(), tab.size());
-        return nt;
-    } catch (const std::exception& ex) { fail(ex); return -1; }
-}
-
 int64_t jots_space_patches(jots_space_t s, const int32_t* ess, int64_t n_ess, int px, int py, int* record_ints, double* fill, int32_t* out) {
     try {
         std::vector<int> e(ess, ess + n_ess);
@@ -421,7 +409,6 @@ int jots_ctx_stats(jots_ctx_t c, int64_t out[12], double norms[2]) {
     if (norms) { norms[0] = s.last_linear_norm; norms[1] = s.last_newton_norm; }
     return 0;
 }
-int64_t jots_ctx_rowtile_applies(jots_ctx_t c) { return c->c->stats.rowtile_applies; }
 int jots_ctx_patch_info(jots_ctx_t c, int64_t* n_patches, double* fill, int64_t* applies) {
     if (n_patches) *n_patches = c->c->n_patches;
     if (fill) *fill = c->c->patch_fill;

@@ -61,7 +61,6 @@ void Ctx::init(const Space& s, int dev) {
     own_stream = true;
     n = s.ndof; n_owned = s.ndof;
     if (const char* ev = std::getenv("JOTS_DISABLE_SLAB")) use_slab = !(ev[0] == '1');
-    if (const char* ev = std::getenv("JOTS_OVERLAP_HALO")) overlap_halo = (ev[0] == '1');
     if (const char* ev = std::getenv("JOTS_SLAB_VARIANT")) slab_variant = std::atoi(ev);
     fill_tables(tabs, s.dim, s.p);
     // geometry: affine elements get one record each (one shared record when all are identical);
@@ -166,8 +165,9 @@ void Ctx::set_stream(cudaStream_t s) {
 }
 
 void Ctx::expand_owned(double* v) {
-    if (!halo || n_owned >= n) return;
-    JOTS_CUDA(cudaMemsetAsync(v + n_owned, 0, (size_t)(n - n_owned) * sizeof(double), stream));
+    if (!halo) return;
+    // collective: a rank that owns every DOF it touches (the lowest rank) still has to serve its neighbours
+    if (n_owned < n) JOTS_CUDA(cudaMemsetAsync(v + n_owned, 0, (size_t)(n - n_owned) * sizeof(double), stream));
     halo_sum_exchange(*this, v);
 }
 
@@ -215,7 +215,6 @@ void Ctx::set_bcs(const std::vector<BCSpec>& b) {
     for (auto& g : ge) if (em[g]) g = ~g;
     d_gather_ess.upload(ge);
     d_gattr.alloc(std::max<size_t>(bcs.size(), 1));
-    build_rowtiles();
     build_patches();
 }
 
@@ -236,22 +235,6 @@ void Ctx::build_patches() {
     d_patches.upload(tab);
     n_patches = (int)np;
     patch_fill = fill;
-}
-
-// Row-structured tiles of apply_slab4.cuh (make_rowtiles, mesh.cpp): all-or-nothing, rebuilt with the essential set
-void Ctx::build_rowtiles() {
-    d_rowtiles.release();
-    n_rowtiles = 0;
-    if (space.dim != 3 || !geom_diag || !use_slab || (slab_variant != 4 && slab_variant != 5) || space.nelem == 0) return;
-    const int E = slab4_tile_elems(space.p);
-    if (E <= 0) return;
-    std::vector<unsigned char> tab;
-    // JOTS_SLAB_VARIANT=5 keeps short tiles too (tests on small bricks)
-    const int64_t nt = make_rowtiles(space, ess, E, slab_variant == 4 ? 0.75 : 0.0, tab);
-    if (nt <= 0) return;
-    d_rowtiles.upload(tab);
-    n_rowtiles = (int)nt;
-    rowtile_elems = E;
 }
 
 bool Ctx::any_flux() const {
@@ -280,9 +263,6 @@ FormArgs Ctx::make_args(const FormSpec& f, const double* x, double* y, bool for_
     a.diag_one = (f.diag_one && f.mask_out && !halo && !for_diag) ? 1 : 0;   // multi-GPU: after the interface sum
     a.cm = f.cm; a.ck = f.ck; a.cb = f.cb; a.m0 = f.m0; a.a0 = f.a0; a.inv_rc = f.inv_rc;
     a.mat = mat;
-    a.rowtiles = (n_rowtiles > 0 && !for_diag) ? d_rowtiles.p : nullptr;
-    a.n_rowtiles = n_rowtiles;
-    a.rowtile_elems = rowtile_elems;
     a.nvec = n;
     a.patches = (n_patches > 0 && !for_diag) ? d_patches.p : nullptr;
     a.n_patches = n_patches;
@@ -316,39 +296,13 @@ static FaceArgs base_face_args(const Ctx& c, int nq) {
 void Ctx::apply_form(const FormSpec& f, const double* x, double* y) {
     zero(y);
     FormArgs a = make_args(f, x, y, false);
-    const int64_t n_if = (halo && overlap_halo && !(f.bdr_mass_scale != 0.0 && any_flux())) ? halo_interface_elems(*this) : 0;
-    bool overlapped = false;
-    int rc;
-    if (n_if > 0 && n_if < space.nelem) {
-        // interface elements first, their exchange overlaps the interior elements
-        a.rowtiles = nullptr; a.n_rowtiles = 0;   // element sub-ranges: gather-table kernels only
-        a.patches = nullptr; a.n_patches = 0;
-        FormArgs ai = a;
-        ai.nelem = (int)n_if;
-        rc = launch_form_apply(space.dim, space.p, f.op, f.cf, ai, tabs, stream);
-        if (!rc) {
-            halo_exchange_begin(*this, y);
-            FormArgs ar = a;
-            ar.gather = a.gather + (size_t)n_if * space.nloc;
-            ar.geom = a.geom + (size_t)n_if * a.geom_stride;
-            if (a.geomq) ar.geomq = a.geomq + (size_t)n_if * (tabs.Q * tabs.Q * tabs.QZ) * 10;
-            ar.nelem = (int)(space.nelem - n_if);
-            ar.nonpersistent = 1;   // blocks retire continuously, so the high-priority exchange kernels get SMs
-            rc = launch_form_apply(space.dim, space.p, f.op, f.cf, ar, tabs, stream);
-            halo_exchange_end(*this);
-            overlapped = true;
-            ++stats.kernel_launches;
-        }
-    } else {
-        // bricks: row-structured TMA kernel (no gather table); otherwise / when not instantiated the gather-table kernels
-        rc = (a.rowtiles && a.geom_diag && space.dim == 3) ? launch_form_apply_slab4(space.p, f.op, f.cf, a, tabs, stream) : 1;
-        if (!rc) ++stats.rowtile_applies;
-        if (rc && a.patches && a.geom_diag && space.dim == 3 && !a.zc) {
-            rc = launch_form_apply_patch(space.p, f.op, f.cf, a, tabs, stream);
-            if (!rc) ++stats.patch_applies;
-        }
-        if (rc) rc = launch_form_apply(space.dim, space.p, f.op, f.cf, a, tabs, stream);
+    // lattice meshes: unique-pencil patch kernels; otherwise / when not instantiated the gather-table kernels
+    int rc = 1;
+    if (a.patches && a.geom_diag && space.dim == 3 && !a.zc) {
+        rc = launch_form_apply_patch(space.p, f.op, f.cf, a, tabs, stream);
+        if (!rc) ++stats.patch_applies;
     }
+    if (rc) rc = launch_form_apply(space.dim, space.p, f.op, f.cf, a, tabs, stream);
     if (rc) throw std::runtime_error("form (op=" + std::to_string(f.op) + ", cf=" + std::to_string(f.cf) + ") is not instantiated, rc=" + std::to_string(rc));
     stats.kernel_launches += 2;
     last_kernel = last_element_kernel();
@@ -358,7 +312,7 @@ void Ctx::apply_form(const FormSpec& f, const double* x, double* y) {
         launch_face(FACE_MASS_APPLY, fa, stream);
         ++stats.kernel_launches;
     }
-    if (halo && !overlapped) halo_sum_exchange(*this, y);
+    if (halo) halo_sum_exchange(*this, y);
     if (f.diag_one && !a.diag_one) { v_copy_idx(stream, (int)ess.size(), d_ess.p, x, y); stats.kernel_launches += !ess.empty(); }
     JOTS_CUDA(cudaGetLastError());
     ++stats.applies;

@@ -69,7 +69,7 @@ struct FormSpec {
 
 struct Stats {
     long long applies = 0, diag_assemblies = 0, krylov_iters = 0, newton_iters = 0, residual_evals = 0, steps = 0,
-              kernel_launches = 0, dots = 0, halo_exchanges = 0, rowtile_applies = 0, patch_applies = 0;
+              kernel_launches = 0, dots = 0, halo_exchanges = 0, patch_applies = 0;
     double last_linear_norm = 0, last_newton_norm = 0;
     int last_linear_converged = 1, last_newton_converged = 1, last_linear_iters = 0, last_newton_iters = 0;
 };
@@ -104,11 +104,7 @@ public:
     std::vector<DArr<int>> d_bc_dofs;
     DArr<double> d_geom, d_geomq, d_bdr_corner, d_gattr;
     DArr<unsigned char> d_essmark;
-    DArr<unsigned char> d_rowtiles;   // RowTile<D> table of the row-structured slab kernel (empty: not applicable)
-    int n_rowtiles = 0, rowtile_elems = 0;
-    int slab_variant = 7;             // JOTS_SLAB_VARIANT: 7 unique-pencil patch kernel where the mesh is a lattice (default), 3 pipelined gather-table kernel,
-                                      // 2 non-persistent, 4 / 5 row-structured (TMA), 6 experimental warp-specialised
-    void build_rowtiles();            // from space.gather + essential marks; all-or-nothing
+    int slab_variant = 7;             // JOTS_SLAB_VARIANT: 7 unique-pencil patch kernels where the mesh is a lattice (default), 3 gather-table kernel only
     DArr<int> d_patches;              // element patches of the unique-pencil kernel (patches.cpp); empty: not applicable
     int n_patches = 0;
     double patch_fill = 0.0;          // nelem / (patches * elements per patch)
@@ -116,8 +112,6 @@ public:
     int geom_stride = 10;
     bool geom_diag = false;   // diagonal metric on every element
     bool use_slab = true;     // JOTS_DISABLE_SLAB=1 forces the generic kernel
-    bool overlap_halo = false; // JOTS_OVERLAP_HALO=1: exchange the interface elements' sums while the interior
-                               // elements run (measured neutral at 2 GPUs, so off by default)
     DArr<double> d_scal, d_partial;
     DArr<double> mat_state;   // vector the nodal property polynomials were last evaluated on (UpdateMatProps)
     void set_mat_state(const double* u) { mat_state.alloc(n); copy(u, mat_state.p); }

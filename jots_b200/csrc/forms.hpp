@@ -52,7 +52,6 @@ struct FormArgs {
     const double* geom;   // [nelem*10]: invJ[a][i] (9, row-major: a = reference axis) + detJ
     int geom_stride;      // 10, or 0 when every element shares geom[0..9]
     int geom_diag;        // metric invJ invJ^T is diagonal on every element (axis-aligned bricks)
-    int nonpersistent;    // prefer the non-persistent kernel variant (lets a concurrent communication kernel in)
     const double* geomq;  // non-affine (general multilinear) meshes: [nelem][NQ][10] per quadrature point, else null
     const double* x;      // input vector
     const double* z;      // frozen state (coefficients + grad z); may be null for CF_CONST/OP_LIN
@@ -67,28 +66,12 @@ struct FormArgs {
     double m0, a0;        // CF_CONST
     double inv_rc;        // CF_K
     MatSet mat;
-    // row-structured tiles (apply_slab4.cuh): null unless every element lies in a run of elements whose L-vector
-    // DOFs are contiguous along the fastest lattice axis (bricks); built by Ctx::build_rowtiles
-    const void* rowtiles;
-    int n_rowtiles;
-    int rowtile_elems;    // tile length E the table was built for
     long long nvec;       // length of x / z / y
     // element patches of the unique-pencil kernel (apply_patch.cuh, patches.cpp): null when the mesh is not (mostly) a lattice
     const int* patches;
     int n_patches;
     // device flag: the kernel returns at once when *skip != 0 (iterations enqueued ahead of a converged Krylov solve)
     const double* skip;
-};
-
-// Row-structured tile of the slab4 kernel: nv <= E consecutive elements (in element order) forming a row along the
-// fastest lattice axis, with DOF (i, j, k) of element el at base[k*D + j] + (D-1)*el + i.  Replaces nv*D^3 gather
-// entries by D^2 row starts (+ one bit per row node for the essential DOFs); sized to a multiple of 16 bytes so that
-// one bulk copy brings it into shared memory.
-template <int D>
-struct alignas(16) RowTile {
-    int e0, nv, any_ess, pad;
-    int base[D * D + (D * D) % 2];
-    unsigned long long ess[D * D];
 };
 
 // 1-D tables; DZ = QZ = 1 turns the hex kernel into the quad kernel

@@ -55,9 +55,6 @@ struct Halo {
     DArr<int> d_send_idx, d_red_dof, d_red_ptr, d_red_src;
     DArr<double> d_send, d_recv;
     DArr<int64_t> d_gid;
-    int64_t n_interface_elems = 0;
-    cudaStream_t comm_stream = nullptr;
-    cudaEvent_t ev_ready = nullptr, ev_done = nullptr;
 };
 
 Halo* halo_create(const Partition& P, Comm* comm) {
@@ -70,52 +67,16 @@ Halo* halo_create(const Partition& P, Comm* comm) {
     h->d_send.alloc(h->n_send > 0 ? h->n_send : 1);
     h->d_recv.alloc(h->n_send > 0 ? h->n_send : 1);
     h->d_gid.upload(P.global_id);
-    h->n_interface_elems = P.n_interface_elems;
-    {
-        int lo = 0, hi = 0;
-        JOTS_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-        JOTS_CUDA(cudaStreamCreateWithPriority(&h->comm_stream, cudaStreamNonBlocking, hi));
-    }
-    JOTS_CUDA(cudaEventCreateWithFlags(&h->ev_ready, cudaEventDisableTiming));
-    JOTS_CUDA(cudaEventCreateWithFlags(&h->ev_done, cudaEventDisableTiming));
     return h;
 }
 void halo_destroy(Halo* h) {
     if (!h) return;
-    if (h->ev_ready) cudaEventDestroy(h->ev_ready);
-    if (h->ev_done) cudaEventDestroy(h->ev_done);
-    if (h->comm_stream) cudaStreamDestroy(h->comm_stream);
     delete h;
 }
-
-static void exchange_on(Ctx& c, Halo* h, double* y, cudaStream_t st);
 
 void halo_sum_exchange(Ctx& c, double* y) {
     Halo* h = c.halo;
     if (!h || h->nbr_rank.empty()) return;
-    exchange_on(c, h, y, c.stream);
-}
-
-int64_t halo_interface_elems(const Ctx& c) { return c.halo ? c.halo->n_interface_elems : 0; }
-
-void halo_exchange_begin(Ctx& c, double* y) {
-    Halo* h = c.halo;
-    if (!h || h->nbr_rank.empty()) return;
-    // the interface elements are complete on the main stream: exchange on the communication stream
-    JOTS_CUDA(cudaEventRecord(h->ev_ready, c.stream));
-    JOTS_CUDA(cudaStreamWaitEvent(h->comm_stream, h->ev_ready, 0));
-    exchange_on(c, h, y, h->comm_stream);
-    JOTS_CUDA(cudaEventRecord(h->ev_done, h->comm_stream));
-}
-
-void halo_exchange_end(Ctx& c) {
-    Halo* h = c.halo;
-    if (!h || h->nbr_rank.empty()) return;
-    JOTS_CUDA(cudaStreamWaitEvent(c.stream, h->ev_done, 0));
-}
-
-static void exchange_on(Ctx& c, Halo* h, double* y, cudaStream_t st_) {
-    struct StreamSwap { Ctx& c; cudaStream_t old; StreamSwap(Ctx& cc, cudaStream_t s) : c(cc), old(cc.stream) { c.stream = s; } ~StreamSwap() { c.stream = old; } } swap(c, st_);
     v_pack(c.stream, h->n_send, h->d_send_idx.p, y, h->d_send.p);
     nccl_check(ncclGroupStart(), "ncclGroupStart");
     for (size_t k = 0; k < h->nbr_rank.size(); ++k) {

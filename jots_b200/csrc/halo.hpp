@@ -18,11 +18,6 @@ int comm_size(const Comm* c);
 Halo* halo_create(const Partition& P, Comm* comm);
 void halo_destroy(Halo* h);
 void halo_sum_exchange(Ctx& c, double* y);
-// overlapped variant: call halo_exchange_begin after the interface elements have been launched on the
-// main stream, launch the interior elements, then halo_exchange_end
-void halo_exchange_begin(Ctx& c, double* y);
-void halo_exchange_end(Ctx& c);
-int64_t halo_interface_elems(const Ctx& c);
 void halo_allreduce(Ctx& c, double* d_vals, int nv);
 void halo_allreduce_max(Ctx& c, double* d_vals, int nv);
 int halo_rank(const Ctx& c);

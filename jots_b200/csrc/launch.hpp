@@ -17,11 +17,9 @@ std::string kernel_label(const char* base, int D, int Q, int op, int cf, const c
 // returns 0 on success, non-zero when the (shape, op, cf) combination is not instantiated
 int launch_form_apply(int dim, int p, int op, int cf, const FormArgs& a, const TablesRT& t, cudaStream_t st);
 int launch_form_apply_slab(int p, int op, int cf, const FormArgs& a, const TablesRT& t, cudaStream_t st);
-int launch_form_apply_slab4(int p, int op, int cf, const FormArgs& a, const TablesRT& t, cudaStream_t st);
 int launch_form_apply_patch(int p, int op, int cf, const FormArgs& a, const TablesRT& t, cudaStream_t st);
 int patch_items(int p, unsigned* out);   // phase-3 items (pencil | visits << 8 | (el << 5 | ij) << 10 | ... << 20), at most 128
 void patch_shape(int p, int& px, int& py);   // patch size for order p (0: no patch kernel)
-int slab4_tile_elems(int p);   // elements per RowTile for order p (0: none)
 int launch_form_diag_slab(int p, int op, int cf, const FormArgs& a, const TablesRT& t, cudaStream_t st);
 int launch_form_diag(int dim, int p, int op, int cf, const FormArgs& a, const TablesRT& t, cudaStream_t st);
 int launch_face(int mode, const FaceArgs& a, cudaStream_t st);

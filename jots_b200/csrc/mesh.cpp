@@ -534,47 +534,4 @@ void h1_dof_map(int dim, int p, std::vector<int>& map) {
     for (int k = 1; k < p; ++k) for (int j = 1; j < p; ++j) for (int i = 1; i < p; ++i) at(i, j, k) = o++;
 }
 
-int64_t make_rowtiles(const Space& s, const std::vector<int>& ess, int E, double min_fill, std::vector<unsigned char>& tab) {
-    tab.clear();
-    const int p = s.p, D = s.D, DD = D * D, ND = DD * D;
-    if (s.dim != 3 || s.nelem == 0 || E <= 0 || p * E + 1 > 64 || s.nloc != ND || D > 4 || s.ndof > 0x7fffffffLL) return 0;
-    // == sizeof(RowTile<D>): header (e0, nv, any_ess, pad), base[D*D (+1 if odd)], ess[D*D]
-    const size_t off_base = 16, off_ess = off_base + 4 * (size_t)(DD + DD % 2), rec = off_ess + 8 * (size_t)DD;
-    std::vector<unsigned char> em((size_t)s.ndof, 0);
-    for (int d : ess) em[d] = 1;
-    tab.reserve((size_t)(s.nelem / E + 1) * rec);
-    const int* G = s.gather.data();
-    int64_t e = 0, ntile = 0;
-    while (e < s.nelem) {
-        const int* g0 = G + (size_t)e * ND;
-        int base[16];
-        for (int r = 0; r < DD; ++r) base[r] = g0[r * D];    // local index i + D*j + D*D*k, row r = k*D + j
-        int nv = 0;
-        while (nv < E && e + nv < s.nelem) {
-            const int* g = G + (size_t)(e + nv) * ND;
-            bool ok = true;
-            for (int r = 0; r < DD && ok; ++r)
-                for (int i = 0; i < D; ++i)
-                    if (g[r * D + i] != base[r] + p * nv + i) { ok = false; break; }
-            if (!ok) break;
-            ++nv;
-        }
-        if (nv == 0) { tab.clear(); return 0; }   // not even a single contiguous element: no row structure
-        const size_t o = tab.size();
-        tab.resize(o + rec, 0);
-        int hdr[4] = {(int)e, nv, 0, 0};
-        unsigned long long essb[16] = {0};
-        for (int r = 0; r < DD; ++r)
-            for (int m = 0; m <= p * nv; ++m)
-                if (em[(size_t)base[r] + m]) { essb[r] |= 1ull << m; hdr[2] = 1; }
-        std::memcpy(&tab[o], hdr, 16);
-        std::memcpy(&tab[o + off_base], base, 4 * (size_t)DD);
-        std::memcpy(&tab[o + off_ess], essb, 8 * (size_t)DD);
-        e += nv;
-        ++ntile;
-    }
-    if ((double)s.nelem < min_fill * (double)ntile * (double)E) { tab.clear(); return 0; }
-    return ntile;
-}
-
 }  // namespace jots

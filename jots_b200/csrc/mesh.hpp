@@ -78,13 +78,6 @@ Space make_space(const Mesh& m, int p);
 // should assert it against GetDofMap() of the element it actually uses.
 void h1_dof_map(int dim, int p, std::vector<int>& map);
 
-// Row-structured tiles (RowTile<D> records of forms.hpp, apply_slab4.cuh): greedy segmentation of the element order
-// into runs of at most E elements in which DOF (i, j, k) of the m-th element is base[k*D + j] + p*m + i (contiguous
-// rows along the fastest lattice axis).  Returns the number of tiles, or 0 when some element is not even a run of
-// length one (file meshes numbered in first-appearance order, subdomains with owned-first numbering) or when the
-// tiles are on average less than min_fill full.  ess: sorted essential DOFs (one bit per row node in the record).
-int64_t make_rowtiles(const Space& s, const std::vector<int>& ess, int E, double min_fill, std::vector<unsigned char>& tab);
-
 // Element patches of the unique-pencil slab kernel (apply_patch.cuh): PX x PY x 1 lattice-adjacent hexes with aligned local
 // axes, their (D-1)PX+1 x (D-1)PY+1 x D nodes listed once.  Record (ints): nodes [k][J][I] (essential DOFs as ~index,
 // 0x80000000 where no element of the patch touches the slot), then PX*PY element ids (-1: hole), padded to a multiple of 4.

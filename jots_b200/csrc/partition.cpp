@@ -123,20 +123,12 @@ Partition make_partition(const Space& G, const std::vector<int>& elem_rank, int 
     L.ndof = P.n_local;
     const int nv = 1 << G.dim;
     std::vector<int64_t> e_g2l(G.nelem, -1);
-    // interface elements (touching a DOF shared with another rank) first, so that the interface
-    // exchange can overlap the interior elements; global element order is kept inside each group
-    for (int pass = 0; pass < 2; ++pass) {
-        for (int64_t e = 0; e < G.nelem; ++e) {
-            if (elem_rank[e] != rank) continue;
-            bool iface = false;
-            for (int l = 0; l < nloc && !iface; ++l) iface = (mask[G.gather[e * nloc + l]] & ~mybit) != 0;
-            if (iface != (pass == 0)) continue;
-            e_g2l[e] = (int64_t)P.local_elems.size();
-            P.local_elems.push_back(e);
-            for (int l = 0; l < nloc; ++l) L.gather.push_back(g2l[G.gather[e * nloc + l]]);
-            L.elem_corner.insert(L.elem_corner.end(), G.elem_corner.begin() + e * nv * G.dim, G.elem_corner.begin() + (e + 1) * nv * G.dim);
-        }
-        if (pass == 0) P.n_interface_elems = (int64_t)P.local_elems.size();
+    for (int64_t e = 0; e < G.nelem; ++e) {
+        if (elem_rank[e] != rank) continue;
+        e_g2l[e] = (int64_t)P.local_elems.size();
+        P.local_elems.push_back(e);
+        for (int l = 0; l < nloc; ++l) L.gather.push_back(g2l[G.gather[e * nloc + l]]);
+        L.elem_corner.insert(L.elem_corner.end(), G.elem_corner.begin() + e * nv * G.dim, G.elem_corner.begin() + (e + 1) * nv * G.dim);
     }
     L.nelem = (int64_t)P.local_elems.size();
     const int nfv = 1 << (G.dim - 1);

@@ -29,7 +29,6 @@ struct Partition {
     std::vector<int> red_dof, red_ptr, red_src;
     std::vector<int> send_idx;                   // concatenated per-neighbour send lists (local indices)
     std::vector<int> nbr_offset;                 // [n_nbr+1] offsets into send/recv buffers
-    int64_t n_interface_elems = 0;               // local elements touching a shared DOF come first
 };
 
 // element -> rank; dims (px,py,pz) optional for bricks

@@ -31,24 +31,6 @@ struct PerDevice {
 };
 
 template <int D, int Q, int OP, int CF, int E>
-static int launch_slab2e(const FormArgs& a, const TablesRT& r, cudaStream_t st) {
-    // E elements per block, 2*Q threads per element in phase 2, D*D threads per element in phases 1/3
-    constexpr int T = ((E * (2 * Q > D * D ? 2 * Q : D * D)) + 31) / 32 * 32;
-    typedef SlabCfg<OP, CF> C;
-    Slab2Tables<D, Q> t;
-    fill_slab2_tables<D, Q>(r, t);
-    const size_t smem = (size_t)E * Elem2Stride<D, Q, C::NP>::value * sizeof(double);
-    auto kern = form_apply_slab2_kernel<D, Q, OP, CF, E, T>;
-    static PerDevice pd;
-    pd.get(kern, T, smem);
-    const int grid = (a.nelem + E - 1) / E;
-    kern<<<grid, T, smem, st>>>(a, t);
-    static const std::string label = kernel_label("form_apply_slab2_kernel", D, Q, OP, CF, ("," + std::to_string(E) + "," + std::to_string(T)).c_str());
-    last_element_kernel() = label.c_str();
-    return 0;
-}
-
-template <int D, int Q, int OP, int CF, int E, bool SPLIT = false>
 static int launch_slab3e(const FormArgs& a, const TablesRT& r, cudaStream_t st) {
     // thread count follows phase 2 (2Q threads per element); phases 1/3 read shared memory and loop
     constexpr int T = (E * 2 * Q + 31) / 32 * 32;
@@ -56,48 +38,25 @@ static int launch_slab3e(const FormArgs& a, const TablesRT& r, cudaStream_t st) 
     Slab2Tables<D, Q> t;
     fill_slab2_tables<D, Q>(r, t);
     const size_t smem = Slab3Smem<D, Q, C::NP, E>::total;
-    auto kern = form_apply_slab3_kernel<D, Q, OP, CF, E, T, SPLIT>;
+    auto kern = form_apply_slab3_kernel<D, Q, OP, CF, E, T>;
     static PerDevice pd;
     const int grid_max = pd.get(kern, T, smem);
     const int ntiles = (a.nelem + E - 1) / E;
     kern<<<ntiles < grid_max ? ntiles : grid_max, T, smem, st>>>(a, t);
-    static const std::string label = kernel_label("form_apply_slab3_kernel", D, Q, OP, CF, ("," + std::to_string(E) + "," + std::to_string(T) + (SPLIT ? ",split" : "")).c_str());
+    static const std::string label = kernel_label("form_apply_slab3_kernel", D, Q, OP, CF, ("," + std::to_string(E) + "," + std::to_string(T)).c_str());
     last_element_kernel() = label.c_str();
     return 0;
-}
-static int slab_elems() {
-    static int v = -1;
-    if (v < 0) { const char* e = getenv("JOTS_SLAB_ELEMS"); v = e ? atoi(e) : 16; }
-    return v;
 }
 template <int D, int Q, int OP, int CF>
 static int launch_slab3(const FormArgs& a, const TablesRT& r, cudaStream_t st) {
     if constexpr (Q == 4) {
-        // E = 12 / 16 with two staging buffers measured 13 % / 17 % slower than 14 (16: three blocks per SM); E = 16 with
-        // one staging buffer keeps four blocks and all 128 threads busy in phase 2: Jacobian apply 1.32 -> 1.29 ms,
-        // residual 1.19 -> 1.13 ms at 17 M DOFs (JOTS_SLAB_ELEMS=14 selects the old tile).  Fusing phase 3 of a tile with
-        // phase 1 of the next (two barriers per tile) measured 1.5 % slower and was dropped.
-        if constexpr (CF != CF_FULL && CF != CF_FULLC) {
-            // JOTS_SLAB_SPLIT=1: left-over pencils of phases 1 / 3 as one pass of short pieces (apply_slab.cuh, SPLIT)
-            static const bool split = [] { const char* e = getenv("JOTS_SLAB_SPLIT"); return e && e[0] == '1'; }();
-            if (slab_elems() == 16) return split ? launch_slab3e<D, Q, OP, CF, 16, true>(a, r, st) : launch_slab3e<D, Q, OP, CF, 16>(a, r, st);
-        }
-        return launch_slab3e<D, Q, OP, CF, 14>(a, r, st);
+        // Q2: 16-element tiles with one staging buffer keep four blocks per SM and all 128 threads busy in phase 2 (measured
+        // against E = 12 / 14 / 16 with two buffers, profiles/README.md r1j); the rho(T) / C(T) forms need the smaller tile
+        if constexpr (CF != CF_FULL && CF != CF_FULLC) return launch_slab3e<D, Q, OP, CF, 16>(a, r, st);
+        else return launch_slab3e<D, Q, OP, CF, 14>(a, r, st);
     }
     else if constexpr (Q == 5) return launch_slab3e<D, Q, OP, CF, 12>(a, r, st);
     else return launch_slab3e<D, Q, OP, CF, 32>(a, r, st);
-}
-
-template <int D, int Q, int OP, int CF>
-static int launch_slab2(const FormArgs& a, const TablesRT& r, cudaStream_t st) {
-    if constexpr (Q == 4) return slab_elems() == 28 ? launch_slab2e<D, Q, OP, CF, 28>(a, r, st) : launch_slab2e<D, Q, OP, CF, 14>(a, r, st);
-    else return launch_slab2e<D, Q, OP, CF, 32>(a, r, st);
-}
-
-static int slab_variant() {
-    static int v = -1;
-    if (v < 0) { const char* e = getenv("JOTS_SLAB_VARIANT"); v = e ? atoi(e) : 3; }
-    return v;
 }
 
 static bool slab_klin() {
@@ -110,15 +69,8 @@ template <int D, int Q>
 static int dispatch(int op, int cf, const FormArgs& a, const TablesRT& t, cudaStream_t st) {
     // k(T) linear (two coefficients, the reference's own cases): k'_h is uniform, one property field less in the
     // Jacobian apply (JOTS_SLAB_KLIN=0 keeps the general kernel)
-    if (op == OP_JAC && cf == CF_K && a.mat.k.n == 2 && slab_klin() && !(slab_variant() == 2 || a.nonpersistent))
-        return launch_slab3<D, Q, OP_JAC, CF_KL>(a, t, st);
-#define CASE(OPV, CFV)                                                                              \
-    if (op == OPV && cf == CFV) {                                                                   \
-        if constexpr (Q < 5) {                                                                      \
-            if (slab_variant() == 2 || a.nonpersistent) return launch_slab2<D, Q, OPV, CFV>(a, t, st); \
-        }                                                                                           \
-        return launch_slab3<D, Q, OPV, CFV>(a, t, st);                                              \
-    }
+    if (op == OP_JAC && cf == CF_K && a.mat.k.n == 2 && slab_klin()) return launch_slab3<D, Q, OP_JAC, CF_KL>(a, t, st);
+#define CASE(OPV, CFV) if (op == OPV && cf == CFV) return launch_slab3<D, Q, OPV, CFV>(a, t, st);
     CASE(OP_LIN, CF_CONST) CASE(OP_LIN, CF_K) CASE(OP_JAC, CF_K) CASE(OP_RES, CF_CONST) CASE(OP_RES, CF_K)
 #undef CASE
     // rho(T) / C(T): pipelined kernel only

@@ -64,7 +64,6 @@ def load_library():
         "jots_space_copy_bdr": (C.c_int, [_P, _P, _P, _P, _P]),
         "jots_space_copy_nodes": (C.c_int, [_P, _P]),
         "jots_space_essential_dofs": (C.c_int64, [_P, _P, C.c_int, _P]),
-        "jots_space_rowtiles": (C.c_int64, [_P, _P, C.c_int64, C.c_int, C.c_double, _P, _P]),
         "jots_space_patches": (C.c_int64, [_P, _P, C.c_int64, C.c_int, C.c_int, _P, _P, _P]),
         "jots_patch_shape": (C.c_int, [C.c_int, _P, _P, _P]),
         "jots_h1_dof_map": (C.c_int, [C.c_int, C.c_int, _P]),
@@ -91,7 +90,6 @@ def load_library():
         "jots_ctx_patch_info": (C.c_int, [_P, _P, _P, _P]),
         "jots_ctx_last_kernel": (C.c_char_p, [_P]),
         "jots_ctx_reset_stats": (C.c_int, [_P]),
-        "jots_ctx_rowtile_applies": (C.c_int64, [_P]),
         "jots_op_create": (_P, [_P, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int,
                                 C.c_double, C.c_double, C.c_int]),
         "jots_op_destroy": (None, [_P]),
@@ -348,25 +346,6 @@ class Space:
         load_library().jots_space_essential_dofs(self._h, _ptr(a), a.size, _ptr(out))
         return out
 
-    def rowtiles(self, ess, tile_elems, min_fill=0.0):
-        """Row-structured tiles of the TMA element kernel: structured array (e0, nv, any_ess, base[D*D], ess[D*D]),
-        empty when the space has no row structure."""
-        ess = np.ascontiguousarray(ess, dtype=np.int32)
-        rec = C.c_int(0)
-        lib = load_library()
-        n = lib.jots_space_rowtiles(self._h, _ptr(ess), ess.size, tile_elems, min_fill, C.byref(rec), None)
-        if n < 0:
-            raise JotsError(_err())
-        dd = (self.order + 1) ** 2
-        dt = np.dtype([("e0", "<i4"), ("nv", "<i4"), ("any_ess", "<i4"), ("pad", "<i4"), ("base", "<i4", (dd + dd % 2,)),
-                       ("ess", "<u8", (dd,))])
-        if n == 0:
-            return np.empty(0, dtype=dt)
-        assert rec.value == dt.itemsize, (rec.value, dt.itemsize)
-        buf = np.empty(n * rec.value, dtype=np.uint8)
-        lib.jots_space_rowtiles(self._h, _ptr(ess), ess.size, tile_elems, min_fill, C.byref(rec), _ptr(buf))
-        return buf.view(dt)
-
     def patches(self, ess, px=4, py=4):
         """Element patches of the unique-pencil kernel: (records [n_patches, record_ints] int32, fill); record = nodes
         [k][J][I] (essential as ~index, 0x80000000 unused), then px*py element ids (-1: hole).  Empty when not a lattice."""
@@ -474,7 +453,6 @@ class Context:
                 "dots", "last_linear_iters", "last_linear_converged", "last_newton_iters", "last_newton_converged"]
         d = {k: int(v) for k, v in zip(keys, out)}
         d["last_linear_norm"], d["last_newton_norm"] = float(norms[0]), float(norms[1])
-        d["rowtile_applies"] = int(load_library().jots_ctx_rowtile_applies(self._h))
         npch, fill, app = C.c_int64(0), C.c_double(0.0), C.c_int64(0)
         load_library().jots_ctx_patch_info(self._h, C.byref(npch), C.byref(fill), C.byref(app))
         d["n_patches"], d["patch_fill"], d["patch_applies"] = int(npch.value), float(fill.value), int(app.value)

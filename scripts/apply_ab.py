@@ -11,14 +11,9 @@ import tempfile
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CONFIGS = {
-    "slab3_gather_E14": {"JOTS_SLAB_VARIANT": "3", "JOTS_SLAB_ELEMS": "14"},
-    "slab3_gather_E16": {"JOTS_SLAB_VARIANT": "3", "JOTS_SLAB_ELEMS": "16"},
-    "slab3_split_E16": {"JOTS_SLAB_VARIANT": "3", "JOTS_SLAB_ELEMS": "16", "JOTS_SLAB_SPLIT": "1"},
+    "slab3_gather_E16": {"JOTS_SLAB_VARIANT": "3"},                   # gather-table kernel (round-1 default)
     "patch3_4x4": {"JOTS_SLAB_VARIANT": "7", "JOTS_PATCH2": "0"},     # three-phase unique-pencil patch kernel
     "patch2_4x4": {"JOTS_SLAB_VARIANT": "7"},                         # two-phase patch kernel (default)
-    "slab4_rows_E16": {"JOTS_SLAB_VARIANT": "4", "JOTS_SLAB4_ELEMS": "16"},
-    "slab4_rows_E14": {"JOTS_SLAB_VARIANT": "4", "JOTS_SLAB4_ELEMS": "14"},
-    "slab4_cpasync_E16": {"JOTS_SLAB_VARIANT": "4", "JOTS_SLAB4_ELEMS": "16", "JOTS_SLAB4_STAGE": "cpasync"},
 }
 
 

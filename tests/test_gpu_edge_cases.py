@@ -151,7 +151,7 @@ def test_restart_files_round_trip_and_continuation(J, tmp_path, dim, order):
     assert d0.run() == n
     u_n = d0.get_u()
     dr = J.Driver(write("restarted.ini", 2 * n, restart_from=n))
-    assert abs(dr.time() - d0.time()) < 1e-15 and dr.n == d0.n
+    assert abs(dr.time - d0.time) < 1e-15 and dr.n == d0.n
     assert np.abs(dr.get_u() - u_n).max() <= 1e-12 * np.abs(u_n).max()       # Restart_Files.cpp: EPSILON = 1e-12
     assert dr.run() == n                                                       # cycles n+1 .. 2n
     d2 = J.Driver(write("straight.ini", 2 * n))

@@ -181,67 +181,6 @@ def test_errors_are_status_codes_not_aborts(tmp_path):
 
 
 @pytest.mark.parametrize("p,E", [(1, 32), (2, 16), (2, 14), (3, 12)])
-@pytest.mark.parametrize("shape", [(6, 3, 2), (40, 5, 3), (33, 2, 2)])
-def test_rowtiles_reproduce_the_gather_table_bit_exact(p, E, shape):
-    """Row-structured tiles of the TMA element kernel (apply_slab4.cuh): decoding the D^2 row starts and the essential
-    bits must give back the gather table and the essential marker exactly, every element covered once, and the
-    kernel's unique-pencil mapping (phase 1 / phase 3) must visit every (element, local node) exactly once."""
-    import jots_b200 as J
-    D, DD = p + 1, (p + 1) ** 2
-    s = J.Space(J.Mesh.brick(*shape, 0.01, 0.02, 0.03), p)
-    g = s.gather()
-    ess = s.essential_dofs([1, 4, 5])
-    em = np.zeros(s.n_dof, bool)
-    em[ess] = True
-    tiles = s.rowtiles(ess, E)
-    assert len(tiles) > 0
-    covered = 0
-    contrib = np.zeros(s.n_dof, np.int64)
-    nnmax = p * E + 1
-    for r in tiles:
-        e0, nv = int(r["e0"]), int(r["nv"])
-        assert e0 == covered and 1 <= nv <= E
-        covered += nv
-        el, i = np.meshgrid(np.arange(nv), np.arange(D), indexing="ij")
-        for k in range(D):
-            for j in range(D):
-                idx = int(r["base"][k * D + j]) + p * el + i
-                assert (idx == g[e0:e0 + nv, D * j + DD * k:D * j + DD * k + D]).all()
-                bits = (int(r["ess"][k * D + j]) >> (p * el + i)) & 1
-                assert (bits.astype(bool) == em[idx]).all()
-        assert (r["any_ess"] != 0) == any(int(b) != 0 for b in r["ess"])
-        # the kernel's mapping of unique pencils (node n, j) onto elements
-        seen = set()
-        for u in range(nnmax * D):
-            j, n = divmod(u, nnmax)
-            if n >= p * nv + 1:
-                continue
-            ea, ib = divmod(n, p)
-            dests = ([(ea, j * D + ib)] if ea < nv else []) + ([(ea - 1, j * D + p)] if ib == 0 and ea >= 1 else [])
-            for k in range(D):
-                idx = int(r["base"][k * D + j]) + n
-                for (e_, ij) in dests:
-                    assert (e_, ij, k) not in seen and g[e0 + e_, ij + DD * k] == idx
-                    seen.add((e_, ij, k))
-                contrib[idx] += len(dests)
-        assert len(seen) == nv * DD * D
-    assert covered == s.n_elem
-    assert (contrib == np.bincount(g.ravel(), minlength=s.n_dof)).all()
-
-
-def test_rowtiles_absent_without_row_structure(tmp_path):
-    """File meshes (first-appearance numbering) and too short rows keep the gather-table kernel."""
-    import jots_b200 as J
-    from cases import write_brick_mesh
-    path = str(tmp_path / "m.mesh")
-    write_brick_mesh(path, 6, 3, 2, 0.01, 0.02, 0.015)
-    s = J.Space(J.Mesh.read(path), 2)
-    assert len(s.rowtiles(np.zeros(0, np.int32), 16)) == 0
-    s = J.Space(J.Mesh.brick(6, 3, 2, 0.01, 0.02, 0.03), 2)
-    assert len(s.rowtiles(np.zeros(0, np.int32), 16, min_fill=0.75)) == 0
-    assert len(s.rowtiles(np.zeros(0, np.int32), 16, min_fill=0.0)) == 6
-
-
 def _config_pairs(path):
     """(library Config, oracle Config) of one .ini as comparable dicts."""
     import jots_b200 as J
