@@ -142,6 +142,8 @@ void Ctx::init(const Space& s, int dev) {
     d_partial.alloc((size_t)DOT_MAX_BLOCKS * 4);
     d_counter.alloc(1);
     JOTS_CUDA(cudaMemset(d_counter.p, 0, sizeof(unsigned int)));
+    d_sched.alloc(2);
+    JOTS_CUDA(cudaMemset(d_sched.p, 0, 2 * sizeof(unsigned int)));
     JOTS_CUDA(cudaMallocHost((void**)&h_scal, 64 * sizeof(double)));
     std::vector<unsigned char> em((size_t)n, 0);
     d_essmark.upload(em);
@@ -267,6 +269,7 @@ FormArgs Ctx::make_args(const FormSpec& f, const double* x, double* y, bool for_
     a.patches = (n_patches > 0 && !for_diag) ? d_patches.p : nullptr;
     a.n_patches = n_patches;
     a.skip = for_diag ? nullptr : apply_skip;
+    a.sched = d_sched.p;
     return a;
 }
 

@@ -116,6 +116,7 @@ public:
     DArr<double> mat_state;   // vector the nodal property polynomials were last evaluated on (UpdateMatProps)
     void set_mat_state(const double* u) { mat_state.alloc(n); copy(u, mat_state.p); }
     DArr<unsigned int> d_counter;
+    DArr<unsigned int> d_sched;   // tile / exit counters of the patch kernel's dynamic scheduler (self-resetting)
     double* h_scal = nullptr;  // pinned
 
     // --- setup

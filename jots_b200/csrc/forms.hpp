@@ -72,6 +72,8 @@ struct FormArgs {
     int n_patches;
     // device flag: the kernel returns at once when *skip != 0 (iterations enqueued ahead of a converged Krylov solve)
     const double* skip;
+    // two zero-initialised counters of the dynamic tile scheduler of apply_patch2.cuh (tile counter, exit counter)
+    unsigned int* sched;
 };
 
 // 1-D tables; DZ = QZ = 1 turns the hex kernel into the quad kernel
