@@ -427,7 +427,9 @@ template <int D, int Q> struct Slab3Layout {   // D = 2: no conflict-free mirror
     static constexpr int PS = 5, PAD = 0, ESM = 4; static constexpr bool MIRROR = false;
 };
 template <> struct Slab3Layout<3, 4> { static constexpr int PS = 12, PAD = 2, ESM = 9; static constexpr bool MIRROR = true; };
-template <> struct Slab3Layout<4, 5> { static constexpr int PS = 17, PAD = 0, ESM = 0; static constexpr bool MIRROR = false; };  // mirrored addressing spills at 255 registers
+// Q3: mirrored addressing spills at 255 registers; (PS, PAD, ESM) = (17, 3, 13) makes the phase-2 plane loads and result stores of a
+// half-warp (10 lanes per element) conflict free -- (17, 0, 0) of round 1 took 1.9 wavefronts for each (profiles/r2p_phases_slab3_q3_*)
+template <> struct Slab3Layout<4, 5> { static constexpr int PS = 17, PAD = 3, ESM = 13; static constexpr bool MIRROR = false; };
 template <int D, int Q, int NP> struct Elem3Stride {
     static constexpr int PS = Slab3Layout<D, Q>::PS;
     static constexpr int PSET = Q * PS + Slab3Layout<D, Q>::PAD;

@@ -298,6 +298,10 @@ void Krylov::gmres(const double* b, double* x, bool flexible) {
     auto V = [&](int i) { return w(2 + i); };
     auto Z = [&](int i) { return w(2 + m + 1 + i); };
     auto P = [&](const double* in, double* out) { if (prec) prec->mult(in, out); else c->copy(in, out); };
+    // JOTS_MGS_SMALL=0 keeps the chained per-vector launches (the path large and partitioned problems take)
+    static const bool sweep_ok = [] { const char* e = std::getenv("JOTS_MGS_SMALL"); return !e || e[0] != '0'; }();
+    const bool small_mgs = sweep_ok && !c->halo && n <= 32768 && m + 2 <= 64;     // d_scal holds 64 scalars
+    bool vptr_valid = false;
     c->zero(x);
     if (flexible) c->copy(b, r); else P(b, r);
     double beta = c->norm(r);
@@ -325,6 +329,17 @@ void Krylov::gmres(const double* b, double* x, bool flexible) {
             else { apply(V(i), tmp); P(tmp, r); }
             // modified Gram-Schmidt, device-chained: step k subtracts the previous projection and forms
             // the next inner product in one pass; the i+2 scalars come back in a single copy
+            if (small_mgs) {
+                // small problems on one GPU: the whole sweep in one block (vec.cu: k_mgs_sweep_small)
+                if (i == 0 || !vptr_valid) {
+                    std::vector<const double*> hp(m + 1);
+                    for (int k = 0; k <= m; ++k) hp[k] = V(k);
+                    d_vptr.upload(hp);
+                    vptr_valid = true;
+                }
+                v_mgs_sweep_small(st, (int)n, r, d_vptr.p, i + 1, c->d_scal.p);
+                ++c->stats.kernel_launches;
+            } else
             for (int k = 0; k <= i + 1; ++k) {
                 v_mgs_step(st, n, c->n_owned, r, k > 0 ? V(k - 1) : nullptr, k > 0 ? c->d_scal.p + (k - 1) : nullptr,
                            k <= i ? V(k) : nullptr, c->dot_scratch(), c->d_scal.p + k);

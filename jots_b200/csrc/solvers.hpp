@@ -95,6 +95,7 @@ private:
         double* h = nullptr;         // pinned: NSLOT polling slots + the initial values
         cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     } cgd;
+    DArr<const double*> d_vptr;      // basis-vector pointers of the one-block Gram-Schmidt sweep
     void cg_device_loop(double* x, double* r, double* z, double* d, const double* dinv, double nom, double den, double r0);
     double* w(int i);
     void cg(const double* b, double* x);

@@ -242,6 +242,38 @@ void v_mgs_step(cudaStream_t st, int64_t n, int64_t n_owned, double* r, const do
                 DotScratch s, double* result) {
     k_mgs_step<<<grid_for(n, 8), VEC_THREADS, 0, st>>>(n, n_owned, r, Vprev, hprev, Vk, s, result);
 }
+// The whole modified Gram-Schmidt sweep of one (F)GMRES iteration in ONE block, for problems so small that a launch per basis
+// vector is pure latency (the shipped 1 791-DOF cases spent 60 % of their launches here):
+//   for k = 0 .. nv-1:  out[k] = (r, V_k);  r -= out[k] V_k;      then out[nv] = (r, r)
+// Same operation order as the chained k_mgs_step launches (deterministic block reduction).
+__global__ void __launch_bounds__(1024) k_mgs_sweep_small(int n, double* r, const double* const* V, int nv, double* out) {
+    __shared__ double sh[32];
+    __shared__ double hk;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for (int k = 0; k <= nv; ++k) {
+        const double* v = k < nv ? V[k] : r;
+        double s = 0.0;
+        for (int j = threadIdx.x; j < n; j += blockDim.x) s += r[j] * v[j];
+        s = warp_sum(s);
+        if (lane == 0) sh[wid] = s;
+        __syncthreads();
+        if (wid == 0) {
+            double t = lane < nw ? sh[lane] : 0.0;
+            t = warp_sum(t);
+            if (lane == 0) { hk = t; out[k] = t; }
+        }
+        __syncthreads();
+        if (k < nv) {
+            const double h = hk;
+            for (int j = threadIdx.x; j < n; j += blockDim.x) r[j] -= h * v[j];
+        }
+        __syncthreads();
+    }
+}
+void v_mgs_sweep_small(cudaStream_t st, int n, double* r, const double* const* V, int nv, double* out) {
+    k_mgs_sweep_small<<<1, 1024, 0, st>>>(n, r, V, nv, out);
+}
+
 // y = d * x * a + b * z   (Chebyshev Horner step: u = ds * (A t) + c_i * rs)
 __global__ void k_mul_axpby(int64_t n, const double* __restrict__ d, double a, const double* __restrict__ x, double b,
                             const double* __restrict__ z, double* y) {

@@ -33,6 +33,8 @@ void v_mul2(cudaStream_t st, int64_t n, const double* d, const double* x, double
 void v_dots(cudaStream_t st, int64_t n, int nv, const double* const* a, const double* const* b, DotScratch s, double* result);
 void v_cg_update(cudaStream_t st, int64_t n, int64_t n_owned, double alpha, const double* d, const double* Ad, double* x, double* r,
                  const double* dinv, double* z, DotScratch s, double* result);
+// one-block modified Gram-Schmidt sweep for small problems: out[k] = (r, V_k), r -= out[k] V_k (k < nv), out[nv] = (r, r)
+void v_mgs_sweep_small(cudaStream_t st, int n, double* r, const double* const* V, int nv, double* out);
 // device-resident CG scalars (vec.cu: S layout)
 void v_cgd_update(cudaStream_t st, int64_t n, int64_t n_owned, double* S, int i, const double* d, const double* Ad, double* x, double* r,
                   const double* dinv, double* z, DotScratch s);

@@ -463,3 +463,24 @@ def test_print_levels_and_step_lines(J, tmp_path, capfd):
         f.write(ini_text("Nonlinear_Unsteady", "unused", 300, PROPS["k"], [HF0] * 6, newton=5, steps=1, ls_print="Errors, Chatty"))
     with pytest.raises(J.JotsError, match="print level"):
         J.Driver(bad, 0, mesh=J.Mesh.brick(2, 2, 2, 1.0, 1.0, 1.0))
+
+
+@pytest.mark.parametrize("solver", ["GMRES", "FGMRES"])
+def test_one_block_gram_schmidt_sweep_matches_the_chained_launches(J, tmp_path, solver):
+    """Small single-GPU problems run the modified Gram-Schmidt sweep of an (F)GMRES iteration in one block
+    (vec.cu: k_mgs_sweep_small); large and partitioned ones chain one launch per basis vector.  Same operation order:
+    same iteration counts and fields.  JOTS_MGS_SMALL is read once per process, so the chained path runs in a child."""
+    import subprocess, sys, os, json
+    dev, orc = build(J, tmp_path, "Nonlinear_Unsteady", 3, 2, "kc", solver=solver, prec="Chebyshev", n=(6, 3, 2), steps=3)
+    dev.run()
+    st = dev.ctx.stats()
+    u = dev.get_u()
+    assert rel(u, orc.run()) < FIELD_TOL
+    code = ("import sys, json, numpy as np; sys.path.insert(0, %r); import jots_b200 as J; d = J.Driver(%r); d.run(); s = d.ctx.stats(); "
+            "np.save(%r, d.get_u()); print(json.dumps([s['krylov_iters'], s['newton_iters'], s['kernel_launches']]))"
+            % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), str(tmp_path / "c.ini"), str(tmp_path / "u.npy")))
+    out = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, JOTS_MGS_SMALL="0"), capture_output=True, text=True, check=True).stdout
+    k2, n2, launches2 = json.loads(out.strip().splitlines()[-1])
+    assert (k2, n2) == (st["krylov_iters"], st["newton_iters"])
+    assert launches2 > st["kernel_launches"]                      # the chained path launches more kernels
+    assert rel(np.load(str(tmp_path / "u.npy")), u) < 1e-12
