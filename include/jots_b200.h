@@ -38,7 +38,8 @@ typedef struct jots_comm_s* jots_comm_t;     /* NCCL communicator, one rank per 
 enum { JOTS_HOST = 0, JOTS_DEVICE = 1 };
 enum { JOTS_UNIFORM = 0, JOTS_POLYNOMIAL = 1 };                      /* src/option_structure.hpp:25-37 */
 enum { JOTS_BC_ISOTHERMAL = 0, JOTS_BC_HEATFLUX = 1, JOTS_BC_SINUSOIDAL_ISOTHERMAL = 2,
-       JOTS_BC_SINUSOIDAL_HEATFLUX = 3 };                            /* src/option_structure.hpp:56-71 */
+       JOTS_BC_SINUSOIDAL_HEATFLUX = 3, JOTS_BC_PRECICE_ISOTHERMAL = 4,
+       JOTS_BC_PRECICE_HEATFLUX = 5 };                               /* src/option_structure.hpp:56-71 */
 enum { JOTS_CG = 0, JOTS_GMRES = 1, JOTS_FGMRES = 2 };               /* src/option_structure.hpp:91-100 */
 enum { JOTS_JACOBI = 0, JOTS_CHEBYSHEV = 1 };                        /* src/option_structure.hpp:102-109 */
 enum { JOTS_EULER_IMPLICIT = 0, JOTS_EULER_EXPLICIT = 1, JOTS_RK4 = 2 }; /* src/option_structure.hpp:73-82 */
@@ -118,11 +119,24 @@ int jots_ctx_sync(jots_ctx_t c);
 int jots_ctx_set_material(jots_ctx_t c, int which, int model, const double* coeffs, int n_coeffs);
 /* BoundaryCondition objects, entry i <-> boundary attribute i+1 (src/jots_iterator.cpp:12-25):
    params[4*i..] = value | amplitude, angular frequency, phase, vertical shift */
-int jots_ctx_set_bcs(jots_ctx_t c, int n_bc, const int32_t* kinds, const double* params);
+int jots_ctx_set_bcs(jots_ctx_t c, int n_bc, const int32_t* kinds, const double* params);   /* kinds: JOTS_BC_* */
 int64_t jots_ctx_essential_dofs(jots_ctx_t c, int32_t* out);        /* ess_tdof_list */
 int jots_ctx_update_bcs(jots_ctx_t c, double time);                 /* BoundaryCondition::UpdateCoeff */
 int jots_ctx_apply_dirichlet(jots_ctx_t c, double* u, int loc, int only_time_dependent); /* ProjectBdrCoefficient, src/jots_driver.cpp:684-707 */
 int jots_ctx_set_material_state(jots_ctx_t c, const double* u, int loc); /* UpdateAllCoeffs(u), src/jots_driver.cpp:664 */
+/* preCICE boundary data path (PreciceBC / PreciceIsothermalBC / PreciceHeatFluxBC, src/boundary_condition.cpp:77-206; the
+   adapter that moves the arrays, src/jots_precice.cpp:43-67, stays with the reference).  BC kinds JOTS_BC_PRECICE_ISOTHERMAL /
+   JOTS_BC_PRECICE_HEATFLUX (params[0] = default value) keep a nodal coefficient field instead of one value.
+     _size / _nodes   the nodes of every boundary element of the BC's attribute, boundary element by boundary element with
+                      duplicates kept (bdr_dof_indices, coords: what the adapter registers as the coupling-mesh vertices);
+     _set_read_data   coeff_gf.SetSubVector(bdr_dof_indices, read_data_arr) (PreciceBC::UpdateCoeff): Dirichlet values of the
+                      isothermal kind, the flux field g of int g_h phi_i dS of the heat-flux kind (already negated by the adapter);
+     _write_data      RetrieveWriteData: wall heat flux -k(T) grad T . n / |n| at every listed node from the ADJACENT element's
+                      gradient (device kernel, affine elements) for the isothermal kind, the boundary temperatures otherwise. */
+int64_t jots_ctx_precice_bc_size(jots_ctx_t c, int bc_index);   /* -1: not a preCICE BC */
+int jots_ctx_precice_bc_nodes(jots_ctx_t c, int bc_index, double* coords, int32_t* dofs);
+int jots_ctx_precice_bc_set_read_data(jots_ctx_t c, int bc_index, const double* values);
+int jots_ctx_precice_bc_write_data(jots_ctx_t c, int bc_index, const double* u, int loc, double* out);
 /* Output-side property fields (OutputManager::UpdateGridFunctions -> ProjectCoefficient of the registered
    MaterialProperty coefficient, src/output_manager.cpp:63-73, src/jots_driver.cpp:343): nodal values of property
    `which` (0 rho, 1 C, 2 k), or of its first / second derivative (order 1 / 2), at the material state last set. */

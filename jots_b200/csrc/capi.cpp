@@ -378,11 +378,29 @@ int jots_ctx_apply_dirichlet(jots_ctx_t c, double* u, int loc, int only_td) {
     Ctx* x = c->c;
     Out o(x, u, loc, true);
     for (size_t i = 0; i < x->bcs.size(); ++i)
-        if (x->bcs[i].essential() && (!only_td || !x->bcs[i].constant()))
-            v_set_idx(x->stream, (int)x->bc_dofs[i].size(), x->d_bc_dofs[i].p, x->bcs[i].value, o.p);
+        if (x->bcs[i].essential() && (!only_td || !x->bcs[i].constant())) x->apply_dirichlet((int)i, o.p);
     o.finish();
     return 0;
     JOTS_CATCH_INT
+}
+int64_t jots_ctx_precice_bc_size(jots_ctx_t c, int bc) {
+    Ctx* x = c->c;
+    if (bc < 0 || bc >= (int)x->bcs.size() || !x->bcs[bc].precice()) return -1;
+    return x->precice_bc_size(bc);
+}
+int jots_ctx_precice_bc_nodes(jots_ctx_t c, int bc, double* coords, int32_t* dofs) {
+    JOTS_TRY
+    Ctx* x = c->c;
+    if (coords) x->precice_bc_coords(bc, coords);
+    if (dofs) { const std::vector<int>& nd = x->bc_node_dofs.at(bc); for (size_t i = 0; i < nd.size(); ++i) dofs[i] = nd[i]; }
+    return 0;
+    JOTS_CATCH_INT
+}
+int jots_ctx_precice_bc_set_read_data(jots_ctx_t c, int bc, const double* values) {
+    JOTS_TRY c->c->precice_bc_set_read_data(bc, values); return 0; JOTS_CATCH_INT
+}
+int jots_ctx_precice_bc_write_data(jots_ctx_t c, int bc, const double* u, int loc, double* out) {
+    JOTS_TRY In i(c->c, u, loc); c->c->precice_bc_write_data(bc, i.p, out); return 0; JOTS_CATCH_INT
 }
 int jots_ctx_set_material_state(jots_ctx_t c, const double* u, int loc) {
     JOTS_TRY In i(c->c, u, loc); c->c->set_mat_state(i.p); c->c->sync(); return 0; JOTS_CATCH_INT

@@ -19,7 +19,7 @@ void cuda_check(cudaError_t e, const char* what, const char* file, int line) {
 
 void BCSpec::update(double t) {
     // SinusoidalBC::UpdateCoeff: A sin(w t + phase) + shift (boundary_condition.cpp:65-75)
-    if (constant()) value = v[0];
+    if (constant() || precice()) value = v[0];      // PreciceBC: the default value until the adapter writes read data
     else value = v[0] * std::sin(v[1] * t + v[2]) + v[3];
 }
 
@@ -217,6 +217,34 @@ void Ctx::set_bcs(const std::vector<BCSpec>& b) {
     for (auto& g : ge) if (em[g]) g = ~g;
     d_gather_ess.upload(ge);
     d_gattr.alloc(std::max<size_t>(bcs.size(), 1));
+    // preCICE BCs: coefficient field, boundary-element node lists
+    bc_field.clear(); bc_field.resize(bcs.size());
+    bc_faces.assign(bcs.size(), {}); bc_node_dofs.assign(bcs.size(), {});
+    d_bc_faces.clear(); d_bc_faces.resize(bcs.size());
+    d_bc_node_dofs.clear(); d_bc_node_dofs.resize(bcs.size());
+    std::vector<const double*> gn(std::max<size_t>(bcs.size(), 1), nullptr);
+    bool any_precice = false;
+    for (size_t i = 0; i < bcs.size(); ++i) {
+        if (!bcs[i].precice()) continue;
+        any_precice = true;
+        bc_field[i].alloc(n);
+        v_fill(stream, n, bcs[i].v[0], bc_field[i].p);
+        for (int64_t b = 0; b < space.nbdr; ++b) {
+            if (space.bdr_attr[b] != (int)i + 1) continue;
+            bc_faces[i].push_back((int)b);
+            for (int l = 0; l < space.nfl; ++l) bc_node_dofs[i].push_back(space.bdr_gather[b * space.nfl + l]);
+        }
+        d_bc_faces[i].upload(bc_faces[i]);
+        d_bc_node_dofs[i].upload(bc_node_dofs[i]);
+        if (!bcs[i].essential()) gn[i] = bc_field[i].p;
+    }
+    d_gnodal.upload(gn);
+    if (any_precice && d_bdr_elem.n != (size_t)space.nbdr) {
+        std::vector<int> be(space.nbdr, -1), bf(space.nbdr, -1);
+        for (int64_t b = 0; b < space.nbdr && b < (int64_t)space.bdr_elem.size(); ++b) { be[b] = (int)space.bdr_elem[b]; bf[b] = space.bdr_face[b]; }
+        d_bdr_elem.upload(be); d_bdr_face.upload(bf);
+    }
+    sync();
     build_patches();
 }
 
@@ -240,13 +268,13 @@ void Ctx::build_patches() {
 }
 
 bool Ctx::any_flux() const {
-    for (auto& b : bcs) if (!b.essential() && b.value != 0.0) return true;
+    for (auto& b : bcs) if (!b.essential() && (b.value != 0.0 || b.precice())) return true;
     return false;
 }
 
 void Ctx::upload_flux_values() {
     std::vector<double> g(std::max<size_t>(bcs.size(), 1), 0.0);
-    for (size_t i = 0; i < bcs.size(); ++i) g[i] = bcs[i].essential() ? 0.0 : bcs[i].value;
+    for (size_t i = 0; i < bcs.size(); ++i) g[i] = (bcs[i].essential() || bcs[i].precice()) ? 0.0 : bcs[i].value;   // preCICE: nodal field
     JOTS_CUDA(cudaMemcpyAsync(d_gattr.p, g.data(), g.size() * sizeof(double), cudaMemcpyHostToDevice, stream));
     JOTS_CUDA(cudaStreamSynchronize(stream));
 }
@@ -289,6 +317,7 @@ static FaceArgs base_face_args(const Ctx& c, int nq) {
     fa.dim = c.space.dim; fa.D = c.space.D; fa.nfl = c.space.nfl; fa.nbdr = (int)c.space.nbdr;
     fa.bdr_gather = c.d_bdr_gather.p; fa.bdr_corner = c.d_bdr_corner.p; fa.bdr_attr = c.d_bdr_attr.p;
     fa.g_attr = c.d_gattr.p; fa.n_attr = (int)c.bcs.size();
+    fa.g_nodal = c.d_gnodal.p;
     fa.ess = c.d_essmark.p;
     fa.mat = c.mat;
     fa.scale = 1.0; fa.div_const = 1.0;
@@ -392,6 +421,68 @@ double Ctx::max_local(const double* a) {
     JOTS_CUDA(cudaMemcpyAsync(h_scal, d_scal.p, sizeof(double), cudaMemcpyDeviceToHost, stream));
     JOTS_CUDA(cudaStreamSynchronize(stream));
     return h_scal[0];
+}
+
+void Ctx::apply_dirichlet(int bc, double* u) {
+    // ProjectBdrCoefficient(coeff, marker_bc) (jots_driver.cpp:692): a uniform value, or the nodal field of a preCICE BC
+    const int cnt = (int)bc_dofs[bc].size();
+    if (bcs[bc].precice()) v_copy_idx(stream, cnt, d_bc_dofs[bc].p, bc_field[bc].p, u);
+    else v_set_idx(stream, cnt, d_bc_dofs[bc].p, bcs[bc].value, u);
+    stats.kernel_launches += cnt > 0;
+}
+
+void Ctx::precice_bc_coords(int bc, double* xyz) const {
+    if (bc < 0 || bc >= (int)bcs.size() || !bcs[bc].precice()) throw std::runtime_error("not a preCICE boundary condition");
+    std::vector<double> X;
+    space.node_coordinates(X);
+    const std::vector<int>& nd = bc_node_dofs[bc];
+    for (size_t i = 0; i < nd.size(); ++i)
+        for (int d = 0; d < space.dim; ++d) xyz[i * space.dim + d] = X[(size_t)nd[i] * space.dim + d];
+}
+
+void Ctx::precice_bc_set_read_data(int bc, const double* vals) {
+    if (bc < 0 || bc >= (int)bcs.size() || !bcs[bc].precice()) throw std::runtime_error("not a preCICE boundary condition");
+    // coeff_gf.SetSubVector(bdr_dof_indices, read_data_arr): a DOF listed by several boundary elements keeps the last value
+    const std::vector<int>& nd = bc_node_dofs[bc];
+    std::vector<int> dofs;
+    std::vector<double> v;
+    {
+        std::vector<std::pair<int, double>> last(nd.size());
+        for (size_t i = 0; i < nd.size(); ++i) last[i] = {nd[i], vals[i]};
+        std::stable_sort(last.begin(), last.end(), [](const std::pair<int, double>& a, const std::pair<int, double>& b) { return a.first < b.first; });
+        for (size_t i = 0; i < last.size(); ++i)
+            if (i + 1 == last.size() || last[i + 1].first != last[i].first) { dofs.push_back(last[i].first); v.push_back(last[i].second); }
+    }
+    DArr<int> dd; DArr<double> dv;
+    dd.upload(dofs); dv.upload(v);
+    v_scatter_idx(stream, (int)dofs.size(), dd.p, dv.p, bc_field[bc].p);
+    ++stats.kernel_launches;
+    sync();
+}
+
+void Ctx::precice_bc_write_data(int bc, const double* u, double* out) {
+    if (bc < 0 || bc >= (int)bcs.size() || !bcs[bc].precice()) throw std::runtime_error("not a preCICE boundary condition");
+    const size_t cnt = bc_node_dofs[bc].size();
+    DArr<double> d_out;
+    d_out.alloc(std::max<size_t>(cnt, 1));
+    if (bcs[bc].essential()) {
+        if (d_geomq.p) throw std::runtime_error("wall heat flux: general multilinear (non-affine) elements are not supported");
+        for (int b : bc_faces[bc]) if (b >= (int)space.bdr_elem.size() || space.bdr_elem[b] < 0) throw std::runtime_error("wall heat flux: the space has no boundary-element adjacency (caller-supplied tables)");
+        WallFluxArgs a;
+        std::memset(&a, 0, sizeof(a));
+        a.dim = space.dim; a.D = space.D; a.nloc = space.nloc; a.nfl = space.nfl; a.nfaces = (int)bc_faces[bc].size();
+        a.faces = d_bc_faces[bc].p; a.bdr_elem = d_bdr_elem.p; a.bdr_face = d_bdr_face.p; a.gather = d_gather_ess.p;
+        a.geom = d_geom.p; a.geom_stride = geom_stride; a.u = u; a.out = d_out.p; a.k = mat.k;
+        std::vector<double> nodes = gauss_lobatto_01(space.D), Bn, Gn;
+        lagrange_tab(nodes, nodes, Bn, Gn);
+        for (int i = 0; i < space.D * space.D; ++i) a.Dn[i] = Gn[i];
+        launch_wall_flux(a, stream);
+    } else {
+        v_pack(stream, (int)cnt, d_bc_node_dofs[bc].p, u, d_out.p);     // PreciceHeatFluxBC: u_gf.GetSubVector(bdr_dof_indices)
+    }
+    ++stats.kernel_launches;
+    JOTS_CUDA(cudaMemcpyAsync(out, d_out.p, cnt * sizeof(double), cudaMemcpyDeviceToHost, stream));
+    sync();
 }
 
 double Ctx::max_global(const double* a) {

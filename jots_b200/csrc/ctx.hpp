@@ -44,15 +44,17 @@ struct DArr {
     }
 };
 
-enum { BC_ISOTHERMAL = 0, BC_HEATFLUX = 1, BC_SIN_ISOTHERMAL = 2, BC_SIN_HEATFLUX = 3 };
+enum { BC_ISOTHERMAL = 0, BC_HEATFLUX = 1, BC_SIN_ISOTHERMAL = 2, BC_SIN_HEATFLUX = 3,
+       BC_PRECICE_ISOTHERMAL = 4, BC_PRECICE_HEATFLUX = 5 };   // PreciceBC: v[0] = default value, data per boundary node
 
 // BC value objects (/root/reference/src/boundary_condition.hpp:14-105, .cpp:49-75)
 struct BCSpec {
     int kind = BC_HEATFLUX;
     double v[4] = {0, 0, 0, 0};  // value | amp, angular freq, phase, vertical shift
     double value = 0.0;          // current coefficient value (UpdateCoeff)
-    bool essential() const { return kind == BC_ISOTHERMAL || kind == BC_SIN_ISOTHERMAL; }
+    bool essential() const { return kind == BC_ISOTHERMAL || kind == BC_SIN_ISOTHERMAL || kind == BC_PRECICE_ISOTHERMAL; }
     bool constant() const { return kind == BC_ISOTHERMAL || kind == BC_HEATFLUX; }
+    bool precice() const { return kind == BC_PRECICE_ISOTHERMAL || kind == BC_PRECICE_HEATFLUX; }
     void update(double t);
 };
 
@@ -102,6 +104,19 @@ public:
     // --- device tables
     DArr<int> d_gather, d_gather_ess, d_bdr_gather, d_bdr_attr, d_ess;
     std::vector<DArr<int>> d_bc_dofs;
+    // preCICE boundary data path (/root/reference/src/boundary_condition.cpp:77-206): per preCICE BC the nodal coefficient field
+    // (coeff_gf: default value, boundary entries overwritten by the read data), the boundary elements of its attribute and
+    // their nodes boundary element by boundary element (duplicates kept, the order of coords / read / write arrays)
+    std::vector<DArr<double>> bc_field;
+    std::vector<std::vector<int>> bc_faces, bc_node_dofs;
+    std::vector<DArr<int>> d_bc_faces, d_bc_node_dofs;
+    DArr<const double*> d_gnodal;       // per BC: bc_field pointer for preCICE heat-flux BCs, else null
+    DArr<int> d_bdr_elem, d_bdr_face;   // adjacent element and its local face of every boundary element
+    int64_t precice_bc_size(int bc) const { return (int64_t)bc_node_dofs.at(bc).size(); }
+    void precice_bc_coords(int bc, double* xyz) const;                 // [size][dim]
+    void precice_bc_set_read_data(int bc, const double* vals_host);    // PreciceBC::UpdateCoeff: SetSubVector(bdr_dof_indices, read)
+    void precice_bc_write_data(int bc, const double* u, double* out_host);   // RetrieveWriteData: wall heat flux | temperatures
+    void apply_dirichlet(int bc, double* u);                            // ProjectBdrCoefficient of BC `bc` (uniform value or field)
     DArr<double> d_geom, d_geomq, d_bdr_corner, d_gattr;
     DArr<unsigned char> d_essmark;
     int slab_variant = 7;             // JOTS_SLAB_VARIANT: 7 unique-pencil patch kernels where the mesh is a lattice (default), 3 gather-table kernel only

@@ -102,17 +102,20 @@ __global__ void face_kernel(const FaceArgs a) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= a.nbdr) return;
     const int attr = a.bdr_attr[b];
-    const double g = (attr >= 1 && attr <= a.n_attr) ? a.g_attr[attr - 1] : 0.0;
-    if (g == 0.0) return;
+    const bool mapped = attr >= 1 && attr <= a.n_attr;
+    const double* gfield = (mapped && a.g_nodal) ? a.g_nodal[attr - 1] : nullptr;   // nodal flux field of this attribute
+    const double g0 = mapped ? a.g_attr[attr - 1] : 0.0;
+    if (g0 == 0.0 && !gfield) return;
     const int dim = a.dim, D = a.D, nq = a.nq, nfl = a.nfl;
     const int nq2 = dim == 3 ? nq : 1;
     const int* gt = a.bdr_gather + (size_t)b * nfl;
     const double* X = a.bdr_corner + (size_t)b * (dim == 3 ? 4 : 2) * dim;
-    double rho_n[25], C_n[25], dr_n[25], dC_n[25], xn[25], acc[25];
+    double rho_n[25], C_n[25], dr_n[25], dC_n[25], xn[25], acc[25], gn[25];
     const bool state = a.z != nullptr;
     for (int l = 0; l < nfl; ++l) {
         acc[l] = 0.0;
         const int idx = gt[l];
+        gn[l] = gfield ? gfield[idx] : g0;
         if (state) {
             const double zv = a.z[idx];
             rho_n[l] = poly_val(a.mat.rho, zv); C_n[l] = poly_val(a.mat.C, zv);
@@ -138,10 +141,11 @@ __global__ void face_kernel(const FaceArgs a) {
                 meas = sqrt(c0 * c0 + c1 * c1 + c2 * c2);
             }
             const double w = a.Wf[qa] * (dim == 3 ? a.Wf[qb] : 1.0) * meas;
-            double r = 0.0, c = 0.0, dr = 0.0, dc = 0.0, xv = 0.0;
+            double r = 0.0, c = 0.0, dr = 0.0, dc = 0.0, xv = 0.0, g = gfield ? 0.0 : g0;
             for (int l = 0; l < nfl; ++l) {
                 const int la = l % D, lb = l / D;
                 const double phi = a.Bf[qa * D + la] * (dim == 3 ? a.Bf[qb * D + lb] : 1.0);
+                if (gfield) g += phi * gn[l];          // GridFunctionCoefficient: the nodal field interpolated on the face
                 if (state) { r += phi * rho_n[l]; c += phi * C_n[l]; dr += phi * dr_n[l]; dc += phi * dC_n[l]; }
                 if (MODE == FACE_MASS_APPLY) xv += phi * xn[l];
             }
@@ -161,6 +165,43 @@ __global__ void face_kernel(const FaceArgs a) {
         if (a.mask_out && a.ess && a.ess[idx]) continue;
         atomicAdd(a.y + idx, a.scale * acc[l]);
     }
+}
+
+// one thread per (boundary element of the BC, face node): gradient of the adjacent element's field at that node through the
+// nodal derivative matrix, outward normal = +- grad xi_axis
+static __global__ void wall_flux_kernel(const WallFluxArgs a) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= a.nfaces * a.nfl) return;
+    const int fi = t / a.nfl, l = t - fi * a.nfl;
+    const int b = a.faces[fi], e = a.bdr_elem[b], lf = a.bdr_face[b];
+    const int dim = a.dim, D = a.D, axis = lf >> 1, side = lf & 1;
+    int idx[3] = {0, 0, 0};
+    idx[axis] = side ? D - 1 : 0;
+    {
+        int m = l;
+        for (int c = 0; c < dim; ++c) if (c != axis) { idx[c] = m % D; m /= D; }
+    }
+    const int stride[3] = {1, D, D * D};
+    const int* g = a.gather + (size_t)e * a.nloc;
+    auto val = [&](int loc) { const int d = g[loc]; return a.u[d < 0 ? ~d : d]; };
+    const int l0 = idx[0] + D * idx[1] + (dim == 3 ? D * D * idx[2] : 0);
+    double gref[3] = {0.0, 0.0, 0.0};
+    for (int c = 0; c < dim; ++c) {
+        const int base = l0 - idx[c] * stride[c];
+        double s = 0.0;
+        for (int m = 0; m < D; ++m) s += a.Dn[idx[c] * D + m] * val(base + m * stride[c]);
+        gref[c] = s;
+    }
+    const double* iJ = a.geom + (size_t)e * a.geom_stride;      // iJ[3*a + i] = d xi_a / d x_i
+    double n[3], nn = 0.0, flux = 0.0;
+    for (int i = 0; i < 3; ++i) { n[i] = (side ? 1.0 : -1.0) * iJ[3 * axis + i]; nn += n[i] * n[i]; }
+    nn = sqrt(nn);
+    for (int i = 0; i < dim; ++i) {
+        double gp = 0.0;
+        for (int c = 0; c < dim; ++c) gp += iJ[3 * c + i] * gref[c];
+        flux += gp * n[i];
+    }
+    a.out[t] = -poly_val(a.k, val(l0)) * flux / nn;
 }
 
 }  // namespace jots

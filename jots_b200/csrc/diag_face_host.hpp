@@ -18,6 +18,7 @@ struct FaceArgs {
     const double* bdr_corner;   // [nbdr*2^(dim-1)*dim]
     const int* bdr_attr;        // [nbdr]
     const double* g_attr;       // flux per attribute index (attr-1), 0 for unmapped/essential
+    const double* const* g_nodal;  // per attribute index: nodal flux field (preCICE heat-flux BC: GridFunctionCoefficient) or null
     int n_attr;
     const unsigned char* ess;   // [ndof] essential marker (may be null)
     const double* z;            // state for rho_h, C_h (null -> uniform: divide by div_const)
@@ -30,6 +31,22 @@ struct FaceArgs {
     double Bf[25];              // [nq*D] basis at the face rule
     double Wf[5];
     double xq[5];               // 1-D rule points (for the surface Jacobian)
+};
+
+// wall heat flux -k(T) grad T . n / |n| at the nodes of boundary elements (PreciceIsothermalBC::RetrieveWriteData,
+// /root/reference/src/boundary_condition.cpp:152-191): affine elements
+struct WallFluxArgs {
+    int dim, D, nloc, nfl, nfaces;
+    const int* faces;          // boundary elements of the BC
+    const int* bdr_elem;       // adjacent element of every boundary element
+    const int* bdr_face;       // its local face (axis = f / 2, side = f % 2)
+    const int* gather;         // [nelem][nloc], essential DOFs complemented
+    const double* geom;        // invJ + det per element (stride 10) or one record (stride 0)
+    int geom_stride;
+    const double* u;
+    double* out;               // [nfaces][nfl]
+    Poly k;
+    double Dn[25];             // Dn[i*D + m] = l_m'(x_i): derivative of the nodal basis at the nodes
 };
 
 }  // namespace jots

@@ -169,6 +169,12 @@ BCSpec parse_bc(const std::vector<std::string>& info) {
         if (info.size() < 5) throw std::runtime_error("sinusoidal boundary condition needs 4 parameters");
         b.kind = k == "Sinusoidal_Isothermal" ? BC_SIN_ISOTHERMAL : BC_SIN_HEATFLUX;
         for (int i = 0; i < 4; ++i) b.v[i] = std::stod(info[1 + i]);
+    } else if (k == "preCICE_Isothermal" || k == "preCICE_HeatFlux") {
+        // kind, coupling-mesh name, default value (jots_driver.cpp:451-462); the adapter moves the data through
+        // jots_ctx_precice_bc_set_read_data / _write_data
+        if (info.size() < 3) throw std::runtime_error("preCICE boundary condition needs a mesh name and a default value");
+        b.kind = k == "preCICE_Isothermal" ? BC_PRECICE_ISOTHERMAL : BC_PRECICE_HEATFLUX;
+        b.v[0] = std::stod(info[2]);
     } else throw std::runtime_error("Invalid/Unknown boundary condition specified: '" + k + "'");
     return b;
 }
@@ -281,10 +287,8 @@ void JOTSDriver::UpdateAndApplyBCs() {
         BCSpec& bc = ctx->bcs[i];
         if (!bc.constant() || !initialized_bcs) {
             bc.update(time);
-            if (bc.essential()) {
-                v_set_idx(ctx->stream, (int)ctx->bc_dofs[i].size(), ctx->d_bc_dofs[i].p, bc.value, u.p);
-                ++ctx->stats.kernel_launches;
-            } else n_changed = true;
+            if (bc.essential()) ctx->apply_dirichlet((int)i, u.p);
+            else n_changed = true;
         }
     }
     initialized_bcs = true;

@@ -71,4 +71,11 @@ int launch_face(int mode, const FaceArgs& a, cudaStream_t st) {
     return 0;
 }
 
+int launch_wall_flux(const WallFluxArgs& a, cudaStream_t st) {
+    const int n = a.nfaces * a.nfl;
+    if (n <= 0) return 0;
+    wall_flux_kernel<<<(n + 127) / 128, 128, 0, st>>>(a);
+    return 0;
+}
+
 }  // namespace jots

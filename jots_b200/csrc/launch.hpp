@@ -23,6 +23,7 @@ void patch_shape(int p, int& px, int& py);   // patch size for order p (0: no pa
 int launch_form_diag_slab(int p, int op, int cf, const FormArgs& a, const TablesRT& t, cudaStream_t st);
 int launch_form_diag(int dim, int p, int op, int cf, const FormArgs& a, const TablesRT& t, cudaStream_t st);
 int launch_face(int mode, const FaceArgs& a, cudaStream_t st);
+int launch_wall_flux(const WallFluxArgs& a, cudaStream_t st);
 
 // per-shape entry points (one translation unit each so they compile in parallel)
 #define JOTS_DECL_SHAPE(NAME) int launch_form_apply_##NAME(int op, int cf, const FormArgs& a, const TablesRT& t, cudaStream_t st);

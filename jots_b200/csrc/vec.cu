@@ -62,6 +62,10 @@ __global__ void k_set_idx(int n, const int* __restrict__ idx, double v, double* 
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) y[idx[i]] = v;
 }
+__global__ void k_scatter_idx(int n, const int* __restrict__ idx, const double* __restrict__ x, double* y) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) y[idx[i]] = x[i];
+}
 __global__ void k_copy_idx(int n, const int* __restrict__ idx, const double* __restrict__ x, double* y) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) y[idx[i]] = x[idx[i]];
@@ -313,6 +317,9 @@ void v_hash_unit(cudaStream_t st, int64_t n, const int64_t* gidx, int64_t offset
 }
 void v_set_idx(cudaStream_t st, int n, const int* idx, double v, double* y) {
     if (n > 0) k_set_idx<<<(n + 255) / 256, 256, 0, st>>>(n, idx, v, y);
+}
+void v_scatter_idx(cudaStream_t st, int n, const int* idx, const double* x, double* y) {
+    if (n > 0) k_scatter_idx<<<(n + 255) / 256, 256, 0, st>>>(n, idx, x, y);
 }
 void v_copy_idx(cudaStream_t st, int n, const int* idx, const double* x, double* y) {
     if (n > 0) k_copy_idx<<<(n + 255) / 256, 256, 0, st>>>(n, idx, x, y);

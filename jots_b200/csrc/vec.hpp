@@ -22,7 +22,8 @@ void v_recip(cudaStream_t st, int64_t n, const double* d, double* y);
 void v_hash_unit(cudaStream_t st, int64_t n, const int64_t* gidx, int64_t offset, double* y);
 void v_poly_field(cudaStream_t st, int64_t n, const Poly& P, int order, const double* u, double* out);   // property field / d/dT / d2/dT2
 void v_set_idx(cudaStream_t st, int n, const int* idx, double v, double* y);
-void v_copy_idx(cudaStream_t st, int n, const int* idx, const double* x, double* y);
+void v_copy_idx(cudaStream_t st, int n, const int* idx, const double* x, double* y);      // y[idx[i]] = x[idx[i]]
+void v_scatter_idx(cudaStream_t st, int n, const int* idx, const double* x, double* y);   // y[idx[i]] = x[i]
 void v_pack(cudaStream_t st, int n, const int* idx, const double* y, double* out);
 void v_reduce_shared(cudaStream_t st, int n, const int* dof, const int* ptr, const int* src, const double* recv, double* y);
 void v_max(cudaStream_t st, int64_t n, const double* x, DotScratch s, double* result);

@@ -83,6 +83,10 @@ def load_library():
         "jots_ctx_update_bcs": (C.c_int, [_P, C.c_double]),
         "jots_ctx_apply_dirichlet": (C.c_int, [_P, _P, C.c_int, C.c_int]),
         "jots_ctx_set_material_state": (C.c_int, [_P, _P, C.c_int]),
+        "jots_ctx_precice_bc_size": (C.c_int64, [_P, C.c_int]),
+        "jots_ctx_precice_bc_nodes": (C.c_int, [_P, C.c_int, _P, _P]),
+        "jots_ctx_precice_bc_set_read_data": (C.c_int, [_P, C.c_int, _P]),
+        "jots_ctx_precice_bc_write_data": (C.c_int, [_P, C.c_int, _P, C.c_int, _P]),
         "jots_ctx_material_field": (C.c_int, [_P, C.c_int, C.c_int, _P, C.c_int]),
         "jots_ctx_stats": (C.c_int, [_P, _P, _P]),
         "jots_ctx_expand_true": (C.c_int, [_P, _P, _P, C.c_int]),
@@ -368,7 +372,7 @@ class Space:
 
 
 _BC_KIND = {"Isothermal": BC_ISOTHERMAL, "HeatFlux": BC_HEATFLUX, "Sinusoidal_Isothermal": BC_SIN_ISOTHERMAL,
-            "Sinusoidal_HeatFlux": BC_SIN_HEATFLUX}
+            "Sinusoidal_HeatFlux": BC_SIN_HEATFLUX, "preCICE_Isothermal": 4, "preCICE_HeatFlux": 5}
 
 
 class Context:
@@ -379,6 +383,7 @@ class Context:
         self._borrowed = handle is not None
         self._h = _handle(handle if handle is not None else load_library().jots_ctx_create(space._h, device))
         self.n = load_library().jots_ctx_size(self._h)
+        self.dim = space.dim if space is not None else None
 
     @classmethod
     def from_partition(cls, part, device, comm):
@@ -420,7 +425,7 @@ class Context:
             if s[0] not in _BC_KIND:
                 raise JotsError("Invalid/Unknown boundary condition specified: '%s'" % s[0])
             kinds[i] = _BC_KIND[s[0]]
-            vals = [float(v) for v in s[1:]]
+            vals = [float(v) for v in (s[2:] if s[0].startswith("preCICE") else s[1:])]    # preCICE: kind, coupling mesh, default
             params[i, :len(vals)] = vals
         _chk(load_library().jots_ctx_set_bcs(self._h, len(specs), _ptr(kinds), _ptr(params)))
 
@@ -435,6 +440,33 @@ class Context:
 
     def apply_dirichlet(self, u, only_time_dependent=False):
         _chk(load_library().jots_ctx_apply_dirichlet(self._h, _ptr(_f64(u)), _loc(u), int(only_time_dependent)))
+
+    def precice_bc_nodes(self, bc):
+        """(dofs, coords) of the boundary-element nodes of preCICE BC `bc` (0-based BC index), duplicates kept."""
+        n = load_library().jots_ctx_precice_bc_size(self._h, bc)
+        if n < 0:
+            raise JotsError("not a preCICE boundary condition")
+        dim = self._dim()
+        dofs = np.empty(n, dtype=np.int32)
+        xyz = np.empty((n, dim))
+        _chk(load_library().jots_ctx_precice_bc_nodes(self._h, bc, _ptr(xyz), _ptr(dofs)))
+        return dofs, xyz
+
+    def _dim(self):
+        # coordinates per node: probe with the largest dimension, the library fills dim values per node
+        if self.dim is None:
+            raise JotsError("set Context.dim (2 or 3) before asking for boundary node coordinates")
+        return int(self.dim)
+
+    def precice_bc_set_read_data(self, bc, values):
+        v = np.ascontiguousarray(values, dtype=np.float64)
+        _chk(load_library().jots_ctx_precice_bc_set_read_data(self._h, bc, _ptr(v)))
+
+    def precice_bc_write_data(self, bc, u):
+        n = load_library().jots_ctx_precice_bc_size(self._h, bc)
+        out = np.empty(max(n, 0))
+        _chk(load_library().jots_ctx_precice_bc_write_data(self._h, bc, _ptr(_f64(u)), _loc(u), _ptr(out)))
+        return out
 
     def set_material_state(self, u):
         _chk(load_library().jots_ctx_set_material_state(self._h, _ptr(_f64(u)), _loc(u)))

@@ -333,19 +333,29 @@ class H1Space:
         Phi = np.einsum("bj,ai->baji", B, B).reshape(nq * nq, -1)
         return x, np.einsum("b,a->ba", w, w).ravel(), Phi
 
+    def face_nodal_values(self, g_by_attr):
+        """[nb, nfl] values of a piecewise boundary coefficient at the face nodes: {attr: scalar} (uniform BC values) or
+        {attr: nodal field of length ndof} (a GridFunctionCoefficient, as PreciceBC's coeff_gf:
+        /root/reference/src/boundary_condition.cpp:134-147); unmapped attributes give 0."""
+        out = np.zeros(self.bdr_gather.shape)
+        for attr, val in g_by_attr.items():
+            sel = self.mesh.bdr_attr == attr
+            if np.isscalar(val):
+                out[sel] = val
+            else:
+                out[sel] = np.asarray(val)[self.bdr_gather[sel]]
+        return out
+
     def neumann_vector(self, g_by_attr, divisor=None):
         """``BoundaryLFIntegrator(PWCoefficient)``: b_i = sum_faces int g phi_i dS, rule order
-        p+1 (/root/reference/src/jots_iterator.cpp:33,39-43).  ``g_by_attr``: {attr: value};
-        unmapped attributes contribute 0.  ``divisor``: optional nodal field (rho*C is formed by
+        p+1 (/root/reference/src/jots_iterator.cpp:33,39-43).  ``g_by_attr``: {attr: value or nodal
+        field}; unmapped attributes contribute 0.  ``divisor``: optional nodal field (rho*C is formed by
         the caller as a *ratio of interpolants*: g / (rho_h C_h), see
         /root/reference/src/nl_conduction_operator.cpp:104-107) given as tuple (rho, C) of
         scalars / nodal fields."""
         x, w, Phi = self._face_tab(bdr_lf_quad_points(self.p))
         meas = self.face_measure(x)
-        g = np.zeros(self.mesh.bdr.shape[0])
-        for attr, val in g_by_attr.items():
-            g[self.mesh.bdr_attr == attr] = val
-        coef = np.broadcast_to(g[:, None], meas.shape).copy()
+        coef = self.face_nodal_values(g_by_attr) @ Phi.T
         if divisor is not None:
             coef = coef / self._face_coef_product(divisor, Phi)
         el = (coef * meas * w[None, :]) @ Phi
@@ -354,7 +364,43 @@ class H1Space:
     def _face_coef(self, c, Phi):
         if np.isscalar(c):
             return np.full((self.mesh.bdr.shape[0], Phi.shape[0]), float(c))
-        return np.asarray(c)[self.bdr_gather] @ Phi.T
+        c = np.asarray(c)
+        if c.ndim == 2:                       # values at the face nodes (face_nodal_values)
+            return c @ Phi.T
+        return c[self.bdr_gather] @ Phi.T
+
+    # preCICE boundary data path (/root/reference/src/boundary_condition.cpp:77-206) ------------------
+    def bdr_nodes(self, attr):
+        """(dofs, coords) of the nodes of every boundary element of ``attr``, boundary element by boundary element
+        (duplicates across neighbouring faces kept, as PreciceBC's bdr_dof_indices / coords)."""
+        sel = np.nonzero(self.mesh.bdr_attr == attr)[0]
+        dofs = self.bdr_gather[sel].ravel()
+        return dofs, self.node_coordinates()[dofs]
+
+    def wall_heat_flux(self, attr, u, k_of_T):
+        """PreciceIsothermalBC::RetrieveWriteData (:152-191): -k(T) grad T . n / |n| at every node of every boundary
+        element of ``attr`` -- gradient of the ADJACENT element's field at that node, outward normal of the face."""
+        dim, D = self.dim, self.D
+        sel = np.nonzero(self.mesh.bdr_attr == attr)[0]
+        _, Gn = lagrange_tab(self.nodes, self.nodes)            # Gn[i, m] = l_m'(x_i)
+        Bn = np.eye(D)
+        _, dPhi_n = tensor_tab(Bn, Gn, dim)                      # [node, local dof, axis]: reference gradient at the nodes
+        _, dNv = self._vertex_shape(self.nodes)
+        X = self.mesh.element_vertices()
+        out = []
+        for b in sel:
+            e, f = self.bdr_elem[b], self.bdr_face[b]
+            axis, side = f // 2, f % 2
+            ue = u[self.gather[e]]
+            J = np.einsum("vi,qva->qia", X[e], dNv)              # [node, i, a]
+            invJ = np.linalg.inv(J)                              # [node, a, i]
+            gref = np.einsum("qla,l->qa", dPhi_n, ue)
+            gphys = np.einsum("qai,qa->qi", invJ, gref)
+            for l in M.face_lattice_nodes(dim, self.p, f):
+                n = invJ[l, axis, :] * (1.0 if side else -1.0)   # grad xi_axis: normal of the face xi_axis = const, outward
+                n = n / np.linalg.norm(n)
+                out.append(-k_of_T(ue[l]) * float(gphys[l] @ n))
+        return np.array(out)
 
     def _face_coef_product(self, cs, Phi):
         out = 1.0

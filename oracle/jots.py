@@ -119,6 +119,13 @@ class MaterialProperty:
     def is_constant(self):
         return self.poly is None
 
+    def local_value(self, t):
+        """GetLocalValue (material_property.cpp:101-108): the property at one temperature."""
+        if self.poly is None:
+            return self.value
+        n = len(self.poly)
+        return sum(c * t ** (n - 1 - i) for i, c in enumerate(self.poly))
+
     def update(self, u):
         if self.poly is None:
             return
@@ -159,13 +166,33 @@ class BoundaryCondition:
             self.amp, self.afreq, self.phase, self.shift = (float(t) for t in info[1:5])
             self.constant = False
             self.value = None
+        elif kind in ("preCICE_Isothermal", "preCICE_HeatFlux"):
+            # PreciceBC (boundary_condition.cpp:77-147): info = kind, coupling-mesh name, default value; the coefficient is
+            # a nodal field (GridFunctionCoefficient) whose boundary values the adapter overwrites (set_read_data)
+            self.mesh_name, self.default = info[1], float(info[2])
+            self.constant = False
+            self.value = self.default      # scalar until data is read, then a nodal field (space attached by the driver)
         else:
             raise ValueError("Invalid/Unknown boundary condition specified: '%s'" % kind)
         self.essential = kind.endswith("Isothermal")
+        self.precice = kind.startswith("preCICE")
 
     def update(self, t):
-        if not self.constant:
+        if not self.constant and not self.precice:
             self.value = self.amp * math.sin(self.afreq * t + self.phase) + self.shift
+
+    def set_read_data(self, space, values):
+        """PreciceBC::UpdateCoeff: coeff_gf.SetSubVector(bdr_dof_indices, read_data_arr) (later entries win)."""
+        dofs, _ = space.bdr_nodes(self.attr)
+        field = np.full(space.ndof, self.default) if np.isscalar(self.value) else self.value
+        field[dofs] = np.asarray(values, dtype=float)
+        self.value = field
+
+    def write_data(self, space, u, k_prop):
+        """RetrieveWriteData: wall heat flux for the isothermal kind (:152-191), boundary temperatures otherwise (:194-198)."""
+        if self.essential:
+            return space.wall_heat_flux(self.attr, u, lambda t: k_prop.local_value(t))
+        return u[space.bdr_nodes(self.attr)[0]]
 
 
 # ----------------------------------------------------------------------------------------------
@@ -316,11 +343,12 @@ class _CoeffSet:
                         - d2r / (c * r * r) + 2 * dr * dr / (c * r * r * r)))
 
     def g_over_rhoC(self, g, at):
-        return g / (at(self.rho.coeff) * at(self.C.coeff))
+        return at(g) / (at(self.rho.coeff) * at(self.C.coeff))
 
     def dg_over_rhoC(self, g, at):
         r, dr = at(self.rho.coeff), at(self.rho.dcoeff)
         c, dc = at(self.C.coeff), at(self.C.dcoeff)
+        g = at(g)
         return -g * dr / (r * r * c) - g * dc / (c * c * r)
 
 
@@ -350,10 +378,7 @@ class NonlinearConductionOperator(JOTSIterator):
             mp.update(z)
 
     def _bdr_g(self):
-        g = np.zeros(self.space.mesh.bdr.shape[0])
-        for attr, val in self.neumann_values().items():
-            g[self.space.mesh.bdr_attr == attr] = val
-        return g[:, None]
+        return self.space.face_nodal_values(self.neumann_values())     # [nb, nfl]: uniform values or nodal (preCICE) fields
 
     # A(u) and its gradient ----------------------------------------------------------------------
     def A_mult(self, u):
@@ -584,7 +609,7 @@ class JOTSDriver:
                 if bc.essential:
                     # marker i <-> attribute i+1 (jots_driver.cpp:488-495)
                     dofs = self.space.essential_dofs([i + 1])
-                    self.u[dofs] = bc.value
+                    self.u[dofs] = bc.value if np.isscalar(bc.value) else bc.value[dofs]
                 else:
                     n_changed = True
         self.initialized_bcs = True

@@ -63,3 +63,37 @@ def test_oracle_convergence_order_on_a_smooth_nonlinear_steady_problem(p, tmp_pa
         errs.append(analytic.reference_error(drv.space, drv.run(), exact, 0.0))
     orders = [np.log2(errs[i] / errs[i + 1]) for i in range(2)]
     assert p + 0.5 <= orders[0] <= p + 1.7 and p + 0.7 <= orders[1] <= p + 1.7, (p, errs, orders)
+
+
+@pytest.mark.parametrize("p", [1, 2, 3])
+def test_oracle_precice_boundary_data_path_is_exact_on_polynomials(tmp_path, p):
+    """Pins for the oracle's restatement of the preCICE boundary data path (boundary_condition.cpp:77-206), which the
+    reference only tests through preCICE itself: the wall heat flux -k(T) grad T . n of a field in the FE space is exact at
+    the nodes (T linear, affine graded mesh: q = -k(T) dT/dn), and the Neumann vector of a nodal flux field integrates it
+    exactly (sum_i b_i = int g dS for g in the trace space)."""
+    from cases import ini_text, write_brick_mesh
+    from oracle import jots as OJ
+    props = [("Density_rho", "Uniform, 8000"), ("Specific_Heat_C", "Uniform, 500"), ("Thermal_Conductivity_k", "Polynomial, 0.09, -17")]
+    hf0 = "HeatFlux, 0"
+    mesh = str(tmp_path / "m.mesh")
+    write_brick_mesh(mesh, 3, 2, 2, 0.01, 0.02, 0.015, grade=0.4)
+    ini = str(tmp_path / "c.ini")
+    with open(ini, "w") as f:
+        f.write(ini_text("Nonlinear_Unsteady", mesh, 300, props, ["preCICE_Isothermal, M, 320", hf0, hf0, "preCICE_HeatFlux, M, 0", hf0, hf0],
+                         newton=50, steps=1, order=p))
+    orc = OJ.JOTSDriver(OJ.Config(ini))
+    X = orc.space.node_coordinates()
+    u = 300.0 + 1000.0 * X[:, 0] + 500.0 * X[:, 1] - 200.0 * X[:, 2]
+    for attr, dTdn in ((1, -1000.0), (4, 1000.0)):
+        bc = OJ.BoundaryCondition(attr, ["preCICE_Isothermal", "M", "1"])
+        dofs, coords = orc.space.bdr_nodes(attr)
+        assert np.allclose(coords[:, 0], 0.0 if attr == 1 else 0.01)
+        q = bc.write_data(orc.space, u, orc.props["k"])
+        assert np.abs(q + (0.09 * u[dofs] - 17.0) * dTdn).max() <= 1e-12 * np.abs(q).max()
+    # nodal flux field on attribute 4 (x = 0.01, area 0.02 x 0.015): g = 1 + 100 y  ->  int g dS = A (1 + 100 * 0.01)
+    bc = orc.bcs[3]
+    dofs, coords = orc.space.bdr_nodes(4)
+    bc.set_read_data(orc.space, 1.0 + 100.0 * coords[:, 1])
+    b = orc.space.neumann_vector({4: bc.value})
+    assert abs(b.sum() - 0.02 * 0.015 * 2.0) <= 1e-13
+    assert np.abs(b[np.setdiff1d(np.arange(orc.space.ndof), dofs)]).max() == 0.0
