@@ -147,6 +147,8 @@ int jots_ctx_stats(jots_ctx_t c, int64_t out[12], double norms[2]);
 /* element patches of the unique-pencil kernel this context runs (0 patches: the gather-table kernels are in use):
    number of patches, fill = elements / (patches x elements per patch), operator applies that ran the patch kernel */
 int jots_ctx_patch_info(jots_ctx_t c, int64_t* n_patches, double* fill, int64_t* applies);
+/* operator applies of the conjugate-gradient loop that formed (d, A d) inside the element kernel (no separate pass) */
+int jots_ctx_fused_dots(jots_ctx_t c, int64_t* n);
 /* label of the element kernel the last operator apply launched, e.g. "form_apply_patch_kernel<3,4,OP_JAC,CF_KL,4,4,128>" */
 const char* jots_ctx_last_kernel(jots_ctx_t c);
 int jots_ctx_reset_stats(jots_ctx_t c);
@@ -175,6 +177,10 @@ int jots_op_get_neumann(jots_op_t op, double* b, int loc);                     /
 /* building blocks: y = form(x) at frozen state (state may be NULL where the form has none) */
 int jots_op_form_apply(jots_op_t op, int form, const double* x, const double* state, double* y, int loc);
 int jots_op_form_diagonal(jots_op_t op, int form, const double* state, double* d, int loc);
+/* y = form(x) and *dot = (x, form(x)) over the owned rows, all-reduced: what one conjugate-gradient iteration needs
+   (mfem::CGSolver::Mult: den = Dot(d, z) after oper->Mult(d, z)).  *fused = 1 when the element kernel formed the inner product
+   in the same pass (two-phase patch kernel), 0 when a separate pass did.  Bilinear forms only (MASS, STIFFNESS, SYSTEM). */
+int jots_op_form_apply_dot(jots_op_t op, int form, const double* x, const double* state, double* y, int loc, double* dot, int* fused);
 /* repeat y = form(x) `reps` times on device-resident vectors; returns the mean milliseconds per
    apply measured with CUDA events on the context's stream (bench.py's roofline leg) */
 int jots_op_form_time(jots_op_t op, int form, const double* x_dev, const double* state_dev, double* y_dev,

@@ -53,7 +53,8 @@ struct Patch2Smem {
 // Measured dead ends (profiles/README.md r2d, r2e), so that they are not tried again: issuing phase 3 of tile t-1 branch-free
 // inside phase 2 of tile t (registers: 3 % slower); moving the copy-engine role to another warp with every tile to even out
 // the four scheduler partitions (5 % slower).
-template <int D, int Q, int OP, bool KLIN, int PX, int PY, int T>
+// DOT: also add (x, A x) over the rows written to *a.dot (FormArgs::dot; the conjugate-gradient loop's (d, A d)).
+template <int D, int Q, int OP, bool KLIN, int PX, int PY, int T, bool DOT = false>
 __global__ void __launch_bounds__(T, 4) form_apply_patch2_kernel(const FormArgs a, const Slab2Tables<D, Q> t, const PatchItems items) {
     if (a.skip && *a.skip != 0.0) return;   // enqueued ahead of a Krylov solve that has already stopped
     typedef PatchDims<D, PX, PY> PD;
@@ -80,6 +81,8 @@ __global__ void __launch_bounds__(T, 4) form_apply_patch2_kernel(const FormArgs 
     // last 8 % of the launch: sm__cycles_active avg 1.81 M against max 1.97 M, profiles/r2c).  The last block to leave resets
     // the counter for the next launch.
     __shared__ int s_tile[4];
+    __shared__ double s_dot[DOT ? T : 1];    // fused (x, A x): one running sum per phase-3 thread
+    if (DOT) s_dot[tid] = 0.0;
     int pending = 0;               // lane 0 of the copy warp: the claim made one tile earlier (its latency is never waited for)
     auto claim = [&](int i) {      // copy warp only
         int tile = 0;
@@ -161,7 +164,8 @@ __global__ void __launch_bounds__(T, 4) form_apply_patch2_kernel(const FormArgs 
 
     // phase 3 of tile i: transposed z contraction + scatter of this thread's item.  Branch free up to the atomics: the
     // loads are unconditional (every address is valid), contributions of holes are deselected.
-    auto phase3 = [&](int i, unsigned my_item) {
+    // sk (DOT): the pencil's output values, handed back for the fused inner product
+    auto phase3 = [&](int i, unsigned my_item, double (&sk)[D]) {
         const int p3_pencil = my_item & 0xff, p3_nv = (my_item >> 8) & 3;
         const int p3_off0 = (my_item >> 10) & 0x3ff, p3_off1 = (my_item >> 20) & 0x3ff;
         const int* dsc = ring + (i & 3) * REC;
@@ -186,6 +190,7 @@ __global__ void __launch_bounds__(T, 4) form_apply_patch2_kernel(const FormArgs 
 #pragma unroll
             for (int q = 1; q < Q; ++q) { sa += t.B[q * D + k] * Aq[q]; sb += t.G[q * D + k] * Bq[q]; }
             const double sum = sa + sb;
+            if (DOT) sk[k] = sum;
             if (any) {
                 if (g[k] >= 0) atomicAdd(a.y + g[k], sum);
                 else if (g[k] != PATCH_INVALID) {
@@ -323,11 +328,41 @@ __global__ void __launch_bounds__(T, 4) form_apply_patch2_kernel(const FormArgs 
                 op[(m / D) * O::JS + m % D] = mine + other;
             }
         }
+        // fused (x, A x): the pencil's own input values are read from the stage buffer BEFORE the tile's barrier (the copy warp
+        // refills that buffer right after it)
+        double xk[D], sk[D];
+        if (DOT) {
+            const double* sxp = stage + (size_t)(it & 1) * 2 * NN + (my_item & 0xff);
+#pragma unroll
+            for (int k = 0; k < D; ++k) { xk[k] = sxp[k * NPEN]; sk[k] = 0.0; }
+        }
         if (copier) cp_async_wait<0>();      // nodal values of tile it+1 and the descriptor of tile it+2 have landed
         __syncthreads();
 
         // ---------------- phase 3: transposed z contraction + scatter (worker warps; the others run ahead) ---------------
-        if (tid < items.n) phase3(it, my_item);
+        if (tid < items.n) phase3(it, my_item, sk);
+        if (DOT) {
+            // Straight-line code after the divergent region, so that its latency overlaps the start of the next tile's phase 2:
+            // with the FP64 pipe saturated by the other warps every dependent FP64 instruction inside phase 3 costs ~50 cycles
+            // (measured: the same three FMAs inside the k loop +23 us per launch, here +16 us; a separate pass is 44 us).
+            // No selection is needed: the staged input is zero wherever the row is not written (holes; eliminated columns --
+            // the caller fuses only forms with mask_in == mask_out), and threads without an item keep sk = 0.
+            double pr = xk[0] * sk[0];
+#pragma unroll
+            for (int k = 1; k < D; ++k) pr = fma(xk[k], sk[k], pr);
+            s_dot[tid] += pr;
+        }
+    }
+    if (DOT) {
+        __syncthreads();
+        if (warp == 0) {
+            double v = 0.0;
+#pragma unroll
+            for (int m = 0; m < NWARP; ++m) v += s_dot[lane + 32 * m];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (lane == 0) atomicAdd(a.dot, v);
+        }
     }
     // the last block to finish resets the tile counter (atomicInc wraps the exit counter to 0 by itself)
     if (tid == 0 && atomicInc(a.sched + 1, gridDim.x - 1) == gridDim.x - 1) a.sched[0] = 0u;

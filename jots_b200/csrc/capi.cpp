@@ -1,4 +1,5 @@
 // extern "C" boundary of libjots_b200.so (declarations and reference citations: include/jots_b200.h)
+#include <cstdlib>
 #include "../../include/jots_b200.h"
 
 #include <algorithm>
@@ -434,6 +435,7 @@ int jots_ctx_patch_info(jots_ctx_t c, int64_t* n_patches, double* fill, int64_t*
     return 0;
 }
 const char* jots_ctx_last_kernel(jots_ctx_t c) { return c->c->last_kernel; }
+int jots_ctx_fused_dots(jots_ctx_t c, int64_t* n) { if (n) *n = c->c->stats.fused_dots; return 0; }
 int jots_ctx_reset_stats(jots_ctx_t c) { c->c->stats = Stats(); return 0; }
 
 // ---- operators --------------------------------------------------------------------------------
@@ -512,8 +514,10 @@ int jots_op_get_neumann(jots_op_t op, double* b, int loc) {
 }
 
 // resolve a building-block form of an operator into something to run
-static void run_form(jots_op_t op, int form, const double* x, const double* state, double* y, bool diag) {
+static void run_form(jots_op_t op, int form, const double* x, const double* state, double* y, bool diag, double* d_dot = nullptr, bool* fused = nullptr) {
     Ctx* c = op->c;
+    auto apply = [&](const FormSpec& f) { const bool fu = c->apply_form(f, x, y, d_dot); if (fused) *fused = fu; };
+    auto no_dot = [&] { if (d_dot) throw std::runtime_error("this form is not a single bilinear form: no (x, A x)"); };
     if (op->sim_type == JOTS_LINEARIZED_UNSTEADY) {
         auto* L = static_cast<LinearConductionOperator*>(op->it);
         if (state) c->set_mat_state(state);
@@ -521,17 +525,18 @@ static void run_form(jots_op_t op, int form, const double* x, const double* stat
         if (form == JOTS_FORM_MASS) f = L->M_spec();
         else if (form == JOTS_FORM_STIFFNESS) f = L->K_spec();
         else if (form == JOTS_FORM_SYSTEM) f = L->A_spec();
-        else if (form == JOTS_FORM_RESIDUAL && !diag) { L->CalculateRHS(x, y); return; }
+        else if (form == JOTS_FORM_RESIDUAL && !diag) { no_dot(); L->CalculateRHS(x, y); return; }
         else throw std::runtime_error("form not available for this operator");
-        if (diag) c->diag_form(f, y); else c->apply_form(f, x, y);
+        if (diag) c->diag_form(f, y); else apply(f);
     } else if (op->sim_type == JOTS_NONLINEAR_UNSTEADY) {
         auto* N = static_cast<NonlinearConductionOperator*>(op->it);
         if (form == JOTS_FORM_SYSTEM) {
             if (!state) throw std::runtime_error("the nonlinear Jacobian needs a state");
             FormSpec f = N->jacobian_spec(state);
-            if (diag) c->diag_form(f, y); else c->apply_form(f, x, y);
+            if (diag) c->diag_form(f, y); else apply(f);
         } else if (form == JOTS_FORM_RESIDUAL && !diag) {
             if (!state) throw std::runtime_error("the nonlinear residual needs u_n as state");
+            no_dot();
             // R(k = x) with u_n = state
             op->un.alloc(c->n);
             c->copy(state, op->un.p);
@@ -542,15 +547,15 @@ static void run_form(jots_op_t op, int form, const double* x, const double* stat
             FormSpec f;
             f.op = OP_LIN; f.cf = CF_CONST; f.cm = 1.0; f.ck = 0.0; f.m0 = 1.0; f.a0 = 0.0;
             f.mask_in = f.mask_out = f.diag_one = true;
-            if (diag) c->diag_form(f, y); else c->apply_form(f, x, y);
+            if (diag) c->diag_form(f, y); else apply(f);
         } else throw std::runtime_error("form not available for this operator");
     } else {
         auto* S = static_cast<SteadyConductionOperator*>(op->it);
         if (form == JOTS_FORM_SYSTEM) {
             if (!state) throw std::runtime_error("the steady Jacobian needs a state");
             FormOp* J = static_cast<FormOp*>(S->gradient(state));
-            if (diag) J->assemble_diag(y); else J->mult(x, y);
-        } else if (form == JOTS_FORM_RESIDUAL && !diag) S->mult(x, y);
+            if (diag) J->assemble_diag(y); else apply(J->f);
+        } else if (form == JOTS_FORM_RESIDUAL && !diag) { no_dot(); S->mult(x, y); }
         else throw std::runtime_error("form not available for this operator");
     }
 }
@@ -559,6 +564,27 @@ int jots_op_form_apply(jots_op_t op, int form, const double* x, const double* st
     JOTS_TRY
     In ix(op->c, x, loc), is(op->c, state, loc); Out o(op->c, y, loc);
     run_form(op, form, ix.p, is.p, o.p, false);
+    o.finish();
+    return 0;
+    JOTS_CATCH_INT
+}
+int jots_op_form_apply_dot(jots_op_t op, int form, const double* x, const double* state, double* y, int loc, double* dot, int* fused) {
+    JOTS_TRY
+    Ctx* c = op->c;
+    In ix(c, x, loc), is(c, state, loc); Out o(c, y, loc);
+    DArr<double> d_dot;
+    d_dot.alloc(1);
+    JOTS_CUDA(cudaMemsetAsync(d_dot.p, 0, sizeof(double), c->stream));
+    bool fu = false;
+    run_form(op, form, ix.p, is.p, o.p, false, d_dot.p, &fu);
+    double v = 0.0;
+    if (fu) {
+        c->allreduce_scalars(d_dot.p, 1);
+        JOTS_CUDA(cudaMemcpyAsync(&v, d_dot.p, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        c->sync();
+    } else v = c->dot(ix.p, o.p);
+    if (dot) *dot = v;
+    if (fused) *fused = fu ? 1 : 0;
     o.finish();
     return 0;
     JOTS_CATCH_INT
@@ -576,10 +602,13 @@ int jots_op_form_time(jots_op_t op, int form, const double* x, const double* sta
     Ctx* c = op->c;
     cudaEvent_t e0, e1;
     JOTS_CUDA(cudaEventCreate(&e0)); JOTS_CUDA(cudaEventCreate(&e1));
-    run_form(op, form, x, state, y, false);
+    // JOTS_FORM_TIME_DOT=1 times the variant that also forms (x, A x) (what the conjugate-gradient loop launches)
+    const char* ev = std::getenv("JOTS_FORM_TIME_DOT");
+    double* d_dot = (ev && ev[0] == '1' && form != JOTS_FORM_RESIDUAL) ? c->d_scal.p + 63 : nullptr;
+    run_form(op, form, x, state, y, false, d_dot);
     c->sync();
     JOTS_CUDA(cudaEventRecord(e0, c->stream));
-    for (int i = 0; i < reps; ++i) run_form(op, form, x, state, y, false);
+    for (int i = 0; i < reps; ++i) run_form(op, form, x, state, y, false, d_dot);
     JOTS_CUDA(cudaEventRecord(e1, c->stream));
     JOTS_CUDA(cudaEventSynchronize(e1));
     float t = 0;

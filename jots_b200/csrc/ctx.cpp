@@ -210,6 +210,12 @@ void Ctx::set_bcs(const std::vector<BCSpec>& b) {
         ess.erase(std::unique(ess.begin(), ess.end()), ess.end());
     } else space.essential_dofs(attrs, ess);
     d_ess.upload(ess);
+    {
+        std::vector<int> eo;
+        for (int d : ess) if (d < n_owned) eo.push_back(d);
+        n_ess_owned = (int)eo.size();
+        d_ess_owned.upload(eo);
+    }
     std::vector<unsigned char> em((size_t)n, 0);
     for (int d : ess) em[d] = 1;
     d_essmark.upload(em);
@@ -325,9 +331,16 @@ static FaceArgs base_face_args(const Ctx& c, int nq) {
     return fa;
 }
 
-void Ctx::apply_form(const FormSpec& f, const double* x, double* y) {
-    zero(y);
+bool Ctx::apply_form(const FormSpec& f, const double* x, double* y, double* dot) {
     FormArgs a = make_args(f, x, y, false);
+    const bool face_terms = f.bdr_mass_scale != 0.0 && any_flux();
+    // fused (x, A x): symmetric-elimination forms whose apply is the two-phase patch kernel alone
+    const bool fuse = dot && !face_terms && a.patches && a.geom_diag && space.dim == 3 && !a.zc &&
+                      f.mask_in == f.mask_out && patch_kernel_fuses_dot(space.p, f.op, f.cf, a);
+    if (fuse) {
+        a.dot = dot;
+        v_zero_essdot(stream, n, y, (f.diag_one && f.mask_out) ? n_ess_owned : 0, d_ess_owned.p, x, dot, a.skip);
+    } else zero(y);
     // lattice meshes: unique-pencil patch kernels; otherwise / when not instantiated the gather-table kernels
     int rc = 1;
     if (a.patches && a.geom_diag && space.dim == 3 && !a.zc) {
@@ -338,7 +351,7 @@ void Ctx::apply_form(const FormSpec& f, const double* x, double* y) {
     if (rc) throw std::runtime_error("form (op=" + std::to_string(f.op) + ", cf=" + std::to_string(f.cf) + ") is not instantiated, rc=" + std::to_string(rc));
     stats.kernel_launches += 2;
     last_kernel = last_element_kernel();
-    if (f.bdr_mass_scale != 0.0 && any_flux()) {
+    if (face_terms) {
         FaceArgs fa = base_face_args(*this, bdr_mass_quad_points(space.p));
         fa.z = f.state; fa.x = x; fa.y = y; fa.mask_in = f.mask_in; fa.mask_out = f.mask_out; fa.scale = f.bdr_mass_scale;
         launch_face(FACE_MASS_APPLY, fa, stream);
@@ -348,6 +361,8 @@ void Ctx::apply_form(const FormSpec& f, const double* x, double* y) {
     if (f.diag_one && !a.diag_one) { v_copy_idx(stream, (int)ess.size(), d_ess.p, x, y); stats.kernel_launches += !ess.empty(); }
     JOTS_CUDA(cudaGetLastError());
     ++stats.applies;
+    if (fuse) ++stats.fused_dots;
+    return fuse;
 }
 
 void Ctx::diag_form(const FormSpec& f, double* d) {

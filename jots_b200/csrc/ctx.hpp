@@ -71,7 +71,7 @@ struct FormSpec {
 
 struct Stats {
     long long applies = 0, diag_assemblies = 0, krylov_iters = 0, newton_iters = 0, residual_evals = 0, steps = 0,
-              kernel_launches = 0, dots = 0, halo_exchanges = 0, patch_applies = 0;
+              kernel_launches = 0, dots = 0, halo_exchanges = 0, patch_applies = 0, fused_dots = 0;
     double last_linear_norm = 0, last_newton_norm = 0;
     int last_linear_converged = 1, last_newton_converged = 1, last_linear_iters = 0, last_newton_iters = 0;
 };
@@ -102,7 +102,8 @@ public:
     Halo* halo = nullptr;
 
     // --- device tables
-    DArr<int> d_gather, d_gather_ess, d_bdr_gather, d_bdr_attr, d_ess;
+    DArr<int> d_gather, d_gather_ess, d_bdr_gather, d_bdr_attr, d_ess, d_ess_owned;
+    int n_ess_owned = 0;
     std::vector<DArr<int>> d_bc_dofs;
     // preCICE boundary data path (/root/reference/src/boundary_condition.cpp:77-206): per preCICE BC the nodal coefficient field
     // (coeff_gf: default value, boundary entries overwritten by the read data), the boundary elements of its attribute and
@@ -139,7 +140,9 @@ public:
     void set_bcs(const std::vector<BCSpec>& b);
 
     // --- forms
-    void apply_form(const FormSpec& f, const double* x, double* y);
+    // dot != nullptr: also accumulate (x, A x) over the owned rows into *dot when the launched kernel can (returns true; the
+    // caller all-reduces); false = y only
+    bool apply_form(const FormSpec& f, const double* x, double* y, double* dot = nullptr);
     void diag_form(const FormSpec& f, double* d);
     // b_i = sum_faces int (g / divisor) phi_i; state != null -> divisor rho_h(state) C_h(state)
     void neumann_vector(double div_const, const double* state, double* b, bool zero_first = true, double scale = 1.0,

@@ -74,6 +74,9 @@ struct FormArgs {
     const double* skip;
     // two zero-initialised counters of the dynamic tile scheduler of apply_patch2.cuh (tile counter, exit counter)
     unsigned int* sched;
+    // non-null: the kernel adds sum_elements x_e . (A_e x_e) = (x, A x) over the rows it writes to *dot (two-phase patch
+    // kernel only; the conjugate-gradient loop then needs no separate pass for (d, A d))
+    double* dot;
 };
 
 // 1-D tables; DZ = QZ = 1 turns the hex kernel into the quad kernel

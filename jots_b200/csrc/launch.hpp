@@ -18,6 +18,8 @@ std::string kernel_label(const char* base, int D, int Q, int op, int cf, const c
 int launch_form_apply(int dim, int p, int op, int cf, const FormArgs& a, const TablesRT& t, cudaStream_t st);
 int launch_form_apply_slab(int p, int op, int cf, const FormArgs& a, const TablesRT& t, cudaStream_t st);
 int launch_form_apply_patch(int p, int op, int cf, const FormArgs& a, const TablesRT& t, cudaStream_t st);
+// true when launch_form_apply_patch would pick a kernel that honours FormArgs::dot (the two-phase patch kernel)
+bool patch_kernel_fuses_dot(int p, int op, int cf, const FormArgs& a);
 int patch_items(int p, unsigned* out);   // phase-3 items (pencil | visits << 8 | (el << 5 | ij) << 10 | ... << 20), at most 128
 void patch_shape(int p, int& px, int& py);   // patch size for order p (0: no patch kernel)
 int launch_form_diag_slab(int p, int op, int cf, const FormArgs& a, const TablesRT& t, cudaStream_t st);

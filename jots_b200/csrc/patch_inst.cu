@@ -46,22 +46,32 @@ int launch_patch(const FormArgs& a, const TablesRT& r, cudaStream_t st) {
     return 0;
 }
 
-template <int D, int Q, int OP, bool KLIN, int PX, int PY>
-int launch_patch2(const FormArgs& a, const TablesRT& r, cudaStream_t st) {
+template <int D, int Q, int OP, bool KLIN, int PX, int PY, bool DOT>
+int launch_patch2_v(const FormArgs& a, const TablesRT& r, cudaStream_t st) {
     constexpr int T = PX * PY * 2 * Q;
     Slab2Tables<D, Q> t;
     fill_slab2_tables<D, Q>(r, t);
     static const PatchItems items = build_patch2_items<D, PX, PY>();
     const size_t smem = Patch2Smem<D, Q, PX, PY>::total;
-    auto kern = form_apply_patch2_kernel<D, Q, OP, KLIN, PX, PY, T>;
+    auto kern = form_apply_patch2_kernel<D, Q, OP, KLIN, PX, PY, T, DOT>;
     static PerDevicePatch pd;
     const int grid_max = pd.get(kern, T, smem);
     if (items.n > T - 32) return 1;      // phase 3 must be one pass of the worker warps
     kern<<<a.n_patches < grid_max ? a.n_patches : grid_max, T, smem, st>>>(a, t, items);
     static const std::string label = kernel_label("form_apply_patch2_kernel", D, Q, OP, KLIN ? CF_KL : CF_CONST,
-                                                  ("," + std::to_string(PX) + "," + std::to_string(PY) + "," + std::to_string(T)).c_str());
+                                                  ("," + std::to_string(PX) + "," + std::to_string(PY) + "," + std::to_string(T) + (DOT ? ",dot" : "")).c_str());
     last_element_kernel() = label.c_str();
     return 0;
+}
+
+// FormArgs::dot selects the variant that also forms (x, A x); the residual form is not bilinear and has none
+template <int D, int Q, int OP, bool KLIN, int PX, int PY>
+int launch_patch2(const FormArgs& a, const TablesRT& r, cudaStream_t st) {
+    if (a.dot) {
+        if (OP == OP_RES) return 1;
+        return launch_patch2_v<D, Q, OP == OP_RES ? OP_LIN : OP, KLIN, PX, PY, true>(a, r, st);
+    }
+    return launch_patch2_v<D, Q, OP, KLIN, PX, PY, false>(a, r, st);
 }
 
 // JOTS_PATCH2=0 keeps the three-phase patch kernel for the forms the two-phase kernel covers (A/B runs)
@@ -73,6 +83,14 @@ bool patch2_enabled() {
 bool klin_enabled() {
     static const bool v = [] { const char* e = getenv("JOTS_SLAB_KLIN"); return !e || atoi(e) != 0; }();
     return v;
+}
+
+// the forms the two-phase kernel covers
+bool patch2_covers(int op, int cf, const FormArgs& a) {
+    if (!(patch2_enabled() && klin_enabled())) return false;
+    const bool klin = cf == CF_K && a.mat.k.n == 2;
+    if (!(cf == CF_CONST || klin)) return false;
+    return op == OP_LIN || op == OP_RES || (op == OP_JAC && klin);
 }
 
 template <int D, int Q, int PX, int PY>
@@ -99,6 +117,10 @@ int dispatch_patch(int op, int cf, const FormArgs& a, const TablesRT& t, cudaStr
     return 1;
 }
 }  // namespace
+
+bool patch_kernel_fuses_dot(int p, int op, int cf, const FormArgs& a) {
+    return p == 2 && op != OP_RES && a.patches && a.n_patches > 0 && patch2_covers(op, cf, a);
+}
 
 void patch_shape(int p, int& px, int& py) {
     if (p == 2) { px = 4; py = 4; }

@@ -135,6 +135,7 @@ Krylov::Krylov(Ctx* ctx, int kind_, int prec_kind) : c(ctx), kind(kind_) {
     if (prec_kind == PREC_JACOBI) prec.reset(new JacobiPrec(ctx));
     else if (prec_kind == PREC_CHEBYSHEV) prec.reset(new ChebyshevPrec(ctx));
     if (const char* e = std::getenv("JOTS_CG_HOST_SCALARS")) device_scalars = !(e[0] == '1');
+    if (const char* e = std::getenv("JOTS_CG_FUSED_DOT")) fused_dot = !(e[0] == '0');
 }
 
 Krylov::~Krylov() {
@@ -253,13 +254,15 @@ void Krylov::cg_device_loop(double* x, double* r, double* z, double* d, const do
             v_cgd_update(st, n, c->n_owned, S, i, d, z, x, r, dinv, z, c->dot_scratch());
             c->allreduce_scalars(S + (i & 1), 1);
             const bool last = (i == max_iter);
-            v_cgd_direction(st, n, S, i, dinv ? z : r, d, !last);
+            // the direction kernel zeroes the (d, A d) slot; an operator that cannot add to it during the apply leaves it to
+            // the separate pass, which overwrites the slot
+            v_cgd_direction(st, n, S, i, dinv ? z : r, d, !last, fused_dot);
             c->stats.kernel_launches += 2;
             if (last) break;
-            apply(d, z);
-            v_cgd_dot(st, c->n_owned, S, d, z, c->dot_scratch());
+            ++info.applies;
+            if (!(fused_dot ? A->mult_dot(d, z, S + 2) : (A->mult(d, z), false))) { v_cgd_dot(st, c->n_owned, S, d, z, c->dot_scratch()); ++c->stats.kernel_launches; }
             c->allreduce_scalars(S + 2, 1);
-            ++c->stats.kernel_launches; ++c->stats.dots;
+            ++c->stats.dots;
         }
         JOTS_CUDA(cudaMemcpyAsync(cgd.h + 8 * (chunk % NSLOT), S, 8 * sizeof(double), cudaMemcpyDeviceToHost, st));
         JOTS_CUDA(cudaEventRecord(cgd.ev[chunk % NSLOT], st));

@@ -20,6 +20,9 @@ struct LinOp {
     virtual ~LinOp() {}
     virtual void mult(const double* x, double* y) = 0;
     virtual void assemble_diag(double* d) = 0;
+    // y = A x and, when the operator can do it in the same pass, *d_dot += (x, A x) over the owned rows (*d_dot zeroed by the
+    // caller, not yet all-reduced): returns whether it did
+    virtual bool mult_dot(const double* x, double* y, double* d_dot) { (void)d_dot; mult(x, y); return false; }
 };
 
 // a FormSpec bound to a context
@@ -28,6 +31,7 @@ struct FormOp : LinOp {
     FormSpec f;
     FormOp(Ctx* ctx, const FormSpec& spec) : c(ctx), f(spec) {}
     void mult(const double* x, double* y) override { c->apply_form(f, x, y); }
+    bool mult_dot(const double* x, double* y, double* d_dot) override { return c->apply_form(f, x, y, d_dot); }
     void assemble_diag(double* d) override { c->diag_form(f, d); }
 };
 
@@ -88,6 +92,7 @@ struct Krylov {
     // CG with Jacobi / no preconditioner keeps its scalars on the device (no host round trip per iteration);
     // JOTS_CG_HOST_SCALARS=1 selects the host-sequenced loop (same results; kept for A/B timing)
     bool device_scalars = true;
+    bool fused_dot = true;           // (d, A d) formed by the element kernel when it can (JOTS_CG_FUSED_DOT=0: separate pass)
     ~Krylov();
 private:
     struct CgDevice {

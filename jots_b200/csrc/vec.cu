@@ -1,3 +1,4 @@
+#include <cstdint>
 #include "vec.cuh"
 #include "vec.hpp"
 #include "coef.cuh"
@@ -165,6 +166,7 @@ __global__ void __launch_bounds__(VEC_THREADS) k_cgd_direction(int64_t n, double
     if (S[4] != 0.0) return;
     const double betanom = S[i & 1], nom = S[(i + 1) & 1];
     const bool first = blockIdx.x == 0 && threadIdx.x == 0;
+    if (first && update == 2) S[2] = 0.0;     // the operator apply that follows accumulates (d, A d) here (k_zero_essdot, FormArgs::dot)
     if (betanom < 0.0 || betanom <= S[3]) {
         if (first) { S[5] = (double)i; S[6] = betanom; __threadfence(); S[4] = betanom < 0.0 ? 2.0 : 1.0; }
         return;
@@ -186,8 +188,34 @@ void v_cgd_update(cudaStream_t st, int64_t n, int64_t n_owned, double* S, int i,
                   const double* dinv, double* z, DotScratch s) {
     k_cgd_update<<<grid_for(n, 8), VEC_THREADS, 0, st>>>(n, n_owned, S, i, d, Ad, x, r, dinv, z, s);
 }
-void v_cgd_direction(cudaStream_t st, int64_t n, double* S, int i, const double* zz, double* d, bool update) {
-    k_cgd_direction<<<update ? grid_for(n) : 1, VEC_THREADS, 0, st>>>(n, S, i, zz, d, update ? 1 : 0);
+void v_cgd_direction(cudaStream_t st, int64_t n, double* S, int i, const double* zz, double* d, bool update, bool zero_den) {
+    k_cgd_direction<<<update ? grid_for(n) : 1, VEC_THREADS, 0, st>>>(n, S, i, zz, d, update ? (zero_den ? 2 : 1) : 0);
+}
+// y = 0 and *dot += sum over the listed (owned, essential) entries of x^2: what the unit-diagonal rows of an eliminated operator
+// contribute to (x, A x).  Precedes an element kernel that accumulates the rest (FormArgs::dot).  skip as in FormArgs.
+__global__ void __launch_bounds__(VEC_THREADS) k_zero_essdot(int64_t n, double* __restrict__ y, int n_idx, const int* __restrict__ idx,
+                                                              const double* __restrict__ x, double* dot, const double* skip) {
+    if (skip && *skip != 0.0) return;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x, t0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t head = (reinterpret_cast<uintptr_t>(y) & 8) ? 1 : 0;     // work vectors are only 8-byte aligned
+    double2* y2 = reinterpret_cast<double2*>(y + head);
+    const int64_t m2 = (n - head) / 2;
+    for (int64_t k = t0; k < m2; k += stride) y2[k] = make_double2(0.0, 0.0);
+    if (t0 == 0) { if (head) y[0] = 0.0; if ((n - head) & 1) y[n - 1] = 0.0; }
+    double v = 0.0;
+    for (int64_t k = t0; k < n_idx; k += stride) { const double xv = x[idx[k]]; v += xv * xv; }
+    __shared__ double sh[VEC_THREADS / 32];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < VEC_THREADS / 32; ++w) v += sh[w];
+        if (v != 0.0) atomicAdd(dot, v);
+    }
+}
+void v_zero_essdot(cudaStream_t st, int64_t n, double* y, int n_idx, const int* idx, const double* x, double* dot, const double* skip) {
+    k_zero_essdot<<<grid_for(n, 8), VEC_THREADS, 0, st>>>(n, y, n_idx, idx, x, dot, skip);
 }
 void v_cgd_dot(cudaStream_t st, int64_t n_owned, double* S, const double* a, const double* b, DotScratch s) {
     k_cgd_dot<<<grid_for(n_owned, 8), VEC_THREADS, 0, st>>>(n_owned, S, a, b, s);

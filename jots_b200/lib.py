@@ -92,6 +92,7 @@ def load_library():
         "jots_ctx_expand_true": (C.c_int, [_P, _P, _P, C.c_int]),
         "jots_partition_create_from_tables": (_P, [C.c_int, C.c_int, C.c_int64, C.c_int64, _P, _P, C.c_int64, _P, _P, _P, _P, C.c_int64, _P, C.c_int, _P, _P, _P, C.c_int, _P, C.c_int, C.c_int]),
         "jots_ctx_patch_info": (C.c_int, [_P, _P, _P, _P]),
+        "jots_ctx_fused_dots": (C.c_int, [_P, _P]),
         "jots_ctx_last_kernel": (C.c_char_p, [_P]),
         "jots_ctx_reset_stats": (C.c_int, [_P]),
         "jots_op_create": (_P, [_P, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int,
@@ -107,6 +108,7 @@ def load_library():
         "jots_op_get_neumann": (C.c_int, [_P, _P, C.c_int]),
         "jots_op_form_apply": (C.c_int, [_P, C.c_int, _P, _P, _P, C.c_int]),
         "jots_op_form_diagonal": (C.c_int, [_P, C.c_int, _P, _P, C.c_int]),
+        "jots_op_form_apply_dot": (C.c_int, [_P, C.c_int, _P, _P, _P, C.c_int, _P, _P]),
         "jots_op_form_time": (C.c_int, [_P, C.c_int, _P, _P, _P, C.c_int, _D]),
         "jots_partition_create": (_P, [_P, _P, C.c_int, C.c_int, _P]),
         "jots_partition_destroy": (None, [_P]),
@@ -488,6 +490,9 @@ class Context:
         npch, fill, app = C.c_int64(0), C.c_double(0.0), C.c_int64(0)
         load_library().jots_ctx_patch_info(self._h, C.byref(npch), C.byref(fill), C.byref(app))
         d["n_patches"], d["patch_fill"], d["patch_applies"] = int(npch.value), float(fill.value), int(app.value)
+        fd = C.c_int64(0)
+        load_library().jots_ctx_fused_dots(self._h, C.byref(fd))
+        d["fused_dots"] = int(fd.value)
         return d
 
     def last_kernel(self):
@@ -543,6 +548,13 @@ class Operator:
     def form_apply(self, form, x, y, state=None):
         _chk(load_library().jots_op_form_apply(self._h, form, _ptr(_f64(x)), _ptr(state), _ptr(_f64(y)), _loc(x, state, y)))
         return y
+
+    def form_apply_dot(self, form, x, y, state=None):
+        """y = form(x); returns ((x, form(x)) over the owned rows, whether the element kernel formed it in the same pass)."""
+        dot, fused = C.c_double(0.0), C.c_int(0)
+        _chk(load_library().jots_op_form_apply_dot(self._h, form, _ptr(_f64(x)), _ptr(state), _ptr(_f64(y)), _loc(x, state, y),
+                                                   C.byref(dot), C.byref(fused)))
+        return dot.value, bool(fused.value)
 
     def form_diagonal(self, form, d, state=None):
         _chk(load_library().jots_op_form_diagonal(self._h, form, _ptr(state), _ptr(_f64(d)), _loc(state, d)))

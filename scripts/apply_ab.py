@@ -14,6 +14,7 @@ CONFIGS = {
     "slab3_gather_E16": {"JOTS_SLAB_VARIANT": "3"},                   # gather-table kernel (round-1 default)
     "patch3_4x4": {"JOTS_SLAB_VARIANT": "7", "JOTS_PATCH2": "0"},     # three-phase unique-pencil patch kernel
     "patch2_4x4": {"JOTS_SLAB_VARIANT": "7"},                         # two-phase patch kernel (default)
+    "patch2_4x4_dot": {"JOTS_SLAB_VARIANT": "7", "JOTS_FORM_TIME_DOT": "1"},   # the same + (x, A x) formed in phase 3 (CG loop)
 }
 
 

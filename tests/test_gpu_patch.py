@@ -109,3 +109,64 @@ def test_patch_kernel_on_a_brick_with_vectors_on_odd_offsets(J, tmp_path):
     dev.op.form_apply(J.FORM_SYSTEM, x, y1, state=z)
     torch.cuda.synchronize()
     assert float((y0 - y1).abs().max()) <= 1e-12 * float(y0.abs().max())
+
+
+@pytest.mark.parametrize("sim,props", [("Nonlinear_Unsteady", "k"), ("Linearized_Unsteady", "const"), ("Nonlinear_Unsteady", "const"),
+                                       ("Nonlinear_Unsteady", "k2"), ("Steady", "k")])
+@pytest.mark.parametrize("n", [(8, 8, 3), (5, 3, 4), (13, 9, 2)])
+def test_inner_product_formed_inside_the_element_kernel(J, tmp_path, sim, props, n):
+    """(x, A x) accumulated by phase 3 of the two-phase patch kernel (FormArgs::dot: pencil outputs times the staged inputs,
+    unit-diagonal rows added by the zeroing kernel) equals x . (A x) of the oracle's matrix -- x with NON-zero essential entries,
+    ragged patches, graded geometry; forms the two-phase kernel does not cover (quadratic k) report fused = False and the
+    separate pass gives the same number."""
+    dev, orc = build(J, tmp_path, sim, 3, 2, props, grade=0.6, shear=0.0, n=n,
+                     bcs=["HeatFlux, 7.5e5", "Isothermal, 350", HF0, "Isothermal, 300", HF0, HF0])
+    nd = dev.n
+    state = smooth_state(orc)
+    x = rnd(nd, 21)
+    it = orc.it
+    if sim == "Linearized_Unsteady":
+        orc.u = state.copy()
+        orc.update_mat_props(True)
+        A, zs = it.A_mat, state
+    elif sim == "Nonlinear_Unsteady":
+        k = 50.0 * rnd(nd, 22)
+        it.u_n = state
+        it.new_state(k)
+        A, zs = it.gradient(k), state + it.dt * k
+    else:
+        it.new_state(state)
+        A, zs = it.gradient(state), state
+    y = np.empty(nd)
+    dot, fused = dev.op.form_apply_dot(J.FORM_SYSTEM, x, y, state=zs)
+    assert fused == (props != "k2")
+    ref = A @ x
+    assert rel(y, ref) < APPLY_TOL
+    assert abs(dot - x @ ref) <= 1e-12 * np.abs(x * ref).sum(), (dot, x @ ref)
+    assert dev.ctx.stats()["fused_dots"] == (1 if fused else 0)
+
+
+@pytest.mark.parametrize("sim,props,n,max_it", [("Nonlinear_Unsteady", "k", (8, 8, 4), 100), ("Linearized_Unsteady", "const", (9, 5, 3), 100),
+                                                ("Nonlinear_Unsteady", "k", (8, 8, 4), 7), ("Steady", "k", (8, 4, 2), 100)])
+def test_cg_with_the_fused_inner_product_matches_the_separate_pass(J, tmp_path, monkeypatch, sim, props, n, max_it):
+    """cg_device_loop with den = (d, A d) from the element kernel against JOTS_CG_FUSED_DOT=0: same Krylov / Newton counts,
+    same field, and the oracle's field."""
+    out = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("JOTS_CG_FUSED_DOT", mode)
+        dev, orc = build(J, tmp_path, sim, 3, 2, props, solver="CG", prec="Jacobi", n=n, steps=2)
+        if max_it != 100:
+            txt = open(str(tmp_path / "c.ini")).read().replace("Max_Iterations=100\n", "Max_Iterations=%d\n" % max_it, 1)
+            open(str(tmp_path / "c.ini"), "w").write(txt)
+            dev = J.Driver(str(tmp_path / "c.ini"))
+        try:
+            dev.run()
+        except J.JotsError:
+            pass
+        st = dev.ctx.stats()
+        assert (st["fused_dots"] > 0) == (mode == "1"), st
+        out[mode] = (st["krylov_iters"], st["newton_iters"], st["last_linear_iters"], st["last_linear_converged"], dev.get_u())
+    assert out["0"][:4] == out["1"][:4], (out["0"][:4], out["1"][:4])
+    assert rel(out["0"][4], out["1"][4]) < 1e-12
+    if max_it == 100:
+        assert rel(out["0"][4], orc.run()) < FIELD_TOL
