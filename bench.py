@@ -401,7 +401,14 @@ def main():
     drv.get_u(z)
     torch.cuda.synchronize()
     drv.op.form_time(J.FORM_SYSTEM, x, y, state_dev=z, reps=min(20, max(2, args.apply_reps)))   # warm-up applies
-    apply_ms = drv.op.form_time(J.FORM_SYSTEM, x, y, state_dev=z, reps=args.apply_reps)
+    apply_plain_ms = drv.op.form_time(J.FORM_SYSTEM, x, y, state_dev=z, reps=args.apply_reps)
+    apply_ms, fused = apply_plain_ms, st["fused_dots"] > 0
+    if fused:
+        # the conjugate-gradient loop launched the variant that also forms (d, A d): that is the dominant kernel of the step
+        os.environ["JOTS_FORM_TIME_DOT"] = "1"
+        drv.op.form_time(J.FORM_SYSTEM, x, y, state_dev=z, reps=min(20, max(2, args.apply_reps)))
+        apply_ms = drv.op.form_time(J.FORM_SYSTEM, x, y, state_dev=z, reps=args.apply_reps)
+        os.environ.pop("JOTS_FORM_TIME_DOT")
     kernel_label = drv.ctx.last_kernel()          # the element kernel these applies actually launched
     res_ms = drv.op.form_time(J.FORM_RESIDUAL, x, y, state_dev=z, reps=max(2, args.apply_reps // 4))
     peaks = {}
@@ -442,7 +449,8 @@ def main():
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "config": workload_config(args, world),
             "steps_per_s": K / (ms * 1e-3), "krylov_iters": iters, "newton_iters": st["newton_iters"],
-            "apply_gdofs": ndof / (apply_ms * 1e-3) / 1e9, "apply_ms": apply_ms, "residual_ms": res_ms,
+            "apply_gdofs": ndof / (apply_ms * 1e-3) / 1e9, "apply_ms": apply_ms, "apply_without_inner_product_ms": apply_plain_ms,
+            "residual_ms": res_ms, "fused_inner_products": st["fused_dots"],
             "clocks": clk.summary(),
             "e2e": {"value": e2e_value, "unit": "GDOF/s", "h2d_bytes_per_step": 8 * ndof, "d2h_bytes_per_step": 8 * ndof,
                     "ms_per_step": 1e3 * e2e_s / K},
@@ -451,7 +459,7 @@ def main():
                          "traffic": traffic, "algorithmic_bytes": alg_bytes,
                          "kernel": kernel_label,
                          "timed": "Jacobian-vector apply, 24 B/DOF algorithmic (x, z in, y out); CUDA events on the launching stream around "
-                                  "%d applies, each = memset of y + this kernel + the essential-row fix-up" % args.apply_reps,
+                                  "%d applies, each = zeroing of y + this kernel%s" % (args.apply_reps, " (which also forms (x, A x), as in the CG loop)" if fused else ""),
                          "note": "this kernel is FP64-pipe bound (fp64.instr_per_dof FP64 instructions against 24 B/DOF), not HBM "
                                  "bound: fp64.frac_of_peak is the fraction that matters (DESIGN.md 5)",
                          "fp64_pipe_active_pct": fp64_pct,
