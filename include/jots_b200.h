@@ -235,6 +235,17 @@ int jots_mfem_dof_numbering(jots_mesh_t m, jots_space_t s, int64_t* out);
 int jots_restart_write(const char* prefix, int cycle, double time, jots_mesh_t m, jots_space_t s, const double* u_nodes);
 jots_mesh_t jots_restart_read(const char* prefix, int cycle, int* order, int* cycle_out, double* time, int64_t* n_values, double* mfem_values);
 
+/* ---- ParaView output: the ParaViewDataCollection of OutputManager::WriteVizOutput (src/output_manager.cpp:23-28,81-87):
+   <dir>/ParaView.pvd, <dir>/Cycle<cycle:06d>/data.pvtu + proc000000.vtu; one VTK_LAGRANGE_QUADRILATERAL / _HEXAHEDRON cell of the
+   FE order per element with its own points (high-order output, levels of detail = order), inline base64 binary, Float64; the
+   nodal fields are evaluated at the uniform lattice VTK's Lagrange cells use.  mode 0: new collection, 1: add this cycle to an
+   existing .pvd, 2: restart mode (keep the entries before `time`).  The driver shim writes "Rank", "Temperature" and one field per
+   material property of the input file at Visualization_Freq (dir "ParaView", or $JOTS_PARAVIEW_DIR).  Restated from the VTK file
+   format / MFEM 4.7 (paraview.cpp).  jots_vtk_lagrange_order: lex_of_vtk[j] = lexicographic index of VTK node j. */
+int jots_paraview_write(const char* dir, int cycle, double time, jots_mesh_t m, jots_space_t s, int n_fields, const char* const* names,
+                        const double* const* nodal_values, int mode);
+int jots_vtk_lagrange_order(int dim, int p, int32_t* lex_of_vtk);
+
 /* Config (src/config_file.cpp:7-172) parsed on the host, as "key=value" lines (scalars, then "mat:<name>=a|b|..." and
    "bc:<attribute>=a|b|..."): lets the key set, defaults and parsing quirks be compared with the reference's without a
    device.  Returns the length needed (including the terminating 0), -1 on error. */

@@ -11,6 +11,7 @@
 #include "driver.hpp"
 #include "halo.hpp"
 #include "launch.hpp"
+#include "paraview.hpp"
 #include "restart.hpp"
 
 using namespace jots;
@@ -259,6 +260,27 @@ int jots_mfem_dof_numbering(jots_mesh_t m, jots_space_t s, int64_t* out) {
 }
 int jots_restart_write(const char* prefix, int cycle, double time, jots_mesh_t m, jots_space_t s, const double* u_nodes) {
     JOTS_TRY write_restart(prefix, cycle, time, m->m, s->s, u_nodes); return 0; JOTS_CATCH_INT
+}
+int jots_paraview_write(const char* dir, int cycle, double time, jots_mesh_t m, jots_space_t s, int n_fields, const char* const* names,
+                        const double* const* nodal_values, int mode) {
+    JOTS_TRY
+    ParaViewCollection pc;
+    if (dir && dir[0]) pc.dir = dir;
+    pc.append = (mode == 1);
+    pc.restart_mode = (mode == 2);
+    std::vector<VizField> fields;
+    for (int i = 0; i < n_fields; ++i) fields.push_back({names[i], nodal_values[i]});
+    pc.save(cycle, time, s->s, m ? m->m.elem_attr : std::vector<int>(), fields);
+    return 0;
+    JOTS_CATCH_INT
+}
+int jots_vtk_lagrange_order(int dim, int p, int32_t* lex_of_vtk) {
+    JOTS_TRY
+    std::vector<int> v;
+    vtk_lagrange_order(dim, p, v);
+    for (size_t i = 0; i < v.size(); ++i) lex_of_vtk[i] = v[i];
+    return 0;
+    JOTS_CATCH_INT
 }
 jots_mesh_t jots_restart_read(const char* prefix, int cycle, int* order, int* cycle_out, double* time, int64_t* n_values, double* mfem_values) {
     JOTS_TRY

@@ -202,10 +202,15 @@ JOTSDriver::JOTSDriver(const Config& cfg_, int device, const Mesh* mesh_in, Comm
         for (int i = 0; i < cfg.serial_refine + cfg.parallel_refine; ++i) mesh = uniform_refine(mesh);
     }
     Space space = make_space(mesh, order);
-    if (cfg.restart_freq != 0) {
-        // WriteRestartOutput needs the mesh and the (global) space on the host: kept only when restarts are written
+    if (cfg.restart_freq != 0 || cfg.vis_freq != 0) {
+        // the output writers need the mesh and the (global) space on the host: kept only when something is written
         out_mesh.reset(new Mesh(mesh));
         out_space.reset(new Space(space));
+    }
+    if (cfg.vis_freq != 0) {
+        viz.reset(new ParaViewCollection());
+        viz->restart_mode = cfg.use_restart;     // paraview_dc->UseRestartMode(UsesRestart()) (output_manager.cpp:25)
+        if (const char* d = std::getenv("JOTS_PARAVIEW_DIR")) viz->dir = d;
     }
     if (comm && comm_size(comm) > 1) {
         // ParMesh(comm, mesh): one subdomain per rank (jots_driver.cpp:178)
@@ -312,41 +317,92 @@ void JOTSDriver::Step() {
     if (cfg.using_time_integration && cfg.time_print_freq > 0 && it_num % cfg.time_print_freq == 0 && ctx->rank() == 0 && !quiet())
         std::printf("Step #%10i || Time: %1.6e out of %-1.6e || dt: %1.6e \n", it_num, time, dt * max_timesteps, dt);
     if (check_blowup && ctx->max_global(u.p) > 1e10) throw std::runtime_error("JOTS has blown up");
-    // restart output at the input frequency (jots_driver.cpp:774-797; ParaView output stays with the reference's OutputManager)
-    if (cfg.using_time_integration && cfg.restart_freq != 0 && it_num % cfg.restart_freq == 0) WriteRestartOutput();
+    // output at the input frequencies (jots_driver.cpp:773-800): properties refreshed at the new field, ParaView, then restart
+    if (cfg.using_time_integration) {
+        const bool viz_out = cfg.vis_freq != 0 && it_num % cfg.vis_freq == 0;
+        const bool res_out = cfg.restart_freq != 0 && it_num % cfg.restart_freq == 0;
+        if (viz_out || res_out) {
+            UpdateMatProps(false);
+            if (viz_out) WriteVizOutput();
+            if (res_out) WriteRestartOutput();
+        }
+    }
 }
 
 int JOTSDriver::Run(int max_steps) {
     int done = 0;
+    // initial condition to ParaView (jots_driver.cpp:571-573).  Deviation: the reference writes it whenever the run integrates in
+    // time; here only when Visualization_Freq != 0, so that a run that asks for no output writes no files
+    if (it_num == 0 && cfg.using_time_integration && viz) WriteVizOutput();
     while (it_num < max_timesteps) {
         Step();
         ++done;
         if (max_steps >= 0 && done >= max_steps) break;
     }
-    // steady run: one restart file at the end when Restart_Freq != 0 (jots_driver.cpp:750-772)
-    if (!cfg.using_time_integration && cfg.restart_freq != 0 && done > 0) WriteRestartOutput();
+    // steady run: output once at the end when the frequencies are non-zero (jots_driver.cpp:750-772)
+    if (!cfg.using_time_integration && done > 0 && (viz || cfg.restart_freq != 0)) {
+        UpdateMatProps(false);
+        if (viz) WriteVizOutput();
+        if (cfg.restart_freq != 0) WriteRestartOutput();
+    }
     ctx->sync();
     return done;
 }
 
-void JOTSDriver::WriteRestartOutput() {
-    if (!out_mesh) throw std::runtime_error("restart output was not set up (Restart_Freq was 0 when the driver was built)");
-    std::vector<double> nodes;
+void JOTSDriver::collect_nodes(const double* d_vec, std::vector<double>& nodes) {
     if (part) {
-        // rank 0 collects the owned values of every rank (single-domain restart file)
+        // rank 0 collects the owned values of every rank (single-domain output files); collective
         std::vector<int64_t> gid;
         std::vector<double> val;
-        halo_gather_owned(*ctx, u.p, gid, val);
+        halo_gather_owned(*ctx, d_vec, gid, val);
+        nodes.clear();
         if (ctx->rank() != 0) return;
         nodes.assign((size_t)out_space->ndof, 0.0);
         for (size_t i = 0; i < gid.size(); ++i) nodes[(size_t)gid[i]] = val[i];
     } else {
         nodes.resize((size_t)ctx->n);
-        JOTS_CUDA(cudaMemcpyAsync(nodes.data(), u.p, (size_t)ctx->n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        JOTS_CUDA(cudaMemcpyAsync(nodes.data(), d_vec, (size_t)ctx->n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
         ctx->sync();
     }
+}
+
+void JOTSDriver::WriteRestartOutput() {
+    if (!out_mesh) throw std::runtime_error("restart output was not set up (Restart_Freq was 0 when the driver was built)");
+    std::vector<double> nodes;
+    collect_nodes(u.p, nodes);
+    if (ctx->rank() != 0) return;
     if (!quiet()) std::printf("Saving Restart File...\n");
     write_restart(cfg.restart_prefix, it_num, time, *out_mesh, *out_space, nodes.data());
+}
+
+// Fields of the reference's collection: "Rank" (output_manager.cpp:33), "Temperature" (jots_driver.cpp:288) and one field per
+// material property of the input file under its own key (jots_driver.cpp:343), each the nodal projection of the property
+// coefficient at the last material state (OutputManager::UpdateGridFunctions)
+void JOTSDriver::WriteVizOutput() {
+    if (!viz || !out_space) throw std::runtime_error("ParaView output was not set up (Visualization_Freq was 0 when the driver was built)");
+    std::vector<std::pair<std::string, std::vector<double>>> host;
+    DArr<double> tmp;
+    tmp.alloc((size_t)ctx->n);
+    auto add = [&](const std::string& name, const double* d_vec) {
+        host.emplace_back(name, std::vector<double>());
+        collect_nodes(d_vec, host.back().second);
+    };
+    v_fill(ctx->stream, ctx->n, (double)ctx->rank(), tmp.p);
+    add("Rank", tmp.p);
+    add("Temperature", u.p);
+    const char* keys[3] = {"Density_rho", "Specific_Heat_C", "Thermal_Conductivity_k"};
+    const Poly* props[3] = {&ctx->mat.rho, &ctx->mat.C, &ctx->mat.k};
+    for (int i = 0; i < 3; ++i)
+        if (has_prop[i]) {
+            v_poly_field(ctx->stream, ctx->n, *props[i], 0, props[i]->n > 1 ? ctx->mat_state.p : nullptr, tmp.p);
+            ++ctx->stats.kernel_launches;
+            add(keys[i], tmp.p);
+        }
+    if (ctx->rank() != 0) return;
+    if (!quiet()) std::printf("Saving Paraview Data...\n");
+    std::vector<VizField> fields;
+    for (auto& h : host) fields.push_back({h.first, h.second.data()});
+    viz->save(it_num, time, *out_space, out_mesh->elem_attr, fields);
 }
 
 }  // namespace jots

@@ -3,6 +3,7 @@
 // (/root/reference/src/jots_driver.cpp:568-725): UpdateAndApplyBCs -> UpdateMatProps -> Iteration.
 // Output, restart and preCICE stay with the reference's own driver.
 #pragma once
+#include "paraview.hpp"
 #include <map>
 #include <memory>
 #include <string>
@@ -48,7 +49,10 @@ public:
     void Step();               // one pass of the Run() loop body
     int Run(int max_steps);    // max_steps < 0: run to max_timesteps; returns the number of steps done
     void WriteRestartOutput(); // OutputManager::WriteRestartOutput (output_manager.cpp:89-95), restart.cpp
-    std::unique_ptr<Mesh> out_mesh;      // host copies for restart output (only when Restart_Freq != 0)
+    void WriteVizOutput();     // OutputManager::WriteVizOutput (output_manager.cpp:81-87), paraview.cpp
+    std::unique_ptr<ParaViewCollection> viz;   // only when Visualization_Freq != 0
+    void collect_nodes(const double* d_vec, std::vector<double>& nodes);   // device vector -> global nodal values on rank 0
+    std::unique_ptr<Mesh> out_mesh;      // host copies for restart / ParaView output (only when one of the frequencies != 0)
     std::unique_ptr<Space> out_space;
     Config cfg;
     std::unique_ptr<Ctx> ctx;

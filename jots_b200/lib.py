@@ -71,6 +71,8 @@ def load_library():
         "jots_mfem_dof_numbering": (C.c_int, [_P, _P, _P]),
         "jots_restart_write": (C.c_int, [C.c_char_p, C.c_int, C.c_double, _P, _P, _P]),
         "jots_restart_read": (_P, [C.c_char_p, C.c_int, _P, _P, _P, _P, _P]),
+        "jots_paraview_write": (C.c_int, [C.c_char_p, C.c_int, C.c_double, _P, _P, C.c_int, _P, _P, C.c_int]),
+        "jots_vtk_lagrange_order": (C.c_int, [C.c_int, C.c_int, _P]),
         "jots_config_dump": (C.c_int64, [C.c_char_p, _P, C.c_int64]),
         "jots_ctx_create": (_P, [_P, C.c_int]),
         "jots_ctx_destroy": (None, [_P]),
@@ -225,6 +227,23 @@ def mfem_dof_numbering(mesh, space):
 def restart_write(prefix, cycle, time, mesh, space, u_nodes):
     u = np.ascontiguousarray(u_nodes, dtype=np.float64)
     _chk(load_library().jots_restart_write(str(prefix).encode(), int(cycle), float(time), mesh._h, space._h, _ptr(u)))
+
+
+def paraview_write(directory, cycle, time, mesh, space, fields, mode=0):
+    """One cycle of a ParaView collection (<directory>/ParaView.pvd, Cycle%06d/data.pvtu, proc000000.vtu); fields: {name: nodal
+    values in the numbering of `space`}; mode 0 new collection, 1 append, 2 restart mode."""
+    names = [str(k).encode() for k in fields]
+    arrs = [np.ascontiguousarray(v, dtype=np.float64) for v in fields.values()]
+    cn = (C.c_char_p * len(names))(*names)
+    cv = (C.c_void_p * len(arrs))(*[a.ctypes.data for a in arrs])
+    _chk(load_library().jots_paraview_write(str(directory).encode(), int(cycle), float(time), mesh._h if mesh is not None else None,
+                                            space._h, len(names), cn, cv, int(mode)))
+
+
+def vtk_lagrange_order(dim, p):
+    out = np.empty((p + 1) ** dim, dtype=np.int32)
+    _chk(load_library().jots_vtk_lagrange_order(int(dim), int(p), _ptr(out)))
+    return out
 
 
 def restart_read(prefix, cycle):

@@ -104,9 +104,10 @@ def test_partitioned_solve_matches_oracle(tmp_path, sim, props, solver, prec, p)
     assert err < 1e-8, err
 
 
-def test_partitioned_solve_on_a_mesh_file_rcb(tmp_path):
+def test_partitioned_solve_on_a_mesh_file_rcb(tmp_path, monkeypatch):
     """Unstructured path on several GPUs: mesh file -> first-appearance numbering -> recursive coordinate
-    bisection -> NCCL interface exchange, against the single-domain oracle on the same file."""
+    bisection -> NCCL interface exchange, against the single-domain oracle on the same file.  The run also writes ParaView
+    output every step (rank 0 collects the owned values): the last cycle holds the global field and the owner of each node."""
     world = min(_ngpu(), 4)
     if world < 2:
         pytest.skip("needs at least 2 GPUs")
@@ -120,7 +121,9 @@ def test_partitioned_solve_on_a_mesh_file_rcb(tmp_path):
     bcs = ["HeatFlux, 7.5e5", "Isothermal, 350", HF0, "Isothermal, 320", HF0, "HeatFlux, -1e5"]
     ini = str(tmp_path / "c.ini")
     with open(ini, "w") as f:
-        f.write(ini_text("Nonlinear_Unsteady", mesh, 300, PROPS["kc"], bcs, newton=50, solver="FGMRES", prec="Chebyshev", steps=2, order=2))
+        f.write(ini_text("Nonlinear_Unsteady", mesh, 300, PROPS["kc"], bcs, newton=50, solver="FGMRES", prec="Chebyshev", steps=2, order=2)
+                .replace("Visualization_Freq=0", "Visualization_Freq=1"))
+    monkeypatch.setenv("JOTS_PARAVIEW_DIR", str(tmp_path / "ParaView"))       # inherited by the spawned ranks
     uid = J.Comm.unique_id()
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
@@ -136,6 +139,16 @@ def test_partitioned_solve_on_a_mesh_file_rcb(tmp_path):
         u[g[:n_owned]] = ul[:n_owned]
     assert not np.isnan(u).any()
     assert np.linalg.norm(u - u_ref) / np.linalg.norm(u_ref) < 1e-8
+    from oracle import vtkfmt
+    out = str(tmp_path / "ParaView")
+    assert [f for _, f in vtkfmt.read_pvd(out + "/ParaView.pvd")] == ["Cycle%06d/data.pvtu" % c for c in (0, 1, 2)]
+    v = vtkfmt.read_vtu(out + "/Cycle000002/proc000000.vtu")
+    g = J.Space(J.Mesh.read(mesh), 2).gather()
+    assert np.array_equal(v["point_data"]["Temperature"].reshape(-1, 27), u[g])
+    owner = np.full(u_ref.size, -1.0)
+    for rank, steps, gl, n_owned, ul, st in res:
+        owner[gl[:n_owned]] = rank
+    assert np.array_equal(v["point_data"]["Rank"].reshape(-1, 27), owner[g])
 
 
 def _worker_tables(*args):

@@ -159,3 +159,55 @@ def test_restart_files_round_trip_and_continuation(J, tmp_path, dim, order):
     assert rel(dr.get_u(), d2.get_u()) < 1e-10
     with pytest.raises(J.JotsError, match="restart"):
         J.Driver(write("missing.ini", n, restart_from=999))
+
+
+@pytest.mark.parametrize("sim,order", [("Nonlinear_Unsteady", 2), ("Linearized_Unsteady", 3), ("Steady", 2)])
+def test_paraview_output_at_the_visualization_frequency(J, tmp_path, monkeypatch, sim, order):
+    """OutputManager::WriteVizOutput through the driver shim (jots_driver.cpp:571-573, 750-800): the initial condition and every
+    Visualization_Freq-th cycle of a time-integrating run (one output at the end of a steady run), fields Rank, Temperature
+    and one per material property of the input file -- the property evaluated at the field that is written."""
+    from cases import ini_text, write_brick_mesh
+    from oracle import vtkfmt
+    out = str(tmp_path / "ParaView")
+    monkeypatch.setenv("JOTS_PARAVIEW_DIR", out)
+    mesh = str(tmp_path / "m.mesh")
+    write_brick_mesh(mesh, 5, 3, 2, 0.01, 0.02, 0.015, grade=0.3)
+    props = [("Density_rho", "Uniform, 8000"), ("Specific_Heat_C", "Polynomial, 4.5, -850"), ("Thermal_Conductivity_k", "Polynomial, 0.09, -17")]
+    bcs = ["HeatFlux, 7.5e5", "Isothermal, 350", "HeatFlux, 0", "Isothermal, 400", "HeatFlux, 0", "HeatFlux, 0"]
+    steady = sim == "Steady"
+    txt = ini_text(sim, mesh, 300, props if not steady else [props[2]], bcs, time=not steady, steps=4, dt="1e-2", order=order,
+                   newton=None if sim == "Linearized_Unsteady" else 50)
+    txt = txt.replace("Visualization_Freq=0", "Visualization_Freq=2")
+    ini = str(tmp_path / "c.ini")
+    open(ini, "w").write(txt)
+    dev = J.Driver(ini)
+    dev.run()
+    entries = vtkfmt.read_pvd(out + "/ParaView.pvd")
+    if steady:
+        assert len(entries) == 1
+    else:
+        assert [f for _, f in entries] == ["Cycle000000/data.pvtu", "Cycle000002/data.pvtu", "Cycle000004/data.pvtu"]
+        assert np.allclose([t for t, _ in entries], [0.0, 0.02, 0.04], atol=1e-15)
+    names = ["Rank", "Temperature"] + ([p[0] for p in props] if not steady else [props[2][0]])
+    last = out + "/" + entries[-1][1].split("/")[0]
+    assert vtkfmt.read_pvtu(last + "/data.pvtu")["point_arrays"] == names
+    v = vtkfmt.read_vtu(last + "/proc000000.vtu")
+    assert sorted(v["point_data"]) == sorted(names)
+    s = dev.space()
+    g, u = s.gather(), dev.get_u()
+    nloc = (order + 1) ** 3
+    T = v["point_data"]["Temperature"].reshape(-1, nloc)
+    if order <= 2:
+        assert np.array_equal(T, u[g])                     # Gauss-Lobatto nodes = uniform lattice: the nodal values themselves
+    else:
+        # corners are nodes of both lattices; all values stay within the nodal range up to interpolation overshoot
+        corners = [0, order, order * (order + 1), (order + 1) ** 2 - 1]
+        assert np.allclose(T[:, corners], u[g][:, corners], rtol=1e-13)
+    k = v["point_data"]["Thermal_Conductivity_k"].reshape(-1, nloc)
+    if order <= 2:
+        assert np.allclose(k, 0.09 * u[g] - 17.0, rtol=1e-13)
+    assert np.abs(v["point_data"]["Rank"]).max() == 0.0
+    if not steady:
+        v0 = vtkfmt.read_vtu(out + "/Cycle000000/proc000000.vtu")
+        assert np.abs(v0["point_data"]["Temperature"] - 300.0).max() < 1e-12      # the initial condition, before any BC is applied
+        assert np.allclose(v0["point_data"]["Density_rho"], 8000.0) and np.allclose(v0["point_data"]["Specific_Heat_C"], 4.5 * 300.0 - 850.0)

@@ -460,3 +460,57 @@ def test_restart_files_round_trip_and_mfem_numbering(tmp_path, dim, p):
     X2 = s2.node_coordinates()
     key = lambda A: np.lexsort(np.round(A / 1e-9).T[::-1])
     assert np.abs(back[key(X2)] - u[key(X)]).max() <= 1e-13 * np.abs(u).max()
+
+
+@pytest.mark.parametrize("dim,p", [(2, 1), (2, 2), (2, 3), (2, 4), (3, 1), (3, 2), (3, 3), (3, 4)])
+def test_paraview_collection_against_an_independent_reader(tmp_path, dim, p):
+    """ParaView output (OutputManager::WriteVizOutput, output_manager.cpp:23-28,81-87: high-order, binary): the .vtu piece read
+    back by oracle/vtkfmt.py -- one Lagrange cell of order p per element, its nodes at the positions VTK's node order
+    prescribes (constructive restatement, independent of the index formula in paraview.cpp), point data equal to the
+    polynomial the nodal field samples (degree p per variable: the interpolation from the Gauss-Lobatto nodes to VTK's uniform
+    lattice is exact), cell attributes, and the collection file in the three modes (new / append / restart)."""
+    import jots_b200 as J
+    from oracle import vtkfmt
+    mesh = J.Mesh.brick(3, 2, 2, 0.3, 0.2, 0.1) if dim == 3 else J.Mesh.rect(4, 3, 1.0, 0.5)
+    s = J.Space(mesh, p)
+    nodes = vtkfmt.lagrange_nodes(dim, p)
+    D = p + 1
+    assert len(nodes) == D ** dim and len(set(nodes)) == D ** dim
+    lex = [c[0] + D * (c[1] + D * (c[2] if dim == 3 else 0)) for c in nodes]
+    assert list(J.vtk_lagrange_order(dim, p)) == lex
+
+    def poly(X):
+        f = (1.0 + 2.0 * X[:, 0]) ** p * (0.5 - X[:, 1]) ** p
+        return f * (2.0 + 3.0 * X[:, 2]) ** p if dim == 3 else f
+    X = s.node_coordinates()
+    u = 300.0 + 40.0 * poly(X)
+    rank = np.full(s.n_dof, 3.0)
+    d = str(tmp_path / "ParaView")
+    J.paraview_write(d, 0, 0.0, mesh, s, {"Rank": rank, "Temperature": u})
+    J.paraview_write(d, 10, 0.1, mesh, s, {"Rank": rank, "Temperature": u}, mode=1)
+    J.paraview_write(d, 20, 0.2, mesh, s, {"Rank": rank, "Temperature": u}, mode=1)
+    assert vtkfmt.read_pvd(d + "/ParaView.pvd") == [(0.0, "Cycle000000/data.pvtu"), (0.1, "Cycle000010/data.pvtu"), (0.2, "Cycle000020/data.pvtu")]
+    J.paraview_write(d, 15, 0.15, mesh, s, {"Rank": rank, "Temperature": u}, mode=2)      # restarted from t = 0.15: later entries dropped
+    assert vtkfmt.read_pvd(d + "/ParaView.pvd") == [(0.0, "Cycle000000/data.pvtu"), (0.1, "Cycle000010/data.pvtu"), (0.15, "Cycle000015/data.pvtu")]
+    J.paraview_write(d, 0, 0.0, mesh, s, {"Rank": rank, "Temperature": u})                   # a new run starts a new collection
+    assert vtkfmt.read_pvd(d + "/ParaView.pvd") == [(0.0, "Cycle000000/data.pvtu")]
+    hdr = vtkfmt.read_pvtu(d + "/Cycle000010/data.pvtu")
+    assert hdr == {"pieces": ["proc000000.vtu"], "point_arrays": ["Rank", "Temperature"], "cell_arrays": ["attribute"]}
+    v = vtkfmt.read_vtu(d + "/Cycle000010/proc000000.vtu")
+    ne, nloc = s.n_elem, D ** dim
+    assert v["n_cells"] == ne and v["n_points"] == ne * nloc and v["version"] == "2.2"
+    assert (v["types"] == (72 if dim == 3 else 70)).all() and list(v["offsets"]) == [nloc * (e + 1) for e in range(ne)]
+    assert sorted(v["connectivity"]) == list(range(ne * nloc))
+    assert (v["cell_data"]["attribute"] == 1).all()          # the generated meshes carry element attribute 1
+    g = s.gather()
+    P = v["points"]
+    assert P.shape == (ne * nloc, 3) and (dim == 3 or (P[:, 2] == 0).all())
+    for e in range(ne):
+        corner = X[g[e][0]]                                 # lexicographic node 0 = lattice origin of the element
+        far = X[g[e][nloc - 1]]
+        for j, c in enumerate(nodes):
+            pt = P[v["connectivity"][e * nloc + j]]
+            want = [corner[a] + (far[a] - corner[a]) * c[a] / p for a in range(dim)]
+            assert np.allclose(pt[:dim], want, atol=1e-14), (e, j, pt, want)
+    assert np.abs(v["point_data"]["Temperature"] - (300.0 + 40.0 * poly(P))).max() < 1e-10
+    assert np.abs(v["point_data"]["Rank"] - 3.0).max() < 1e-14
