@@ -39,27 +39,56 @@ inline PatchItems build_patch2_items() {
     return it;
 }
 
-template <int D, int Q, int PX, int PY>
+// LAG (the warp-decoupled pipeline, see the kernel): four stage buffers and eight descriptor slots instead of two and four
+template <int D, int Q, int PX, int PY, bool LAG = false>
 struct Patch2Smem {
     typedef PatchDims<D, PX, PY> PD;
     typedef Patch2Out<D, PX, PY> O;
-    static constexpr int stage = 2 * 2 * PD::NN + (2 * 2 * PD::NN) % 2;   // [buffer][x | z][node]
+    static constexpr int NSTG = LAG ? 4 : 2, NRING = LAG ? 8 : 4;
+    static constexpr int stage = NSTG * 2 * PD::NN + (NSTG * 2 * PD::NN) % 2;   // [buffer][x | z][node]
     static constexpr int out = 2 * 2 * Q * O::QS;                          // [buffer][r][QS]
     static constexpr int tab = 2 * Q * D + (2 * Q * D) % 2;                // B rows then G rows
-    static constexpr size_t total = (size_t)(stage + out + tab) * sizeof(double) + (size_t)4 * PD::REC * sizeof(int);
+    static constexpr size_t total = (size_t)(stage + out + tab) * sizeof(double) + (size_t)NRING * PD::REC * sizeof(int);
 };
+
+// shared-memory barriers with split arrive / wait (mbarrier): arrive releases, wait acquires
+__device__ __forceinline__ void mbar_init(unsigned long long* b, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(b)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* b) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"((unsigned)__cvta_generic_to_shared(b)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* b, unsigned parity) {
+    const unsigned addr = (unsigned)__cvta_generic_to_shared(b);
+    unsigned done = 0;
+    for (int spin = 0; spin < (1 << 22); ++spin) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+        if (done) return;
+    }
+    __trap();      // a protocol error must not hang the device
+}
 
 // KLIN: k(T) = c0 T + c1 (else uniform properties).  OP as in forms.hpp.
 // Measured dead ends (profiles/README.md r2d, r2e), so that they are not tried again: issuing phase 3 of tile t-1 branch-free
 // inside phase 2 of tile t (registers: 3 % slower); moving the copy-engine role to another warp with every tile to even out
 // the four scheduler partitions (5 % slower).
 // DOT: also add (x, A x) over the rows written to *a.dot (FormArgs::dot; the conjugate-gradient loop's (d, A d)).
-template <int D, int Q, int OP, bool KLIN, int PX, int PY, int T, bool DOT = false>
+//
+// LAG: the warp-decoupled pipeline.  With one block barrier per tile every warp waits for the slowest one once per tile (14 % of
+// the warp samples, profiles/r2v_phases_*).  Here phase 3 of tile t-1 runs AFTER phase 2 of tile t, and the hand-overs are
+// mbarriers whose other side finished about one tile earlier, so a wait only blocks a warp that is a whole tile ahead:
+//   READY[t & 3]  (copy warp -> all)   nodal values + descriptor of tile t have landed (fetched two / three tiles ahead)
+//   FULL[t & 1]   (all -> all)         result planes of tile t written  (awaited before phase 3 of t, i.e. after phase 2 of t+1)
+//   EMPTY[t & 1]  (all -> all)         phase 3 of tile t done           (awaited before the result stores of tile t+2)
+// The copy warp's refill of stage buffer (t+2) & 3 follows its own FULL wait of tile t-2's successor, two tiles after the last read.
+template <int D, int Q, int OP, bool KLIN, int PX, int PY, int T, bool DOT = false, bool LAG = false>
 __global__ void __launch_bounds__(T, 4) form_apply_patch2_kernel(const FormArgs a, const Slab2Tables<D, Q> t, const PatchItems items) {
     if (a.skip && *a.skip != 0.0) return;   // enqueued ahead of a Krylov solve that has already stopped
     typedef PatchDims<D, PX, PY> PD;
     typedef Patch2Out<D, PX, PY> O;
-    typedef Patch2Smem<D, Q, PX, PY> SM;
+    typedef Patch2Smem<D, Q, PX, PY, LAG> SM;
+    constexpr int SMASK = SM::NSTG - 1, RMASK = SM::NRING - 1;
     constexpr int NPEN = PD::NPEN, NN = PD::NN, E = PD::E, REC = PD::REC, RS = PD::NXN;
     constexpr int DD = D * D, QC = (Q + 1) / 2, NQH = Q * QC;
     constexpr bool X_GRAD = (OP != OP_RES), Z_GRAD = (OP != OP_LIN), NEED_Z = Z_GRAD || KLIN;
@@ -80,7 +109,9 @@ __global__ void __launch_bounds__(T, 4) form_apply_patch2_kernel(const FormArgs 
     // -1 = no tile left), so an SM that runs slower simply takes fewer tiles (a static round-robin left most SMs idle for the
     // last 8 % of the launch: sm__cycles_active avg 1.81 M against max 1.97 M, profiles/r2c).  The last block to leave resets
     // the counter for the next launch.
-    __shared__ int s_tile[4];
+    __shared__ int s_tile[SM::NRING];
+    __shared__ __align__(8) unsigned long long s_bar[8];     // LAG: READY[4], FULL[2], EMPTY[2]
+    unsigned long long* const READY = s_bar; unsigned long long* const FULL = s_bar + 4; unsigned long long* const EMPTY = s_bar + 6;
     __shared__ double s_dot[DOT ? T : 1];    // fused (x, A x): one running sum per phase-3 thread
     if (DOT) s_dot[tid] = 0.0;
     int pending = 0;               // lane 0 of the copy warp: the claim made one tile earlier (its latency is never waited for)
@@ -89,7 +120,7 @@ __global__ void __launch_bounds__(T, 4) form_apply_patch2_kernel(const FormArgs 
         if (lane == 0) {
             tile = pending < ntiles ? pending : -1;
             pending = (int)atomicAdd(a.sched, 1u);
-            s_tile[i & 3] = tile;
+            s_tile[i & RMASK] = tile;
         }
         return __shfl_sync(0xffffffffu, tile, 0);
     };
@@ -97,7 +128,7 @@ __global__ void __launch_bounds__(T, 4) form_apply_patch2_kernel(const FormArgs 
     auto issue_desc = [&](int i, int tile) {
         if (tile >= 0) {
             const int* src = a.patches + (size_t)tile * REC;
-            int* dst = ring + (i & 3) * REC;
+            int* dst = ring + (i & RMASK) * REC;
 #pragma unroll
             for (int m = 0; m < (REC / 4 + 31) / 32; ++m) {
                 const int c = lane + 32 * m;
@@ -106,9 +137,9 @@ __global__ void __launch_bounds__(T, 4) form_apply_patch2_kernel(const FormArgs 
         }
     };
     auto issue_vals = [&](int i) {
-        if (s_tile[i & 3] >= 0) {
-            const int* dsc = ring + (i & 3) * REC;
-            double* sx = stage + (size_t)(i & 1) * 2 * NN;
+        if (s_tile[i & RMASK] >= 0) {
+            const int* dsc = ring + (i & RMASK) * REC;
+            double* sx = stage + (size_t)(i & SMASK) * 2 * NN;
             double* sz = sx + NN;
             int g[(NN + 31) / 32];
 #pragma unroll
@@ -129,15 +160,32 @@ __global__ void __launch_bounds__(T, 4) form_apply_patch2_kernel(const FormArgs 
         }
     };
 
-    if (copier) {
-        if (lane == 0) pending = (int)atomicAdd(a.sched, 1u);
-        const int t0 = claim(0), t1 = claim(1);
-        issue_desc(0, t0); issue_desc(1, t1);
-        cp_async_commit(); cp_async_wait<0>();
+    if (LAG) {
+        if (tid == 0) {
+            for (int b = 0; b < 4; ++b) mbar_init(READY + b, 32);
+            for (int b = 0; b < 2; ++b) { mbar_init(FULL + b, T); mbar_init(EMPTY + b, T); }
+        }
+        __syncthreads();
+        if (copier) {
+            if (lane == 0) pending = (int)atomicAdd(a.sched, 1u);
+            const int t0 = claim(0), t1 = claim(1), t2 = claim(2);
+            issue_desc(0, t0); issue_desc(1, t1); issue_desc(2, t2);
+            cp_async_commit(); cp_async_wait<0>();
+            __syncwarp();
+            issue_vals(0); cp_async_commit(); cp_async_wait<0>(); mbar_arrive(READY + 0);
+            issue_vals(1); cp_async_commit(); cp_async_wait<0>(); mbar_arrive(READY + 1);
+        }
+    } else {
+        if (copier) {
+            if (lane == 0) pending = (int)atomicAdd(a.sched, 1u);
+            const int t0 = claim(0), t1 = claim(1);
+            issue_desc(0, t0); issue_desc(1, t1);
+            cp_async_commit(); cp_async_wait<0>();
+        }
+        __syncthreads();
+        if (copier) { issue_vals(0); cp_async_commit(); cp_async_wait<0>(); }
+        __syncthreads();
     }
-    __syncthreads();
-    if (copier) { issue_vals(0); cp_async_commit(); cp_async_wait<0>(); }
-    __syncthreads();
 
     // thread constants of phase 2
     const int el = tid / (2 * Q), r = tid - el * 2 * Q, qz = r >> 1;
@@ -165,15 +213,21 @@ __global__ void __launch_bounds__(T, 4) form_apply_patch2_kernel(const FormArgs 
     // phase 3 of tile i: transposed z contraction + scatter of this thread's item.  Branch free up to the atomics: the
     // loads are unconditional (every address is valid), contributions of holes are deselected.
     // sk (DOT): the pencil's output values, handed back for the fused inner product
-    auto phase3 = [&](int i, unsigned my_item, double (&sk)[D]) {
+    // xk (DOT, LAG): the pencil's own input values, re-read from the vector (L2) because the stage buffer may already be refilled
+    auto phase3 = [&](int i, unsigned my_item, double (&sk)[D], double (&xk)[D]) {
         const int p3_pencil = my_item & 0xff, p3_nv = (my_item >> 8) & 3;
         const int p3_off0 = (my_item >> 10) & 0x3ff, p3_off1 = (my_item >> 20) & 0x3ff;
-        const int* dsc = ring + (i & 3) * REC;
+        const int* dsc = ring + (i & RMASK) * REC;
         const double* ob = outbuf + (size_t)(i & 1) * 2 * Q * O::QS;
         const bool v0 = dsc[NN + p3_off0 / O::ES] >= 0, v1 = p3_nv > 1 && dsc[NN + p3_off1 / O::ES] >= 0;
         int g[D];
 #pragma unroll
         for (int k = 0; k < D; ++k) g[k] = dsc[k * NPEN + p3_pencil];
+        if (DOT && LAG) {
+#pragma unroll
+            for (int k = 0; k < D; ++k)
+                xk[k] = g[k] >= 0 ? a.x[g[k]] : ((g[k] != PATCH_INVALID && !a.mask_in) ? a.x[~g[k]] : 0.0);
+        }
         double Aq[Q], Bq[Q];
 #pragma unroll
         for (int q = 0; q < Q; ++q) {
@@ -201,16 +255,40 @@ __global__ void __launch_bounds__(T, 4) form_apply_patch2_kernel(const FormArgs 
         }
     };
 
-    for (int it = 0; s_tile[it & 3] >= 0; ++it) {
-        const int* dsc = ring + (it & 3) * REC;
+    // phase 3 of tile i for the threads that own an item, then the fused inner product
+    auto phase3_all = [&](int i, double (&xk)[D]) {
+        double sk[D];
+        if (DOT) {
+#pragma unroll
+            for (int k = 0; k < D; ++k) { sk[k] = 0.0; if (LAG) xk[k] = 0.0; }
+        }
+        if (tid < items.n) phase3(i, my_item, sk, xk);
+        if (DOT) {
+            // Straight-line code after the divergent region, so that its latency overlaps the start of the next tile's phase 2:
+            // with the FP64 pipe saturated by the other warps every dependent FP64 instruction inside phase 3 costs ~50 cycles
+            // (measured: the same three FMAs inside the k loop +23 us per launch, here +16 us; a separate pass is 44 us).
+            // No selection is needed: the staged input is zero wherever the row is not written (holes; eliminated columns --
+            // the caller fuses only forms with mask_in == mask_out), and threads without an item keep sk = 0.
+            double pr = xk[0] * sk[0];
+#pragma unroll
+            for (int k = 1; k < D; ++k) pr = fma(xk[k], sk[k], pr);
+            s_dot[tid] += pr;
+        }
+    };
+
+    int it = 0;
+    for (;; ++it) {
+        if (LAG) mbar_wait(READY + (it & 3), (it >> 2) & 1);
+        if (s_tile[it & RMASK] < 0) break;
+        const int* dsc = ring + (it & RMASK) * REC;
         if (copier) {
-            issue_desc(it + 2, claim(it + 2));
-            issue_vals(it + 1);
+            if (LAG) { issue_desc(it + 3, claim(it + 3)); issue_vals(it + 2); }
+            else { issue_desc(it + 2, claim(it + 2)); issue_vals(it + 1); }
             cp_async_commit();
         }
         // ---------------- phase 2: quadrature planes from the staged nodal values, half a plane per thread ---------------
         {
-            const double* sx = stage + (size_t)(it & 1) * 2 * NN + node0;
+            const double* sx = stage + (size_t)(it & SMASK) * 2 * NN + node0;
             const double* sz = sx + NN;
             const int eid = dsc[NN + el];
             if (a.geom_stride != 0) {
@@ -321,6 +399,7 @@ __global__ void __launch_bounds__(T, 4) form_apply_patch2_kernel(const FormArgs 
             flip_plane<D>(Bp, h);
             // the pair (adjacent lanes) adds its two halves: h = 0 ends up with the in-plane sum, h = 1 with the z part
             double* op = outbuf + (size_t)(it & 1) * 2 * Q * O::QS + (size_t)r * O::QS + el * O::ES;
+            if (LAG && it >= 2) mbar_wait(EMPTY + (it & 1), ((it - 2) >> 1) & 1);      // phase 3 of tile it-2 has read this buffer
 #pragma unroll
             for (int m = 0; m < DD; ++m) {
                 const double mine = h ? Bp[m] : A[m];
@@ -328,30 +407,33 @@ __global__ void __launch_bounds__(T, 4) form_apply_patch2_kernel(const FormArgs 
                 op[(m / D) * O::JS + m % D] = mine + other;
             }
         }
-        // fused (x, A x): the pencil's own input values are read from the stage buffer BEFORE the tile's barrier (the copy warp
-        // refills that buffer right after it)
-        double xk[D], sk[D];
-        if (DOT) {
-            const double* sxp = stage + (size_t)(it & 1) * 2 * NN + (my_item & 0xff);
+        double xk[D];
+        if (!LAG) {
+            // fused (x, A x): the pencil's own input values are read from the stage buffer BEFORE the tile's barrier (the copy
+            // warp refills that buffer right after it)
+            if (DOT) {
+                const double* sxp = stage + (size_t)(it & SMASK) * 2 * NN + (my_item & 0xff);
 #pragma unroll
-            for (int k = 0; k < D; ++k) { xk[k] = sxp[k * NPEN]; sk[k] = 0.0; }
+                for (int k = 0; k < D; ++k) xk[k] = sxp[k * NPEN];
+            }
+            if (copier) cp_async_wait<0>();      // nodal values of tile it+1 and the descriptor of tile it+2 have landed
+            __syncthreads();
+            // ---------------- phase 3: transposed z contraction + scatter (worker warps; the others run ahead) -----------
+            phase3_all(it, xk);
+        } else {
+            mbar_arrive(FULL + (it & 1));
+            if (copier) { cp_async_wait<0>(); __syncwarp(); mbar_arrive(READY + ((it + 2) & 3)); }
+            if (it >= 1) {
+                mbar_wait(FULL + ((it - 1) & 1), ((it - 1) >> 1) & 1);
+                phase3_all(it - 1, xk);
+                mbar_arrive(EMPTY + ((it - 1) & 1));
+            }
         }
-        if (copier) cp_async_wait<0>();      // nodal values of tile it+1 and the descriptor of tile it+2 have landed
-        __syncthreads();
-
-        // ---------------- phase 3: transposed z contraction + scatter (worker warps; the others run ahead) ---------------
-        if (tid < items.n) phase3(it, my_item, sk);
-        if (DOT) {
-            // Straight-line code after the divergent region, so that its latency overlaps the start of the next tile's phase 2:
-            // with the FP64 pipe saturated by the other warps every dependent FP64 instruction inside phase 3 costs ~50 cycles
-            // (measured: the same three FMAs inside the k loop +23 us per launch, here +16 us; a separate pass is 44 us).
-            // No selection is needed: the staged input is zero wherever the row is not written (holes; eliminated columns --
-            // the caller fuses only forms with mask_in == mask_out), and threads without an item keep sk = 0.
-            double pr = xk[0] * sk[0];
-#pragma unroll
-            for (int k = 1; k < D; ++k) pr = fma(xk[k], sk[k], pr);
-            s_dot[tid] += pr;
-        }
+    }
+    if (LAG && it >= 1) {      // drain: phase 3 of the block's last tile
+        double xk[D];
+        mbar_wait(FULL + ((it - 1) & 1), ((it - 1) >> 1) & 1);
+        phase3_all(it - 1, xk);
     }
     if (DOT) {
         __syncthreads();

@@ -46,20 +46,20 @@ int launch_patch(const FormArgs& a, const TablesRT& r, cudaStream_t st) {
     return 0;
 }
 
-template <int D, int Q, int OP, bool KLIN, int PX, int PY, bool DOT>
+template <int D, int Q, int OP, bool KLIN, int PX, int PY, bool DOT, bool LAG = false>
 int launch_patch2_v(const FormArgs& a, const TablesRT& r, cudaStream_t st) {
     constexpr int T = PX * PY * 2 * Q;
     Slab2Tables<D, Q> t;
     fill_slab2_tables<D, Q>(r, t);
     static const PatchItems items = build_patch2_items<D, PX, PY>();
-    const size_t smem = Patch2Smem<D, Q, PX, PY>::total;
-    auto kern = form_apply_patch2_kernel<D, Q, OP, KLIN, PX, PY, T, DOT>;
+    const size_t smem = Patch2Smem<D, Q, PX, PY, LAG>::total;
+    auto kern = form_apply_patch2_kernel<D, Q, OP, KLIN, PX, PY, T, DOT, LAG>;
     static PerDevicePatch pd;
     const int grid_max = pd.get(kern, T, smem);
     if (items.n > T - 32) return 1;      // phase 3 must be one pass of the worker warps
     kern<<<a.n_patches < grid_max ? a.n_patches : grid_max, T, smem, st>>>(a, t, items);
     static const std::string label = kernel_label("form_apply_patch2_kernel", D, Q, OP, KLIN ? CF_KL : CF_CONST,
-                                                  ("," + std::to_string(PX) + "," + std::to_string(PY) + "," + std::to_string(T) + (DOT ? ",dot" : "")).c_str());
+                                                  ("," + std::to_string(PX) + "," + std::to_string(PY) + "," + std::to_string(T) + (DOT ? ",dot" : "") + (LAG ? ",lag" : "")).c_str());
     last_element_kernel() = label.c_str();
     return 0;
 }
@@ -67,11 +67,14 @@ int launch_patch2_v(const FormArgs& a, const TablesRT& r, cudaStream_t st) {
 // FormArgs::dot selects the variant that also forms (x, A x); the residual form is not bilinear and has none
 template <int D, int Q, int OP, bool KLIN, int PX, int PY>
 int launch_patch2(const FormArgs& a, const TablesRT& r, cudaStream_t st) {
+    // JOTS_PATCH2_LAG=0: one block barrier per tile instead of the warp-decoupled pipeline (A/B runs)
+    static const bool lag = [] { const char* e = getenv("JOTS_PATCH2_LAG"); return !e || atoi(e) != 0; }();
     if (a.dot) {
         if (OP == OP_RES) return 1;
-        return launch_patch2_v<D, Q, OP == OP_RES ? OP_LIN : OP, KLIN, PX, PY, true>(a, r, st);
+        constexpr int OPD = OP == OP_RES ? OP_LIN : OP;
+        return lag ? launch_patch2_v<D, Q, OPD, KLIN, PX, PY, true, true>(a, r, st) : launch_patch2_v<D, Q, OPD, KLIN, PX, PY, true, false>(a, r, st);
     }
-    return launch_patch2_v<D, Q, OP, KLIN, PX, PY, false>(a, r, st);
+    return lag ? launch_patch2_v<D, Q, OP, KLIN, PX, PY, false, true>(a, r, st) : launch_patch2_v<D, Q, OP, KLIN, PX, PY, false, false>(a, r, st);
 }
 
 // JOTS_PATCH2=0 keeps the three-phase patch kernel for the forms the two-phase kernel covers (A/B runs)

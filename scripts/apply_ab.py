@@ -11,9 +11,11 @@ import tempfile
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CONFIGS = {
+    "patch2_barrier": {"JOTS_SLAB_VARIANT": "7", "JOTS_PATCH2_LAG": "0"},          # two-phase patch kernel, one block barrier per tile
+    "patch2_barrier_dot": {"JOTS_SLAB_VARIANT": "7", "JOTS_PATCH2_LAG": "0", "JOTS_FORM_TIME_DOT": "1"},
     "slab3_gather_E16": {"JOTS_SLAB_VARIANT": "3"},                   # gather-table kernel (round-1 default)
     "patch3_4x4": {"JOTS_SLAB_VARIANT": "7", "JOTS_PATCH2": "0"},     # three-phase unique-pencil patch kernel
-    "patch2_4x4": {"JOTS_SLAB_VARIANT": "7"},                         # two-phase patch kernel (default)
+    "patch2_4x4": {"JOTS_SLAB_VARIANT": "7"},                         # two-phase patch kernel, warp-decoupled pipeline (default)
     "patch2_4x4_dot": {"JOTS_SLAB_VARIANT": "7", "JOTS_FORM_TIME_DOT": "1"},   # the same + (x, A x) formed in phase 3 (CG loop)
 }
 
