@@ -61,15 +61,21 @@ __device__ __forceinline__ void mbar_arrive(unsigned long long* b) {
 __device__ __forceinline__ void mbar_wait(unsigned long long* b, unsigned parity) {
     const unsigned addr = (unsigned)__cvta_generic_to_shared(b);
     unsigned done = 0;
-    for (int spin = 0; spin < (1 << 22); ++spin) {
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                     : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+    // the hardware suspends the warp up to the hint (ns) per try, so a warp that is ahead does not spin on issue slots
+#pragma unroll 1
+    for (int spin = 0; spin < (1 << 16); ++spin) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(addr), "r"(parity), "r"(100000u) : "memory");
         if (done) return;
     }
     __trap();      // a protocol error must not hang the device
 }
 
 // KLIN: k(T) = c0 T + c1 (else uniform properties).  OP as in forms.hpp.
+// Measured dead ends of the decoupled pipeline (profiles/README.md r2z): rotating the warp that sits out phase 3 so that all four
+// carry the same load (8 % / 6 % slower for a 4- / 6-tile rotation), shorter FMA chains in phase 3 (no change: its latency is no
+// longer exposed), three or five blocks per SM (168 registers without spills: 6 % slower; 96 registers: 30 % slower), the fused
+// inner product reading its inputs from eight x stage buffers instead of L2 (no change).
 // Measured dead ends (profiles/README.md r2d, r2e), so that they are not tried again: issuing phase 3 of tile t-1 branch-free
 // inside phase 2 of tile t (registers: 3 % slower); moving the copy-engine role to another warp with every tile to even out
 // the four scheduler partitions (5 % slower).
