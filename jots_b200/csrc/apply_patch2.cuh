@@ -75,7 +75,8 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* b, unsigned parity
 // Measured dead ends of the decoupled pipeline (profiles/README.md r2z): rotating the warp that sits out phase 3 so that all four
 // carry the same load (8 % / 6 % slower for a 4- / 6-tile rotation), shorter FMA chains in phase 3 (no change: its latency is no
 // longer exposed), three or five blocks per SM (168 registers without spills: 6 % slower; 96 registers: 30 % slower), the fused
-// inner product reading its inputs from eight x stage buffers instead of L2 (no change).
+// inner product reading its inputs from eight x stage buffers instead of L2 (no change), or handed to the copy warp (the pencil
+// sums or products left in shared memory: 2 % / 10 % slower -- the copy warp is not idle, it paces the block).
 // Measured dead ends (profiles/README.md r2d, r2e), so that they are not tried again: issuing phase 3 of tile t-1 branch-free
 // inside phase 2 of tile t (registers: 3 % slower); moving the copy-engine role to another warp with every tile to even out
 // the four scheduler partitions (5 % slower).
