@@ -246,6 +246,10 @@ void Ctx::set_bcs(const std::vector<BCSpec>& b) {
     }
     d_gnodal.upload(gn);
     if (any_precice && d_bdr_elem.n != (size_t)space.nbdr) {
+        fill_boundary_adjacency(space);        // spaces from caller-supplied tables: matched through the DOF ids
+        std::vector<int> nl;
+        boundary_node_locals(space, nl);
+        d_bdr_node_loc.upload(nl);
         std::vector<int> be(space.nbdr, -1), bf(space.nbdr, -1);
         for (int64_t b = 0; b < space.nbdr && b < (int64_t)space.bdr_elem.size(); ++b) { be[b] = (int)space.bdr_elem[b]; bf[b] = space.bdr_face[b]; }
         d_bdr_elem.upload(be); d_bdr_face.upload(bf);
@@ -486,7 +490,7 @@ void Ctx::precice_bc_write_data(int bc, const double* u, double* out) {
         WallFluxArgs a;
         std::memset(&a, 0, sizeof(a));
         a.dim = space.dim; a.D = space.D; a.nloc = space.nloc; a.nfl = space.nfl; a.nfaces = (int)bc_faces[bc].size();
-        a.faces = d_bc_faces[bc].p; a.bdr_elem = d_bdr_elem.p; a.bdr_face = d_bdr_face.p; a.gather = d_gather_ess.p;
+        a.faces = d_bc_faces[bc].p; a.bdr_elem = d_bdr_elem.p; a.bdr_face = d_bdr_face.p; a.node_loc = d_bdr_node_loc.p; a.gather = d_gather_ess.p;
         a.geom = d_geom.p; a.geom_stride = geom_stride; a.u = u; a.out = d_out.p; a.k = mat.k;
         std::vector<double> nodes = gauss_lobatto_01(space.D), Bn, Gn;
         lagrange_tab(nodes, nodes, Bn, Gn);

@@ -112,7 +112,7 @@ public:
     std::vector<std::vector<int>> bc_faces, bc_node_dofs;
     std::vector<DArr<int>> d_bc_faces, d_bc_node_dofs;
     DArr<const double*> d_gnodal;       // per BC: bc_field pointer for preCICE heat-flux BCs, else null
-    DArr<int> d_bdr_elem, d_bdr_face;   // adjacent element and its local face of every boundary element
+    DArr<int> d_bdr_elem, d_bdr_face, d_bdr_node_loc;   // adjacent element, its local face, node places of every boundary element
     int64_t precice_bc_size(int bc) const { return (int64_t)bc_node_dofs.at(bc).size(); }
     void precice_bc_coords(int bc, double* xyz) const;                 // [size][dim]
     void precice_bc_set_read_data(int bc, const double* vals_host);    // PreciceBC::UpdateCoeff: SetSubVector(bdr_dof_indices, read)

@@ -175,16 +175,12 @@ static __global__ void wall_flux_kernel(const WallFluxArgs a) {
     const int fi = t / a.nfl, l = t - fi * a.nfl;
     const int b = a.faces[fi], e = a.bdr_elem[b], lf = a.bdr_face[b];
     const int dim = a.dim, D = a.D, axis = lf >> 1, side = lf & 1;
-    int idx[3] = {0, 0, 0};
-    idx[axis] = side ? D - 1 : 0;
-    {
-        int m = l;
-        for (int c = 0; c < dim; ++c) if (c != axis) { idx[c] = m % D; m /= D; }
-    }
+    // the node's place in the adjacent element comes from a table (the boundary element may list its DOFs in any order)
+    const int l0 = a.node_loc[(size_t)b * a.nfl + l];
+    const int idx[3] = {l0 % D, (l0 / D) % D, l0 / (D * D)};
     const int stride[3] = {1, D, D * D};
     const int* g = a.gather + (size_t)e * a.nloc;
     auto val = [&](int loc) { const int d = g[loc]; return a.u[d < 0 ? ~d : d]; };
-    const int l0 = idx[0] + D * idx[1] + (dim == 3 ? D * D * idx[2] : 0);
     double gref[3] = {0.0, 0.0, 0.0};
     for (int c = 0; c < dim; ++c) {
         const int base = l0 - idx[c] * stride[c];

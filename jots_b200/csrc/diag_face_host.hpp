@@ -39,6 +39,7 @@ struct WallFluxArgs {
     int dim, D, nloc, nfl, nfaces;
     const int* faces;          // boundary elements of the BC
     const int* bdr_elem;       // adjacent element of every boundary element
+    const int* node_loc;       // [nbdr*nfl] local lattice index of every boundary-element node in that element
     const int* bdr_face;       // its local face (axis = f / 2, side = f % 2)
     const int* gather;         // [nelem][nloc], essential DOFs complemented
     const double* geom;        // invJ + det per element (stride 10) or one record (stride 0)

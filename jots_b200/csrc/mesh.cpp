@@ -535,3 +535,69 @@ void h1_dof_map(int dim, int p, std::vector<int>& map) {
 }
 
 }  // namespace jots
+
+namespace jots {
+
+void fill_boundary_adjacency(Space& s) {
+    if ((int64_t)s.bdr_elem.size() != s.nbdr) { s.bdr_elem.assign((size_t)s.nbdr, -1); s.bdr_face.assign((size_t)s.nbdr, -1); }
+    bool missing = false;
+    for (int64_t b = 0; b < s.nbdr; ++b) missing = missing || s.bdr_elem[b] < 0;
+    if (!missing) return;
+    const int dim = s.dim, p = s.p, D = s.D, nfv = 1 << (dim - 1);
+    // corner DOFs (sorted) of a face lattice given as nfl node ids, lower free axis fastest
+    auto corners = [&](const int* nodes, std::array<int, 4>& key) {
+        key = {-1, -1, -1, -1};
+        if (dim == 2) { key[0] = nodes[0]; key[1] = nodes[D - 1]; }
+        else { key[0] = nodes[0]; key[1] = nodes[D - 1]; key[2] = nodes[(D - 1) * D]; key[3] = nodes[D * D - 1]; }
+        for (int i = 1; i < nfv; ++i)        // insertion sort of two or four ids
+            for (int j = i; j > 0 && key[j - 1] > key[j]; --j) std::swap(key[j - 1], key[j]);
+    };
+    std::map<std::array<int, 4>, std::pair<int64_t, int>> faces;
+    std::vector<int> fl, nodes((size_t)s.nfl);
+    std::vector<std::vector<int>> face_nodes(2 * dim);
+    for (int f = 0; f < 2 * dim; ++f) face_lattice_nodes(dim, p, f, face_nodes[f]);
+    // only the faces that carry a DOF of a boundary element can match: mark those DOFs first
+    std::vector<unsigned char> on_bdr((size_t)s.ndof, 0);
+    for (int g : s.bdr_gather) on_bdr[g] = 1;
+    for (int64_t e = 0; e < s.nelem; ++e) {
+        const int* g = &s.gather[(size_t)e * s.nloc];
+        for (int f = 0; f < 2 * dim; ++f) {
+            const std::vector<int>& fn = face_nodes[f];
+            if (!on_bdr[g[fn[0]]] || !on_bdr[g[fn[s.nfl - 1]]]) continue;
+            for (int m = 0; m < s.nfl; ++m) nodes[m] = g[fn[m]];
+            std::array<int, 4> key;
+            corners(nodes.data(), key);
+            faces[key] = {e, f};
+        }
+    }
+    for (int64_t b = 0; b < s.nbdr; ++b) {
+        if (s.bdr_elem[b] >= 0) continue;
+        std::array<int, 4> key;
+        corners(&s.bdr_gather[(size_t)b * s.nfl], key);
+        auto it = faces.find(key);
+        if (it == faces.end()) throw std::runtime_error("boundary element " + std::to_string(b) + " matches no element face (boundary DOF table inconsistent with the element table)");
+        s.bdr_elem[b] = it->second.first;
+        s.bdr_face[b] = it->second.second;
+    }
+}
+
+void boundary_node_locals(const Space& s, std::vector<int>& loc) {
+    loc.assign((size_t)s.nbdr * s.nfl, -1);
+    std::vector<int> fn;
+    for (int64_t b = 0; b < s.nbdr && b < (int64_t)s.bdr_elem.size(); ++b) {
+        const int64_t e = s.bdr_elem[b];
+        if (e < 0) continue;
+        face_lattice_nodes(s.dim, s.p, s.bdr_face[b], fn);
+        const int* g = &s.gather[(size_t)e * s.nloc];
+        for (int m = 0; m < s.nfl; ++m) {
+            const int dof = s.bdr_gather[(size_t)b * s.nfl + m];
+            int found = -1;
+            if (g[fn[m]] == dof) found = fn[m];                       // the usual case: same order as the element's face lattice
+            else for (int q = 0; q < s.nfl; ++q) if (g[fn[q]] == dof) { found = fn[q]; break; }
+            if (found < 0) throw std::runtime_error("boundary element " + std::to_string(b) + ": DOF not on the matched element face");
+            loc[(size_t)b * s.nfl + m] = found;
+        }
+    }
+}
+
+}  // namespace jots

@@ -70,6 +70,13 @@ struct Space {
 
 Space make_space(const Mesh& m, int p);
 
+// Boundary-element adjacency through the DOF ids (spaces built from caller-supplied tables carry none): bdr_elem / bdr_face of
+// every boundary element whose adjacent element is unknown, found by matching the face's corner DOFs against the element faces.
+void fill_boundary_adjacency(Space& s);
+// loc[b * nfl + m] = local lattice index, in the adjacent element, of the DOF bdr_gather[b * nfl + m] (any face DOF order);
+// -1 where the adjacency is unknown
+void boundary_node_locals(const Space& s, std::vector<int>& loc);
+
 // MFEM's native local DOF order of the H1 tensor elements (H1_QuadrilateralElement / H1_HexahedronElement::GetDofMap,
 // fem/fe/fe_h1.cpp of MFEM 4.7): vertices, then edge interiors (edge by edge, each in the direction of
 // increasing coordinate on hexes; quads run edges 2 and 3 backwards), then face interiors, then the element interior.

@@ -116,3 +116,39 @@ def test_coupled_like_time_steps(J, tmp_path, kind):
         assert rel(w, w_ref) < 1e-7
     assert rel(dev.get_u(), orc.u) < FIELD_TOL
     assert dev.ctx.stats()["newton_iters"] == orc.it.stats["newton_iters"]
+
+
+@pytest.mark.parametrize("dim,p", [(3, 2), (2, 3), (3, 3)])
+def test_wall_heat_flux_on_caller_supplied_tables(J, tmp_path, dim, p):
+    """A space built from the caller's tables (jots_space_create_from_tables: no mesh, no boundary-element adjacency, boundary
+    faces listing their DOFs in an order of their own) finds the adjacent element of every boundary face through the DOF ids
+    and returns the wall heat flux at the nodes in the caller's order."""
+    dev, orc = make(J, tmp_path, "Nonlinear_Unsteady", dim, p, "k2", bcs_for(dim, "preCICE_Isothermal", 0))
+    s = dev.space()
+    g = s.gather()
+    ec, bc = s.corners()
+    bg, ba = s.boundary()[:2]
+    D = p + 1
+    nfl = D ** (dim - 1)
+    # every boundary face lists its nodes backwards (and, in 3-D, transposed): a rotation / reflection of the face lattice
+    if dim == 3:
+        perm = np.arange(nfl).reshape(D, D).T[::-1, ::-1].ravel()
+        cperm = np.arange(4).reshape(2, 2).T[::-1, ::-1].ravel()
+    else:
+        perm = np.arange(nfl)[::-1]
+        cperm = np.arange(2)[::-1]
+    bg2 = np.ascontiguousarray(bg.reshape(-1, nfl)[:, perm])
+    bc2 = np.ascontiguousarray(bc.reshape(bg2.shape[0], 2 ** (dim - 1), dim)[:, cperm, :])
+    s2 = J.Space.from_tables(dim, p, s.n_dof, g, ec, bg2, bc2, ba)
+    ctx = J.Context(s2)
+    ctx.dim = dim
+    ctx.set_material(J.THERMAL_CONDUCTIVITY, ("Polynomial", 1e-4, 0.09, -17.0))      # PROPS["k2"]
+    nb = 6 if dim == 3 else 4
+    ctx.set_bcs([("preCICE_Isothermal", "Coupling-Mesh", 320.0)] + [("HeatFlux", 0.0)] * (nb - 1))
+    u = smooth_state(orc)
+    q2 = ctx.precice_bc_write_data(0, u)
+    q_ref = orc.bcs[0].write_data(orc.space, u, orc.props["k"])
+    assert rel(q2.reshape(-1, nfl), q_ref.reshape(-1, nfl)[:, perm]) < APPLY_TOL
+    dofs2, _ = ctx.precice_bc_nodes(0)
+    dofs, _ = dev.ctx.precice_bc_nodes(0)
+    assert (dofs2.reshape(-1, nfl) == dofs.reshape(-1, nfl)[:, perm]).all()
