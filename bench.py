@@ -404,8 +404,9 @@ def main():
     apply_plain_ms = drv.op.form_time(J.FORM_SYSTEM, x, y, state_dev=z, reps=args.apply_reps)
     apply_ms, fused = apply_plain_ms, st["fused_dots"] > 0
     if fused:
-        # the conjugate-gradient loop launched the variant that also forms (d, A d): that is the dominant kernel of the step
-        os.environ["JOTS_FORM_TIME_DOT"] = "1"
+        # the conjugate-gradient loop launched the variant that also forms (d, A d) -- and, when it could, carries the loop's
+        # side stream (x += alpha d of the previous iteration, zeroing of the next output): that is the dominant kernel of the step
+        os.environ["JOTS_FORM_TIME_DOT"] = "2" if st.get("side_applies", 0) > 0 else "1"
         drv.op.form_time(J.FORM_SYSTEM, x, y, state_dev=z, reps=min(20, max(2, args.apply_reps)))
         apply_ms = drv.op.form_time(J.FORM_SYSTEM, x, y, state_dev=z, reps=args.apply_reps)
         os.environ.pop("JOTS_FORM_TIME_DOT")
@@ -450,7 +451,7 @@ def main():
             "data": "synthetic", "config": workload_config(args, world),
             "steps_per_s": K / (ms * 1e-3), "krylov_iters": iters, "newton_iters": st["newton_iters"],
             "apply_gdofs": ndof / (apply_ms * 1e-3) / 1e9, "apply_ms": apply_ms, "apply_without_inner_product_ms": apply_plain_ms,
-            "residual_ms": res_ms, "fused_inner_products": st["fused_dots"],
+            "residual_ms": res_ms, "fused_inner_products": st["fused_dots"], "side_stream_applies": st.get("side_applies", 0),
             "clocks": clk.summary(),
             "e2e": {"value": e2e_value, "unit": "GDOF/s", "h2d_bytes_per_step": 8 * ndof, "d2h_bytes_per_step": 8 * ndof,
                     "ms_per_step": 1e3 * e2e_s / K},
@@ -459,7 +460,11 @@ def main():
                          "traffic": traffic, "algorithmic_bytes": alg_bytes,
                          "kernel": kernel_label,
                          "timed": "Jacobian-vector apply, 24 B/DOF algorithmic (x, z in, y out); CUDA events on the launching stream around "
-                                  "%d applies, each = zeroing of y + this kernel%s" % (args.apply_reps, " (which also forms (x, A x), as in the CG loop)" if fused else ""),
+                                  "%d applies, each = %s" % (args.apply_reps,
+                                      "this kernel as the CG loop launches it: it also forms (x, A x) and carries the loop's side stream "
+                                      "(x_sol += alpha d_old, zeroing of the next output: 4 more vector passes, not counted in the 24 B/DOF)"
+                                      if st.get("side_applies", 0) > 0 else
+                                      "zeroing of y + this kernel" + (" (which also forms (x, A x), as in the CG loop)" if fused else "")),
                          "note": "this kernel is FP64-pipe bound (fp64.instr_per_dof FP64 instructions against 24 B/DOF), not HBM "
                                  "bound: fp64.frac_of_peak is the fraction that matters (DESIGN.md 5)",
                          "fp64_pipe_active_pct": fp64_pct,

@@ -149,6 +149,9 @@ int jots_ctx_stats(jots_ctx_t c, int64_t out[12], double norms[2]);
 int jots_ctx_patch_info(jots_ctx_t c, int64_t* n_patches, double* fill, int64_t* applies);
 /* operator applies of the conjugate-gradient loop that formed (d, A d) inside the element kernel (no separate pass) */
 int jots_ctx_fused_dots(jots_ctx_t c, int64_t* n);
+/* ... and of those, the applies that also carried the loop's side stream (x += alpha d of the previous iteration and the zeroing
+   of the next output buffer, done by the FP64-bound element kernel while HBM is idle: DESIGN.md 6) */
+int jots_ctx_side_applies(jots_ctx_t c, int64_t* n);
 /* label of the element kernel the last operator apply launched, e.g. "form_apply_patch_kernel<3,4,OP_JAC,CF_KL,4,4,128>" */
 const char* jots_ctx_last_kernel(jots_ctx_t c);
 int jots_ctx_reset_stats(jots_ctx_t c);
@@ -181,6 +184,12 @@ int jots_op_form_diagonal(jots_op_t op, int form, const double* state, double* d
    (mfem::CGSolver::Mult: den = Dot(d, z) after oper->Mult(d, z)).  *fused = 1 when the element kernel formed the inner product
    in the same pass (two-phase patch kernel), 0 when a separate pass did.  Bilinear forms only (MASS, STIFFNESS, SYSTEM). */
 int jots_op_form_apply_dot(jots_op_t op, int form, const double* x, const double* state, double* y, int loc, double* dot, int* fused);
+/* The apply one iteration of the device-resident conjugate-gradient loop launches when the element kernel can carry the loop's
+   side stream (mfem::CGSolver::Mult: oper->Mult(d, z); den = Dot(d, z); add(x, alpha, d, x) of the PREVIOUS iteration):
+   y = form(x), *dot = (x, form(x)), side_x += alpha * side_d, side_zero = 0, one element-kernel launch.  Device pointers
+   only (loc = JOTS_DEVICE), 16-byte aligned.  *carried = 0 (and nothing computed) when this form's kernel has no side stream. */
+int jots_op_form_apply_side(jots_op_t op, int form, const double* x, const double* state, double* y, int loc, double* dot,
+                            double alpha, const double* side_d, double* side_x, double* side_zero, int* carried);
 /* repeat y = form(x) `reps` times on device-resident vectors; returns the mean milliseconds per
    apply measured with CUDA events on the context's stream (bench.py's roofline leg) */
 int jots_op_form_time(jots_op_t op, int form, const double* x_dev, const double* state_dev, double* y_dev,

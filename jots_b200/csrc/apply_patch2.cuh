@@ -430,10 +430,36 @@ __global__ void __launch_bounds__(T, 4) form_apply_patch2_kernel(const FormArgs 
         } else {
             mbar_arrive(FULL + (it & 1));
             if (copier) { cp_async_wait<0>(); __syncwarp(); mbar_arrive(READY + ((it + 2) & 3)); }
+            // Side stream of the conjugate-gradient loop (FormArgs::side_*): this tile's slice of x += alpha d_old and of the
+            // zeroing of the next apply's output.  The loads are issued here, where the register peak of phase 2 is over, and
+            // consumed after phase 3 of the previous tile (about a microsecond later: their latency is not waited for); streaming
+            // cache hints keep the slices from displacing the gathered nodal values in L2.  The copy warp paces the block and
+            // takes no part.
+            double2 side_xv = make_double2(0.0, 0.0), side_dv = side_xv;
+            double side_al = 0.0;
+            long long side_k = 0;
+            int side_mode = 0;             // 2: a pair of entries, 1: the last entry of an odd-length vector
+            if (DOT && a.side_chunk != 0 && !copier && 2 * tid < a.side_chunk) {
+                side_k = (long long)s_tile[it & RMASK] * a.side_chunk + 2 * tid;
+                side_mode = side_k + 1 < a.nvec ? 2 : (side_k < a.nvec ? 1 : 0);
+                if (side_mode == 2) {
+                    side_xv = __ldcs(reinterpret_cast<const double2*>(a.side_x + side_k));
+                    side_dv = __ldcs(reinterpret_cast<const double2*>(a.side_d + side_k));
+                } else if (side_mode == 1) { side_xv.x = __ldcs(a.side_x + side_k); side_dv.x = __ldcs(a.side_d + side_k); }
+                side_al = __ldg(a.side_alpha);
+            }
             if (it >= 1) {
                 mbar_wait(FULL + ((it - 1) & 1), ((it - 1) >> 1) & 1);
                 phase3_all(it - 1, xk);
                 mbar_arrive(EMPTY + ((it - 1) & 1));
+            }
+            if (DOT && side_mode != 0) {
+                side_xv.x = fma(side_al, side_dv.x, side_xv.x);
+                if (side_mode == 2) {
+                    side_xv.y = fma(side_al, side_dv.y, side_xv.y);
+                    __stcs(reinterpret_cast<double2*>(a.side_x + side_k), side_xv);
+                    __stcs(reinterpret_cast<double2*>(a.side_zero + side_k), make_double2(0.0, 0.0));
+                } else { __stcs(a.side_x + side_k, side_xv.x); __stcs(a.side_zero + side_k, 0.0); }
             }
         }
     }

@@ -458,6 +458,7 @@ int jots_ctx_patch_info(jots_ctx_t c, int64_t* n_patches, double* fill, int64_t*
 }
 const char* jots_ctx_last_kernel(jots_ctx_t c) { return c->c->last_kernel; }
 int jots_ctx_fused_dots(jots_ctx_t c, int64_t* n) { if (n) *n = c->c->stats.fused_dots; return 0; }
+int jots_ctx_side_applies(jots_ctx_t c, int64_t* n) { if (n) *n = c->c->stats.side_applies; return 0; }
 int jots_ctx_reset_stats(jots_ctx_t c) { c->c->stats = Stats(); return 0; }
 
 // ---- operators --------------------------------------------------------------------------------
@@ -536,9 +537,11 @@ int jots_op_get_neumann(jots_op_t op, double* b, int loc) {
 }
 
 // resolve a building-block form of an operator into something to run
-static void run_form(jots_op_t op, int form, const double* x, const double* state, double* y, bool diag, double* d_dot = nullptr, bool* fused = nullptr) {
+// side: the launch also carries the conjugate-gradient side stream (y already zero; throws when the form's kernel has none)
+static void run_form(jots_op_t op, int form, const double* x, const double* state, double* y, bool diag, double* d_dot = nullptr, bool* fused = nullptr,
+                     const CgSide* side = nullptr) {
     Ctx* c = op->c;
-    auto apply = [&](const FormSpec& f) { const bool fu = c->apply_form(f, x, y, d_dot); if (fused) *fused = fu; };
+    auto apply = [&](const FormSpec& f) { const bool fu = c->apply_form(f, x, y, d_dot, side); if (fused) *fused = fu; };
     auto no_dot = [&] { if (d_dot) throw std::runtime_error("this form is not a single bilinear form: no (x, A x)"); };
     if (op->sim_type == JOTS_LINEARIZED_UNSTEADY) {
         auto* L = static_cast<LinearConductionOperator*>(op->it);
@@ -611,6 +614,30 @@ int jots_op_form_apply_dot(jots_op_t op, int form, const double* x, const double
     return 0;
     JOTS_CATCH_INT
 }
+int jots_op_form_apply_side(jots_op_t op, int form, const double* x, const double* state, double* y, int loc, double* dot,
+                            double alpha, const double* side_d, double* side_x, double* side_zero, int* carried) {
+    JOTS_TRY
+    Ctx* c = op->c;
+    if (loc != JOTS_DEVICE) throw std::runtime_error("jots_op_form_apply_side: device vectors only");
+    if (carried) *carried = 0;
+    DArr<double> d_s;
+    d_s.alloc(2);
+    const double hs[2] = {0.0, alpha};
+    JOTS_CUDA(cudaMemcpyAsync(d_s.p, hs, sizeof(hs), cudaMemcpyHostToDevice, c->stream));
+    c->zero(y);
+    const CgSide side{side_x, side_d, d_s.p + 1, side_zero};
+    bool fu = false;
+    try { run_form(op, form, x, state, y, false, d_s.p, &fu, &side); }
+    catch (const std::runtime_error&) { c->sync(); return 0; }      // *carried stays 0: this form has no side stream
+    c->allreduce_scalars(d_s.p, 1);
+    double v = 0.0;
+    JOTS_CUDA(cudaMemcpyAsync(&v, d_s.p, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    c->sync();
+    if (dot) *dot = v;
+    if (carried) *carried = 1;
+    return 0;
+    JOTS_CATCH_INT
+}
 int jots_op_form_diagonal(jots_op_t op, int form, const double* state, double* d, int loc) {
     JOTS_TRY
     In is(op->c, state, loc); Out o(op->c, d, loc);
@@ -624,13 +651,26 @@ int jots_op_form_time(jots_op_t op, int form, const double* x, const double* sta
     Ctx* c = op->c;
     cudaEvent_t e0, e1;
     JOTS_CUDA(cudaEventCreate(&e0)); JOTS_CUDA(cudaEventCreate(&e1));
-    // JOTS_FORM_TIME_DOT=1 times the variant that also forms (x, A x) (what the conjugate-gradient loop launches)
+    // JOTS_FORM_TIME_DOT=1 times the variant that also forms (x, A x); =2 that variant carrying the side stream of the
+    // conjugate-gradient loop (x_sol += alpha d_old, zeroing of the next output) -- what the loop launches when it can
     const char* ev = std::getenv("JOTS_FORM_TIME_DOT");
-    double* d_dot = (ev && ev[0] == '1' && form != JOTS_FORM_RESIDUAL) ? c->d_scal.p + 63 : nullptr;
-    run_form(op, form, x, state, y, false, d_dot);
+    const int mode = (ev && form != JOTS_FORM_RESIDUAL) ? std::atoi(ev) : 0;
+    double* d_dot = mode >= 1 ? c->d_scal.p + 63 : nullptr;
+    DArr<double> sx, y2;
+    if (mode >= 2) {
+        sx.alloc(c->n); y2.alloc(c->n);
+        c->zero(sx.p); c->zero(y2.p); c->zero(y);
+        JOTS_CUDA(cudaMemsetAsync(c->d_scal.p + 62, 0, sizeof(double), c->stream));     // alpha = 0
+    }
+    double* Y[2] = {y, mode >= 2 ? y2.p : y};
+    auto one = [&](int i) {
+        if (mode >= 2) { const CgSide side{sx.p, x, c->d_scal.p + 62, Y[(i + 1) & 1]}; run_form(op, form, x, state, Y[i & 1], false, d_dot, nullptr, &side); }
+        else run_form(op, form, x, state, y, false, d_dot);
+    };
+    one(0);
     c->sync();
     JOTS_CUDA(cudaEventRecord(e0, c->stream));
-    for (int i = 0; i < reps; ++i) run_form(op, form, x, state, y, false, d_dot);
+    for (int i = 0; i < reps; ++i) one(i + 1);
     JOTS_CUDA(cudaEventRecord(e1, c->stream));
     JOTS_CUDA(cudaEventSynchronize(e1));
     float t = 0;

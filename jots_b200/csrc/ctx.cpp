@@ -335,15 +335,38 @@ static FaceArgs base_face_args(const Ctx& c, int nq) {
     return fa;
 }
 
-bool Ctx::apply_form(const FormSpec& f, const double* x, double* y, double* dot) {
+// fused (x, A x): symmetric-elimination forms whose apply is the two-phase patch kernel alone
+static bool form_fuses_dot(const Ctx& c, const FormSpec& f, const FormArgs& a) {
+    const bool face_terms = f.bdr_mass_scale != 0.0 && c.any_flux();
+    return !face_terms && a.patches && a.geom_diag && c.space.dim == 3 && !a.zc && f.mask_in == f.mask_out &&
+           patch_kernel_fuses_dot(c.space.p, f.op, f.cf, a);
+}
+
+int Ctx::form_side_chunk(const FormSpec& f) const {
+    const FormArgs a = make_args(f, nullptr, nullptr, false);
+    if (!form_fuses_dot(*this, f, a) || n_patches <= 0) return 0;
+    int64_t chunk = (n + n_patches - 1) / n_patches;
+    chunk += chunk & 1;
+    return chunk <= patch_kernel_side_capacity(space.p, f.op, f.cf, a) ? (int)chunk : 0;
+}
+
+bool Ctx::apply_form(const FormSpec& f, const double* x, double* y, double* dot, const CgSide* side) {
     FormArgs a = make_args(f, x, y, false);
     const bool face_terms = f.bdr_mass_scale != 0.0 && any_flux();
-    // fused (x, A x): symmetric-elimination forms whose apply is the two-phase patch kernel alone
-    const bool fuse = dot && !face_terms && a.patches && a.geom_diag && space.dim == 3 && !a.zc &&
-                      f.mask_in == f.mask_out && patch_kernel_fuses_dot(space.p, f.op, f.cf, a);
+    const bool fuse = dot && form_fuses_dot(*this, f, a);
+    if (side) {
+        a.side_chunk = fuse ? form_side_chunk(f) : 0;
+        auto misaligned = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) != 0; };
+        if (!a.side_chunk || misaligned(side->x) || misaligned(side->d) || misaligned(side->zero))
+            throw std::runtime_error("apply_form: this form / these vectors cannot carry the CG side stream");
+        a.side_x = side->x; a.side_d = side->d; a.side_alpha = side->alpha; a.side_zero = side->zero;
+    }
     if (fuse) {
         a.dot = dot;
-        v_zero_essdot(stream, n, y, (f.diag_one && f.mask_out) ? n_ess_owned : 0, d_ess_owned.p, x, dot, a.skip);
+        // with a side stream y was zeroed by the previous launch: only the unit-diagonal rows' share of (x, A x) is left
+        const int n_idx = (f.diag_one && f.mask_out) ? n_ess_owned : 0;
+        if (!side) v_zero_essdot(stream, n, y, n_idx, d_ess_owned.p, x, dot, a.skip);
+        else if (n_idx) v_zero_essdot(stream, 0, y, n_idx, d_ess_owned.p, x, dot, a.skip);
     } else zero(y);
     // lattice meshes: unique-pencil patch kernels; otherwise / when not instantiated the gather-table kernels
     int rc = 1;
@@ -353,7 +376,7 @@ bool Ctx::apply_form(const FormSpec& f, const double* x, double* y, double* dot)
     }
     if (rc) rc = launch_form_apply(space.dim, space.p, f.op, f.cf, a, tabs, stream);
     if (rc) throw std::runtime_error("form (op=" + std::to_string(f.op) + ", cf=" + std::to_string(f.cf) + ") is not instantiated, rc=" + std::to_string(rc));
-    stats.kernel_launches += 2;
+    stats.kernel_launches += (side && !(f.diag_one && f.mask_out && n_ess_owned)) ? 1 : 2;
     last_kernel = last_element_kernel();
     if (face_terms) {
         FaceArgs fa = base_face_args(*this, bdr_mass_quad_points(space.p));
@@ -366,6 +389,7 @@ bool Ctx::apply_form(const FormSpec& f, const double* x, double* y, double* dot)
     JOTS_CUDA(cudaGetLastError());
     ++stats.applies;
     if (fuse) ++stats.fused_dots;
+    if (side) ++stats.side_applies;
     return fuse;
 }
 

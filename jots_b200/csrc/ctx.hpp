@@ -71,7 +71,7 @@ struct FormSpec {
 
 struct Stats {
     long long applies = 0, diag_assemblies = 0, krylov_iters = 0, newton_iters = 0, residual_evals = 0, steps = 0,
-              kernel_launches = 0, dots = 0, halo_exchanges = 0, patch_applies = 0, fused_dots = 0;
+              kernel_launches = 0, dots = 0, halo_exchanges = 0, patch_applies = 0, fused_dots = 0, side_applies = 0;
     double last_linear_norm = 0, last_newton_norm = 0;
     int last_linear_converged = 1, last_newton_converged = 1, last_linear_iters = 0, last_newton_iters = 0;
 };
@@ -142,7 +142,10 @@ public:
     // --- forms
     // dot != nullptr: also accumulate (x, A x) over the owned rows into *dot when the launched kernel can (returns true; the
     // caller all-reduces); false = y only
-    bool apply_form(const FormSpec& f, const double* x, double* y, double* dot = nullptr);
+    // side != nullptr (only after form_side_chunk(f) > 0, dot != nullptr and y ALREADY zero): the launch also carries the
+    // conjugate-gradient loop's side stream, side->x += *side->alpha * side->d and side->zero = 0 (FormArgs::side_*)
+    bool apply_form(const FormSpec& f, const double* x, double* y, double* dot = nullptr, const CgSide* side = nullptr);
+    int form_side_chunk(const FormSpec& f) const;   // entries per tile of the side stream for this form; 0 = not available
     void diag_form(const FormSpec& f, double* d);
     // b_i = sum_faces int (g / divisor) phi_i; state != null -> divisor rho_h(state) C_h(state)
     void neumann_vector(double div_const, const double* state, double* b, bool zero_first = true, double scale = 1.0,

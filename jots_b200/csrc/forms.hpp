@@ -77,6 +77,26 @@ struct FormArgs {
     // non-null: the kernel adds sum_elements x_e . (A_e x_e) = (x, A x) over the rows it writes to *dot (two-phase patch
     // kernel only; the conjugate-gradient loop then needs no separate pass for (d, A d))
     double* dot;
+    // Side stream of the conjugate-gradient loop (two-phase patch kernel, dot variant of the decoupled pipeline only;
+    // side_chunk == 0: none).  The kernel is FP64-issue bound and leaves HBM idle, so the two vector passes of an iteration
+    // that are off its critical path ride along: the block that processes tile t also does, over entries
+    // [t * side_chunk, (t + 1) * side_chunk) of the vectors,
+    //     side_x += *side_alpha * side_d      (the solution update x += alpha_{i-1} d_{i-1}, deferred by one apply)
+    //     side_zero = 0                       (the output buffer of the NEXT apply; this launch's y was zeroed by the previous one)
+    // n_patches * side_chunk >= nvec, side_chunk even and <= 2 * (threads - 32); all three vectors 16-byte aligned.
+    double* side_x;
+    const double* side_d;
+    const double* side_alpha;
+    double* side_zero;
+    int side_chunk;
+};
+
+// the side stream of FormArgs as the solvers hand it down (ctx.hpp: Ctx::apply_form)
+struct CgSide {
+    double* x;
+    const double* d;
+    const double* alpha;    // device scalar
+    double* zero;
 };
 
 // 1-D tables; DZ = QZ = 1 turns the hex kernel into the quad kernel

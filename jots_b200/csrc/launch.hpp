@@ -20,6 +20,8 @@ int launch_form_apply_slab(int p, int op, int cf, const FormArgs& a, const Table
 int launch_form_apply_patch(int p, int op, int cf, const FormArgs& a, const TablesRT& t, cudaStream_t st);
 // true when launch_form_apply_patch would pick a kernel that honours FormArgs::dot (the two-phase patch kernel)
 bool patch_kernel_fuses_dot(int p, int op, int cf, const FormArgs& a);
+// entries per tile of the CG side stream (FormArgs::side_*) that kernel can carry; 0 = it has none
+int patch_kernel_side_capacity(int p, int op, int cf, const FormArgs& a);
 int patch_items(int p, unsigned* out);   // phase-3 items (pencil | visits << 8 | (el << 5 | ij) << 10 | ... << 20), at most 128
 void patch_shape(int p, int& px, int& py);   // patch size for order p (0: no patch kernel)
 int launch_form_diag_slab(int p, int op, int cf, const FormArgs& a, const TablesRT& t, cudaStream_t st);

@@ -60,15 +60,22 @@ int launch_patch2_v(const FormArgs& a, const TablesRT& r, cudaStream_t st) {
     kern<<<a.n_patches < grid_max ? a.n_patches : grid_max, T, smem, st>>>(a, t, items);
     static const std::string label = kernel_label("form_apply_patch2_kernel", D, Q, OP, KLIN ? CF_KL : CF_CONST,
                                                   ("," + std::to_string(PX) + "," + std::to_string(PY) + "," + std::to_string(T) + (DOT ? ",dot" : "") + (LAG ? ",lag" : "")).c_str());
-    last_element_kernel() = label.c_str();
+    static const std::string label_side = label.substr(0, label.size() - 1) + ",side>";    // carrying the CG side stream
+    last_element_kernel() = (DOT && LAG && a.side_chunk) ? label_side.c_str() : label.c_str();
     return 0;
 }
 
 // FormArgs::dot selects the variant that also forms (x, A x); the residual form is not bilinear and has none
+// JOTS_PATCH2_LAG=0: one block barrier per tile instead of the warp-decoupled pipeline (A/B runs)
+bool patch2_lag_enabled() {
+    static const bool v = [] { const char* e = getenv("JOTS_PATCH2_LAG"); return !e || atoi(e) != 0; }();
+    return v;
+}
+
 template <int D, int Q, int OP, bool KLIN, int PX, int PY>
 int launch_patch2(const FormArgs& a, const TablesRT& r, cudaStream_t st) {
-    // JOTS_PATCH2_LAG=0: one block barrier per tile instead of the warp-decoupled pipeline (A/B runs)
-    static const bool lag = [] { const char* e = getenv("JOTS_PATCH2_LAG"); return !e || atoi(e) != 0; }();
+    const bool lag = patch2_lag_enabled();
+    if (a.side_chunk && !(a.dot && lag)) return 1;      // the side stream exists in the dot variant of the decoupled pipeline only
     if (a.dot) {
         if (OP == OP_RES) return 1;
         constexpr int OPD = OP == OP_RES ? OP_LIN : OP;
@@ -123,6 +130,12 @@ int dispatch_patch(int op, int cf, const FormArgs& a, const TablesRT& t, cudaStr
 
 bool patch_kernel_fuses_dot(int p, int op, int cf, const FormArgs& a) {
     return p == 2 && op != OP_RES && a.patches && a.n_patches > 0 && patch2_covers(op, cf, a);
+}
+
+// entries of the CG side stream (FormArgs::side_*) one tile can carry: two per thread of the worker warps; 0 = not available
+int patch_kernel_side_capacity(int p, int op, int cf, const FormArgs& a) {
+    if (!patch_kernel_fuses_dot(p, op, cf, a) || !patch2_lag_enabled()) return 0;
+    return 2 * (4 * 4 * 2 * 4 - 32);
 }
 
 void patch_shape(int p, int& px, int& py) {

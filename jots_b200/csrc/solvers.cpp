@@ -136,6 +136,7 @@ Krylov::Krylov(Ctx* ctx, int kind_, int prec_kind) : c(ctx), kind(kind_) {
     else if (prec_kind == PREC_CHEBYSHEV) prec.reset(new ChebyshevPrec(ctx));
     if (const char* e = std::getenv("JOTS_CG_HOST_SCALARS")) device_scalars = !(e[0] == '1');
     if (const char* e = std::getenv("JOTS_CG_FUSED_DOT")) fused_dot = !(e[0] == '0');
+    if (const char* e = std::getenv("JOTS_CG_SIDE")) side_stream = !(e[0] == '0');
 }
 
 Krylov::~Krylov() {
@@ -241,6 +242,16 @@ void Krylov::cg_device_loop(double* x, double* r, double* z, double* d, const do
     init[0] = nom; init[1] = 0.0; init[2] = den; init[3] = r0; init[4] = 0.0; init[5] = 0.0; init[6] = nom; init[7] = 0.0;
     JOTS_CUDA(cudaMemcpyAsync(S, init, 8 * sizeof(double), cudaMemcpyHostToDevice, st));
     c->apply_skip = S + 4;
+    // Side-stream loop: the element kernel is FP64-issue bound and leaves HBM idle, so the two vector passes that are off the
+    // critical path of an iteration ride along with it (FormArgs::side_*): x += alpha_i d_i is deferred to the apply of d_{i+1}
+    // (d ping-pongs between two buffers so that d_i is still there), and that apply also zeroes the buffer the one after it
+    // accumulates into (A d / z ping-pong as well).  The arithmetic of every entry is unchanged, so x, r, the iteration count
+    // and the norms are those of the plain loop bit for bit; only the update that is still pending when the iteration stops is
+    // applied after the loop.  Vector traffic per iteration: 8 passes instead of 12 (update 5, direction 3).
+    const bool side = fused_dot && side_stream && A->side_chunk() > 0;
+    double* D[2] = {d, side ? w(3) : d};
+    double* Z[2] = {z, side ? w(4) : z};
+    if (side) c->zero(Z[1]);
     int launched = 0, chunk = 0;
     bool stopped = false;
     while (launched < max_iter && !stopped) {
@@ -251,16 +262,23 @@ void Krylov::cg_device_loop(double* x, double* r, double* z, double* d, const do
         }
         for (int k = 0; k < CHUNK && launched < max_iter; ++k) {
             const int i = ++launched;
-            v_cgd_update(st, n, c->n_owned, S, i, d, z, x, r, dinv, z, c->dot_scratch());
+            const int p = side ? ((i - 1) & 1) : 0;       // d_i is in D[p], A d_i (then z_i) in Z[p]
+            v_cgd_update(st, n, c->n_owned, S, i, D[p], Z[p], side ? nullptr : x, r, dinv, Z[p], c->dot_scratch());
             c->allreduce_scalars(S + (i & 1), 1);
             const bool last = (i == max_iter);
             // the direction kernel zeroes the (d, A d) slot; an operator that cannot add to it during the apply leaves it to
             // the separate pass, which overwrites the slot
-            v_cgd_direction(st, n, S, i, dinv ? z : r, d, !last, fused_dot);
+            v_cgd_direction(st, n, S, i, dinv ? Z[p] : r, D[p], D[side ? 1 - p : p], !last, fused_dot);
             c->stats.kernel_launches += 2;
             if (last) break;
             ++info.applies;
-            if (!(fused_dot ? A->mult_dot(d, z, S + 2) : (A->mult(d, z), false))) { v_cgd_dot(st, c->n_owned, S, d, z, c->dot_scratch()); ++c->stats.kernel_launches; }
+            if (side) {
+                const CgSide sj{x, D[p], S + 7, Z[p]};
+                A->mult_dot_side(D[1 - p], Z[1 - p], S + 2, sj);
+            } else if (!(fused_dot ? A->mult_dot(d, z, S + 2) : (A->mult(d, z), false))) {
+                v_cgd_dot(st, c->n_owned, S, d, z, c->dot_scratch());
+                ++c->stats.kernel_launches;
+            }
             c->allreduce_scalars(S + 2, 1);
             ++c->stats.dots;
         }
@@ -277,6 +295,11 @@ void Krylov::cg_device_loop(double* x, double* r, double* z, double* d, const do
     if (code != 0) { info.iterations = (int)h[5]; betanom = h[6]; info.converged = (code == 1); }
     else { info.iterations = max_iter; betanom = h[6]; }
     info.final_norm = std::sqrt(std::fabs(betanom));
+    if (side && code != 3 && info.iterations >= 1) {
+        // the update of the stopping iteration: its apply was skipped (or never enqueued)
+        v_axpy(st, n, h[7], D[(info.iterations - 1) & 1], x);
+        ++c->stats.kernel_launches;
+    }
 }
 
 static void gen_rot(double dx, double dy, double& cs, double& sn) {

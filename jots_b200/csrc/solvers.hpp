@@ -23,6 +23,10 @@ struct LinOp {
     // y = A x and, when the operator can do it in the same pass, *d_dot += (x, A x) over the owned rows (*d_dot zeroed by the
     // caller, not yet all-reduced): returns whether it did
     virtual bool mult_dot(const double* x, double* y, double* d_dot) { (void)d_dot; mult(x, y); return false; }
+    // > 0: mult_dot_side is available -- y = A x into a y that is ALREADY zero, *d_dot += (x, A x), and in the same launch the
+    // conjugate-gradient side stream side.x += *side.alpha * side.d, side.zero = 0 (FormArgs::side_*)
+    virtual int side_chunk() { return 0; }
+    virtual void mult_dot_side(const double* x, double* y, double* d_dot, const CgSide& side) { (void)x; (void)y; (void)d_dot; (void)side; throw std::runtime_error("operator has no side stream"); }
 };
 
 // a FormSpec bound to a context
@@ -33,6 +37,8 @@ struct FormOp : LinOp {
     void mult(const double* x, double* y) override { c->apply_form(f, x, y); }
     bool mult_dot(const double* x, double* y, double* d_dot) override { return c->apply_form(f, x, y, d_dot); }
     void assemble_diag(double* d) override { c->diag_form(f, d); }
+    int side_chunk() override { return c->form_side_chunk(f); }
+    void mult_dot_side(const double* x, double* y, double* d_dot, const CgSide& side) override { c->apply_form(f, x, y, d_dot, &side); }
 };
 
 struct Precond {
@@ -93,6 +99,8 @@ struct Krylov {
     // JOTS_CG_HOST_SCALARS=1 selects the host-sequenced loop (same results; kept for A/B timing)
     bool device_scalars = true;
     bool fused_dot = true;           // (d, A d) formed by the element kernel when it can (JOTS_CG_FUSED_DOT=0: separate pass)
+    bool side_stream = true;         // x += alpha d and the zeroing of the next output carried by the element kernel when it can
+                                     // (JOTS_CG_SIDE=0: in the vector kernels)
     ~Krylov();
 private:
     struct CgDevice {

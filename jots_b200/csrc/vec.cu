@@ -137,22 +137,26 @@ __global__ void __launch_bounds__(VEC_THREADS) k_cg_update(int64_t n, int64_t n_
 // ---- device-resident CG: the scalars of mfem::CGSolver::Mult live in device memory, so an iteration needs no host round trip.
 // S[0], S[1] = (B r, r) ping-pong: iteration i reads nom = S[(i+1)&1] and writes betanom = S[i&1];  S[2] = den = (d, A d);
 // S[3] = r0 (stopping threshold);  S[4] = stop code (0 running, 1 converged, 2 negative (B r, r), 3 den == 0);
-// S[5] = iteration at which it stopped;  S[6] = last (B r, r).  Every decision is a function of fully reduced scalars that
+// S[5] = iteration at which it stopped;  S[6] = last (B r, r);  S[7] = alpha of the last update (side-stream loop).  Every decision is a function of fully reduced scalars that
 // were final before the kernel started, so all blocks of a kernel take the same branch (grid_reduce needs that).
+// SIDE: x += alpha d is not done here but handed to the next operator apply as its side stream (FormArgs::side_*), which
+// reads alpha from S[7]; the loop's epilogue applies the one update that is still pending when the iteration stops.
+template <bool SIDE>
 __global__ void __launch_bounds__(VEC_THREADS) k_cgd_update(int64_t n, int64_t n_owned, double* S, int i, const double* __restrict__ d,
                                                              const double* Ad, double* x, double* r, const double* __restrict__ dinv,
                                                              double* z, DotScratch s) {
     if (S[4] != 0.0) return;
     const double den = S[2], nom = S[(i + 1) & 1];
     if (den == 0.0) {
-        if (blockIdx.x == 0 && threadIdx.x == 0) { S[5] = (double)i; S[6] = nom; __threadfence(); S[4] = 3.0; }
+        if (blockIdx.x == 0 && threadIdx.x == 0) { S[7] = 0.0; S[5] = (double)i; S[6] = nom; __threadfence(); S[4] = 3.0; }
         return;
     }
     const double alpha = nom / den;
+    if (SIDE && blockIdx.x == 0 && threadIdx.x == 0) S[7] = alpha;
     double v[1] = {0.0};
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += stride) {
-        x[k] += alpha * d[k];
+        if (!SIDE) x[k] += alpha * d[k];
         const double ri = r[k] - alpha * Ad[k];
         r[k] = ri;
         double zi = ri;
@@ -161,8 +165,9 @@ __global__ void __launch_bounds__(VEC_THREADS) k_cgd_update(int64_t n, int64_t n
     }
     grid_reduce<1>(v, s, &S[i & 1]);
 }
-// convergence test of iteration i, then d = zz + beta d (update == 0: test only, the last iteration)
-__global__ void __launch_bounds__(VEC_THREADS) k_cgd_direction(int64_t n, double* S, int i, const double* __restrict__ zz, double* d, int update) {
+// convergence test of iteration i, then dout = zz + beta d (update == 0: test only, the last iteration); dout may be d
+__global__ void __launch_bounds__(VEC_THREADS) k_cgd_direction(int64_t n, double* S, int i, const double* __restrict__ zz, const double* d, double* dout,
+                                                                int update) {
     if (S[4] != 0.0) return;
     const double betanom = S[i & 1], nom = S[(i + 1) & 1];
     const bool first = blockIdx.x == 0 && threadIdx.x == 0;
@@ -175,7 +180,7 @@ __global__ void __launch_bounds__(VEC_THREADS) k_cgd_direction(int64_t n, double
     if (!update) return;
     const double beta = betanom / nom;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += stride) d[k] = zz[k] + beta * d[k];
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += stride) dout[k] = zz[k] + beta * d[k];
 }
 __global__ void __launch_bounds__(VEC_THREADS) k_cgd_dot(int64_t n, double* S, const double* __restrict__ a, const double* __restrict__ b, DotScratch s) {
     if (S[4] != 0.0) return;
@@ -186,10 +191,11 @@ __global__ void __launch_bounds__(VEC_THREADS) k_cgd_dot(int64_t n, double* S, c
 }
 void v_cgd_update(cudaStream_t st, int64_t n, int64_t n_owned, double* S, int i, const double* d, const double* Ad, double* x, double* r,
                   const double* dinv, double* z, DotScratch s) {
-    k_cgd_update<<<grid_for(n, 8), VEC_THREADS, 0, st>>>(n, n_owned, S, i, d, Ad, x, r, dinv, z, s);
+    if (x) k_cgd_update<false><<<grid_for(n, 8), VEC_THREADS, 0, st>>>(n, n_owned, S, i, d, Ad, x, r, dinv, z, s);
+    else k_cgd_update<true><<<grid_for(n, 8), VEC_THREADS, 0, st>>>(n, n_owned, S, i, nullptr, Ad, nullptr, r, dinv, z, s);
 }
-void v_cgd_direction(cudaStream_t st, int64_t n, double* S, int i, const double* zz, double* d, bool update, bool zero_den) {
-    k_cgd_direction<<<update ? grid_for(n) : 1, VEC_THREADS, 0, st>>>(n, S, i, zz, d, update ? (zero_den ? 2 : 1) : 0);
+void v_cgd_direction(cudaStream_t st, int64_t n, double* S, int i, const double* zz, const double* d, double* dout, bool update, bool zero_den) {
+    k_cgd_direction<<<update ? grid_for(n) : 1, VEC_THREADS, 0, st>>>(n, S, i, zz, d, dout, update ? (zero_den ? 2 : 1) : 0);
 }
 // y = 0 and *dot += sum over the listed (owned, essential) entries of x^2: what the unit-diagonal rows of an eliminated operator
 // contribute to (x, A x).  Precedes an element kernel that accumulates the rest (FormArgs::dot).  skip as in FormArgs.
@@ -201,7 +207,7 @@ __global__ void __launch_bounds__(VEC_THREADS) k_zero_essdot(int64_t n, double* 
     double2* y2 = reinterpret_cast<double2*>(y + head);
     const int64_t m2 = (n - head) / 2;
     for (int64_t k = t0; k < m2; k += stride) y2[k] = make_double2(0.0, 0.0);
-    if (t0 == 0) { if (head) y[0] = 0.0; if ((n - head) & 1) y[n - 1] = 0.0; }
+    if (t0 == 0 && n > 0) { if (head) y[0] = 0.0; if ((n - head) & 1) y[n - 1] = 0.0; }
     double v = 0.0;
     for (int64_t k = t0; k < n_idx; k += stride) { const double xv = x[idx[k]]; v += xv * xv; }
     __shared__ double sh[VEC_THREADS / 32];
@@ -215,7 +221,8 @@ __global__ void __launch_bounds__(VEC_THREADS) k_zero_essdot(int64_t n, double* 
     }
 }
 void v_zero_essdot(cudaStream_t st, int64_t n, double* y, int n_idx, const int* idx, const double* x, double* dot, const double* skip) {
-    k_zero_essdot<<<grid_for(n, 8), VEC_THREADS, 0, st>>>(n, y, n_idx, idx, x, dot, skip);
+    // n == 0: only the listed entries (y was zeroed elsewhere)
+    k_zero_essdot<<<grid_for(n > 0 ? n : (int64_t)n_idx * 8, 8), VEC_THREADS, 0, st>>>(n, y, n_idx, idx, x, dot, skip);
 }
 void v_cgd_dot(cudaStream_t st, int64_t n_owned, double* S, const double* a, const double* b, DotScratch s) {
     k_cgd_dot<<<grid_for(n_owned, 8), VEC_THREADS, 0, st>>>(n_owned, S, a, b, s);

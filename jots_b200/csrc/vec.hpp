@@ -39,7 +39,7 @@ void v_mgs_sweep_small(cudaStream_t st, int n, double* r, const double* const* V
 // device-resident CG scalars (vec.cu: S layout)
 void v_cgd_update(cudaStream_t st, int64_t n, int64_t n_owned, double* S, int i, const double* d, const double* Ad, double* x, double* r,
                   const double* dinv, double* z, DotScratch s);
-void v_cgd_direction(cudaStream_t st, int64_t n, double* S, int i, const double* zz, double* d, bool update, bool zero_den);
+void v_cgd_direction(cudaStream_t st, int64_t n, double* S, int i, const double* zz, const double* d, double* dout, bool update, bool zero_den);
 void v_zero_essdot(cudaStream_t st, int64_t n, double* y, int n_idx, const int* idx, const double* x, double* dot, const double* skip);
 void v_cgd_dot(cudaStream_t st, int64_t n_owned, double* S, const double* a, const double* b, DotScratch s);
 }  // namespace jots

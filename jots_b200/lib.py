@@ -95,6 +95,7 @@ def load_library():
         "jots_partition_create_from_tables": (_P, [C.c_int, C.c_int, C.c_int64, C.c_int64, _P, _P, C.c_int64, _P, _P, _P, _P, C.c_int64, _P, C.c_int, _P, _P, _P, C.c_int, _P, C.c_int, C.c_int]),
         "jots_ctx_patch_info": (C.c_int, [_P, _P, _P, _P]),
         "jots_ctx_fused_dots": (C.c_int, [_P, _P]),
+        "jots_ctx_side_applies": (C.c_int, [_P, _P]),
         "jots_ctx_last_kernel": (C.c_char_p, [_P]),
         "jots_ctx_reset_stats": (C.c_int, [_P]),
         "jots_op_create": (_P, [_P, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int,
@@ -111,6 +112,7 @@ def load_library():
         "jots_op_form_apply": (C.c_int, [_P, C.c_int, _P, _P, _P, C.c_int]),
         "jots_op_form_diagonal": (C.c_int, [_P, C.c_int, _P, _P, C.c_int]),
         "jots_op_form_apply_dot": (C.c_int, [_P, C.c_int, _P, _P, _P, C.c_int, _P, _P]),
+        "jots_op_form_apply_side": (C.c_int, [_P, C.c_int, _P, _P, _P, C.c_int, _P, C.c_double, _P, _P, _P, _P]),
         "jots_op_form_time": (C.c_int, [_P, C.c_int, _P, _P, _P, C.c_int, _D]),
         "jots_partition_create": (_P, [_P, _P, C.c_int, C.c_int, _P]),
         "jots_partition_destroy": (None, [_P]),
@@ -512,6 +514,8 @@ class Context:
         fd = C.c_int64(0)
         load_library().jots_ctx_fused_dots(self._h, C.byref(fd))
         d["fused_dots"] = int(fd.value)
+        load_library().jots_ctx_side_applies(self._h, C.byref(fd))
+        d["side_applies"] = int(fd.value)
         return d
 
     def last_kernel(self):
@@ -574,6 +578,14 @@ class Operator:
         _chk(load_library().jots_op_form_apply_dot(self._h, form, _ptr(_f64(x)), _ptr(state), _ptr(_f64(y)), _loc(x, state, y),
                                                    C.byref(dot), C.byref(fused)))
         return dot.value, bool(fused.value)
+
+    def form_apply_side(self, form, x, y, state, alpha, side_d, side_x, side_zero):
+        """The conjugate-gradient loop's apply with its side stream (device tensors): y = form(x), side_x += alpha side_d,
+        side_zero = 0 in one element-kernel launch; returns ((x, form(x)), whether the kernel carried it)."""
+        dot, carried = C.c_double(0.0), C.c_int(0)
+        _chk(load_library().jots_op_form_apply_side(self._h, form, _ptr(x), _ptr(state), _ptr(y), DEVICE, C.byref(dot), float(alpha),
+                                                    _ptr(side_d), _ptr(side_x), _ptr(side_zero), C.byref(carried)))
+        return dot.value, bool(carried.value)
 
     def form_diagonal(self, form, d, state=None):
         _chk(load_library().jots_op_form_diagonal(self._h, form, _ptr(state), _ptr(_f64(d)), _loc(state, d)))

@@ -17,6 +17,8 @@ CONFIGS = {
     "patch3_4x4": {"JOTS_SLAB_VARIANT": "7", "JOTS_PATCH2": "0"},     # three-phase unique-pencil patch kernel
     "patch2_4x4": {"JOTS_SLAB_VARIANT": "7"},                         # two-phase patch kernel, warp-decoupled pipeline (default)
     "patch2_4x4_dot": {"JOTS_SLAB_VARIANT": "7", "JOTS_FORM_TIME_DOT": "1"},   # the same + (x, A x) formed in phase 3 (CG loop)
+    # the same + the CG loop's side stream (x_sol += alpha d_old, zeroing of the next output) instead of the zeroing pass
+    "patch2_4x4_dot_side": {"JOTS_SLAB_VARIANT": "7", "JOTS_FORM_TIME_DOT": "2"},
 }
 
 

@@ -170,3 +170,84 @@ def test_cg_with_the_fused_inner_product_matches_the_separate_pass(J, tmp_path, 
     assert rel(out["0"][4], out["1"][4]) < 1e-12
     if max_it == 100:
         assert rel(out["0"][4], orc.run()) < FIELD_TOL
+
+
+@pytest.mark.parametrize("sim,props", [("Nonlinear_Unsteady", "k"), ("Linearized_Unsteady", "const")])
+@pytest.mark.parametrize("n", [(8, 8, 3), (5, 3, 4), (13, 9, 2), (4, 4, 1)])
+def test_side_stream_carried_by_the_element_kernel(J, tmp_path, sim, props, n):
+    """The apply the conjugate-gradient loop launches (FormArgs::side_*): besides y = A x and (x, A x) the block that processes
+    tile t does x_sol += alpha d_old and zeroes the next output buffer over slice t of the vectors.  y and the inner product
+    against the oracle's matrix, x_sol against alpha * d_old + x_sol entry by entry (one fused multiply-add each), the zeroed
+    buffer NaN-filled beforehand so that a slice nobody visited shows; odd vector lengths, ragged patches.  A single patch holds
+    more entries than one tile can carry: the kernel reports that it did not, and the loop keeps the vector kernels."""
+    import torch
+    dev, orc = build(J, tmp_path, sim, 3, 2, props, grade=0.6, shear=0.0, n=n,
+                     bcs=["HeatFlux, 7.5e5", "Isothermal, 350", HF0, "Isothermal, 300", HF0, HF0])
+    nd = dev.n
+    state = smooth_state(orc)
+    x = rnd(nd, 31)
+    it = orc.it
+    if sim == "Linearized_Unsteady":
+        orc.u = state.copy()
+        orc.update_mat_props(True)
+        A, zs = it.A_mat, state
+    else:
+        k = 50.0 * rnd(nd, 32)
+        it.u_n = state
+        it.new_state(k)
+        A, zs = it.gradient(k), state + it.dt * k
+    alpha = -0.37
+    d_old, x_sol = rnd(nd, 33), 10.0 * rnd(nd, 34)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    tx, tz, td, txs = t(x), t(zs), t(d_old), t(x_sol)
+    ty = torch.full((nd,), float("nan"), dtype=torch.float64, device="cuda")
+    tzero = torch.full((nd,), float("nan"), dtype=torch.float64, device="cuda")
+    torch.cuda.synchronize()
+    dot, carried = dev.op.form_apply_side(J.FORM_SYSTEM, tx, ty, tz, alpha, td, txs, tzero)
+    torch.cuda.synchronize()
+    if n == (4, 4, 1):
+        assert not carried and dev.ctx.stats()["side_applies"] == 0
+        return
+    assert carried and dev.ctx.stats()["side_applies"] == 1 and dev.ctx.last_kernel().endswith(",side>")
+    ref = A @ x
+    assert rel(ty.cpu().numpy(), ref) < APPLY_TOL
+    assert abs(dot - x @ ref) <= 1e-12 * np.abs(x * ref).sum(), (dot, x @ ref)
+    got = txs.cpu().numpy()
+    want = x_sol + alpha * d_old
+    assert np.all(np.abs(got - want) <= 2.3e-16 * (np.abs(x_sol) + np.abs(alpha * d_old))), np.abs(got - want).max()
+    assert np.array_equal(tzero.cpu().numpy(), np.zeros(nd))
+    assert np.array_equal(td.cpu().numpy(), d_old) and np.array_equal(tx.cpu().numpy(), x)
+
+
+@pytest.mark.parametrize("sim,props,n,max_it", [("Nonlinear_Unsteady", "k", (8, 8, 4), 100), ("Linearized_Unsteady", "const", (9, 5, 3), 100),
+                                                ("Nonlinear_Unsteady", "k", (8, 8, 4), 7), ("Nonlinear_Unsteady", "k", (8, 8, 4), 1),
+                                                ("Steady", "k", (8, 4, 2), 100)])
+def test_cg_with_the_side_stream_matches_the_plain_loop(J, tmp_path, monkeypatch, sim, props, n, max_it):
+    """cg_device_loop with x += alpha d and the zeroing of the next output carried by the element kernel against JOTS_CG_SIDE=0
+    (both in the vector kernels): every vector entry sees the same operations in the same order (only the summation order of the
+    element kernel's atomics varies from launch to launch), so the counts are equal and norms and field agree to rounding --
+    early convergence, a stop inside a chunk, Max_Iterations (odd and even, so both buffers of the ping-pong end up holding the
+    pending update) -- and the field is the oracle's."""
+    out = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("JOTS_CG_SIDE", mode)
+        dev, orc = build(J, tmp_path, sim, 3, 2, props, solver="CG", prec="Jacobi", n=n, steps=2)
+        if max_it != 100:
+            txt = open(str(tmp_path / "c.ini")).read().replace("Max_Iterations=100\n", "Max_Iterations=%d\n" % max_it, 1)
+            open(str(tmp_path / "c.ini"), "w").write(txt)
+            dev = J.Driver(str(tmp_path / "c.ini"))
+        try:
+            dev.run()
+        except J.JotsError:
+            pass
+        st = dev.ctx.stats()
+        assert (st["side_applies"] > 0) == (mode == "1" and max_it > 1), st
+        assert st["fused_dots"] > 0 or max_it == 1
+        out[mode] = (st["krylov_iters"], st["newton_iters"], st["last_linear_iters"], st["last_linear_converged"], st["last_linear_norm"],
+                     dev.get_u())
+    assert out["0"][:4] == out["1"][:4], (out["0"][:4], out["1"][:4])
+    # the final (B r, r) sits 20 orders of magnitude below the first one: the atomics' summation order shows in its digits
+    assert abs(out["0"][4] - out["1"][4]) <= 1e-4 * abs(out["0"][4])
+    assert rel(out["0"][5], out["1"][5]) < 1e-12
+    if max_it == 100:
+        assert rel(out["0"][5], orc.run()) < FIELD_TOL
