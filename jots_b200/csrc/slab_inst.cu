@@ -87,7 +87,7 @@ static int dispatch(int op, int cf, const FormArgs& a, const TablesRT& t, cudaSt
 
 template <int D, int Q, int OP, int CF>
 static int launch_diag_slab(const FormArgs& a, const TablesRT& r, cudaStream_t st) {
-    constexpr int E = (Q == 4) ? 14 : 32;
+    constexpr int E = (Q == 4) ? 14 : (Q == 5) ? 12 : 32;      // Q3: 83 KB of planes per block (OP_JAC, CF_K), two blocks per SM
     constexpr int T = ((E * (2 * Q > D * D ? 2 * Q : D * D)) + 31) / 32 * 32;
     constexpr int NF = CoefNF<CF, OP>::value;
     constexpr int NPI = NF + (OP == OP_JAC ? 2 : 0);
@@ -124,6 +124,7 @@ static int dispatch_diag(int op, int cf, const FormArgs& a, const TablesRT& t, c
 int launch_form_diag_slab(int p, int op, int cf, const FormArgs& a, const TablesRT& t, cudaStream_t st) {
     if (p == 1) return dispatch_diag<2, 3>(op, cf, a, t, st);
     if (p == 2) return dispatch_diag<3, 4>(op, cf, a, t, st);
+    if (p == 3) return dispatch_diag<4, 5>(op, cf, a, t, st);
     return 1;
 }
 
