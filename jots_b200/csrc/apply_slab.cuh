@@ -800,6 +800,12 @@ __global__ void __launch_bounds__(T) form_apply_slab3_kernel(const FormArgs a, c
     __syncthreads();
     issue_vals(0);
 
+    // FormArgs::dot (the conjugate-gradient loop's (d, A d) = sum over elements of d_e . (A_e d_e)): phase 3 multiplies every
+    // row it adds to y with the staged input of that row.  Needs the values of tile `it` intact during its phase 3, i.e. two
+    // staging buffers (the launcher offers the fused inner product only for those instantiations).
+    const bool with_dot = NSTG == 2 && a.dot != nullptr;
+    double dsum = 0.0;
+
     // geometry of a uniform mesh is loop invariant
     double gxx = 0, gyy = 0, gzz = 0, det = 0;
     if (a.geom_stride == 0) {
@@ -886,6 +892,28 @@ __global__ void __launch_bounds__(T) form_apply_slab3_kernel(const FormArgs a, c
         }
         __syncthreads();
 
+        // Side stream of the conjugate-gradient loop (FormArgs::side_*, see apply_patch2.cuh): this tile's slice of
+        // x_sol += alpha d_old and of the zeroing of the next apply's output, at most two pairs of entries per thread.  The
+        // loads are issued before phase 3 and consumed after it.
+        double2 side_xv[2], side_dv[2];
+        double side_al = 0.0;
+        const long long side_k0 = (long long)tile * a.side_chunk;
+        if (a.side_chunk != 0) {
+            side_al = __ldg(a.side_alpha);
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                const int o = 2 * (tid + r * T);
+                const long long k = side_k0 + o;
+                side_xv[r] = make_double2(0.0, 0.0); side_dv[r] = side_xv[r];
+                if (o < a.side_chunk) {
+                    if (k + 1 < a.nvec) {
+                        side_xv[r] = __ldcs(reinterpret_cast<const double2*>(a.side_x + k));
+                        side_dv[r] = __ldcs(reinterpret_cast<const double2*>(a.side_d + k));
+                    } else if (k < a.nvec) { side_xv[r].x = __ldcs(a.side_x + k); side_dv[r].x = __ldcs(a.side_d + k); }
+                }
+            }
+        }
+
         // ---------------- phase 3: transposed z contraction + scatter ----------------------------
 #pragma unroll 1
         for (int item = tid; item < nv * DD; item += T) {
@@ -902,15 +930,49 @@ __global__ void __launch_bounds__(T) form_apply_slab3_kernel(const FormArgs a, c
                 double s = 0.0;
 #pragma unroll
                 for (int qz = 0; qz < Q; ++qz) s += t.B[qz * D + k] * Aq[qz] + t.G[qz * D + k] * Bq[qz];
-                const int g = ix[el * ND + ij + DD * k];
+                const int m = el * ND + ij + DD * k;
+                const int g = ix[m];
                 if (g >= 0) atomicAdd(a.y + g, s);
                 else if (!a.mask_out) atomicAdd(a.y + (~g), s);
                 else if (a.diag_one) a.y[~g] = a.x[~g];   // every writer stores the same value
+                // rows that are not written have a zero input (the caller fuses only forms with mask_in == mask_out)
+                if (with_dot) dsum = fma((g < 0 && a.mask_in) ? 0.0 : sx[m], s, dsum);
+            }
+        }
+        if (a.side_chunk != 0) {
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+                const int o = 2 * (tid + r * T);
+                const long long k = side_k0 + o;
+                if (o < a.side_chunk) {
+                    if (k + 1 < a.nvec) {
+                        side_xv[r].x = fma(side_al, side_dv[r].x, side_xv[r].x);
+                        side_xv[r].y = fma(side_al, side_dv[r].y, side_xv[r].y);
+                        __stcs(reinterpret_cast<double2*>(a.side_x + k), side_xv[r]);
+                        __stcs(reinterpret_cast<double2*>(a.side_zero + k), make_double2(0.0, 0.0));
+                    } else if (k < a.nvec) {
+                        __stcs(a.side_x + k, fma(side_al, side_dv[r].x, side_xv[r].x));
+                        __stcs(a.side_zero + k, 0.0);
+                    }
+                }
             }
         }
         __syncthreads();
     }
     cp_async_wait<0>();
+    if (with_dot) {
+        __shared__ double s_dsum[T / 32];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) dsum += __shfl_xor_sync(0xffffffffu, dsum, o);
+        if ((tid & 31) == 0) s_dsum[tid >> 5] = dsum;
+        __syncthreads();
+        if (tid == 0) {
+            double v = s_dsum[0];
+#pragma unroll
+            for (int w = 1; w < T / 32; ++w) v += s_dsum[w];
+            atomicAdd(a.dot, v);
+        }
+    }
 }
 
 }  // namespace jots

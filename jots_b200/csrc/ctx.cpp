@@ -335,25 +335,35 @@ static FaceArgs base_face_args(const Ctx& c, int nq) {
     return fa;
 }
 
-// fused (x, A x): symmetric-elimination forms whose apply is the two-phase patch kernel alone
-static bool form_fuses_dot(const Ctx& c, const FormSpec& f, const FormArgs& a) {
+// Fused (x, A x): symmetric-elimination forms whose apply is ONE element kernel that honours FormArgs::dot -- the two-phase
+// patch kernel on Q2 lattices, the gather-table kernel where it has two staging buffers (Q1, Q3, Q2 with rho(T) / C(T) on
+// meshes without patches).  Returns the number of tiles of that launch (0: not fused) and the entries per tile its side
+// stream can carry.
+static int form_dot_tiles(const Ctx& c, const FormSpec& f, const FormArgs& a, int* side_capacity) {
     const bool face_terms = f.bdr_mass_scale != 0.0 && c.any_flux();
-    return !face_terms && a.patches && a.geom_diag && c.space.dim == 3 && !a.zc && f.mask_in == f.mask_out &&
-           patch_kernel_fuses_dot(c.space.p, f.op, f.cf, a);
+    if (face_terms || !a.geom_diag || c.space.dim != 3 || a.zc || f.mask_in != f.mask_out) return 0;
+    if (a.patches && a.n_patches > 0 && c.space.p == 2) {      // apply_form takes the patch kernels
+        if (!patch_kernel_fuses_dot(c.space.p, f.op, f.cf, a)) return 0;
+        if (side_capacity) *side_capacity = patch_kernel_side_capacity(c.space.p, f.op, f.cf, a);
+        return a.n_patches;
+    }
+    return slab_kernel_dot_tiles(c.space.p, f.op, f.cf, a, side_capacity);
 }
 
 int Ctx::form_side_chunk(const FormSpec& f) const {
     const FormArgs a = make_args(f, nullptr, nullptr, false);
-    if (!form_fuses_dot(*this, f, a) || n_patches <= 0) return 0;
-    int64_t chunk = (n + n_patches - 1) / n_patches;
+    int cap = 0;
+    const int tiles = form_dot_tiles(*this, f, a, &cap);
+    if (tiles <= 0) return 0;
+    int64_t chunk = (n + tiles - 1) / tiles;
     chunk += chunk & 1;
-    return chunk <= patch_kernel_side_capacity(space.p, f.op, f.cf, a) ? (int)chunk : 0;
+    return chunk <= cap ? (int)chunk : 0;
 }
 
 bool Ctx::apply_form(const FormSpec& f, const double* x, double* y, double* dot, const CgSide* side) {
     FormArgs a = make_args(f, x, y, false);
     const bool face_terms = f.bdr_mass_scale != 0.0 && any_flux();
-    const bool fuse = dot && form_fuses_dot(*this, f, a);
+    const bool fuse = dot && form_dot_tiles(*this, f, a, nullptr) > 0;
     if (side) {
         a.side_chunk = fuse ? form_side_chunk(f) : 0;
         auto misaligned = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) != 0; };
@@ -378,6 +388,7 @@ bool Ctx::apply_form(const FormSpec& f, const double* x, double* y, double* dot,
     if (rc) throw std::runtime_error("form (op=" + std::to_string(f.op) + ", cf=" + std::to_string(f.cf) + ") is not instantiated, rc=" + std::to_string(rc));
     stats.kernel_launches += (side && !(f.diag_one && f.mask_out && n_ess_owned)) ? 1 : 2;
     last_kernel = last_element_kernel();
+    if (fuse && !std::strstr(last_kernel, ",dot")) throw std::runtime_error(std::string("apply_form: (x, A x) was promised by a kernel that cannot form it: ") + last_kernel);
     if (face_terms) {
         FaceArgs fa = base_face_args(*this, bdr_mass_quad_points(space.p));
         fa.z = f.state; fa.x = x; fa.y = y; fa.mask_in = f.mask_in; fa.mask_out = f.mask_out; fa.scale = f.bdr_mass_scale;

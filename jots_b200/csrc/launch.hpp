@@ -22,6 +22,9 @@ int launch_form_apply_patch(int p, int op, int cf, const FormArgs& a, const Tabl
 bool patch_kernel_fuses_dot(int p, int op, int cf, const FormArgs& a);
 // entries per tile of the CG side stream (FormArgs::side_*) that kernel can carry; 0 = it has none
 int patch_kernel_side_capacity(int p, int op, int cf, const FormArgs& a);
+// the same two questions for the gather-table kernel: tiles of the launch when it honours FormArgs::dot (else 0), entries per
+// tile its side stream can carry
+int slab_kernel_dot_tiles(int p, int op, int cf, const FormArgs& a, int* side_capacity);
 int patch_items(int p, unsigned* out);   // phase-3 items (pencil | visits << 8 | (el << 5 | ij) << 10 | ... << 20), at most 128
 void patch_shape(int p, int& px, int& py);   // patch size for order p (0: no patch kernel)
 int launch_form_diag_slab(int p, int op, int cf, const FormArgs& a, const TablesRT& t, cudaStream_t st);

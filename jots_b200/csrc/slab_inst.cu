@@ -42,9 +42,11 @@ static int launch_slab3e(const FormArgs& a, const TablesRT& r, cudaStream_t st) 
     static PerDevice pd;
     const int grid_max = pd.get(kern, T, smem);
     const int ntiles = (a.nelem + E - 1) / E;
-    kern<<<ntiles < grid_max ? ntiles : grid_max, T, smem, st>>>(a, t);
     static const std::string label = kernel_label("form_apply_slab3_kernel", D, Q, OP, CF, ("," + std::to_string(E) + "," + std::to_string(T)).c_str());
-    last_element_kernel() = label.c_str();
+    static const std::string label_dot = label.substr(0, label.size() - 1) + ",dot>", label_side = label.substr(0, label.size() - 1) + ",dot,side>";
+    if ((a.dot || a.side_chunk) && (Slab3Stages<Q, E>::value != 2 || OP == OP_RES || !a.dot)) return 1;   // see slab_kernel_dot_tiles
+    last_element_kernel() = a.side_chunk ? label_side.c_str() : a.dot ? label_dot.c_str() : label.c_str();
+    kern<<<ntiles < grid_max ? ntiles : grid_max, T, smem, st>>>(a, t);
     return 0;
 }
 template <int D, int Q, int OP, int CF>
@@ -126,6 +128,29 @@ int launch_form_diag_slab(int p, int op, int cf, const FormArgs& a, const Tables
     if (p == 2) return dispatch_diag<3, 4>(op, cf, a, t, st);
     if (p == 3) return dispatch_diag<4, 5>(op, cf, a, t, st);
     return 1;
+}
+
+// Tiles of the gather-table kernel launch_form_apply_slab would run for this form when that kernel honours FormArgs::dot (two
+// staging buffers: every order but the 16-element Q2 tiles; bilinear forms only), else 0.  *side_capacity = entries per tile the
+// side stream (FormArgs::side_*) can carry: two pairs per thread.
+template <int D, int Q>
+static int dot_tiles(int op, int cf, const FormArgs& a, int* side_capacity) {
+    if (op == OP_RES) return 0;
+    int E = (Q == 5) ? 12 : (Q == 4) ? 16 : 32;
+    if (Q == 4 && cf == CF_FULL) E = 14;
+    const bool full = cf == CF_FULL;
+    const bool covered = (op == OP_LIN && (cf == CF_CONST || cf == CF_K || cf == CF_LINFIELDS)) || (op == OP_JAC && (cf == CF_K || (full && Q < 5)));
+    if (!covered || (Q == 4 && E >= 16)) return 0;
+    const int T = (E * 2 * Q + 31) / 32 * 32;
+    if (side_capacity) *side_capacity = 4 * T;
+    return (a.nelem + E - 1) / E;
+}
+int slab_kernel_dot_tiles(int p, int op, int cf, const FormArgs& a, int* side_capacity) {
+    if (a.nelem <= 0) return 0;
+    if (p == 1) return dot_tiles<2, 3>(op, cf, a, side_capacity);
+    if (p == 2) return dot_tiles<3, 4>(op, cf, a, side_capacity);
+    if (p == 3) return dot_tiles<4, 5>(op, cf, a, side_capacity);
+    return 0;
 }
 
 // returns 0 when launched, non-zero when this (order, op, cf) has no slab instantiation

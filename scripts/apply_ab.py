@@ -14,6 +14,9 @@ CONFIGS = {
     "patch2_barrier": {"JOTS_SLAB_VARIANT": "7", "JOTS_PATCH2_LAG": "0"},          # two-phase patch kernel, one block barrier per tile
     "patch2_barrier_dot": {"JOTS_SLAB_VARIANT": "7", "JOTS_PATCH2_LAG": "0", "JOTS_FORM_TIME_DOT": "1"},
     "slab3_gather_E16": {"JOTS_SLAB_VARIANT": "3"},                   # gather-table kernel (round-1 default)
+    # gather-table kernel + (x, A x) in phase 3 / + the CG loop's side stream (two staging buffers: Q1, Q3 -- AB_ORDER=3 AB_N=84)
+    "slab3_dot": {"JOTS_SLAB_VARIANT": "3", "JOTS_FORM_TIME_DOT": "1"},
+    "slab3_dot_side": {"JOTS_SLAB_VARIANT": "3", "JOTS_FORM_TIME_DOT": "2"},
     "patch3_4x4": {"JOTS_SLAB_VARIANT": "7", "JOTS_PATCH2": "0"},     # three-phase unique-pencil patch kernel
     "patch2_4x4": {"JOTS_SLAB_VARIANT": "7"},                         # two-phase patch kernel, warp-decoupled pipeline (default)
     "patch2_4x4_dot": {"JOTS_SLAB_VARIANT": "7", "JOTS_FORM_TIME_DOT": "1"},   # the same + (x, A x) formed in phase 3 (CG loop)

@@ -173,15 +173,16 @@ def test_cg_with_the_fused_inner_product_matches_the_separate_pass(J, tmp_path, 
 
 
 @pytest.mark.parametrize("sim,props", [("Nonlinear_Unsteady", "k"), ("Linearized_Unsteady", "const")])
-@pytest.mark.parametrize("n", [(8, 8, 3), (5, 3, 4), (13, 9, 2), (4, 4, 1)])
-def test_side_stream_carried_by_the_element_kernel(J, tmp_path, sim, props, n):
+@pytest.mark.parametrize("p,n", [(2, (8, 8, 3)), (2, (5, 3, 4)), (2, (13, 9, 2)), (2, (4, 4, 1)), (3, (5, 3, 4)), (3, (7, 5, 3)), (1, (13, 9, 2))])
+def test_side_stream_carried_by_the_element_kernel(J, tmp_path, sim, props, p, n):
     """The apply the conjugate-gradient loop launches (FormArgs::side_*): besides y = A x and (x, A x) the block that processes
     tile t does x_sol += alpha d_old and zeroes the next output buffer over slice t of the vectors.  y and the inner product
     against the oracle's matrix, x_sol against alpha * d_old + x_sol entry by entry (one fused multiply-add each), the zeroed
     buffer NaN-filled beforehand so that a slice nobody visited shows; odd vector lengths, ragged patches.  A single patch holds
-    more entries than one tile can carry: the kernel reports that it did not, and the loop keeps the vector kernels."""
+    more entries than one tile can carry: the kernel reports that it did not, and the loop keeps the vector kernels.  Q2: the
+    two-phase patch kernel; Q1 and Q3: the gather-table kernel (two staging buffers)."""
     import torch
-    dev, orc = build(J, tmp_path, sim, 3, 2, props, grade=0.6, shear=0.0, n=n,
+    dev, orc = build(J, tmp_path, sim, 3, p, props, grade=0.6, shear=0.0, n=n,
                      bcs=["HeatFlux, 7.5e5", "Isothermal, 350", HF0, "Isothermal, 300", HF0, HF0])
     nd = dev.n
     state = smooth_state(orc)
@@ -219,10 +220,11 @@ def test_side_stream_carried_by_the_element_kernel(J, tmp_path, sim, props, n):
     assert np.array_equal(td.cpu().numpy(), d_old) and np.array_equal(tx.cpu().numpy(), x)
 
 
-@pytest.mark.parametrize("sim,props,n,max_it", [("Nonlinear_Unsteady", "k", (8, 8, 4), 100), ("Linearized_Unsteady", "const", (9, 5, 3), 100),
-                                                ("Nonlinear_Unsteady", "k", (8, 8, 4), 7), ("Nonlinear_Unsteady", "k", (8, 8, 4), 1),
-                                                ("Steady", "k", (8, 4, 2), 100)])
-def test_cg_with_the_side_stream_matches_the_plain_loop(J, tmp_path, monkeypatch, sim, props, n, max_it):
+@pytest.mark.parametrize("sim,props,p,n,max_it", [("Nonlinear_Unsteady", "k", 2, (8, 8, 4), 100), ("Linearized_Unsteady", "const", 2, (9, 5, 3), 100),
+                                                  ("Nonlinear_Unsteady", "k", 2, (8, 8, 4), 7), ("Nonlinear_Unsteady", "k", 2, (8, 8, 4), 1),
+                                                  ("Steady", "k", 2, (8, 4, 2), 100), ("Nonlinear_Unsteady", "k", 3, (5, 3, 4), 100),
+                                                  ("Nonlinear_Unsteady", "k", 3, (5, 3, 4), 6), ("Linearized_Unsteady", "k", 1, (13, 9, 2), 100)])
+def test_cg_with_the_side_stream_matches_the_plain_loop(J, tmp_path, monkeypatch, sim, props, p, n, max_it):
     """cg_device_loop with x += alpha d and the zeroing of the next output carried by the element kernel against JOTS_CG_SIDE=0
     (both in the vector kernels): every vector entry sees the same operations in the same order (only the summation order of the
     element kernel's atomics varies from launch to launch), so the counts are equal and norms and field agree to rounding --
@@ -231,7 +233,7 @@ def test_cg_with_the_side_stream_matches_the_plain_loop(J, tmp_path, monkeypatch
     out = {}
     for mode in ("1", "0"):
         monkeypatch.setenv("JOTS_CG_SIDE", mode)
-        dev, orc = build(J, tmp_path, sim, 3, 2, props, solver="CG", prec="Jacobi", n=n, steps=2)
+        dev, orc = build(J, tmp_path, sim, 3, p, props, solver="CG", prec="Jacobi", n=n, steps=2)
         if max_it != 100:
             txt = open(str(tmp_path / "c.ini")).read().replace("Max_Iterations=100\n", "Max_Iterations=%d\n" % max_it, 1)
             open(str(tmp_path / "c.ini"), "w").write(txt)
