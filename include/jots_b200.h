@@ -76,6 +76,11 @@ jots_space_t jots_space_create(jots_mesh_t m, int order);
 jots_space_t jots_space_create_from_tables(int dim, int order, int64_t n_elem, int64_t n_dof, const int32_t* gather,
                                            const double* elem_corners, int64_t n_bdr, const int32_t* bdr_gather,
                                            const double* bdr_corners, const int32_t* bdr_attr);
+/* Host only.  For every boundary element: the element it belongs to, that element's local face (0..2 dim - 1) and, for each of its
+   (p+1)^(dim-1) nodes in the CALLER's order, the node's place in the element's (p+1)^dim lattice -- what the wall heat flux of
+   PreciceIsothermalBC::RetrieveWriteData (src/boundary_condition.cpp:160-206) needs.  A space built from tables carries no
+   adjacency: it is recovered by matching DOF ids.  Any output may be NULL. */
+int jots_space_boundary_adjacency(jots_space_t s, int32_t* bdr_elem, int32_t* bdr_face, int32_t* node_loc);
 int jots_space_copy_corners(jots_space_t s, double* elem_corners, double* bdr_corners);
 void jots_space_destroy(jots_space_t s);
 int jots_space_info(jots_space_t s, int* dim, int* order, int64_t* n_elem, int64_t* n_dof, int64_t* n_bdr,

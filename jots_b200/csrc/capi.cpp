@@ -126,6 +126,21 @@ int jots_mesh_set_vertices(jots_mesh_t m, const double* verts) {
 jots_space_t jots_space_create(jots_mesh_t m, int order) {
     JOTS_TRY auto* h = new jots_space_s; h->s = make_space(m->m, order); return h; JOTS_CATCH_PTR
 }
+// host only: the adjacency the preCICE write path needs (Ctx::set_bcs), exposed so that the index contract is testable without a GPU
+int jots_space_boundary_adjacency(jots_space_t sp, int32_t* bdr_elem, int32_t* bdr_face, int32_t* node_loc) {
+    JOTS_TRY
+    Space s = sp->s;      // a copy: the handle keeps what the caller gave it
+    fill_boundary_adjacency(s);
+    std::vector<int> nl;
+    boundary_node_locals(s, nl);
+    for (int64_t b = 0; b < s.nbdr; ++b) {
+        if (bdr_elem) bdr_elem[b] = (int32_t)s.bdr_elem[b];
+        if (bdr_face) bdr_face[b] = (int32_t)s.bdr_face[b];
+    }
+    if (node_loc) std::copy(nl.begin(), nl.end(), node_loc);
+    return 0;
+    JOTS_CATCH_INT
+}
 jots_space_t jots_space_create_from_tables(int dim, int order, int64_t n_elem, int64_t n_dof, const int32_t* gather,
                                            const double* elem_corners, int64_t n_bdr, const int32_t* bdr_gather,
                                            const double* bdr_corners, const int32_t* bdr_attr) {
@@ -380,7 +395,7 @@ int jots_ctx_set_bcs(jots_ctx_t c, int n_bc, const int32_t* kinds, const double*
     if ((size_t)n_bc != c->c->space.attributes.size()) throw std::runtime_error("Input file BC count and mesh BC counts do not match.");
     std::vector<BCSpec> b(n_bc);
     for (int i = 0; i < n_bc; ++i) {
-        if (kinds[i] < 0 || kinds[i] > 3) throw std::runtime_error("Invalid/Unknown boundary condition specified");
+        if (kinds[i] < 0 || kinds[i] > BC_PRECICE_HEATFLUX) throw std::runtime_error("Invalid/Unknown boundary condition specified");
         b[i].kind = kinds[i];
         for (int j = 0; j < 4; ++j) b[i].v[j] = params[4 * i + j];
         b[i].update(0.0);

@@ -57,6 +57,7 @@ def load_library():
         "jots_mesh_set_vertices": (C.c_int, [_P, _P]),
         "jots_space_create": (_P, [_P, C.c_int]),
         "jots_space_destroy": (None, [_P]),
+        "jots_space_boundary_adjacency": (C.c_int, [_P, _P, _P, _P]),
         "jots_space_create_from_tables": (_P, [C.c_int, C.c_int, C.c_int64, C.c_int64, _P, _P, C.c_int64, _P, _P, _P]),
         "jots_space_copy_corners": (C.c_int, [_P, _P, _P]),
         "jots_space_info": (C.c_int, [_P, C.POINTER(C.c_int), C.POINTER(C.c_int), _I64, _I64, _I64, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
@@ -358,6 +359,15 @@ class Space:
         bf = np.empty(self.n_bdr, dtype=np.int32)
         _chk(load_library().jots_space_copy_bdr(self._h, _ptr(bg), _ptr(ba), _ptr(be), _ptr(bf)))
         return bg, ba, be, bf
+
+    def boundary_adjacency(self):
+        """(adjacent element, its local face, place of every boundary node in that element's lattice) per boundary element;
+        recovered from the DOF ids when the space came from tables (host only)."""
+        be = np.empty(self.n_bdr, dtype=np.int32)
+        bf = np.empty(self.n_bdr, dtype=np.int32)
+        nl = np.empty((self.n_bdr, self.dofs_per_face), dtype=np.int32)
+        _chk(load_library().jots_space_boundary_adjacency(self._h, _ptr(be), _ptr(bf), _ptr(nl)))
+        return be, bf, nl
 
     def node_coordinates(self):
         x = np.empty((self.n_dof, self.dim))

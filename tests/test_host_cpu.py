@@ -96,6 +96,45 @@ def test_space_from_caller_tables_round_trip():
         J.Space.from_tables(3, 2, 5, sp.gather(), ec, bg, bc, ba)
 
 
+@pytest.mark.parametrize("dim,p", [(3, 1), (3, 2), (3, 3), (2, 2), (2, 3)])
+def test_boundary_adjacency_recovered_from_the_dof_ids(tmp_path, dim, p):
+    """jots_space_boundary_adjacency (what the wall heat flux of the preCICE write path needs): a space built from the
+    caller's tables carries no boundary-element adjacency and may list the DOFs of a boundary face in an order of its own
+    (here: transposed and reversed).  The adjacent element and its face must be the mesh's own, and every node must be
+    placed where the mesh-built space places it -- integer compare."""
+    mesh = str(tmp_path / "m.mesh")
+    if dim == 3:
+        write_brick_mesh(mesh, 4, 3, 2, 0.01, 0.02, 0.015, grade=0.4)
+    else:
+        write_quad_mesh(mesh, 6, 4, 0.02, 0.01, grade=0.4)
+    sp = J.Space(J.Mesh.read(mesh), p)
+    ec, bc = sp.corners()
+    bg, ba, be, bf = sp.boundary()
+    D = p + 1
+    nfl = D ** (dim - 1)
+    if dim == 3:
+        perm = np.arange(nfl).reshape(D, D).T[::-1, ::-1].ravel()
+        cperm = np.arange(4).reshape(2, 2).T[::-1, ::-1].ravel()
+    else:
+        perm = np.arange(nfl)[::-1]
+        cperm = np.arange(2)[::-1]
+    bg2 = np.ascontiguousarray(bg.reshape(-1, nfl)[:, perm])
+    bc2 = np.ascontiguousarray(bc.reshape(bg2.shape[0], 2 ** (dim - 1), dim)[:, cperm, :])
+    sp2 = J.Space.from_tables(dim, p, sp.n_dof, sp.gather(), ec, bg2, bc2, ba)
+    e1, f1, nl1 = sp.boundary_adjacency()
+    e2, f2, nl2 = sp2.boundary_adjacency()
+    assert (e1 == be).all() and (f1 == bf).all()
+    assert (e2 == be).all() and (f2 == bf).all()
+    assert (nl2 == nl1[:, perm]).all()
+    g = sp.gather()
+    assert (g[e2[:, None], nl2] == bg2).all()          # the place really holds the DOF the caller listed
+    # a boundary table that does not belong to the element table is an error, not a wrong flux
+    bad = bg2.copy()
+    bad[0, 0] = bad[-1, -1]
+    with pytest.raises(J.JotsError, match="matches no element face|not on the matched element face"):
+        J.Space.from_tables(dim, p, sp.n_dof, sp.gather(), ec, bad, bc2, ba).boundary_adjacency()
+
+
 def _emulated_exchange(parts, vals):
     """pairwise exchange + canonical-order reduction, as halo_sum_exchange does on the device"""
     recv = []
