@@ -283,6 +283,9 @@ __global__ void __launch_bounds__(T, 4) form_apply_patch2_kernel(const FormArgs 
         }
     };
 
+    const int side_chunk = (DOT && LAG) ? a.side_chunk : 0;
+    const bool side_warp = side_chunk != 0 && !copier && 64 * warp < side_chunk;      // warp-uniform
+    const int side_last = (int)a.nvec - 1;
     int it = 0;
     for (;; ++it) {
         if (LAG) mbar_wait(READY + (it & 3), (it >> 2) & 1);
@@ -431,35 +434,33 @@ __global__ void __launch_bounds__(T, 4) form_apply_patch2_kernel(const FormArgs 
             mbar_arrive(FULL + (it & 1));
             if (copier) { cp_async_wait<0>(); __syncwarp(); mbar_arrive(READY + ((it + 2) & 3)); }
             // Side stream of the conjugate-gradient loop (FormArgs::side_*): this tile's slice of x += alpha d_old and of the
-            // zeroing of the next apply's output.  The loads are issued here, where the register peak of phase 2 is over, and
-            // consumed after phase 3 of the previous tile (about a microsecond later: their latency is not waited for); streaming
-            // cache hints keep the slices from displacing the gathered nodal values in L2.  The copy warp paces the block and
-            // takes no part.
+            // zeroing of the next output, one pair of entries per thread of the first warps (the copy warp paces the block and
+            // takes no part; warps without entries skip the section).  The loads are issued here, where the register peak of
+            // phase 2 is over, and consumed after phase 3 of the previous tile (about a microsecond later: their latency is not
+            // waited for); streaming cache hints keep the slices from displacing the gathered nodal values in L2.  Vector
+            // lengths are below 2^31 (DOF ids are 32-bit), so the index arithmetic is 32-bit.
             double2 side_xv = make_double2(0.0, 0.0), side_dv = side_xv;
             double side_al = 0.0;
-            long long side_k = 0;
-            int side_mode = 0;             // 2: a pair of entries, 1: the last entry of an odd-length vector
-            if (DOT && a.side_chunk != 0 && !copier && 2 * tid < a.side_chunk) {
-                side_k = (long long)s_tile[it & RMASK] * a.side_chunk + 2 * tid;
-                side_mode = side_k + 1 < a.nvec ? 2 : (side_k < a.nvec ? 1 : 0);
-                if (side_mode == 2) {
-                    side_xv = __ldcs(reinterpret_cast<const double2*>(a.side_x + side_k));
-                    side_dv = __ldcs(reinterpret_cast<const double2*>(a.side_d + side_k));
-                } else if (side_mode == 1) { side_xv.x = __ldcs(a.side_x + side_k); side_dv.x = __ldcs(a.side_d + side_k); }
-                side_al = __ldg(a.side_alpha);
+            int side_k = -1;
+            if (DOT && side_warp) {
+                const int k = s_tile[it & RMASK] * side_chunk + 2 * tid;
+                if (2 * tid < side_chunk && k < side_last) {          // a whole pair; an odd last entry is done after the loop
+                    side_k = k;
+                    side_xv = __ldcs(reinterpret_cast<const double2*>(a.side_x + k));
+                    side_dv = __ldcs(reinterpret_cast<const double2*>(a.side_d + k));
+                    side_al = __ldg(a.side_alpha);
+                }
             }
             if (it >= 1) {
                 mbar_wait(FULL + ((it - 1) & 1), ((it - 1) >> 1) & 1);
                 phase3_all(it - 1, xk);
                 mbar_arrive(EMPTY + ((it - 1) & 1));
             }
-            if (DOT && side_mode != 0) {
+            if (DOT && side_k >= 0) {
                 side_xv.x = fma(side_al, side_dv.x, side_xv.x);
-                if (side_mode == 2) {
-                    side_xv.y = fma(side_al, side_dv.y, side_xv.y);
-                    __stcs(reinterpret_cast<double2*>(a.side_x + side_k), side_xv);
-                    __stcs(reinterpret_cast<double2*>(a.side_zero + side_k), make_double2(0.0, 0.0));
-                } else { __stcs(a.side_x + side_k, side_xv.x); __stcs(a.side_zero + side_k, 0.0); }
+                side_xv.y = fma(side_al, side_dv.y, side_xv.y);
+                __stcs(reinterpret_cast<double2*>(a.side_x + side_k), side_xv);
+                __stcs(reinterpret_cast<double2*>(a.side_zero + side_k), make_double2(0.0, 0.0));
             }
         }
     }
@@ -467,6 +468,10 @@ __global__ void __launch_bounds__(T, 4) form_apply_patch2_kernel(const FormArgs 
         double xk[D];
         mbar_wait(FULL + ((it - 1) & 1), ((it - 1) >> 1) & 1);
         phase3_all(it - 1, xk);
+    }
+    if (DOT && side_chunk != 0 && blockIdx.x == 0 && tid == 0 && (a.nvec & 1)) {      // the last entry of an odd-length vector
+        a.side_x[side_last] = fma(__ldg(a.side_alpha), a.side_d[side_last], a.side_x[side_last]);
+        a.side_zero[side_last] = 0.0;
     }
     if (DOT) {
         __syncthreads();
