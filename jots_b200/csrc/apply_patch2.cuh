@@ -81,6 +81,8 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* b, unsigned parity
 // inside phase 2 of tile t (registers: 3 % slower); moving the copy-engine role to another warp with every tile to even out
 // the four scheduler partitions (5 % slower).
 // DOT: also add (x, A x) over the rows written to *a.dot (FormArgs::dot; the conjugate-gradient loop's (d, A d)).
+// Side stream (FormArgs::side_*, DOT and LAG): measured dead end -- pulling the tile's slices into L2 at the start of the tile
+// (prefetch.global.L2) so that their loads after phase 2 hit L2: 0.9084 -> 0.9094 ms (profiles/r3h).
 //
 // LAG: the warp-decoupled pipeline.  With one block barrier per tile every warp waits for the slowest one once per tile (14 % of
 // the warp samples, profiles/r2v_phases_*).  Here phase 3 of tile t-1 runs AFTER phase 2 of tile t, and the hand-overs are
