@@ -204,8 +204,10 @@ def workload_config(args, world):
     nd = 1
     for k in ne:
         nd *= k * args.order + 1
-    return {"workload": "configs[3]: synthetic refined brick, %dx%dx%d Q%d hexes, %d DOFs, nonlinear unsteady (backward Euler, "
-                        "dt=1e-2), k(T)=0.09T-17%s, Newton + %s/%s rel 1e-10" % (ne[0], ne[1], ne[2], args.order, nd,
+    # BASELINE.json: configs[3] = Q2, ~16 M DOFs on one B200 (the default); configs[4] = Q3, ~128 M DOFs over 2/4/8 B200
+    which = "configs[4]" if args.order == 3 else "configs[3]" if args.order == 2 else "configs[3] physics at another order"
+    return {"workload": "%s: synthetic refined brick, %dx%dx%d Q%d hexes, %d DOFs, nonlinear unsteady (backward Euler, "
+                        "dt=1e-2), k(T)=0.09T-17%s, Newton + %s/%s rel 1e-10" % (which, ne[0], ne[1], ne[2], args.order, nd,
                                                                                     ", C(T)=4.5T-850" if args.variant == "B" else "", args.solver, args.prec),
             "n_elem": ne, "order": args.order, "n_dof": nd, "solver": args.solver, "preconditioner": args.prec,
             "parallelism": ("box partition %s, 1 subdomain per GPU, NCCL interface sum-exchange + scalar all-reduce" % "x".join(map(str, box_dims(world))))
