@@ -640,7 +640,7 @@ int jots_op_form_apply_side(jots_op_t op, int form, const double* x, const doubl
     const double hs[2] = {0.0, alpha};
     JOTS_CUDA(cudaMemcpyAsync(d_s.p, hs, sizeof(hs), cudaMemcpyHostToDevice, c->stream));
     c->zero(y);
-    const CgSide side{side_x, side_d, d_s.p + 1, side_zero};
+    const CgSide side{side_x, side_d, d_s.p + 1, side_zero, 0};
     bool fu = false;
     try { run_form(op, form, x, state, y, false, d_s.p, &fu, &side); }
     catch (const std::runtime_error&) { c->sync(); return 0; }      // *carried stays 0: this form has no side stream
@@ -679,7 +679,7 @@ int jots_op_form_time(jots_op_t op, int form, const double* x, const double* sta
     }
     double* Y[2] = {y, mode >= 2 ? y2.p : y};
     auto one = [&](int i) {
-        if (mode >= 2) { const CgSide side{sx.p, x, c->d_scal.p + 62, Y[(i + 1) & 1]}; run_form(op, form, x, state, Y[i & 1], false, d_dot, nullptr, &side); }
+        if (mode >= 2) { const CgSide side{sx.p, x, c->d_scal.p + 62, Y[(i + 1) & 1], 0}; run_form(op, form, x, state, Y[i & 1], false, d_dot, nullptr, &side); }
         else run_form(op, form, x, state, y, false, d_dot);
     };
     one(0);

@@ -350,6 +350,18 @@ static int form_dot_tiles(const Ctx& c, const FormSpec& f, const FormArgs& a, in
     return slab_kernel_dot_tiles(c.space.p, f.op, f.cf, a, side_capacity);
 }
 
+bool Ctx::ess_rows_are_zero(const double* v) {
+    if (n_ess_owned == 0) return true;
+    double* acc = d_scal.p + 61;
+    JOTS_CUDA(cudaMemsetAsync(acc, 0, sizeof(double), stream));
+    v_zero_essdot(stream, 0, nullptr, n_ess_owned, d_ess_owned.p, v, acc, nullptr);     // sum of squares over the listed entries
+    ++stats.kernel_launches;
+    double h = 1.0;
+    JOTS_CUDA(cudaMemcpyAsync(&h, acc, sizeof(double), cudaMemcpyDeviceToHost, stream));
+    sync();
+    return h == 0.0;
+}
+
 int Ctx::form_side_chunk(const FormSpec& f) const {
     const FormArgs a = make_args(f, nullptr, nullptr, false);
     int cap = 0;
@@ -376,7 +388,7 @@ bool Ctx::apply_form(const FormSpec& f, const double* x, double* y, double* dot,
         // with a side stream y was zeroed by the previous launch: only the unit-diagonal rows' share of (x, A x) is left
         const int n_idx = (f.diag_one && f.mask_out) ? n_ess_owned : 0;
         if (!side) v_zero_essdot(stream, n, y, n_idx, d_ess_owned.p, x, dot, a.skip);
-        else if (n_idx) v_zero_essdot(stream, 0, y, n_idx, d_ess_owned.p, x, dot, a.skip);
+        else if (n_idx && !side->ess_zero) v_zero_essdot(stream, 0, y, n_idx, d_ess_owned.p, x, dot, a.skip);
     } else zero(y);
     // lattice meshes: unique-pencil patch kernels; otherwise / when not instantiated the gather-table kernels
     int rc = 1;
@@ -386,7 +398,7 @@ bool Ctx::apply_form(const FormSpec& f, const double* x, double* y, double* dot,
     }
     if (rc) rc = launch_form_apply(space.dim, space.p, f.op, f.cf, a, tabs, stream);
     if (rc) throw std::runtime_error("form (op=" + std::to_string(f.op) + ", cf=" + std::to_string(f.cf) + ") is not instantiated, rc=" + std::to_string(rc));
-    stats.kernel_launches += (side && !(f.diag_one && f.mask_out && n_ess_owned)) ? 1 : 2;
+    stats.kernel_launches += (side && (side->ess_zero || !(f.diag_one && f.mask_out && n_ess_owned))) ? 1 : 2;
     last_kernel = last_element_kernel();
     if (fuse && !std::strstr(last_kernel, ",dot")) throw std::runtime_error(std::string("apply_form: (x, A x) was promised by a kernel that cannot form it: ") + last_kernel);
     if (face_terms) {

@@ -145,6 +145,7 @@ public:
     // side != nullptr (only after form_side_chunk(f) > 0, dot != nullptr and y ALREADY zero): the launch also carries the
     // conjugate-gradient loop's side stream, side->x += *side->alpha * side->d and side->zero = 0 (FormArgs::side_*)
     bool apply_form(const FormSpec& f, const double* x, double* y, double* dot = nullptr, const CgSide* side = nullptr);
+    bool ess_rows_are_zero(const double* v);        // v[i] == 0 on every owned essential DOF (one small kernel + a synchronisation)
     int form_side_chunk(const FormSpec& f) const;   // entries per tile of the side stream for this form; 0 = not available
     void diag_form(const FormSpec& f, double* d);
     // b_i = sum_faces int (g / divisor) phi_i; state != null -> divisor rho_h(state) C_h(state)

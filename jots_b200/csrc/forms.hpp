@@ -97,6 +97,7 @@ struct CgSide {
     const double* d;
     const double* alpha;    // device scalar
     double* zero;
+    int ess_zero;           // the input is known to vanish on the essential rows: their share of (x, A x) needs no kernel
 };
 
 // 1-D tables; DZ = QZ = 1 turns the hex kernel into the quad kernel

@@ -252,6 +252,9 @@ void Krylov::cg_device_loop(double* x, double* r, double* z, double* d, const do
     double* D[2] = {d, side ? w(3) : d};
     double* Z[2] = {z, side ? w(4) : z};
     if (side) c->zero(Z[1]);
+    // r vanishes on the essential rows (the right-hand sides of the reference's operators do: rhs[ess] = 0) => so does every
+    // direction, exactly (unit diagonal rows: r -= alpha * d keeps a zero), and their share of (d, A d) needs no kernel
+    const bool ess_zero = side && c->ess_rows_are_zero(r);
     int launched = 0, chunk = 0;
     bool stopped = false;
     while (launched < max_iter && !stopped) {
@@ -273,7 +276,7 @@ void Krylov::cg_device_loop(double* x, double* r, double* z, double* d, const do
             if (last) break;
             ++info.applies;
             if (side) {
-                const CgSide sj{x, D[p], S + 7, Z[p]};
+                const CgSide sj{x, D[p], S + 7, Z[p], ess_zero ? 1 : 0};
                 A->mult_dot_side(D[1 - p], Z[1 - p], S + 2, sj);
             } else if (!(fused_dot ? A->mult_dot(d, z, S + 2) : (A->mult(d, z), false))) {
                 v_cgd_dot(st, c->n_owned, S, d, z, c->dot_scratch());

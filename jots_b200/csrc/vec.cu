@@ -1,4 +1,5 @@
 #include <cstdint>
+#include <cstdlib>
 #include "vec.cuh"
 #include "vec.hpp"
 #include "coef.cuh"
@@ -141,6 +142,9 @@ __global__ void __launch_bounds__(VEC_THREADS) k_cg_update(int64_t n, int64_t n_
 // were final before the kernel started, so all blocks of a kernel take the same branch (grid_reduce needs that).
 // SIDE: x += alpha d is not done here but handed to the next operator apply as its side stream (FormArgs::side_*), which
 // reads alpha from S[7]; the loop's epilogue applies the one update that is still pending when the iteration stops.
+// Measured dead end (profiles/README.md r3j): L2 residency hints between the two vector kernels -- the update kernel streaming r,
+// A d, D^-1 as evict-first and leaving z behind as evict-last lines (createpolicy + st.global.L2::cache_hint) so that the direction
+// kernel's read of z is served from L2: 318.2 -> 319.8 ms per step.
 template <bool SIDE>
 __global__ void __launch_bounds__(VEC_THREADS) k_cgd_update(int64_t n, int64_t n_owned, double* S, int i, const double* __restrict__ d,
                                                              const double* Ad, double* x, double* r, const double* __restrict__ dinv,
