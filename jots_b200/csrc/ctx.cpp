@@ -366,7 +366,7 @@ int Ctx::form_side_chunk(const FormSpec& f) const {
     const FormArgs a = make_args(f, nullptr, nullptr, false);
     int cap = 0;
     const int tiles = form_dot_tiles(*this, f, a, &cap);
-    if (tiles <= 0) return 0;
+    if (tiles <= 0 || n > 2000000000LL) return 0;      // the kernels index the slices with 32-bit arithmetic
     int64_t chunk = (n + tiles - 1) / tiles;
     chunk += chunk & 1;
     return chunk <= cap ? (int)chunk : 0;
