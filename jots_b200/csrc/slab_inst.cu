@@ -49,6 +49,16 @@ static int launch_slab3e(const FormArgs& a, const TablesRT& r, cudaStream_t st) 
     kern<<<ntiles < grid_max ? ntiles : grid_max, T, smem, st>>>(a, t);
     return 0;
 }
+// Q3 tile: 6 elements on 64 threads (four blocks of two warps per SM) for the bilinear forms -- the blocks' latency-bound phases 1
+// and 3 overlap other blocks' phase 2 better than with 12 elements on 128 threads (two blocks per SM): Jacobian apply 1.072 ->
+// 1.054 ms, with inner product and side stream 1.104 -> 1.089 ms; the residual form is faster with 12 (0.977 vs 0.987 ms)
+// (profiles/r3m).  JOTS_SLAB3_Q3_E = 6 | 12 forces one size for every form.
+static int q3_tile(int op) {
+    static const int forced = [] { const char* e = getenv("JOTS_SLAB3_Q3_E"); return e ? atoi(e) : 0; }();
+    if (forced == 6 || forced == 12) return forced;
+    return op == OP_RES ? 12 : 6;
+}
+
 template <int D, int Q, int OP, int CF>
 static int launch_slab3(const FormArgs& a, const TablesRT& r, cudaStream_t st) {
     if constexpr (Q == 4) {
@@ -57,7 +67,7 @@ static int launch_slab3(const FormArgs& a, const TablesRT& r, cudaStream_t st) {
         if constexpr (CF != CF_FULL && CF != CF_FULLC) return launch_slab3e<D, Q, OP, CF, 16>(a, r, st);
         else return launch_slab3e<D, Q, OP, CF, 14>(a, r, st);
     }
-    else if constexpr (Q == 5) return launch_slab3e<D, Q, OP, CF, 12>(a, r, st);
+    else if constexpr (Q == 5) return q3_tile(OP) == 6 ? launch_slab3e<D, Q, OP, CF, 6>(a, r, st) : launch_slab3e<D, Q, OP, CF, 12>(a, r, st);
     else return launch_slab3e<D, Q, OP, CF, 32>(a, r, st);
 }
 
@@ -136,7 +146,7 @@ int launch_form_diag_slab(int p, int op, int cf, const FormArgs& a, const Tables
 template <int D, int Q>
 static int dot_tiles(int op, int cf, const FormArgs& a, int* side_capacity) {
     if (op == OP_RES) return 0;
-    int E = (Q == 5) ? 12 : (Q == 4) ? 16 : 32;
+    int E = (Q == 5) ? q3_tile(op) : (Q == 4) ? 16 : 32;
     if (Q == 4 && cf == CF_FULL) E = 14;
     const bool full = cf == CF_FULL;
     const bool covered = (op == OP_LIN && (cf == CF_CONST || cf == CF_K || cf == CF_LINFIELDS)) || (op == OP_JAC && (cf == CF_K || (full && Q < 5)));
