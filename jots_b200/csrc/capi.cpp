@@ -643,7 +643,7 @@ int jots_op_form_apply_side(jots_op_t op, int form, const double* x, const doubl
     const CgSide side{side_x, side_d, d_s.p + 1, side_zero, 0};
     bool fu = false;
     try { run_form(op, form, x, state, y, false, d_s.p, &fu, &side); }
-    catch (const std::runtime_error&) { c->sync(); return 0; }      // *carried stays 0: this form has no side stream
+    catch (const NoSideStream&) { c->sync(); return 0; }      // *carried stays 0: this form has no side stream
     c->allreduce_scalars(d_s.p, 1);
     double v = 0.0;
     JOTS_CUDA(cudaMemcpyAsync(&v, d_s.p, sizeof(double), cudaMemcpyDeviceToHost, c->stream));

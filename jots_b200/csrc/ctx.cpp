@@ -380,7 +380,7 @@ bool Ctx::apply_form(const FormSpec& f, const double* x, double* y, double* dot,
         a.side_chunk = fuse ? form_side_chunk(f) : 0;
         auto misaligned = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) != 0; };
         if (!a.side_chunk || misaligned(side->x) || misaligned(side->d) || misaligned(side->zero))
-            throw std::runtime_error("apply_form: this form / these vectors cannot carry the CG side stream");
+            throw NoSideStream("apply_form: this form / these vectors cannot carry the CG side stream");
         a.side_x = side->x; a.side_d = side->d; a.side_alpha = side->alpha; a.side_zero = side->zero;
     }
     if (fuse) {

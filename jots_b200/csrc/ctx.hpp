@@ -18,6 +18,10 @@ namespace jots {
 struct CudaError : std::runtime_error {
     using std::runtime_error::runtime_error;
 };
+// apply_form was asked to carry the CG side stream with a form / vectors that cannot (callers probe with form_side_chunk first)
+struct NoSideStream : std::runtime_error {
+    using std::runtime_error::runtime_error;
+};
 void cuda_check(cudaError_t e, const char* what, const char* file, int line);
 #define JOTS_CUDA(x) ::jots::cuda_check((x), #x, __FILE__, __LINE__)
 
