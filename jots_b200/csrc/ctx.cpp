@@ -5,6 +5,8 @@
 #include <cstdlib>
 #include <cstring>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "basis.hpp"
 #include "halo.hpp"
 #include "launch.hpp"
@@ -16,6 +18,9 @@ void cuda_check(cudaError_t e, const char* what, const char* file, int line) {
     if (e == cudaSuccess) return;
     throw CudaError(std::string("CUDA error: ") + cudaGetErrorString(e) + " in " + what + " (" + file + ":" + std::to_string(line) + ")");
 }
+
+NvtxRange::NvtxRange(const char* name) { nvtxRangePushA(name); }
+NvtxRange::~NvtxRange() { nvtxRangePop(); }
 
 void BCSpec::update(double t) {
     // SinusoidalBC::UpdateCoeff: A sin(w t + phase) + shift (boundary_condition.cpp:65-75)
@@ -417,6 +422,7 @@ bool Ctx::apply_form(const FormSpec& f, const double* x, double* y, double* dot,
 }
 
 void Ctx::diag_form(const FormSpec& f, double* d) {
+    NvtxRange range("jots:diagonal");
     zero(d);
     FormArgs a = make_args(f, nullptr, d, true);
     a.mask_out = (f.mask_out || f.diag_one) ? 1 : 0;

@@ -25,6 +25,15 @@ struct NoSideStream : std::runtime_error {
 void cuda_check(cudaError_t e, const char* what, const char* file, int line);
 #define JOTS_CUDA(x) ::jots::cuda_check((x), #x, __FILE__, __LINE__)
 
+// NVTX range for the tools (`ncu --nvtx --nvtx-include "jots:krylov/"` profiles only the kernels of the Krylov solves):
+// step > newton > krylov, diagonal.  Two calls through a function pointer that is null when no tool is attached.
+struct NvtxRange {
+    explicit NvtxRange(const char* name);
+    ~NvtxRange();
+    NvtxRange(const NvtxRange&) = delete;
+    NvtxRange& operator=(const NvtxRange&) = delete;
+};
+
 // simple owning device array
 template <class T>
 struct DArr {

@@ -308,6 +308,7 @@ void JOTSDriver::Iteration() {
 }
 
 void JOTSDriver::Step() {
+    NvtxRange range("jots:step");
     UpdateAndApplyBCs();
     UpdateMatProps(true);
     Iteration();

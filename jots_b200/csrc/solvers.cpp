@@ -151,6 +151,7 @@ double* Krylov::w(int i) {
 }
 
 void Krylov::mult(const double* b, double* x) {
+    NvtxRange range("jots:krylov");
     info = SolveInfo();
     if (!A) throw std::runtime_error("Krylov solver has no operator");
     if (kind == SOLVER_CG) cg(b, x);
@@ -410,6 +411,7 @@ void Krylov::gmres(const double* b, double* x, bool flexible) {
 // Newton (mfem::NewtonSolver::Mult + JOTSNewtonSolver::ProcessNewState)
 // ------------------------------------------------------------------------------------------------
 void Newton::mult(NewtonOp& op, Krylov& lin, const double* b, double* x) {
+    NvtxRange range("jots:newton");
     const int64_t n = c->n;
     r.alloc(n); cvec.alloc(n);
     op.new_state(x);
