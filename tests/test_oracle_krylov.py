@@ -104,3 +104,27 @@ def test_gmres_iterates_minimise_their_residual_norms(tmp_path, k, flexible):
     ref = W @ y
     assert np.linalg.norm(x - ref) <= 1e-8 * np.linalg.norm(ref)
     assert abs(s.info.final_norm - norm) <= 1e-8 * norm
+
+
+def test_chebyshev_smoother_is_hypres_degree_one_polynomial(tmp_path):
+    """HypreSmoother::Chebyshev as MFEM sets it up (type 16, poly_order 2 -> hypre's cheby_order 1, fraction 0.3): one
+    application is z = D^-1/2 p(A^) D^-1/2 r with A^ = D^-1/2 A D^-1/2 and hypre's p(t) = (delta - t + 2 theta) / (theta^2 +
+    delta theta) (par_cheby.c, case 1), whose residual polynomial 1 - t p(t) has its roots at theta and at the upper bound
+    1.1 lambda_max; evaluated here through a dense eigendecomposition instead of the operator recurrence."""
+    A, b = system(tmp_path, "Linearized_Unsteady")
+    sm = OS.ChebyshevSmoother()
+    sm.set_operator(A, A.diagonal())
+    ds = 1.0 / np.sqrt(A.diagonal())
+    Ah = (ds[:, None] * A.toarray()) * ds[None, :]
+    lam, Q = np.linalg.eigh(0.5 * (Ah + Ah.T))
+    # the Lanczos estimate after 10 steps brackets nothing exactly, but must sit inside the spectrum and near its top
+    assert lam[0] - 1e-12 <= sm.lmin <= sm.lmax <= lam[-1] + 1e-12 and sm.lmax > 0.9 * lam[-1]
+    ub = 1.1 * sm.lmax
+    lb = sm.lmin + 0.3 * (ub - sm.lmin)
+    theta, delta = 0.5 * (ub + lb), 0.5 * (ub - lb)
+    p = lambda t: (delta - t + 2.0 * theta) / (theta * theta + delta * theta)
+    assert abs(1.0 - theta * p(theta)) < 1e-14 and abs(1.0 - ub * p(ub)) < 1e-14
+    z = sm.mult(b)
+    ref = ds * (Q @ (p(lam) * (Q.T @ (ds * b))))
+    assert np.linalg.norm(z - ref) <= 1e-12 * np.linalg.norm(ref)
+    assert sm.order == 1 and sm.c.size == 2
