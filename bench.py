@@ -460,6 +460,9 @@ def main():
             "gpu_launches": st["kernel_launches"],
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "algorithmic_bytes": alg_bytes,
+                         # what the launch moves on top of the apply's 24 B/DOF when it carries the CG loop's side stream (x in / out,
+                         # d_old in, zeroing of the next output: 32 B/DOF); `achieved` does not count it, `traffic` contains it
+                         "side_stream_bytes": (32.0 * ndof if st.get("side_applies", 0) > 0 else 0.0),
                          "kernel": kernel_label,
                          "timed": "Jacobian-vector apply, 24 B/DOF algorithmic (x, z in, y out); CUDA events on the launching stream around "
                                   "%d applies, each = %s" % (args.apply_reps,
