@@ -19,8 +19,15 @@ pin results only through analytic solutions with tolerances
 (tests/test_helper.hpp.in:107-159, :261-376).  This oracle is pinned against all
 of those (tests/test_oracle_analytic.py: Reinert B1/B2/B3 linearized + nonlinear
 at 1e-8, Danish model 1 Dirichlet + Neumann at 3e-5, using the reference's own
-error functional, tests/test_helper.hpp.in:134).  Everything finer than those
-tolerances (quadrature orders, nodal-interpolated coefficients, Krylov stopping
-rules: SURVEY.md App. A) follows MFEM 4.7's published algorithm as restated in
-the module docstrings: for those details **parity is unpinned**.
+error functional, tests/test_helper.hpp.in:134).  Below those tolerances the
+oracle is checked against things that do not depend on it: exact integrals of the
+Lagrange basis (tests/test_oracle_exact.py -- on affine hexes of order <= 3 MFEM's
+default rule integrates the benchmarked forms exactly, so the discrete operator IS
+the exact Galerkin integral; on quads the (p + 1)-point Gauss sum, which is not),
+the defining minimisation problems of CG / GMRES / FGMRES and SciPy's CG
+(tests/test_oracle_krylov.py), hypre's degree-one Chebyshev polynomial, and the
+expected convergence orders.  What no test here can establish is that MFEM 4.7 /
+hypre really use those rules, stopping criteria and nodal-interpolation semantics
+(restated in the module docstrings): against the reference
+itself **parity is unpinned**.
 """
